@@ -1,0 +1,170 @@
+"""Seeded synthetic ScanRefer-shaped inputs.
+
+Mirrors what the reference's loader hands to ``InstanceRefer.forward`` — the dict built in
+``lib/dataset.py:255-298`` and batched by ``collate_fn`` (``lib/dataset.py:456-469``) — without
+ScanNet/ScanRefer/GloVe data: an axis-aligned room with its min corner at the origin (so the
+reference's ``SparseCrop`` keeps everything, ``models/scene_module.py:22-23``), box-shaped
+objects standing on the floor, exactly ``num_points`` points with
+``[x,y,z, r,g,b, height]`` features (``lib/dataset.py:105,121-123``), 1024-point instance
+samples (``lib/dataset.py:224``) and GloVe-scaled language features (``lib/dataset.py:73-86``).
+
+numpy only; no CUDA, no oracle imports.  The scene voxelisation at 5 cm is the *loader's* job
+in the reference (host numpy, ``lib/dataset.py:255-261``); ``quantize_first`` restates it here so
+the generated ``lidar`` tensor looks like the loader's output.
+"""
+import numpy as np
+
+MAX_DES_LEN = 126          # lib/config.py:74
+NUM_CLASSES = 18           # config/InstanceRefer.yaml:8
+
+
+def quantize_first(xyz, feats, voxel):
+    """floor(xyz / voxel) in float64; one row per voxel = first point in input order,
+    rows kept in first-occurrence order.  -> (coords int32 (V,3), feats[idx])."""
+    disc = np.floor(xyz.astype(np.float64) / voxel).astype(np.int64)
+    key = ((disc[:, 0] + 32768) << 32) | ((disc[:, 1] + 32768) << 16) | (disc[:, 2] + 32768)
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    return disc[first].astype(np.int32), feats[first]
+
+
+def _box_surface(rng, n, centre, size):
+    """n points on the 5 visible faces (top + 4 sides) of an axis-aligned box."""
+    sx, sy, sz = size
+    areas = np.array([sx * sy, sx * sz, sx * sz, sy * sz, sy * sz])
+    face = rng.choice(5, size=n, p=areas / areas.sum())
+    u = rng.uniform(-0.5, 0.5, (n, 3)) * size
+    u[face == 0, 2] = 0.5 * sz
+    u[face == 1, 1] = -0.5 * sy
+    u[face == 2, 1] = 0.5 * sy
+    u[face == 3, 0] = -0.5 * sx
+    u[face == 4, 0] = 0.5 * sx
+    return u + centre
+
+
+def _room_surface(rng, n, room):
+    lx, ly, lz = room
+    areas = np.array([lx * ly, lx * lz, lx * lz, ly * lz, ly * lz])
+    face = rng.choice(5, size=n, p=areas / areas.sum())
+    p = rng.uniform(0.0, 1.0, (n, 3)) * np.array(room)
+    p[face == 0, 2] = 0.0
+    p[face == 1, 1] = 0.0
+    p[face == 2, 1] = ly - 1e-3
+    p[face == 3, 0] = 0.0
+    p[face == 4, 0] = lx - 1e-3
+    return p
+
+
+def make_scene(seed, num_points=40000, n_inst=32, n_cand=32, n_tokens=20,
+               room=(8.0, 6.0, 3.0), target_class=None):
+    """One (scene, utterance) sample in the loader's per-sample format."""
+    rng = np.random.default_rng(seed)
+    room = np.asarray(room, np.float64)
+    per_obj = max(16, min(int(0.8 * num_points / max(n_inst, 1)), 2048))
+    n_room = num_points - per_obj * n_inst
+    assert n_room > 0
+    pts = [_room_surface(rng, n_room, room)]
+    labels = [np.zeros(n_room, np.int64)]
+    for j in range(n_inst):
+        size = rng.uniform(0.4, 1.2, 3)
+        centre = np.array([rng.uniform(0.5 * size[0], room[0] - 0.5 * size[0]),
+                           rng.uniform(0.5 * size[1], room[1] - 0.5 * size[1]),
+                           0.5 * size[2]])
+        pts.append(_box_surface(rng, per_obj, centre, size))
+        labels.append(np.full(per_obj, j + 1, np.int64))
+    xyz = np.concatenate(pts, 0)
+    labels = np.concatenate(labels, 0)
+    perm = rng.permutation(num_points)
+    xyz, labels = xyz[perm], labels[perm]
+    rgb = rng.uniform(-0.5, 0.5, (num_points, 3))
+    height = xyz[:, 2] - np.percentile(xyz[:, 2], 0.99)
+    pc = np.concatenate([xyz, rgb, height[:, None]], 1).astype(np.float32)
+
+    if target_class is None:
+        target_class = int(rng.integers(0, NUM_CLASSES))
+    others = [c for c in range(NUM_CLASSES) if c != target_class]
+    cls = np.array([target_class] * n_cand + [others[int(rng.integers(0, 17))]
+                                              for _ in range(n_inst - n_cand)], np.int64)
+    cls = cls[rng.permutation(n_inst)] if n_inst else cls
+
+    inst_pts, inst_obbs = [], []
+    for j in range(n_inst):
+        x = pc[labels == j + 1]
+        p = x[:, :3]
+        centre = 0.5 * (p.min(0) + p.max(0))
+        size = p.max(0) - p.min(0)
+        inst_obbs.append(np.concatenate([centre, size, np.array([0])]).astype(np.float64))
+        choice = rng.choice(x.shape[0], 1024, replace=x.shape[0] < 1024)
+        inst_pts.append(np.ascontiguousarray(x[choice]))
+
+    lang = np.zeros((MAX_DES_LEN, 300), np.float32)
+    lang[:n_tokens] = rng.normal(0.0, 0.4, (n_tokens, 300)).astype(np.float32)
+    return dict(point_cloud=pc, instance_points=inst_pts, instance_obbs=inst_obbs,
+                instance_class=[int(c) for c in cls], object_cat=np.int64(target_class),
+                lang_feat=lang, lang_len=np.int64(n_tokens),
+                point_min=pc[:, :3].min(0), point_max=pc[:, :3].max(0))
+
+
+def make_batch(seed, batch_size=1, voxel_size_glp=0.05, n_cand=32, n_tokens=20, **kw):
+    """Batch in the collated layout.  ``n_cand`` / ``n_tokens`` may be ints or per-scene lists.
+    Returns plain numpy + nested lists; ``to_data_dict`` turns it into the forward's dict."""
+    scenes = []
+    for b in range(batch_size):
+        nc = n_cand[b] if isinstance(n_cand, (list, tuple)) else n_cand
+        nt = n_tokens[b] if isinstance(n_tokens, (list, tuple)) else n_tokens
+        scenes.append(make_scene(seed + b, n_cand=nc, n_tokens=nt, **kw))
+    coords, feats = [], []
+    for b, s in enumerate(scenes):
+        c, f = quantize_first(s['point_cloud'][:, :3], s['point_cloud'], voxel_size_glp)
+        coords.append(np.concatenate([c, np.full((c.shape[0], 1), b, np.int32)], 1))
+        feats.append(f)
+    return dict(
+        lidar_coords=np.concatenate(coords, 0).astype(np.int32),
+        lidar_feats=np.concatenate(feats, 0).astype(np.float32),
+        lang_feat=np.stack([s['lang_feat'] for s in scenes], 0),
+        lang_len=np.stack([s['lang_len'] for s in scenes], 0),
+        object_cat=np.stack([s['object_cat'] for s in scenes], 0),
+        point_min=np.stack([s['point_min'] for s in scenes], 0),
+        point_max=np.stack([s['point_max'] for s in scenes], 0),
+        instance_points=[s['instance_points'] for s in scenes],
+        instance_obbs=[s['instance_obbs'] for s in scenes],
+        instance_class=[s['instance_class'] for s in scenes],
+    )
+
+
+def shift_batch(batch, shift):
+    """Translate a whole batch (points, obbs, lidar re-quantised) — used to exercise negative
+    coordinates, which the reference's SparseCrop silently drops."""
+    shift = np.asarray(shift, np.float32)
+    out = dict(batch)
+    out['instance_points'] = [[np.concatenate([p[:, :3] + shift, p[:, 3:]], 1).astype(np.float32)
+                               for p in scene] for scene in batch['instance_points']]
+    out['instance_obbs'] = [[np.concatenate([o[:3] + shift.astype(np.float64), o[3:]]) for o in scene]
+                            for scene in batch['instance_obbs']]
+    c = batch['lidar_coords'].copy()
+    c[:, :3] += np.round(shift / 0.05).astype(np.int32)
+    f = batch['lidar_feats'].copy()
+    f[:, :3] += shift
+    out['lidar_coords'], out['lidar_feats'] = c, f
+    out['point_min'] = batch['point_min'] + shift
+    out['point_max'] = batch['point_max'] + shift
+    return out
+
+
+def to_data_dict(batch, sparse_tensor_cls, device='cpu'):
+    """Build the dict ``InstanceRefer.forward`` consumes (after ``lib/solver.py:242-245`` moved
+    the whitelisted tensors to ``device``)."""
+    import torch
+    lidar = sparse_tensor_cls(torch.from_numpy(batch['lidar_feats']).to(device),
+                              torch.from_numpy(batch['lidar_coords']).to(device))
+    return dict(
+        lidar=lidar,
+        lang_feat=torch.from_numpy(batch['lang_feat']).to(device),
+        lang_len=torch.from_numpy(batch['lang_len']).to(device),
+        object_cat=torch.from_numpy(batch['object_cat']).to(device),
+        point_min=torch.from_numpy(batch['point_min']).to(device),
+        point_max=torch.from_numpy(batch['point_max']).to(device),
+        instance_points=batch['instance_points'],
+        instance_obbs=batch['instance_obbs'],
+        instance_class=batch['instance_class'],
+    )
