@@ -1,0 +1,195 @@
+/* instancerefer_b200 — C ABI of the B200-native (sm_100a) InstanceRefer hot path.
+ *
+ * This is the operator boundary SURVEY.md §8(b) defines: what a maintainer of
+ * CurryYuan/InstanceRefer binds (ctypes) to replace the native code the
+ * reference reaches through torchsparse / torch_cluster / torch_scatter / cuDNN on
+ * InstanceRefer.forward (models/instancerefer.py:37-70).
+ *
+ * Conventions: every function returns IR_OK (0) or a negative error code and never throws;
+ * `ir_last_error()` holds the message.  Nothing allocates: inputs, outputs and workspaces are
+ * caller-owned DEVICE buffers (raw pointers + explicit sizes).  Everything is asynchronous on
+ * `stream` (a cudaStream_t), with no host synchronisation and device-side counts.  sm_100a only;
+ * there is no CPU fallback.
+ */
+#ifndef INSTANCEREFER_B200_H
+#define INSTANCEREFER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IR_OK 0
+#define IR_ERR_ARG (-1)
+#define IR_ERR_CUDA (-2)
+#define IR_ERR_UNSUPPORTED (-3)
+
+typedef void* ir_stream_t; /* cudaStream_t */
+
+int ir_version(void);
+const char* ir_last_error(void);
+/* IR_OK iff `device` is compute capability 10.x (B200). */
+int ir_check_device(int device);
+
+/* ------------------------------------------------------------------ sparse-voxel encoder
+ * SparseConvEncoder / BEVEncoder (models/basic_blocks.py:59-95,136-171): 13 sparse convs
+ * (stem k3; 4 x [k2 s2 down, residual k3 k3]) with eval-mode BatchNorm, ReLU and the identity
+ * skip fused into each conv's reduce epilogue.  Layer order everywhere below:
+ *   0 stem | 1 s1.down 2 s1.res_a 3 s1.res_b | 4..6 stage2 | 7..9 stage3 | 10..12 stage4      */
+#define IR_ENC_LAYERS 13
+#define IR_ENC_LEVELS 5
+
+typedef struct {
+    int32_t cin;                           /* input channels (7 = xyz+rgb+height)               */
+    int32_t use_tc;                        /* 0: SIMT fp32 pair-GEMM, 1: tcgen05 3xTF32          */
+    const float* weight[IR_ENC_LAYERS];    /* (K,Cin,Cout) fp32, reference `kernel` layout        */
+    const float* wprep[IR_ENC_LAYERS];     /* ir_spconv_prepare_weights images (use_tc=1) or NULL */
+    const float* bn_scale[IR_ENC_LAYERS];  /* gamma / sqrt(var+eps)                               */
+    const float* bn_shift[IR_ENC_LAYERS];  /* beta - mean * scale                                 */
+} ir_encoder_params;
+
+/* Byte offsets inside an encoder workspace (for tests / tracing; all counts are device ints). */
+typedef struct {
+    int64_t n_max, cap, total_bytes;
+    int64_t off_nlvl;                      /* int32[8]  : rows per level (stride 1,2,4,8,16)      */
+    int64_t off_kcount;                    /* int32[9][32]: pairs per offset; maps 0-4 = k3 at
+                                              level l, maps 5-8 = k2s2 from level l to l+1        */
+    int64_t off_scan, scan_stride;         /* u64[5][scan_stride] compaction state                */
+    int64_t zero_bytes;                    /* bytes cleared from off_nlvl on reset                 */
+    int64_t off_keys, off_vals;            /* 5 tables: keys u64[cap]; vals {minrow,row} i32[cap]  */
+    int64_t off_coords[IR_ENC_LEVELS];     /* int32 (n_max,4) [x,y,z,b] per level                 */
+    int64_t off_pslot;
+    int64_t off_k3_in[IR_ENC_LEVELS], off_k3_slot[IR_ENC_LEVELS]; /* in_idx[27][n_max], slot[n_max][32] */
+    int64_t off_k2_in[4], off_k2_slot[4];                         /* in_idx[8][n_max],  slot[n_max][8]  */
+    int64_t off_feat0;                     /* fp32 (n_max, 8)  voxelised level-0 features          */
+    int64_t off_feat[3];                   /* fp32 (n_max,128) rotating activations               */
+    int64_t off_T;                         /* fp32 (27*n_max,128) pair products                   */
+} ir_encoder_layout_t;
+
+int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* out);
+size_t ir_encoder_workspace_bytes(int64_t n_max);
+
+/* Clears counters and hash tables of a workspace (3 memsets).  Call before ir_voxelize. */
+int ir_encoder_reset(void* ws, int64_t n_max, ir_stream_t stream);
+
+/* First-point-wins voxelisation of candidate instances (sparse_quantize + sparse_collate_tensors,
+ * models/attribute_module.py:65-71,101): pts (n_inst, ppi, fdim) fp32; candidate m reads
+ * instance cand[m]; coords = floor((double)xyz / voxel), batch index = m.  Output (level-0 coords,
+ * features, count, hash table) stays inside `ws`; rows are in first-occurrence order.
+ * Requires n_cand*ppi <= n_max. */
+int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand, int32_t ppi, int32_t fdim,
+                double voxel, void* ws, int64_t n_max, ir_stream_t stream);
+
+/* Builds levels 1-4 and all 9 kernel maps.  coords0==NULL: level 0 comes from ir_voxelize in
+ * `ws`; otherwise coords0 (n0,4) int32 is hashed here (ir_encoder_reset is implied). */
+int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* ws, int64_t n_max,
+                          ir_stream_t stream);
+
+/* Feature pass over prebuilt maps.  feats0==NULL: use the voxelised features in `ws`.
+ * feats_out (n_max,128) fp32; row count = nlvl[4] inside ws, coords = off_coords[4]. */
+int ir_encoder_features(const ir_encoder_params* p, const float* feats0, void* ws, int64_t n_max,
+                        float* feats_out, ir_stream_t stream);
+
+/* One sparse conv layer on explicit buffers (unit tests / tracing). */
+int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K, int32_t KP,
+                    const int32_t* in_idx, int64_t seg_cap, const int32_t* slot,
+                    const int32_t* count, const int32_t* n_out_dev, int64_t n_max,
+                    const float* weight, const float* wprep, int32_t use_tc, const float* scale,
+                    const float* shift, const float* resid, int32_t relu, float* T, float* out,
+                    ir_stream_t stream);
+
+/* tcgen05 operand images for one conv weight (K,Cin,Cout): per offset k the transposed weight
+ * [Cout][Cin] split into tf32 hi / lo parts, stored in the 128B-swizzled K-major shared-memory
+ * layout the MMA reads.  out holds ir_spconv_wprep_floats(K,cin,cout) floats. */
+int64_t ir_spconv_wprep_floats(int32_t K, int32_t cin, int32_t cout);
+int ir_spconv_prepare_weights(const float* weight, int32_t K, int32_t cin, int32_t cout,
+                              float* out, ir_stream_t stream);
+
+/* spnn.GlobalMaxPooling (models/attribute_module.py:105): out[m,:] = max over rows with b==m.
+ * enc_scratch: uint32 (n_seg, C) scratch. */
+int ir_segmax(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
+              int32_t C, int32_t n_seg, uint32_t* enc_scratch, float* out, ir_stream_t stream);
+
+/* ------------------------------------------------------------------ scene head
+ * SparseCrop + ToDenseBEVConvolution + BatchNorm2d + ReLU (models/basic_blocks.py:174-243,
+ * models/scene_module.py:25-30): keep 0<=xyz<(240,400,80); f' = f @ kernel[z/stride];
+ * dense[b, x/stride, y/stride, :] = relu(bn(sum f')), NHWC (B,15,25,128).  tmp: (n_max,128) fp32,
+ * cell: int32 (n_max). */
+int ir_bev(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
+           int32_t stride, const float* kernel, const float* bn_scale, const float* bn_shift,
+           int32_t B, float* tmp, int32_t* cell, float* out, ir_stream_t stream);
+
+/* Conv2d 3x3, no padding, NHWC activations, weight repacked to [ky][kx][Cin][Cout];
+ * y = act(scale*(conv + bias) + shift).  (models/scene_module.py:33-38) */
+int ir_conv2d_3x3(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, const float* wpack,
+                  const float* bias, const float* scale, const float* shift, int32_t relu,
+                  float* out, ir_stream_t stream);
+
+/* Language-guided attention over BEV cells (models/scene_module.py:73-83):
+ * atten = softmax_cells(feats . q / sqrt(C)); scene_feat = sum atten * feats. */
+int ir_scene_attention(const float* feats, const float* q, int32_t B, int32_t ncell, int32_t C,
+                       float* atten, float* scene_feat, ir_stream_t stream);
+
+/* ------------------------------------------------------------------ language
+ * y = act(x W^T + b) (nn.Linear; models/lang_module.py:33-37 and the hoisted GRU input GEMMs). */
+int ir_linear(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t N,
+              int32_t relu, float* y, ir_stream_t stream);
+
+/* One bidirectional GRU layer over packed sequences (models/lang_module.py:53-57): xproj
+ * (B,L,2,3H) = x W_ih^T + b_ih per direction; whh (2,3H,H); bhh (2,3H); out (B,L,2H), zeros at
+ * t >= len[b]; the reverse direction starts at each sample's own last token.  H = 128. */
+int ir_gru_layer(const float* xproj, const float* whh, const float* bhh, const int64_t* lengths,
+                 int32_t B, int32_t L, int32_t H, float* out, ir_stream_t stream);
+
+/* Four masked attention poolings over tokens (models/lang_module.py:60-83): logits = fc(feats);
+ * softmax over L, * mask, renormalise; pooled = atten @ embed.  fcw (4,D), fcb (4);
+ * atten (4,B,L), pooled (4,B,E). */
+int ir_token_attention(const float* feats, const float* embed, int64_t embed_stride,
+                       const int64_t* lengths, const float* fcw, const float* fcb, int32_t B,
+                       int32_t L, int32_t D, int32_t E, float* atten, float* pooled,
+                       ir_stream_t stream);
+
+/* ------------------------------------------------------------------ matching heads
+ * Fused 2-layer head: h = relu(norm(x W1^T + b1)); y = h W2^T + b2, then
+ *   mode 0: write y;  1: write y/max(|y|,1e-12);
+ *   2: score[r] = <y/max(|y|,1e-12), partner[seg[r]]>;  3: score[r] = cos(y, partner[seg[r]]), eps 1e-8.
+ * norm 0: none, 1: per-channel affine (eval BatchNorm1d), 2: LayerNorm(eps 1e-5).
+ * (models/attribute_module.py:88-90,108-126; relation_module.py:82,101-103;
+ *  scene_module.py:44-57,84-104).  Dims <= 256. */
+int ir_mlp_head(const float* x, int32_t M, int32_t K, const float* W1, const float* b1, int32_t N1,
+                int32_t norm, const float* g, const float* beta, const float* W2, const float* b2,
+                int32_t N2, int32_t mode, const float* partner, const int32_t* seg, float* y,
+                float* score, ir_stream_t stream);
+
+/* Per-scene softmax / argmax over candidates of the summed score (extra fused output; the
+ * reference sums and arg-maxes on the host, lib/eval_helper.py:61-67).  seg_ofs (n_seg+1). */
+int ir_candidate_softmax(const float* s_attr, const float* s_rel, const float* s_scene,
+                         const int32_t* seg_ofs, int32_t n_seg, float* prob, int32_t* argmax,
+                         ir_stream_t stream);
+
+/* ------------------------------------------------------------------ relation
+ * Per-instance column means of (n_inst, ppi, fdim) point blocks (models/relation_module.py:67). */
+int ir_instance_mean(const float* pts, int32_t n_inst, int32_t ppi, int32_t fdim, float* mean,
+                     ir_stream_t stream);
+
+/* Brute-force kNN inside scene segments (torch_cluster.knn semantics, models/basic_blocks.py:120):
+ * for query q (row qidx[q] of support) the k nearest support rows of the same segment, ascending
+ * squared distance, ties -> lower index; nbr (nq,k) int32, -1 padded.  seg_ofs (n_seg+1) row
+ * offsets of each scene in `xyz`; qseg (nq) scene of each query. */
+int ir_knn(const float* xyz, const int32_t* seg_ofs, const int32_t* qidx, const int32_t* qseg,
+           int32_t nq, int32_t k, int32_t* nbr, ir_stream_t stream);
+
+/* DynamicEdgeConv message + max aggregation (models/basic_blocks.py:125-133): x (S,F) with the
+ * class one-hot in the last `ncls` columns; per edge j->i: w = W2w relu(W1w [p_j-p_i, oh_i, oh_j]),
+ * msg = W2m relu(W1m [x_i, w, x_j]); out[i] = max_j msg (0 if no edge).  F<=32, hidden 64/128. */
+int ir_edgeconv(const float* x, const float* xyz, const int32_t* qidx, const int32_t* nbr,
+                int32_t nq, int32_t k, int32_t F, int32_t ncls, const float* Ww1, const float* bw1,
+                const float* Ww2, const float* bw2, const float* Wm1, const float* bm1,
+                const float* Wm2, const float* bm2, int32_t Fout, float* out, ir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

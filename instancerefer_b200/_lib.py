@@ -1,0 +1,94 @@
+"""ctypes binding of ``libinstancerefer_b200.so`` (the C ABI declared in
+``include/instancerefer_b200.h``).  There is no fallback of any kind: if the shared library is
+missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libinstancerefer_b200.so")
+
+ENC_LAYERS = 13
+ENC_LEVELS = 5
+
+p = C.c_void_p
+i32 = C.c_int32
+i64 = C.c_int64
+f64 = C.c_double
+
+
+class EncoderParams(C.Structure):
+    _fields_ = [("cin", i32), ("use_tc", i32),
+                ("weight", p * ENC_LAYERS), ("wprep", p * ENC_LAYERS),
+                ("bn_scale", p * ENC_LAYERS), ("bn_shift", p * ENC_LAYERS)]
+
+
+class EncoderLayout(C.Structure):
+    _fields_ = [("n_max", i64), ("cap", i64), ("total_bytes", i64),
+                ("off_nlvl", i64), ("off_kcount", i64), ("off_scan", i64), ("scan_stride", i64),
+                ("zero_bytes", i64), ("off_keys", i64), ("off_vals", i64),
+                ("off_coords", i64 * ENC_LEVELS), ("off_pslot", i64),
+                ("off_k3_in", i64 * ENC_LEVELS), ("off_k3_slot", i64 * ENC_LEVELS),
+                ("off_k2_in", i64 * 4), ("off_k2_slot", i64 * 4),
+                ("off_feat0", i64), ("off_feat", i64 * 3), ("off_T", i64)]
+
+
+# name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
+SIGNATURES = {
+    "ir_version": (i32, []),
+    "ir_last_error": (C.c_char_p, []),
+    "ir_check_device": (i32, [i32]),
+    "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),
+    "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),
+    "ir_encoder_reset": (i32, [p, i64, p]),
+    "ir_voxelize": (i32, [p, p, i32, i32, i32, f64, p, i64, p]),
+    "ir_encoder_build_maps": (i32, [p, i32, p, i64, p]),
+    "ir_encoder_features": (i32, [C.POINTER(EncoderParams), p, p, i64, p, p]),
+    "ir_spconv_layer": (i32, [p, i32, i32, i32, i32, p, i64, p, p, p, i64, p, p, i32, p, p, p, i32, p, p, p]),
+    "ir_spconv_wprep_floats": (i64, [i32, i32, i32]),
+    "ir_spconv_prepare_weights": (i32, [p, i32, i32, i32, p, p]),
+    "ir_segmax": (i32, [p, p, p, i64, i32, i32, p, p, p]),
+    "ir_bev": (i32, [p, p, p, i64, i32, p, p, p, i32, p, p, p, p]),
+    "ir_conv2d_3x3": (i32, [p, i32, i32, i32, i32, p, p, p, p, i32, p, p]),
+    "ir_scene_attention": (i32, [p, p, i32, i32, i32, p, p, p]),
+    "ir_linear": (i32, [p, i32, i32, p, p, i32, i32, p, p]),
+    "ir_gru_layer": (i32, [p, p, p, p, i32, i32, i32, p, p]),
+    "ir_token_attention": (i32, [p, p, i64, p, p, p, i32, i32, i32, i32, p, p, p]),
+    "ir_mlp_head": (i32, [p, i32, i32, p, p, i32, i32, p, p, p, p, i32, i32, p, p, p, p, p]),
+    "ir_candidate_softmax": (i32, [p, p, p, p, i32, p, p, p]),
+    "ir_instance_mean": (i32, [p, i32, i32, i32, p, p]),
+    "ir_knn": (i32, [p, p, p, p, i32, i32, p, p]),
+    "ir_edgeconv": (i32, [p, p, p, p, i32, i32, i32, i32, p, p, p, p, p, p, p, p, i32, p, p]),
+}
+
+_lib = None
+
+
+class IrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built — the product path never
+    falls back to PyTorch/CPU code."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise IrError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                      f"g.build()'` (nvcc, sm_100a). There is no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an ``int ir_*`` entry point; raise IrError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise IrError(f"{name} failed ({rc}): {lib.ir_last_error().decode(errors='replace')}")
+    return rc

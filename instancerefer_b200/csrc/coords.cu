@@ -1,0 +1,255 @@
+// Coordinate pipeline: hash build, first-wins voxelisation, stride-2 downsample, kernel maps.
+// Integer work, bit-exact against oracle/sparse_ref.py (first-occurrence row order; rulebook
+// compared after canonicalisation inside each kernel offset).  Replaces what the reference reaches
+// through torchsparse at models/basic_blocks.py:14,32,39 (kernel-map build inside spnn.Conv3d),
+// :68,73,78,83 (stride-2 downsample) and models/attribute_module.py:65-71,101
+// (sparse_quantize + sparse_collate_tensors).  No host sync anywhere: all counts stay on device.
+#include "common.cuh"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------ chained ordered compaction
+// Single-pass ordered stream compaction: tiles are handed out by an atomic ticket; each tile waits
+// for its predecessor's inclusive prefix (one 64-bit word: ready bit | prefix).
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+template <class FlagFn, class EmitFn>
+__device__ __forceinline__ void compact_ordered(int n, unsigned long long* state, int* n_out,
+                                                FlagFn flag, EmitFn emit) {
+    __shared__ int s_tile, s_prefix, s_warp[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n == 0 && blockIdx.x == 0 && tid == 0) *n_out = 0;
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd((unsigned int*)state, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const int base = tile * SCAN_TILE + tid * SCAN_ITEMS;
+        int f[SCAN_ITEMS], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            const int idx = base + j;
+            f[j] = (idx < n) ? (flag(idx) ? 1 : 0) : 0;
+            cnt += f[j];
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int ws = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+            int winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            const int tile_sum = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
+            if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - ws;      // exclusive warp offsets
+            if (lane == 0) {
+                unsigned long long p = 0;
+                if (tile > 0) {
+                    volatile unsigned long long* prev = state + 1 + (tile - 1);
+                    do { p = *prev; } while (p == 0ull);
+                }
+                const unsigned prefix = (unsigned)(p & 0xFFFFFFFFull);
+                atomicExch(state + 1 + tile, (1ull << 32) | (unsigned long long)(prefix + (unsigned)tile_sum));
+                s_prefix = (int)prefix;
+                if (tile == ntiles - 1) *n_out = (int)prefix + tile_sum;
+            }
+        }
+        __syncthreads();
+        int pos = s_prefix + s_warp[w] + (inc - cnt);
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j)
+            if (f[j]) emit(base + j, pos++);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+__global__ void k_hash_build(const int4* __restrict__ coords, const int* __restrict__ n_dev,
+                             IrTable t) {
+    const int n = *n_dev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = coords[i];
+        const int s = ir_ht_insert(t, ir_pack_key(c.x, c.y, c.z, c.w));
+        atomicMin(&t.minrow[s], i);
+        atomicMin(&t.row[s], i);
+    }
+}
+
+__device__ __forceinline__ int4 parent_coord(int4 c, int new_stride) {
+    // floor(c / ns) * ns for power-of-two ns, negatives included (two's complement floor)
+    const int m = ~(new_stride - 1);
+    return make_int4(c.x & m, c.y & m, c.z & m, c.w);
+}
+
+__global__ void k_ds_insert(const int4* __restrict__ coords, const int* __restrict__ n_dev,
+                            int new_stride, IrTable t, int* __restrict__ pslot) {
+    const int n = *n_dev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 p = parent_coord(coords[i], new_stride);
+        const int s = ir_ht_insert(t, ir_pack_key(p.x, p.y, p.z, p.w));
+        atomicMin(&t.minrow[s], i);
+        pslot[i] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_ds_compact(const int4* __restrict__ coords, const int* __restrict__ n_dev, int new_stride,
+             IrTable t, const int* __restrict__ pslot, int4* __restrict__ coords_out,
+             int* __restrict__ n_out, unsigned long long* state) {
+    const int n = *n_dev;
+    compact_ordered(
+        n, state, n_out,
+        [&](int i) { return t.minrow[pslot[i]] == i; },
+        [&](int i, int r) {
+            coords_out[r] = parent_coord(coords[i], new_stride);
+            t.row[pslot[i]] = r;
+        });
+}
+
+// points (n_inst, ppi, fdim) fp32; candidate m uses instance cand[m]; voxel key = (floor(xyz/voxel), m)
+__global__ void k_vox_insert(const float* __restrict__ pts, const int* __restrict__ cand, int n_pts,
+                             int ppi, int fdim, double voxel, IrTable t, int* __restrict__ pslot) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pts; p += gridDim.x * blockDim.x) {
+        const int m = p / ppi, j = p - m * ppi;
+        const float* src = pts + ((long long)cand[m] * ppi + j) * fdim;
+        const int x = (int)floor((double)src[0] / voxel);
+        const int y = (int)floor((double)src[1] / voxel);
+        const int z = (int)floor((double)src[2] / voxel);
+        const int s = ir_ht_insert(t, ir_pack_key(x, y, z, m));
+        atomicMin(&t.minrow[s], p);
+        pslot[p] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n_pts, int ppi,
+              int fdim, double voxel, IrTable t, const int* __restrict__ pslot,
+              int4* __restrict__ coords_out, float* __restrict__ feats_out, int* __restrict__ n_out,
+              unsigned long long* state) {
+    compact_ordered(
+        n_pts, state, n_out,
+        [&](int p) { return t.minrow[pslot[p]] == p; },
+        [&](int p, int r) {
+            const int m = p / ppi, j = p - m * ppi;
+            const float* src = pts + ((long long)cand[m] * ppi + j) * fdim;
+            coords_out[r] = make_int4((int)floor((double)src[0] / voxel), (int)floor((double)src[1] / voxel),
+                                      (int)floor((double)src[2] / voxel), m);
+            for (int c = 0; c < fdim; ++c) feats_out[(long long)r * fdim + c] = src[c];
+            t.row[pslot[p]] = r;
+        });
+}
+
+// Kernel map for out[o] += F[j] @ W[k], j at C_out[o] + off_k (Appendix A offset enumeration):
+//   KS=3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
+//   KS=2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
+// Emits, per offset k: in_idx[k*seg_cap + pos] (input row of pair `pos`), count[k];
+// per output row: slot[o*KP + k] = pos or -1.  Pair order inside k is append order (unordered).
+template <int KS>
+__global__ void k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev,
+                       IrTable tin, int stride, int* __restrict__ in_idx, long long seg_cap,
+                       int* __restrict__ slot, int* __restrict__ count) {
+    constexpr int K = KS * KS * KS;
+    constexpr int KP = (KS == 3) ? 32 : 8;
+    const int n = *n_out_dev;
+    const int lane = threadIdx.x & 31;
+    const int n_round = (n + 31) & ~31;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
+        const bool live = o < n;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (live) c = coords_out[o];
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            int dx, dy, dz;
+            if (KS == 3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
+            else         { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
+            int j = -1;
+            if (live) {
+                if (KS == 3 && k == 13) j = o;
+                else {
+                    const int s = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
+                    if (s >= 0) j = tin.row[s];
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+            int pos = -1;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&count[k], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (j >= 0) {
+                    pos = base + __popc(m & ((1u << lane) - 1u));
+                    in_idx[(long long)k * seg_cap + pos] = j;
+                }
+            }
+            if (live) slot[(long long)o * KP + k] = pos;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host launchers (internal)
+int irk_set_int(int* p, int v, cudaStream_t st) {
+    k_set_int<<<1, 1, 0, st>>>(p, v);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+
+static inline int grid_for(long long n, int threads) {
+    int g = ir_div_up(n > 0 ? n : 1, threads);
+    const int cap = IR_NUM_SMS * 8;
+    return g < cap ? g : cap;
+}
+
+int irk_hash_build(const int32_t* coords, const int* n_dev, long long n_max, IrTable t,
+                   cudaStream_t st) {
+    k_hash_build<<<grid_for(n_max, 256), 256, 0, st>>>((const int4*)coords, n_dev, t);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+int irk_downsample(const int32_t* coords, const int* n_dev, long long n_max, int new_stride,
+                   IrTable t, int* pslot, int32_t* coords_out, int* n_out_dev,
+                   unsigned long long* scan_state, cudaStream_t st) {
+    k_ds_insert<<<grid_for(n_max, 256), 256, 0, st>>>((const int4*)coords, n_dev, new_stride, t, pslot);
+    IR_CHECK_LAUNCH();
+    k_ds_compact<<<ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, SCAN_TILE), IR_NUM_SMS * 4), SCAN_THREADS, 0, st>>>(
+        (const int4*)coords, n_dev, new_stride, t, pslot, (int4*)coords_out, n_out_dev, scan_state);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdim, double voxel,
+                 IrTable t, int* pslot, int32_t* coords_out, float* feats_out,
+                 int* n_out_dev, unsigned long long* scan_state, cudaStream_t st) {
+    const long long n_pts = (long long)n_cand * ppi;
+    k_vox_insert<<<grid_for(n_pts, 256), 256, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, t, pslot);
+    IR_CHECK_LAUNCH();
+    k_vox_compact<<<ir_min_i(ir_div_up(n_pts > 0 ? n_pts : 1, SCAN_TILE), IR_NUM_SMS * 4), SCAN_THREADS, 0, st>>>(
+        pts, cand, (int)n_pts, ppi, fdim, voxel, t, pslot, (int4*)coords_out, feats_out, n_out_dev, scan_state);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+int irk_kmap(int ks, const int32_t* coords_out, const int* n_out_dev, long long n_max,
+             IrTable t, int stride, int* in_idx, long long seg_cap, int* slot,
+             int* count, cudaStream_t st) {
+    const int g = grid_for(n_max, 128);
+    if (ks == 3) k_kmap<3><<<g, 128, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
+    else if (ks == 2) k_kmap<2><<<g, 128, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
+    else { ir_set_error("kmap: unsupported kernel size %d", ks); return IR_ERR_UNSUPPORTED; }
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

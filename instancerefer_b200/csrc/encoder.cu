@@ -1,0 +1,262 @@
+// Sparse-voxel encoder orchestration + C ABI: workspace layout, reset, voxelise, map build,
+// 13-layer feature pass, segmented max-pool.  One call = one chain of async launches on `stream`;
+// no allocation, no host sync, device-side counts.
+// Reference: SparseConvEncoder / BEVEncoder (models/basic_blocks.py:59-95,136-171),
+// GlobalMaxPooling (models/attribute_module.py:105).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+void ir_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* ir_last_error(void) { return g_err; }
+extern "C" int ir_version(void) { return 100; }
+extern "C" int ir_check_device(int device) {
+    cudaDeviceProp prop;
+    IR_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        ir_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                     prop.major, prop.minor);
+        return IR_ERR_UNSUPPORTED;
+    }
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ layout
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* L) {
+    IR_CHECK_ARG(n_max > 0 && n_max < (1ll << 26) && L != nullptr);
+    memset(L, 0, sizeof(*L));
+    L->n_max = n_max;
+    int64_t cap = 1024;
+    while (cap < 2 * n_max) cap <<= 1;
+    L->cap = cap;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 1024); return o; };
+    L->off_nlvl = take(8 * 4);
+    L->off_kcount = take(9 * 32 * 4);
+    L->scan_stride = 1 + (n_max + 2047) / 2048 + 1;
+    L->off_scan = take(5 * L->scan_stride * 8);
+    L->zero_bytes = off - L->off_nlvl;
+    L->off_keys = take(5 * cap * 8);
+    L->off_vals = take(5 * cap * 8);
+    for (int l = 0; l < IR_ENC_LEVELS; ++l) L->off_coords[l] = take(n_max * 16);
+    L->off_pslot = take(n_max * 4);
+    for (int l = 0; l < IR_ENC_LEVELS; ++l) {
+        L->off_k3_in[l] = take(27 * n_max * 4);
+        L->off_k3_slot[l] = take(32 * n_max * 4);
+    }
+    for (int l = 0; l < 4; ++l) {
+        L->off_k2_in[l] = take(8 * n_max * 4);
+        L->off_k2_slot[l] = take(8 * n_max * 4);
+    }
+    L->off_feat0 = take(n_max * 8 * 4);
+    for (int i = 0; i < 3; ++i) L->off_feat[i] = take(n_max * 128 * 4);
+    L->off_T = take(27 * n_max * 128 * 4);
+    L->total_bytes = off;
+    return IR_OK;
+}
+
+extern "C" size_t ir_encoder_workspace_bytes(int64_t n_max) {
+    ir_encoder_layout_t L;
+    if (ir_encoder_layout(n_max, &L) != IR_OK) return 0;
+    return (size_t)L.total_bytes;
+}
+
+struct Ws {
+    ir_encoder_layout_t L;
+    char* base;
+    int* nlvl() const { return (int*)(base + L.off_nlvl); }
+    int* kcount(int map) const { return (int*)(base + L.off_kcount) + map * 32; }
+    unsigned long long* scan(int i) const { return (unsigned long long*)(base + L.off_scan) + i * L.scan_stride; }
+    IrTable table(int l) const {
+        return ir_table_view2(base + L.off_keys + (int64_t)l * L.cap * 8,
+                              base + L.off_vals + (int64_t)l * L.cap * 8, L.cap);
+    }
+    int32_t* coords(int l) const { return (int32_t*)(base + L.off_coords[l]); }
+    int* pslot() const { return (int*)(base + L.off_pslot); }
+    int* k3_in(int l) const { return (int*)(base + L.off_k3_in[l]); }
+    int* k3_slot(int l) const { return (int*)(base + L.off_k3_slot[l]); }
+    int* k2_in(int l) const { return (int*)(base + L.off_k2_in[l]); }
+    int* k2_slot(int l) const { return (int*)(base + L.off_k2_slot[l]); }
+    float* feat0() const { return (float*)(base + L.off_feat0); }
+    float* feat(int i) const { return (float*)(base + L.off_feat[i]); }
+    float* T() const { return (float*)(base + L.off_T); }
+};
+
+static int ws_open(void* ws, int64_t n_max, Ws* w) {
+    IR_CHECK_ARG(ws != nullptr);
+    int r = ir_encoder_layout(n_max, &w->L);
+    if (r != IR_OK) return r;
+    w->base = (char*)ws;
+    return IR_OK;
+}
+
+extern "C" int ir_encoder_reset(void* ws, int64_t n_max, ir_stream_t stream) {
+    Ws w;
+    int r = ws_open(ws, n_max, &w);
+    if (r != IR_OK) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_nlvl, 0, (size_t)w.L.zero_bytes, st));
+    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_keys, 0xFF, (size_t)(5 * w.L.cap * 8), st));
+    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_vals, 0x7F, (size_t)(5 * w.L.cap * 8), st));
+    return IR_OK;
+}
+
+extern "C" int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand, int32_t ppi,
+                           int32_t fdim, double voxel, void* ws, int64_t n_max,
+                           ir_stream_t stream) {
+    Ws w;
+    int r = ws_open(ws, n_max, &w);
+    if (r != IR_OK) return r;
+    IR_CHECK_ARG(pts && cand && n_cand > 0 && ppi > 0 && fdim >= 3 && fdim <= 8 && voxel > 0);
+    IR_CHECK_ARG((int64_t)n_cand * ppi <= n_max && n_cand < 65536);
+    return irk_voxelize(pts, cand, n_cand, ppi, fdim, voxel, w.table(0), w.pslot(), w.coords(0),
+                        w.feat0(), w.nlvl() + 0, w.scan(0), (cudaStream_t)stream);
+}
+
+extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* ws, int64_t n_max,
+                                     ir_stream_t stream) {
+    Ws w;
+    int r = ws_open(ws, n_max, &w);
+    if (r != IR_OK) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t* c0 = w.coords(0);
+    if (coords0 != nullptr) {
+        IR_CHECK_ARG(n0 >= 0 && n0 <= n_max);
+        if ((r = ir_encoder_reset(ws, n_max, stream)) != IR_OK) return r;
+        if ((r = irk_set_int(w.nlvl() + 0, n0, st)) != IR_OK) return r;
+        if ((r = irk_hash_build(coords0, w.nlvl() + 0, n0, w.table(0), st)) != IR_OK) return r;
+        c0 = coords0;
+    }
+    // levels 1..4 (stride 2,4,8,16)
+    const int32_t* cprev = c0;
+    for (int l = 0; l < 4; ++l) {
+        if ((r = irk_downsample(cprev, w.nlvl() + l, n_max, 2 << l, w.table(l + 1), w.pslot(),
+                                w.coords(l + 1), w.nlvl() + l + 1, w.scan(l + 1), st)) != IR_OK) return r;
+        cprev = w.coords(l + 1);
+    }
+    // kernel maps: k3 at every level, k2s2 between levels
+    for (int l = 0; l < IR_ENC_LEVELS; ++l) {
+        const int32_t* cl = (l == 0) ? c0 : w.coords(l);
+        if ((r = irk_kmap(3, cl, w.nlvl() + l, n_max, w.table(l), 1 << l, w.k3_in(l), n_max,
+                          w.k3_slot(l), w.kcount(l), st)) != IR_OK) return r;
+    }
+    for (int l = 0; l < 4; ++l) {
+        if ((r = irk_kmap(2, w.coords(l + 1), w.nlvl() + l + 1, n_max, w.table(l), 1 << l, w.k2_in(l),
+                          n_max, w.k2_slot(l), w.kcount(5 + l), st)) != IR_OK) return r;
+    }
+    return IR_OK;
+}
+
+static int conv_layer(const float* fin, int cin, int cout, int K, int KP, const int* in_idx,
+                      long long seg_cap, const int* slot, const int* count, const int* n_out_dev,
+                      long long n_max, const float* weight, const float* wprep, int use_tc,
+                      const float* scale, const float* shift, const float* resid, int relu, float* T,
+                      float* out, cudaStream_t st) {
+    int r;
+    const long long pairs_max = (long long)K * n_max;
+    if (use_tc && wprep != nullptr && cin >= 32)
+        r = irk_pairgemm_tc(fin, cin, cout, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
+    else
+        r = irk_pairgemm_simt(fin, cin, cout, K, in_idx, seg_cap, count, weight, T, pairs_max, st);
+    if (r != IR_OK) return r;
+    return irk_reduce_epilogue(T, cout, K, KP, slot, count, n_out_dev, n_max, scale, shift, resid,
+                               relu, out, st);
+}
+
+extern "C" int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,
+                               int32_t KP, const int32_t* in_idx, int64_t seg_cap,
+                               const int32_t* slot, const int32_t* count,
+                               const int32_t* n_out_dev, int64_t n_max, const float* weight,
+                               const float* wprep, int32_t use_tc, const float* scale,
+                               const float* shift, const float* resid, int32_t relu, float* T,
+                               float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(feat_in && in_idx && slot && count && n_out_dev && weight && T && out);
+    return conv_layer(feat_in, cin, cout, K, KP, in_idx, seg_cap, slot, count, n_out_dev, n_max,
+                      weight, wprep, use_tc, scale, shift, resid, relu, T, out, (cudaStream_t)stream);
+}
+
+extern "C" int ir_encoder_features(const ir_encoder_params* p, const float* feats0, void* ws,
+                                   int64_t n_max, float* feats_out, ir_stream_t stream) {
+    Ws w;
+    int r = ws_open(ws, n_max, &w);
+    if (r != IR_OK) return r;
+    IR_CHECK_ARG(p != nullptr && feats_out != nullptr && p->cin >= 1 && p->cin <= 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* f0 = feats0 ? feats0 : w.feat0();
+    static const int ch[5] = {32, 64, 128, 128, 128};
+    float* A = w.feat(0);
+    float* X = w.feat(1);
+    float* Y = w.feat(2);
+#define LAYER(idx, fin, cin_, cout_, K_, KP_, in_, slot_, cnt_, nout_, resid_, out_)                      \
+    if ((r = conv_layer(fin, cin_, cout_, K_, KP_, in_, n_max, slot_, cnt_, nout_, n_max, p->weight[idx], \
+                        p->wprep[idx], p->use_tc, p->bn_scale[idx], p->bn_shift[idx], resid_, 1, w.T(),   \
+                        out_, st)) != IR_OK) return r;
+    // stem: k3 at level 0
+    LAYER(0, f0, p->cin, ch[0], 27, 32, w.k3_in(0), w.k3_slot(0), w.kcount(0), w.nlvl() + 0, nullptr, A);
+    for (int s = 1; s <= 4; ++s) {
+        const int l = s - 1, li = 1 + 3 * (s - 1);
+        float* outp = (s == 4) ? feats_out : A;
+        // down: k2 s2, level l -> l+1
+        LAYER(li + 0, A, ch[l], ch[s], 8, 8, w.k2_in(l), w.k2_slot(l), w.kcount(5 + l), w.nlvl() + s, nullptr, X);
+        // residual block at level s: relu(bn(conv(relu(bn(conv(X))))) + X)
+        LAYER(li + 1, X, ch[s], ch[s], 27, 32, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, nullptr, Y);
+        LAYER(li + 2, Y, ch[s], ch[s], 27, 32, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, X, outp);
+    }
+#undef LAYER
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ segmented max (GlobalMaxPooling)
+__device__ __forceinline__ unsigned enc_f32(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(unsigned e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
+}
+
+__global__ void k_segmax_scatter(const float* __restrict__ F, const int4* __restrict__ coords,
+                                 const int* __restrict__ n_dev, int C, int n_seg,
+                                 unsigned* __restrict__ enc) {
+    const int n = *n_dev;
+    const long long total = (long long)n * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / C), c = (int)(i - (long long)row * C);
+        const int b = coords[row].w;
+        if (b >= 0 && b < n_seg) atomicMax(&enc[(long long)b * C + c], enc_f32(F[i]));
+    }
+}
+__global__ void k_segmax_decode(const unsigned* __restrict__ enc, int total, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const unsigned e = enc[i];
+        out[i] = e ? dec_f32(e) : 0.f;
+    }
+}
+
+extern "C" int ir_segmax(const float* feats, const int32_t* coords, const int32_t* n_dev,
+                         int64_t n_max, int32_t C, int32_t n_seg, uint32_t* enc_scratch,
+                         float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(feats && coords && n_dev && enc_scratch && out && C > 0 && n_seg > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    IR_CHECK_CUDA(cudaMemsetAsync(enc_scratch, 0, (size_t)n_seg * C * 4, st));
+    const int grid = ir_min_i(ir_div_up(n_max * C > 0 ? n_max * C : 1, 256), IR_NUM_SMS * 8);
+    k_segmax_scatter<<<grid, 256, 0, st>>>(feats, (const int4*)coords, n_dev, C, n_seg, enc_scratch);
+    IR_CHECK_LAUNCH();
+    k_segmax_decode<<<ir_div_up((long long)n_seg * C, 256), 256, 0, st>>>(enc_scratch, n_seg * C, out);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

@@ -1,0 +1,180 @@
+// Language encoder kernels: small-M linear (warp-shuffle reductions), packed bidirectional GRU layer
+// with the recurrent matrix resident in shared memory, masked token-attention pooling.
+// Reference: models/lang_module.py:22-37,51-108.
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+
+// ------------------------------------------------------------------ y = act(x W^T + b), small M
+#define LIN_TM 8
+#define LIN_MAXK 512
+__global__ void __launch_bounds__(256)
+k_linear(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
+         const float* __restrict__ b, int N, int relu, float* __restrict__ y) {
+    __shared__ float xs[LIN_TM][LIN_MAXK];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int r0 = blockIdx.y * LIN_TM;
+    const int rows = min(LIN_TM, M - r0);
+    for (int i = tid; i < LIN_TM * K; i += 256) {
+        const int r = i / K, k = i - r * K;
+        xs[r][k] = (r < rows) ? x[(long long)(r0 + r) * K + k] : 0.f;
+    }
+    __syncthreads();
+    const int n = blockIdx.x * 8 + w;
+    if (n >= N) return;
+    float acc[LIN_TM];
+#pragma unroll
+    for (int r = 0; r < LIN_TM; ++r) acc[r] = 0.f;
+    const float* wr = W + (long long)n * K;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = wr[k];
+#pragma unroll
+        for (int r = 0; r < LIN_TM; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);
+    }
+    const float bv = b ? b[n] : 0.f;
+#pragma unroll
+    for (int r = 0; r < LIN_TM; ++r) {
+        float v = warp_sum(acc[r]) + bv;
+        if (relu) v = fmaxf(v, 0.f);
+        if (lane == 0 && r < rows) y[(long long)(r0 + r) * N + n] = v;
+    }
+}
+
+extern "C" int ir_linear(const float* x, int32_t M, int32_t K, const float* W, const float* b,
+                         int32_t N, int32_t relu, float* y, ir_stream_t stream) {
+    IR_CHECK_ARG(x && W && y && M > 0 && N > 0 && K > 0 && K <= LIN_MAXK);
+    dim3 grid(ir_div_up(N, 8), ir_div_up(M, LIN_TM));
+    k_linear<<<grid, 256, 0, (cudaStream_t)stream>>>(x, M, K, W, b, N, relu, y);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ GRU layer (both directions)
+// grid (B, 2); 3H threads; W_hh^T resident in shared memory (H*3H floats = 192 KB for H=128).
+__global__ void k_gru_layer(const float* __restrict__ xproj, const float* __restrict__ whh,
+                            const float* __restrict__ bhh, const long long* __restrict__ lengths,
+                            int L, int H, float* __restrict__ out) {
+    extern __shared__ float smem[];
+    const int G = 3 * H;
+    float* WT = smem;               // [H][G]
+    float* s_h = WT + (size_t)H * G;  // [H]
+    float* s_hp = s_h + H;          // [G]
+    const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
+    const float* Wd = whh + (size_t)dir * G * H;
+    for (int i = j; i < G * H; i += G) {
+        const int row = i / H, k = i - row * H;   // coalesced global read of W[row][k]
+        WT[(size_t)k * G + row] = Wd[i];
+    }
+    if (j < H) s_h[j] = 0.f;
+    const float bj = bhh[dir * G + j];
+    int len = (int)lengths[b];
+    len = max(0, min(len, L));
+    __syncthreads();
+    for (int s = 0; s < len; ++s) {
+        const int t = dir ? (len - 1 - s) : s;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) acc = fmaf(WT[(size_t)k * G + j], s_h[k], acc);
+        s_hp[j] = acc + bj;
+        __syncthreads();
+        if (j < H) {
+            const float* xp = xproj + (((size_t)b * L + t) * 2 + dir) * G;
+            const float r = 1.f / (1.f + expf(-(xp[j] + s_hp[j])));
+            const float z = 1.f / (1.f + expf(-(xp[H + j] + s_hp[H + j])));
+            const float n = tanhf(xp[2 * H + j] + r * s_hp[2 * H + j]);
+            const float h = (1.f - z) * n + z * s_h[j];
+            out[((size_t)b * L + t) * (2 * H) + dir * H + j] = h;
+            s_h[j] = h;
+        }
+        __syncthreads();
+    }
+    if (j < H)
+        for (int t = len; t < L; ++t) out[((size_t)b * L + t) * (2 * H) + dir * H + j] = 0.f;
+}
+
+extern "C" int ir_gru_layer(const float* xproj, const float* whh, const float* bhh,
+                            const int64_t* lengths, int32_t B, int32_t L, int32_t H, float* out,
+                            ir_stream_t stream) {
+    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && B > 0 && L > 0 && H == 128);
+    const size_t smem = ((size_t)H * 3 * H + H + 3 * H) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_gru_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_gru_layer<<<dim3(B, 2), 3 * H, smem, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, L, H, out);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ token attention pooling (x4)
+#define TA_MAXL 128
+__global__ void __launch_bounds__(256)
+k_token_attention(const float* __restrict__ feats, const float* __restrict__ embed,
+                  long long embed_stride, const long long* __restrict__ lengths,
+                  const float* __restrict__ fcw, const float* __restrict__ fcb, int B, int L, int D,
+                  int E, float* __restrict__ atten, float* __restrict__ pooled) {
+    __shared__ float s_a[4][TA_MAXL];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int len = (int)lengths[b];
+    for (int p = w; p < 4 * L; p += 8) {
+        const int h = p / L, t = p - h * L;
+        const float* f = feats + ((long long)b * L + t) * D;
+        float a = 0.f;
+        for (int d = lane; d < D; d += 32) a = fmaf(f[d], fcw[h * D + d], a);
+        a = warp_sum(a);
+        if (lane == 0) s_a[h][t] = a + fcb[h];
+    }
+    __syncthreads();
+    if (w < 4) {
+        const int h = w;
+        float m = -INFINITY;
+        for (int t = lane; t < L; t += 32) m = fmaxf(m, s_a[h][t]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int t = lane; t < L; t += 32) {
+            const float e = expf(s_a[h][t] - m);
+            s_a[h][t] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        float s2 = 0.f;
+        for (int t = lane; t < L; t += 32) {
+            const float a = (s_a[h][t] / s) * ((t < len) ? 1.f : 0.f);
+            s_a[h][t] = a;
+            s2 += a;
+        }
+        s2 = warp_sum(s2);
+        for (int t = lane; t < L; t += 32) {
+            const float a = s_a[h][t] / s2;
+            s_a[h][t] = a;
+            atten[((long long)h * B + b) * L + t] = a;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < E; e += 256) {
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int t = 0; t < L; ++t) {
+            const float v = embed[(long long)b * embed_stride + (long long)t * E + e];
+            acc0 = fmaf(s_a[0][t], v, acc0);
+            acc1 = fmaf(s_a[1][t], v, acc1);
+            acc2 = fmaf(s_a[2][t], v, acc2);
+            acc3 = fmaf(s_a[3][t], v, acc3);
+        }
+        pooled[((long long)0 * B + b) * E + e] = acc0;
+        pooled[((long long)1 * B + b) * E + e] = acc1;
+        pooled[((long long)2 * B + b) * E + e] = acc2;
+        pooled[((long long)3 * B + b) * E + e] = acc3;
+    }
+}
+
+extern "C" int ir_token_attention(const float* feats, const float* embed, int64_t embed_stride,
+                                  const int64_t* lengths, const float* fcw, const float* fcb,
+                                  int32_t B, int32_t L, int32_t D, int32_t E, float* atten,
+                                  float* pooled, ir_stream_t stream) {
+    IR_CHECK_ARG(feats && embed && lengths && fcw && fcb && atten && pooled);
+    IR_CHECK_ARG(B > 0 && L > 0 && L <= TA_MAXL && D > 0 && E > 0);
+    k_token_attention<<<B, 256, 0, (cudaStream_t)stream>>>(feats, embed, embed_stride, (const long long*)lengths,
+                                                          fcw, fcb, B, L, D, E, atten, pooled);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

@@ -1,0 +1,209 @@
+// Scene head kernels: SparseCrop + ToDenseBEVConvolution (+BN2d+ReLU), Conv2d 3x3, language-guided
+// attention over BEV cells.  Reference: models/basic_blocks.py:174-243, models/scene_module.py:25-38,
+// 69-83.  Activations are NHWC; all reductions run in a fixed order (deterministic).
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+
+#define BEV_X 240
+#define BEV_Y 400
+#define BEV_Z 80
+#define BEV_H 15
+#define BEV_W 25
+#define BEV_C 128
+
+// one CTA (128 threads = output channels) per voxel row: crop test, z-slice matvec
+__global__ void __launch_bounds__(BEV_C)
+k_bev_matvec(const float* __restrict__ F, const int4* __restrict__ coords, const int* __restrict__ n_dev,
+             int stride, const float* __restrict__ kern, int B, float* __restrict__ tmp,
+             int* __restrict__ cell) {
+    __shared__ float f[BEV_C];
+    const int n = *n_dev;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const int4 c = coords[r];
+        const bool keep = c.x >= 0 && c.y >= 0 && c.z >= 0 && c.x < BEV_X && c.y < BEV_Y && c.z < BEV_Z &&
+                          c.w >= 0 && c.w < B;
+        if (!keep) {
+            if (threadIdx.x == 0) cell[r] = -1;
+            continue;
+        }
+        __syncthreads();
+        f[threadIdx.x] = F[(long long)r * BEV_C + threadIdx.x];
+        __syncthreads();
+        const float* kz = kern + (long long)(c.z / stride) * BEV_C * BEV_C + threadIdx.x;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int ci = 0; ci < BEV_C; ++ci) acc = fmaf(f[ci], kz[(long long)ci * BEV_C], acc);
+        tmp[(long long)r * BEV_C + threadIdx.x] = acc;
+        if (threadIdx.x == 0) cell[r] = c.w * (BEV_H * BEV_W) + (c.x / stride) * BEV_W + (c.y / stride);
+    }
+}
+
+// one CTA per dense cell: sum matching rows in ascending row order, BN2d affine, ReLU
+__global__ void __launch_bounds__(BEV_C)
+k_bev_cell(const float* __restrict__ tmp, const int* __restrict__ cell, const int* __restrict__ n_dev,
+           const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+    __shared__ int s_list[16];
+    __shared__ int s_wcnt[BEV_C / 32];
+    __shared__ int s_total;
+    const int n = *n_dev;
+    const int me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < n; r0 += BEV_C) {
+        const int r = r0 + tid;
+        const bool m = (r < n) && (cell[r] == me);
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) s_wcnt[w] = __popc(bal);
+        __syncthreads();
+        int base = s_total;
+        for (int i = 0; i < w; ++i) base += s_wcnt[i];
+        if (m) {
+            const int p = base + __popc(bal & ((1u << lane) - 1u));
+            if (p < 16) s_list[p] = r;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = s_total;
+            for (int i = 0; i < BEV_C / 32; ++i) t += s_wcnt[i];
+            s_total = t;
+        }
+        __syncthreads();
+    }
+    const int cnt = min(s_total, 16);
+    float acc = 0.f;
+    for (int i = 0; i < cnt; ++i) acc += tmp[(long long)s_list[i] * BEV_C + tid];
+    out[(long long)me * BEV_C + tid] = fmaxf(fmaf(acc, scale[tid], shift[tid]), 0.f);
+}
+
+extern "C" int ir_bev(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
+                      int32_t stride, const float* kernel, const float* bn_scale,
+                      const float* bn_shift, int32_t B, float* tmp, int32_t* cell, float* out,
+                      ir_stream_t stream) {
+    IR_CHECK_ARG(feats && coords && n_dev && kernel && bn_scale && bn_shift && tmp && cell && out);
+    IR_CHECK_ARG(stride == 16 && B > 0 && n_max > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_bev_matvec<<<ir_min_i(n_max, IR_NUM_SMS * 16), BEV_C, 0, st>>>(feats, (const int4*)coords, n_dev, stride,
+                                                                     kernel, B, tmp, cell);
+    IR_CHECK_LAUNCH();
+    k_bev_cell<<<B * BEV_H * BEV_W, BEV_C, 0, st>>>(tmp, cell, n_dev, bn_scale, bn_shift, out);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ conv2d 3x3 (valid), NHWC, C=128
+#define C2_TPX 4
+#define C2_KS 4   // cin slices
+__global__ void __launch_bounds__(BEV_C * C2_KS)
+k_conv2d_3x3(const float* __restrict__ in, int H, int W, const float* __restrict__ wpack,
+             const float* __restrict__ bias, const float* __restrict__ scale,
+             const float* __restrict__ shift, int relu, float* __restrict__ out) {
+    constexpr int C = BEV_C;
+    __shared__ float patch[3][C2_TPX + 2][C];
+    __shared__ float red[C2_KS][C2_TPX][C];
+    const int Ho = H - 2, Wo = W - 2;
+    const int x0 = blockIdx.x * C2_TPX, y = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, co = tid & (C - 1), ks = tid / C;
+    for (int i = tid; i < 3 * (C2_TPX + 2) * C; i += C * C2_KS) {
+        const int c = i % C, px = (i / C) % (C2_TPX + 2), py = i / (C * (C2_TPX + 2));
+        const int xx = x0 + px;
+        patch[py][px][c] = (xx < W) ? in[(((long long)b * H + (y + py)) * W + xx) * C + c] : 0.f;
+    }
+    __syncthreads();
+    float acc[C2_TPX];
+#pragma unroll
+    for (int p = 0; p < C2_TPX; ++p) acc[p] = 0.f;
+    const int c_lo = ks * (C / C2_KS), c_hi = c_lo + C / C2_KS;
+    for (int kk = 0; kk < 9; ++kk) {
+        const int ky = kk / 3, kx = kk % 3;
+        const float* wk = wpack + ((long long)kk * C + c_lo) * C + co;
+#pragma unroll 4
+        for (int ci = c_lo; ci < c_hi; ++ci) {
+            const float wv = wk[(long long)(ci - c_lo) * C];
+#pragma unroll
+            for (int p = 0; p < C2_TPX; ++p) acc[p] = fmaf(wv, patch[ky][p + kx][ci], acc[p]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < C2_TPX; ++p) red[ks][p][co] = acc[p];
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+        for (int p = 0; p < C2_TPX; ++p) {
+            if (x0 + p < Wo) {
+                float v = ((red[0][p][co] + red[1][p][co]) + red[2][p][co]) + red[3][p][co];
+                v += bias ? bias[co] : 0.f;
+                if (scale) v = fmaf(v, scale[co], shift[co]);
+                if (relu) v = fmaxf(v, 0.f);
+                out[(((long long)b * Ho + y) * Wo + (x0 + p)) * C + co] = v;
+            }
+        }
+    }
+}
+
+extern "C" int ir_conv2d_3x3(const float* in, int32_t B, int32_t H, int32_t W, int32_t C,
+                             const float* wpack, const float* bias, const float* scale,
+                             const float* shift, int32_t relu, float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(in && wpack && out && C == BEV_C && H >= 3 && W >= 3 && B > 0);
+    dim3 grid(ir_div_up(W - 2, C2_TPX), H - 2, B);
+    k_conv2d_3x3<<<grid, BEV_C * C2_KS, 0, (cudaStream_t)stream>>>(in, H, W, wpack, bias, scale, shift, relu, out);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ attention over BEV cells
+__global__ void __launch_bounds__(256)
+k_scene_attention(const float* __restrict__ feats, const float* __restrict__ q, int ncell, int C,
+                  float* __restrict__ atten, float* __restrict__ scene_feat) {
+    extern __shared__ float s_att[];             // ncell logits
+    __shared__ float s_red[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float* fb = feats + (long long)b * ncell * C;
+    const float* qb = q + (long long)b * C;
+    const float inv = 1.0f / sqrtf((float)C);
+    for (int cell = w; cell < ncell; cell += 8) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(fb[(long long)cell * C + c], qb[c], a);
+        a = warp_sum(a);
+        if (lane == 0) s_att[cell] = a * inv;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int i = tid; i < ncell; i += 256) m = fmaxf(m, s_att[i]);
+    m = warp_max(m);
+    if (lane == 0) s_red[w] = m;
+    __syncthreads();
+    m = s_red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = tid; i < ncell; i += 256) {
+        const float e = expf(s_att[i] - m);
+        s_att[i] = e;
+        s += e;
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_red[w] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    const float rs = 1.0f / s;
+    for (int i = tid; i < ncell; i += 256) {
+        const float a = s_att[i] * rs;
+        s_att[i] = a;
+        atten[(long long)b * ncell + i] = a;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float acc = 0.f;
+        for (int cell = 0; cell < ncell; ++cell) acc = fmaf(fb[(long long)cell * C + c], s_att[cell], acc);
+        scene_feat[(long long)b * C + c] = acc;
+    }
+}
+
+extern "C" int ir_scene_attention(const float* feats, const float* q, int32_t B, int32_t ncell,
+                                  int32_t C, float* atten, float* scene_feat, ir_stream_t stream) {
+    IR_CHECK_ARG(feats && q && atten && scene_feat && B > 0 && ncell > 0 && ncell <= 8192 && C > 0);
+    k_scene_attention<<<B, 256, ncell * sizeof(float), (cudaStream_t)stream>>>(feats, q, ncell, C, atten, scene_feat);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

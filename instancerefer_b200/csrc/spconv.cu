@@ -1,0 +1,183 @@
+// Sparse convolution = pair-GEMM (gather rows -> per-offset dense contraction -> T) followed by a
+// deterministic output-stationary reduce with the BatchNorm / residual / ReLU epilogue fused in.
+// Replaces torchsparse's sparseconv_forward host loop reached from models/basic_blocks.py:14-21,
+// 32-44 (spnn.Conv3d + spnn.BatchNorm + spnn.ReLU) and the `+` at :55.
+//
+// This file: the SIMT fp32 pair-GEMM (exact fp32 FMA chain; the reference kernel the tcgen05
+// version in spconv_tc.cu is validated against), the reduce/epilogue, segmented max-pool.
+//
+//   T[kofs[k] + pos, :] = F[in_idx[k][pos], :] @ W[k]            (pair-GEMM, weight-stationary)
+//   out[o, :] = act( scale * sum_{k asc} T[kofs[k] + slot[o][k], :] + shift (+ resid[o, :]) )
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define PG_TP 32
+#define PG_THREADS 128
+#define PG_MAXC 128
+
+template <int COUT>
+__global__ void __launch_bounds__(PG_THREADS)
+k_pairgemm_simt(const float* __restrict__ F, int cin, int K, const int* __restrict__ in_idx,
+                long long seg_cap, const int* __restrict__ count, const float* __restrict__ W,
+                float* __restrict__ T) {
+    constexpr int G = PG_THREADS / COUT;      // pair groups per block
+    constexpr int PPT = PG_TP / G;            // pairs per thread
+    __shared__ __align__(16) float As[PG_TP][PG_MAXC];
+    __shared__ int s_kofs[33], s_tofs[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int a = 0, t = 0;
+        for (int k = 0; k < K; ++k) {
+            s_kofs[k] = a; s_tofs[k] = t;
+            const int c = count[k];
+            a += c; t += (c + PG_TP - 1) / PG_TP;
+        }
+        s_kofs[K] = a; s_tofs[K] = t;
+    }
+    __syncthreads();
+    const int ntiles = s_tofs[K];
+    const int cp = (cin + 3) & ~3;
+    const int co = tid % COUT, g = tid / COUT;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int k = 0;
+        while (tile >= s_tofs[k + 1]) ++k;
+        const int p0 = (tile - s_tofs[k]) * PG_TP;
+        const int np = min(PG_TP, (s_kofs[k + 1] - s_kofs[k]) - p0);
+        for (int r = warp; r < PG_TP; r += PG_THREADS / 32) {
+            const int j = (r < np) ? in_idx[(long long)k * seg_cap + p0 + r] : -1;
+            for (int c = lane; c < cp; c += 32)
+                As[r][c] = (j >= 0 && c < cin) ? F[(long long)j * cin + c] : 0.f;
+        }
+        __syncthreads();
+        float acc[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) acc[p] = 0.f;
+        const float* Wk = W + (long long)k * cin * COUT + co;
+        for (int c4 = 0; c4 < cp; c4 += 4) {
+            const float w0 = Wk[(long long)(c4 + 0) * COUT];
+            const float w1 = (c4 + 1 < cin) ? Wk[(long long)(c4 + 1) * COUT] : 0.f;
+            const float w2 = (c4 + 2 < cin) ? Wk[(long long)(c4 + 2) * COUT] : 0.f;
+            const float w3 = (c4 + 3 < cin) ? Wk[(long long)(c4 + 3) * COUT] : 0.f;
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[g * PPT + p][c4]);
+                acc[p] = fmaf(a.x, w0, acc[p]);
+                acc[p] = fmaf(a.y, w1, acc[p]);
+                acc[p] = fmaf(a.z, w2, acc[p]);
+                acc[p] = fmaf(a.w, w3, acc[p]);
+            }
+        }
+        float* Trow = T + (long long)(s_kofs[k] + p0 + g * PPT) * COUT + co;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+            if (g * PPT + p < np) Trow[(long long)p * COUT] = acc[p];
+        __syncthreads();
+    }
+}
+
+int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int* in_idx,
+                      long long seg_cap, const int* count, const float* weight, float* T,
+                      long long pairs_max, cudaStream_t st) {
+    IR_CHECK_ARG(cin >= 1 && cin <= PG_MAXC && K <= 32);
+    long long tiles = pairs_max / PG_TP + K;
+    const int grid = ir_min_i(tiles > 0 ? tiles : 1, IR_NUM_SMS * 16);
+    switch (cout) {
+        case 32:  k_pairgemm_simt<32><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
+        case 64:  k_pairgemm_simt<64><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
+        case 128: k_pairgemm_simt<128><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
+        default: ir_set_error("pairgemm_simt: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
+    }
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ reduce + epilogue
+template <int COUT, int KP>
+__global__ void __launch_bounds__(256)
+k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ slot,
+                  const int* __restrict__ count, const int* __restrict__ n_dev,
+                  const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ resid, int relu, float* __restrict__ out) {
+    constexpr int V = COUT / 32;
+    __shared__ int s_kofs[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        const int v = (lane < K) ? count[lane] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_kofs[lane] = inc - v;
+    }
+    __syncthreads();
+    const int n = *n_dev;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        sc[v] = scale ? scale[lane * V + v] : 1.f;
+        sh[v] = shift ? shift[lane * V + v] : 0.f;
+    }
+    const int wpb = blockDim.x >> 5;
+    for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
+        const int my = (lane < KP) ? slot[o * KP + lane] : -1;
+        float acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const int pos = __shfl_sync(0xffffffffu, my, k);
+            if (pos >= 0) {
+                const float* row = T + (long long)(s_kofs[k] + pos) * COUT + lane * V;
+                if (V == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(row);
+                    acc[0] += t.x; acc[1 % V] += t.y; acc[2 % V] += t.z; acc[3 % V] += t.w;
+                } else if (V == 2) {
+                    const float2 t = *reinterpret_cast<const float2*>(row);
+                    acc[0] += t.x; acc[1 % V] += t.y;
+                } else {
+                    acc[0] += row[0];
+                }
+            }
+        }
+        float* orow = out + o * COUT + lane * V;
+        const float* rrow = resid ? resid + o * COUT + lane * V : nullptr;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            float y = fmaf(acc[v], sc[v], sh[v]);
+            if (rrow) y += rrow[v];
+            if (relu) y = fmaxf(y, 0.f);
+            acc[v] = y;
+        }
+        if (V == 4) *reinterpret_cast<float4*>(orow) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+        else if (V == 2) *reinterpret_cast<float2*>(orow) = make_float2(acc[0], acc[1 % V]);
+        else orow[0] = acc[0];
+    }
+}
+
+int irk_reduce_epilogue(const float* T, int cout, int K, int KP, const int* slot, const int* count,
+                        const int* n_out_dev, long long n_max, const float* scale,
+                        const float* shift, const float* resid, int relu, float* out,
+                        cudaStream_t st) {
+    IR_CHECK_ARG((KP == 32 || KP == 8) && K <= KP);
+    const int grid = ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, 8), IR_NUM_SMS * 8);
+#define LAUNCH_RE(CO, KPV) k_reduce_epilogue<CO, KPV><<<grid, 256, 0, st>>>(T, K, slot, count, n_out_dev, scale, shift, resid, relu, out)
+    if (KP == 32) {
+        switch (cout) {
+            case 32: LAUNCH_RE(32, 32); break;
+            case 64: LAUNCH_RE(64, 32); break;
+            case 128: LAUNCH_RE(128, 32); break;
+            default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
+        }
+    } else {
+        switch (cout) {
+            case 32: LAUNCH_RE(32, 8); break;
+            case 64: LAUNCH_RE(64, 8); break;
+            case 128: LAUNCH_RE(128, 8); break;
+            default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
+        }
+    }
+#undef LAUNCH_RE
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

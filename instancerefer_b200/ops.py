@@ -1,0 +1,257 @@
+"""torch-tensor front end of the C ABI: pointer extraction, workspace ownership, stream plumbing.
+PyTorch is used only for device memory and streams; all arithmetic happens in the CUDA library."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import EncoderLayout, EncoderParams, call
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.IrError("expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.IrError("expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.IrError(f"expected dtype {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def check_device(device_index=None):
+    if not torch.cuda.is_available():
+        raise _lib.IrError("no CUDA device: instancerefer_b200 has no CPU fallback")
+    idx = torch.cuda.current_device() if device_index is None else device_index
+    call("ir_check_device", idx)
+
+
+# ----------------------------------------------------------------------------- encoder workspace
+
+def round_rows(n):
+    """Row-capacity bucket: workspaces are cached per bucket so allocations stay stable."""
+    return max(8192, (int(n) + 8191) // 8192 * 8192)
+
+
+class EncoderWorkspace:
+    """Caller-owned scratch for one sparse-encoder pass (hash tables, level coords, rulebooks,
+    activations, pair products).  ``view_*`` helpers expose the device-side tables for tests."""
+
+    def __init__(self, n_max, device):
+        self.n_max = int(n_max)
+        self.layout = EncoderLayout()
+        call("ir_encoder_layout", self.n_max, C.byref(self.layout))
+        self.buf = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=device)
+        self.ptr = C.c_void_p(self.buf.data_ptr())
+
+    def _view(self, off, nbytes, dtype):
+        return self.buf[off:off + nbytes].view(dtype)
+
+    def nlvl(self):
+        return self._view(self.layout.off_nlvl, 32, torch.int32)[:5]
+
+    def kcount(self):
+        return self._view(self.layout.off_kcount, 9 * 32 * 4, torch.int32).view(9, 32)
+
+    def coords(self, level):
+        return self._view(self.layout.off_coords[level], self.n_max * 16, torch.int32).view(self.n_max, 4)
+
+    def feat0(self, fdim):
+        return self._view(self.layout.off_feat0, self.n_max * 8 * 4, torch.float32)[: self.n_max * fdim].view(self.n_max, fdim)
+
+    def k3(self, level):
+        L = self.layout
+        return (self._view(L.off_k3_in[level], 27 * self.n_max * 4, torch.int32).view(27, self.n_max),
+                self._view(L.off_k3_slot[level], 32 * self.n_max * 4, torch.int32).view(self.n_max, 32))
+
+    def k2(self, level):
+        L = self.layout
+        return (self._view(L.off_k2_in[level], 8 * self.n_max * 4, torch.int32).view(8, self.n_max),
+                self._view(L.off_k2_slot[level], 8 * self.n_max * 4, torch.int32).view(self.n_max, 8))
+
+    def T(self):
+        return self._view(self.layout.off_T, 27 * self.n_max * 128 * 4, torch.float32)
+
+
+def encoder_reset(ws):
+    call("ir_encoder_reset", ws.ptr, ws.n_max, _stream())
+
+
+def voxelize(pts, cand, voxel, ws):
+    """pts (n_inst, ppi, fdim) fp32 cuda; cand (M,) int32 cuda.  Result stays in ``ws`` level 0."""
+    n_inst, ppi, fdim = pts.shape
+    call("ir_voxelize", _p(pts, torch.float32), _p(cand, torch.int32), cand.numel(), ppi, fdim,
+         float(voxel), ws.ptr, ws.n_max, _stream())
+
+
+def encoder_build_maps(ws, coords0=None):
+    if coords0 is None:
+        call("ir_encoder_build_maps", None, 0, ws.ptr, ws.n_max, _stream())
+    else:
+        call("ir_encoder_build_maps", _p(coords0, torch.int32), coords0.shape[0], ws.ptr, ws.n_max, _stream())
+
+
+def make_encoder_params(cin, weights, bn_scale, bn_shift, wprep=None, use_tc=False):
+    """Returns (struct, keepalive list).  13 tensors each, layer order of the header."""
+    P = EncoderParams()
+    P.cin = cin
+    P.use_tc = 1 if use_tc else 0
+    keep = []
+    for i in range(_lib.ENC_LAYERS):
+        P.weight[i] = weights[i].data_ptr()
+        P.bn_scale[i] = bn_scale[i].data_ptr()
+        P.bn_shift[i] = bn_shift[i].data_ptr()
+        P.wprep[i] = wprep[i].data_ptr() if (wprep is not None and wprep[i] is not None) else None
+        keep += [weights[i], bn_scale[i], bn_shift[i]]
+        if wprep is not None:
+            keep.append(wprep[i])
+    return P, keep
+
+
+def encoder_features(params, ws, feats0, out):
+    call("ir_encoder_features", C.byref(params), _p(feats0, torch.float32), ws.ptr, ws.n_max,
+         _p(out, torch.float32), _stream())
+
+
+def spconv_wprep(weight):
+    """(K,Cin,Cout) fp32 -> tcgen05 operand image tensor (see ir_spconv_prepare_weights)."""
+    K, cin, cout = weight.shape
+    n = _lib.load().ir_spconv_wprep_floats(K, cin, cout)
+    out = torch.empty(n, dtype=torch.float32, device=weight.device)
+    call("ir_spconv_prepare_weights", _p(weight.contiguous(), torch.float32), K, cin, cout, _p(out), _stream())
+    return out
+
+
+def spconv_layer(feat_in, in_idx, slot, count, n_out_dev, n_max, weight, scale, shift, resid, relu,
+                 T, out, wprep=None, use_tc=False):
+    K, cin, cout = weight.shape
+    KP = slot.shape[1]
+    call("ir_spconv_layer", _p(feat_in, torch.float32), cin, cout, K, KP, _p(in_idx, torch.int32),
+         in_idx.shape[1], _p(slot, torch.int32), _p(count, torch.int32), _p(n_out_dev, torch.int32),
+         n_max, _p(weight, torch.float32), _p(wprep), 1 if use_tc else 0, _p(scale), _p(shift),
+         _p(resid), 1 if relu else 0, _p(T, torch.float32), _p(out, torch.float32), _stream())
+
+
+def segmax(feats, coords, n_dev, n_max, n_seg):
+    Cc = feats.shape[1]
+    scratch = torch.empty(n_seg * Cc, dtype=torch.int32, device=feats.device)
+    out = torch.empty(n_seg, Cc, dtype=torch.float32, device=feats.device)
+    call("ir_segmax", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), n_max,
+         Cc, n_seg, _p(scratch), _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- scene head
+
+def bev(feats, coords, n_dev, n_max, stride, kernel, scale, shift, B):
+    dev = feats.device
+    tmp = torch.empty(n_max, 128, dtype=torch.float32, device=dev)
+    cell = torch.empty(n_max, dtype=torch.int32, device=dev)
+    out = torch.empty(B, 15, 25, 128, dtype=torch.float32, device=dev)
+    call("ir_bev", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), n_max, stride,
+         _p(kernel, torch.float32), _p(scale), _p(shift), B, _p(tmp), _p(cell), _p(out), _stream())
+    return out
+
+
+def conv2d_3x3(x, wpack, bias, scale, shift, relu):
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, H - 2, W - 2, Cc, dtype=torch.float32, device=x.device)
+    call("ir_conv2d_3x3", _p(x, torch.float32), B, H, W, Cc, _p(wpack, torch.float32), _p(bias), _p(scale),
+         _p(shift), 1 if relu else 0, _p(out), _stream())
+    return out
+
+
+def scene_attention(feats, q):
+    B, ncell, Cc = feats.shape
+    atten = torch.empty(B, ncell, dtype=torch.float32, device=feats.device)
+    sf = torch.empty(B, Cc, dtype=torch.float32, device=feats.device)
+    call("ir_scene_attention", _p(feats, torch.float32), _p(q, torch.float32), B, ncell, Cc, _p(atten), _p(sf), _stream())
+    return atten, sf
+
+
+# ----------------------------------------------------------------------------- language
+
+def linear(x, W, b, relu=False):
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    call("ir_linear", _p(x, torch.float32), M, K, _p(W, torch.float32), _p(b), N, 1 if relu else 0, _p(y), _stream())
+    return y
+
+
+def gru_layer(xproj, whh, bhh, lengths, B, L, H=128):
+    out = torch.empty(B, L, 2 * H, dtype=torch.float32, device=xproj.device)
+    call("ir_gru_layer", _p(xproj, torch.float32), _p(whh, torch.float32), _p(bhh, torch.float32),
+         _p(lengths, torch.int64), B, L, H, _p(out), _stream())
+    return out
+
+
+def token_attention(feats, embed, lengths, fcw, fcb):
+    B, L, D = feats.shape
+    E = embed.shape[-1]
+    atten = torch.empty(4, B, L, dtype=torch.float32, device=feats.device)
+    pooled = torch.empty(4, B, E, dtype=torch.float32, device=feats.device)
+    call("ir_token_attention", _p(feats, torch.float32), _p(embed, torch.float32), embed.shape[1] * E,
+         _p(lengths, torch.int64), _p(fcw, torch.float32), _p(fcb, torch.float32), B, L, D, E,
+         _p(atten), _p(pooled), _stream())
+    return atten, pooled
+
+
+# ----------------------------------------------------------------------------- heads / relation
+
+NORM_NONE, NORM_AFFINE, NORM_LAYER = 0, 1, 2
+MODE_RAW, MODE_L2, MODE_DOT, MODE_COS = 0, 1, 2, 3
+
+
+def mlp_head(x, W1, b1, norm, g, beta, W2, b2, mode, partner=None, seg=None, want_y=False):
+    M, K = x.shape
+    N1, N2 = W1.shape[0], W2.shape[0]
+    dev = x.device
+    y = torch.empty(M, N2, dtype=torch.float32, device=dev) if (mode < 2 or want_y) else None
+    score = torch.empty(M, dtype=torch.float32, device=dev) if mode >= 2 else None
+    call("ir_mlp_head", _p(x, torch.float32), M, K, _p(W1, torch.float32), _p(b1), N1, norm, _p(g), _p(beta),
+         _p(W2, torch.float32), _p(b2), N2, mode, _p(partner), _p(seg, torch.int32) if seg is not None else None,
+         _p(y), _p(score), _stream())
+    return y, score
+
+
+def candidate_softmax(sa, sr, ss, seg_ofs):
+    n_seg = seg_ofs.numel() - 1
+    prob = torch.empty_like(sa)
+    arg = torch.empty(n_seg, dtype=torch.int32, device=sa.device)
+    call("ir_candidate_softmax", _p(sa, torch.float32), _p(sr, torch.float32), _p(ss, torch.float32),
+         _p(seg_ofs, torch.int32), n_seg, _p(prob), _p(arg), _stream())
+    return prob, arg
+
+
+def instance_mean(pts):
+    n_inst, ppi, fdim = pts.shape
+    mean = torch.empty(n_inst, fdim, dtype=torch.float32, device=pts.device)
+    call("ir_instance_mean", _p(pts, torch.float32), n_inst, ppi, fdim, _p(mean), _stream())
+    return mean
+
+
+def knn(xyz, seg_ofs, qidx, qseg, k):
+    nq = qidx.numel()
+    nbr = torch.empty(nq, k, dtype=torch.int32, device=xyz.device)
+    call("ir_knn", _p(xyz, torch.float32), _p(seg_ofs, torch.int32), _p(qidx, torch.int32),
+         _p(qseg, torch.int32), nq, k, _p(nbr), _stream())
+    return nbr
+
+
+def edgeconv(x, xyz, qidx, nbr, ncls, Ww1, bw1, Ww2, bw2, Wm1, bm1, Wm2, bm2):
+    """Weights in (in,out) layout (transposed nn.Linear weights)."""
+    nq, k = nbr.shape
+    F = x.shape[1]
+    Fout = Wm2.shape[1]
+    out = torch.empty(nq, Fout, dtype=torch.float32, device=x.device)
+    call("ir_edgeconv", _p(x, torch.float32), _p(xyz, torch.float32), _p(qidx, torch.int32),
+         _p(nbr, torch.int32), nq, k, F, ncls, _p(Ww1), _p(bw1), _p(Ww2), _p(bw2), _p(Wm1), _p(bm1),
+         _p(Wm2), _p(bm2), Fout, _p(out), _stream())
+    return out

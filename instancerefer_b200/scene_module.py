@@ -1,0 +1,90 @@
+"""Scene (GLP) module, drop-in for the reference's ``models/scene_module.py``: whole-scene sparse
+encoder at 5 cm -> crop -> dense BEV 15x25 (z-slice matvec + scatter-sum, BN, ReLU) -> 2x Conv2d
+3x3 -> language-guided attention over 11x21 cells -> 9-way region classifier and cosine(obj, scene).
+Reference lines: models/scene_module.py:10-58 (ctor), :60-108 (forward)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .basic_blocks import (BEVEncoder, PrepCache, ReLU, SparseCrop, ToDenseBEVConvolution, fold_bn,
+                           require_eval)
+from .candidates import get_pack
+
+
+class GlobalMaxPooling(nn.Module):
+    pass
+
+
+class SceneModule(nn.Module, PrepCache):
+    def __init__(self, input_feature_dim, args, v_dim=128, h_dim=128, l_dim=256, dropout_rate=0.15):
+        super().__init__()
+        self.args = args
+        self.input_feature_dim = input_feature_dim
+        self.voxel_size = np.array([args.voxel_size_glp] * 3)
+        self.net = BEVEncoder(self.input_feature_dim)
+        self.pooling = GlobalMaxPooling()
+        self.to_bev = nn.Sequential(SparseCrop((0, 0, 0), (240, 400, 80)),
+                                    ToDenseBEVConvolution(128, 128, shape=(15, 25, 5), z_dim=2),
+                                    nn.BatchNorm2d(128), ReLU(True))
+        self.h_dim = h_dim
+        self.vis_emb_fc = nn.Sequential(nn.Conv2d(v_dim, h_dim, 3), nn.BatchNorm2d(h_dim), nn.ReLU(),
+                                        nn.Dropout(dropout_rate), nn.Conv2d(h_dim, h_dim, 3))
+        self.vis_emb_fc1 = nn.Sequential(nn.Linear(128, h_dim), nn.LayerNorm(h_dim), nn.ReLU(),
+                                         nn.Dropout(dropout_rate), nn.Linear(h_dim, h_dim))
+        self.lang_emb_fc = nn.Sequential(nn.Linear(l_dim, h_dim), nn.LayerNorm(h_dim), nn.ReLU(),
+                                         nn.Dropout(dropout_rate), nn.Linear(h_dim, h_dim))
+        self.cls = nn.Sequential(nn.Linear(h_dim, h_dim), nn.BatchNorm1d(h_dim), nn.ReLU(),
+                                 nn.Linear(h_dim, 9))
+
+    def _prep_key(self):
+        mods = (self.to_bev, self.vis_emb_fc, self.vis_emb_fc1, self.lang_emb_fc, self.cls)
+        ts = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _prepare(self):
+        f = lambda t: t.detach().float().contiguous()
+        pk = lambda conv: conv.weight.detach().float().permute(2, 3, 1, 0).contiguous()   # [ky][kx][Cin][Cout]
+        bs, bb = fold_bn(self.to_bev[2])
+        c1s, c1b = fold_bn(self.vis_emb_fc[1])
+        cs, cb = fold_bn(self.cls[1])
+        v1, l = self.vis_emb_fc1, self.lang_emb_fc
+        return dict(bev_kernel=f(self.to_bev[1].kernel), bev_s=bs, bev_b=bb,
+                    c1w=pk(self.vis_emb_fc[0]), c1bias=f(self.vis_emb_fc[0].bias), c1s=c1s, c1b=c1b,
+                    c2w=pk(self.vis_emb_fc[4]), c2bias=f(self.vis_emb_fc[4].bias),
+                    ow1=f(v1[0].weight), ob1=f(v1[0].bias), og=f(v1[1].weight), obeta=f(v1[1].bias),
+                    ow2=f(v1[4].weight), ob2=f(v1[4].bias),
+                    lw1=f(l[0].weight), lb1=f(l[0].bias), lg=f(l[1].weight), lbeta=f(l[1].bias),
+                    lw2=f(l[4].weight), lb2=f(l[4].bias),
+                    kw1=f(self.cls[0].weight), kb1=f(self.cls[0].bias), kg=cs, kbeta=cb,
+                    kw2=f(self.cls[3].weight), kb2=f(self.cls[3].bias))
+
+    def forward(self, data_dict):
+        require_eval(self)
+        ops.check_device()
+        p = self.prepared()
+        lidar = data_dict['lidar']
+        B = data_dict['point_min'].shape[0]                                     # (:62-63)
+        lang = data_dict['lang_scene_feats']
+        dev = lang.device
+        F0 = lidar.F.to(dev, torch.float32).contiguous()
+        C0 = lidar.C.to(dev, torch.int32).contiguous()
+        ws = self.net.workspace(F0.shape[0], dev)
+        f4, c4, n4 = self.net.encode(ws, F0, C0)                                # (:69)
+        bev = ops.bev(f4, c4, n4, ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)   # (:70) NHWC
+        x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
+        x = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)         # (:71) (B,11,21,128)
+        h, w = x.shape[1], x.shape[2]
+        q, _ = ops.mlp_head(lang.float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER, p['lg'], p['lbeta'],
+                            p['lw2'], p['lb2'], ops.MODE_RAW)
+        atten, scene_feats = ops.scene_attention(x.view(B, h * w, -1), q)       # (:73-83)
+        data_dict['vis_atten'] = atten.view(B, h, w)
+        seg, _ = ops.mlp_head(scene_feats, p['kw1'], p['kb1'], ops.NORM_AFFINE, p['kg'], p['kbeta'],
+                              p['kw2'], p['kb2'], ops.MODE_RAW)                 # (:84)
+        data_dict['seg_scores'] = seg
+        pack = get_pack(data_dict, self.args, dev)
+        _, scores = ops.mlp_head(data_dict['obj_feats'], p['ow1'], p['ob1'], ops.NORM_LAYER, p['og'],
+                                 p['obeta'], p['ow2'], p['ob2'], ops.MODE_COS, partner=scene_feats,
+                                 seg=pack.cand_scene)                            # (:89-104)
+        data_dict['scene_scores'] = scores
+        return data_dict

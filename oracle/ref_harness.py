@@ -96,6 +96,10 @@ def build_reference_model(args=None, input_feature_dim=7, seed=123):
     assert available(), "reference tree not present"
     _setup_paths()
     args = args or load_args()
+    for name in ('lang_module', 'attribute_module', 'relation_module', 'scene_module'):
+        m = sys.modules.get(name)                       # a drop-in with the same bare name may be cached
+        if m is not None and not os.path.abspath(getattr(m, '__file__', '')).startswith(REF):
+            del sys.modules[name]
     with cpu_patches():
         mod = importlib.import_module("models.instancerefer")
         torch.manual_seed(seed)

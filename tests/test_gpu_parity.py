@@ -1,0 +1,368 @@
+"""GPU parity tests (B200): every CUDA op through the C ABI against the CPU oracle on the same seeded
+inputs.  Integer / index work is compared bit-exactly (rulebooks after canonicalisation inside each
+kernel offset); fp32 values within 1e-4 abs (BASELINE.json north_star)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import model_ref
+import sparse_ref as R
+from instancerefer_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def ops(lib_built):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from instancerefer_b200 import ops as _ops
+    _ops.check_device()
+    return _ops
+
+
+def rand_coords(rng, n, lo, hi, nb):
+    pts = rng.integers(lo, hi, (n * 2, 4))
+    pts[:, 3] = rng.integers(0, nb, n * 2)
+    pts = pts[np.sort(np.unique(pts, axis=0, return_index=True)[1])][:n]
+    pts = pts[np.argsort(pts[:, 3], kind='stable')]            # batch ids sorted like a collated batch
+    return pts.astype(np.int32)
+
+
+def rulebook_from_ws(cnt, in_idx, slot, n_out, K):
+    """-> per k: sorted array of (out,in) pairs reconstructed from count / in_idx / slot tables."""
+    out = []
+    cnt = cnt.cpu().numpy()
+    in_idx = in_idx.cpu().numpy()
+    slot = slot.cpu().numpy()[:n_out]
+    for k in range(K):
+        o = np.nonzero(slot[:, k] >= 0)[0]
+        pos = slot[o, k]
+        assert o.size == cnt[k] and (np.sort(pos) == np.arange(cnt[k])).all()
+        out.append(np.stack([o, in_idx[k, pos]], 1))
+    return out
+
+
+def rulebook_from_oracle(ii, oo, kofs):
+    out = []
+    for k in range(len(kofs) - 1):
+        seg = slice(kofs[k], kofs[k + 1])
+        a = np.stack([oo[seg], ii[seg]], 1)
+        out.append(a[np.argsort(a[:, 0], kind='stable')])
+    return out
+
+
+# ----------------------------------------------------------------------------- coordinates
+
+@pytest.mark.parametrize('n,lo,hi,nb', [(1, 0, 4, 1), (700, -20, 20, 2), (30000, -40, 60, 3)])
+def test_maps_bit_exact(ops, n, lo, hi, nb):
+    rng = np.random.default_rng(n)
+    C0 = rand_coords(rng, n, lo, hi, nb)
+    n = C0.shape[0]
+    ws = ops.EncoderWorkspace(ops.round_rows(n), 'cuda')
+    ops.encoder_build_maps(ws, torch.from_numpy(C0).cuda())
+    torch.cuda.synchronize()
+    nl = ws.nlvl().cpu().tolist()
+    C, s = C0, 1
+    kc = ws.kcount()
+    for l in range(5):
+        assert nl[l] == C.shape[0]
+        if l > 0:
+            assert np.array_equal(ws.coords(l)[:nl[l]].cpu().numpy(), C)      # first-occurrence order
+        ii, oo, kofs = R.build_kmap(C, C, 3, s)
+        got = rulebook_from_ws(kc[l], *ws.k3(l), C.shape[0], 27)
+        for a, b in zip(got, rulebook_from_oracle(ii, oo, kofs)):
+            assert np.array_equal(a, b)
+        if l < 4:
+            Cn, _ = R.downsample_coords(C, s)
+            ii, oo, kofs = R.build_kmap(C, Cn, 2, s)
+            got = rulebook_from_ws(kc[5 + l], *ws.k2(l), Cn.shape[0], 8)
+            for a, b in zip(got, rulebook_from_oracle(ii, oo, kofs)):
+                assert np.array_equal(a, b)
+            C, s = Cn, s * 2
+
+
+def test_voxelize_bit_exact(ops):
+    rng = np.random.default_rng(3)
+    n_inst, ppi = 6, 1024
+    pts = rng.uniform(-0.6, 0.9, (n_inst, ppi, 7)).astype(np.float32)
+    pts[:, 100:200] = pts[:, 0:100]                                      # exact duplicates
+    cand = np.array([4, 0, 5, 2], np.int32)
+    ws = ops.EncoderWorkspace(ops.round_rows(len(cand) * ppi), 'cuda')
+    ops.encoder_reset(ws)
+    ops.voxelize(torch.from_numpy(pts).cuda(), torch.from_numpy(cand).cuda(), 0.02, ws)
+    torch.cuda.synchronize()
+    cl, fl = [], []
+    for m in cand:
+        c, f = R.sparse_quantize(pts[m][:, :3], pts[m], np.array([0.02] * 3))
+        cl.append(c)
+        fl.append(f)
+    Cr, Fr = R.sparse_collate(cl, fl)
+    n = int(ws.nlvl()[0])
+    assert n == Cr.shape[0]
+    assert np.array_equal(ws.coords(0)[:n].cpu().numpy(), Cr.numpy())
+    assert np.array_equal(ws.feat0(7)[:n].cpu().numpy(), Fr.numpy())
+
+
+# ----------------------------------------------------------------------------- sparse conv
+
+def _layer_case(ops, rng, n, cin, cout, ks, use_tc):
+    C0 = rand_coords(rng, n, 0, 24, 2)
+    n = C0.shape[0]
+    ws = ops.EncoderWorkspace(ops.round_rows(n), 'cuda')
+    ops.encoder_build_maps(ws, torch.from_numpy(C0).cuda())
+    if ks == 3:
+        Cout_np, (in_idx, slot), cnt, n_out = C0, ws.k3(0), ws.kcount()[0], ws.nlvl()[0:1]
+    else:
+        Cout_np, _ = R.downsample_coords(C0, 1)
+        (in_idx, slot), cnt, n_out = ws.k2(0), ws.kcount()[5], ws.nlvl()[1:2]
+    F = torch.from_numpy(rng.normal(size=(n, cin)).astype(np.float32))
+    W = torch.from_numpy((rng.normal(size=(ks ** 3, cin, cout)) / np.sqrt(cin * ks ** 3)).astype(np.float32))
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    shift = torch.from_numpy(rng.normal(size=cout).astype(np.float32) * 0.1)
+    n_o = Cout_np.shape[0]
+    resid = torch.from_numpy(rng.normal(size=(n_o, cout)).astype(np.float32))
+    ii, oo, kofs = R.build_kmap(C0, Cout_np, ks, 1)
+    want = torch.relu(R.spconv(F, W, ii, oo, kofs, n_o) * scale + shift + resid)
+    out = torch.empty(ws.n_max, cout, device='cuda')
+    Wd = W.cuda()
+    wprep = ops.spconv_wprep(Wd) if use_tc else None
+    ops.spconv_layer(F.cuda(), in_idx, slot, cnt, n_out, ws.n_max, Wd, scale.cuda(), shift.cuda(),
+                     torch.cat([resid, torch.zeros(ws.n_max - n_o, cout)]).cuda(), True, ws.T(), out,
+                     wprep=wprep, use_tc=use_tc)
+    torch.cuda.synchronize()
+    return out[:n_o].cpu(), want
+
+
+@pytest.mark.parametrize('cin,cout,ks', [(7, 32, 3), (32, 64, 2), (64, 64, 3), (64, 128, 2), (128, 128, 3), (128, 128, 2)])
+def test_spconv_layer_simt(ops, cin, cout, ks):
+    got, want = _layer_case(ops, np.random.default_rng(cin + cout + ks), 3000, cin, cout, ks, False)
+    assert float((got - want).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('cin,cout,ks', [(32, 64, 2), (64, 64, 3), (64, 128, 2), (128, 128, 3), (128, 128, 2)])
+def test_spconv_layer_tcgen05(ops, cin, cout, ks):
+    """3xTF32 tensor-core pair-GEMM vs the oracle (fp32-level accuracy required)."""
+    got, want = _layer_case(ops, np.random.default_rng(cin + cout + ks), 5000, cin, cout, ks, True)
+    assert float((got - want).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('use_tc', [False, True])
+def test_encoder_features(ops, state_dict, use_tc):
+    from instancerefer_b200.basic_blocks import SparseConvEncoder
+    rng = np.random.default_rng(11)
+    b = synthetic.make_batch(9, batch_size=2, num_points=8000, n_inst=6, n_cand=3, n_tokens=4)
+    C0, F0 = b['lidar_coords'], b['lidar_feats']
+    enc = SparseConvEncoder(7)
+    enc.use_tc = use_tc
+    enc.load_state_dict({k[len('scene.net.'):]: v for k, v in state_dict.items() if k.startswith('scene.net.')})
+    enc = enc.cuda().eval()
+    ws = enc.workspace(C0.shape[0], 'cuda')
+    f4, c4, n4 = enc.encode(ws, torch.from_numpy(F0).cuda(), torch.from_numpy(C0).cuda())
+    torch.cuda.synchronize()
+    sd = {k: v.float() for k, v in state_dict.items()}
+    Fr, Cr, s = model_ref.encoder_forward(sd, 'scene.net', torch.from_numpy(F0), torch.from_numpy(C0))
+    n = int(n4)
+    assert n == Fr.shape[0] and s == 16
+    assert np.array_equal(c4[:n].cpu().numpy(), Cr.numpy())
+    assert float((f4[:n].cpu() - Fr).abs().max()) < TOL
+
+
+def test_segmax(ops):
+    rng = np.random.default_rng(5)
+    F = torch.from_numpy(rng.normal(size=(777, 128)).astype(np.float32))
+    C = torch.zeros(777, 4, dtype=torch.int32)
+    C[:, 3] = torch.from_numpy(np.sort(rng.integers(0, 9, 777)).astype(np.int32))
+    n_dev = torch.tensor([700], dtype=torch.int32).cuda()
+    got = ops.segmax(F.cuda(), C.cuda(), n_dev, 777, 9).cpu()
+    want = R.global_max_pool(F[:700], C[:700, 3])
+    assert torch.equal(got[:want.shape[0]], want)
+
+
+# ----------------------------------------------------------------------------- scene head
+
+def test_bev_conv_attention(ops, state_dict):
+    rng = np.random.default_rng(6)
+    sd = {k: v.float() for k, v in state_dict.items()}
+    n, B = 600, 2
+    C = rand_coords(rng, n, -2, 30, B)
+    C[:, :3] *= 16
+    C[:, 2] = (C[:, 2] // 16 % 7 - 1) * 16                                 # z in {-16..80}: some cropped
+    C = C[np.sort(np.unique(C, axis=0, return_index=True)[1])]
+    n = C.shape[0]
+    F = torch.from_numpy(np.abs(rng.normal(size=(n, 128))).astype(np.float32))
+    bn = 'scene.to_bev.2'
+    scale = sd[bn + '.weight'] / torch.sqrt(sd[bn + '.running_var'] + 1e-5)
+    shift = sd[bn + '.bias'] - sd[bn + '.running_mean'] * scale
+    n_dev = torch.tensor([n], dtype=torch.int32).cuda()
+    bev = ops.bev(F.cuda(), torch.from_numpy(C).cuda(), n_dev, n, 16, sd['scene.to_bev.1.kernel'].cuda(),
+                  scale.cuda(), shift.cuda(), B)
+    want = model_ref.bev_forward(sd, 'scene.to_bev', F, torch.from_numpy(C), 16)
+    want = torch.relu(model_ref._bn(sd, bn, want, False))
+    assert float((bev.permute(0, 3, 1, 2).cpu() - want).abs().max()) < TOL
+    # conv2d x2
+    w1, b1 = sd['scene.vis_emb_fc.0.weight'], sd['scene.vis_emb_fc.0.bias']
+    s1 = sd['scene.vis_emb_fc.1.weight'] / torch.sqrt(sd['scene.vis_emb_fc.1.running_var'] + 1e-5)
+    h1 = sd['scene.vis_emb_fc.1.bias'] - sd['scene.vis_emb_fc.1.running_mean'] * s1
+    x = ops.conv2d_3x3(bev, w1.permute(2, 3, 1, 0).contiguous().cuda(), b1.cuda(), s1.cuda(), h1.cuda(), True)
+    xr = torch.relu(model_ref._bn(sd, 'scene.vis_emb_fc.1', torch.nn.functional.conv2d(want, w1, b1), False))
+    assert float((x.permute(0, 3, 1, 2).cpu() - xr).abs().max()) < TOL
+    q = torch.from_numpy(rng.normal(size=(B, 128)).astype(np.float32))
+    att, sf = ops.scene_attention(x.view(B, -1, 128), q.cuda())
+    feats = xr.reshape(B, 128, -1).permute(0, 2, 1)
+    a = torch.softmax(torch.bmm(feats, q.unsqueeze(2)).squeeze(2) / np.sqrt(128), 1)
+    assert float((att.cpu() - a).abs().max()) < 1e-5
+    assert float((sf.cpu() - (feats * a.unsqueeze(2)).sum(1)).abs().max()) < TOL
+
+
+# ----------------------------------------------------------------------------- language
+
+def test_linear_and_gru(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 300, generator=g)
+    W = torch.randn(256, 300, generator=g) / 17
+    b = torch.randn(256, generator=g)
+    y = ops.linear(x.cuda(), W.cuda(), b.cuda(), relu=True).cpu()
+    assert float((y - torch.relu(x @ W.t() + b)).abs().max()) < 1e-5
+    gru = torch.nn.GRU(256, 128, num_layers=1, batch_first=True, bidirectional=True)
+    B, L = 4, 13
+    lens = torch.tensor([13, 1, 7, 10])
+    xin = torch.randn(B, L, 256, generator=g)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(xin, lens, batch_first=True, enforce_sorted=False)
+    want, _ = torch.nn.utils.rnn.pad_packed_sequence(gru(packed)[0], batch_first=True)
+    wih = torch.cat([gru.weight_ih_l0, gru.weight_ih_l0_reverse], 0).detach()
+    bih = torch.cat([gru.bias_ih_l0, gru.bias_ih_l0_reverse], 0).detach()
+    whh = torch.stack([gru.weight_hh_l0, gru.weight_hh_l0_reverse], 0).detach().contiguous()
+    bhh = torch.stack([gru.bias_hh_l0, gru.bias_hh_l0_reverse], 0).detach().contiguous()
+    xp = ops.linear(xin.view(B * L, 256).cuda(), wih.cuda(), bih.cuda())
+    out = ops.gru_layer(xp, whh.cuda(), bhh.cuda(), lens.cuda(), B, L).cpu()
+    assert float((out - want.detach()).abs().max()) < 1e-5
+
+
+def test_lang_module_vs_oracle(gpu_model, state_dict):
+    b = synthetic.make_batch(41, batch_size=3, num_points=3000, n_inst=4, n_cand=2, n_tokens=[5, 17, 1])
+    d = dict(lang_feat=torch.from_numpy(b['lang_feat']).cuda(), lang_len=torch.from_numpy(b['lang_len']).cuda())
+    out = gpu_model.lang(d)
+    ref = model_ref.lang_forward({k: v.float() for k, v in state_dict.items()}, model_ref.data_from_batch(b))
+    for k in ('lang_feat', 'atten_attr', 'atten_rel', 'atten_scene', 'lang_attr_feats', 'lang_cls_feats',
+              'lang_rel_feats', 'lang_scene_feats', 'lang_scores'):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-5, k
+
+
+# ----------------------------------------------------------------------------- heads / relation
+
+@pytest.mark.parametrize('norm,mode', [(1, 1), (2, 2), (2, 3), (1, 0), (0, 0)])
+def test_mlp_head(ops, norm, mode):
+    g = torch.Generator().manual_seed(norm * 10 + mode)
+    M, K, N1, N2, S = 19, 128, 256, 256, 3
+    x = torch.randn(M, K, generator=g)
+    W1, b1 = torch.randn(N1, K, generator=g) / 11, torch.randn(N1, generator=g)
+    W2, b2 = torch.randn(N2, N1, generator=g) / 16, torch.randn(N2, generator=g)
+    gam, beta = torch.rand(N1, generator=g) + 0.5, torch.randn(N1, generator=g) * 0.1
+    partner = torch.randn(S, N2, generator=g)
+    seg = torch.randint(0, S, (M,), generator=g, dtype=torch.int32)
+    h = x @ W1.t() + b1
+    if norm == 2:
+        h = torch.nn.functional.layer_norm(h, (N1,), gam, beta, 1e-5)
+    elif norm == 1:
+        h = h * gam + beta
+    yr = torch.relu(h) @ W2.t() + b2
+    y, score = ops.mlp_head(x.cuda(), W1.cuda(), b1.cuda(), norm, gam.cuda(), beta.cuda(), W2.cuda(), b2.cuda(),
+                            mode, partner=partner.cuda(), seg=seg.cuda())
+    if mode == 0:
+        assert float((y.cpu() - yr).abs().max()) < 2e-5
+    elif mode == 1:
+        assert float((y.cpu() - torch.nn.functional.normalize(yr, dim=1)).abs().max()) < 1e-5
+    elif mode == 2:
+        want = (torch.nn.functional.normalize(yr, dim=1) * partner[seg.long()]).sum(1)
+        assert float((score.cpu() - want).abs().max()) < 2e-5
+    else:
+        want = torch.nn.functional.cosine_similarity(yr, partner[seg.long()], dim=1)
+        assert float((score.cpu() - want).abs().max()) < 1e-5
+
+
+def test_knn_edgeconv(ops, state_dict):
+    rng = np.random.default_rng(8)
+    sd = {k: v.float() for k, v in state_dict.items()}
+    sizes = [5, 40, 9]                                                   # 5 < k exercises short segments
+    S = sum(sizes)
+    xyz = torch.from_numpy(rng.integers(0, 6, (S, 3)).astype(np.float32) * 0.5)   # many exact ties
+    cls = torch.from_numpy(rng.integers(0, 18, S))
+    feats = torch.cat([xyz, torch.from_numpy(rng.normal(size=(S, 4)).astype(np.float32)),
+                       torch.nn.functional.one_hot(cls, 18).float()], 1)
+    bidx = torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)])
+    fidx = torch.from_numpy(np.sort(rng.choice(S, 20, replace=False)))
+    tr = {}
+    want = model_ref.edgeconv_forward(sd, 'relation.gcn', xyz, bidx, fidx, feats, 8, 18, tr)
+    seg_ofs = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32).cuda()
+    nbr = ops.knn(xyz.cuda(), seg_ofs, fidx.int().cuda(), bidx[fidx].int().cuda(), 8).cpu()
+    flat = [(q, int(j)) for q in range(nbr.shape[0]) for j in nbr[q] if j >= 0]
+    assert flat == list(zip(tr['knn_row'].tolist(), tr['knn_col'].tolist()))     # bit-exact incl. tie order
+    t = lambda k: sd[k].t().contiguous().cuda()
+    c = lambda k: sd[k].contiguous().cuda()
+    p = 'relation.gcn.'
+    out = ops.edgeconv(feats.cuda(), xyz.cuda(), fidx.int().cuda(), nbr.cuda(), 18,
+                       t(p + 'weight.0.weight'), c(p + 'weight.0.bias'), t(p + 'weight.2.weight'), c(p + 'weight.2.bias'),
+                       t(p + 'mlp.0.weight'), c(p + 'mlp.0.bias'), t(p + 'mlp.2.weight'), c(p + 'mlp.2.bias')).cpu()
+    assert float((out - want).abs().max()) < 2e-5
+
+
+# ----------------------------------------------------------------------------- whole forward
+
+OUT_KEYS = ['lang_feat', 'atten_attr', 'atten_rel', 'atten_scene', 'lang_cls_feats', 'lang_attr_feats',
+            'lang_rel_feats', 'lang_scene_feats', 'lang_scores', 'obj_feats', 'attribute_scores',
+            'relation_scores', 'scene_scores', 'seg_scores', 'vis_atten']
+
+
+def _run(gpu_model, b):
+    from instancerefer_b200 import SparseTensor
+    out = gpu_model(synthetic.to_data_dict(b, SparseTensor, 'cuda'))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLD, 'golden_*.npz'))))
+def test_forward_vs_golden(gpu_model, path):
+    """Committed outputs of the reference's models/*.py executed verbatim (oracle/make_golden.py)."""
+    z = np.load(path)
+    cfg = json.loads(bytes(z['config_json']).decode())
+    shift, seed = cfg.pop('shift', None), cfg.pop('seed')
+    b = synthetic.make_batch(seed, **cfg)
+    if shift is not None:
+        b = synthetic.shift_batch(b, shift)
+    out = _run(gpu_model, b)
+    for k in OUT_KEYS:
+        assert float(np.abs(out[k].cpu().numpy() - z[k]).max()) < TOL, k
+    assert out['num_filtered_objs'] == z['num_filtered_objs'].tolist()
+    for i, o in enumerate(out['pred_obb_batch']):
+        assert np.array_equal(np.asarray(o).reshape(-1, 7), z[f'pred_obb_{i}'].reshape(-1, 7))
+
+
+def test_forward_c2_vs_oracle(gpu_model, state_dict, args):
+    """BASELINE.json configs[1]: 1 scene, 40k points, 32 candidates, 20 tokens."""
+    b = synthetic.make_batch(123, batch_size=1, num_points=40000, n_inst=32, n_cand=32, n_tokens=20)
+    out = _run(gpu_model, b)
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), args)
+    for k in OUT_KEYS:
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k
+    s = ref['attribute_scores'] + ref['relation_scores'] + ref['scene_scores']
+    assert int(out['ref_pred'][0]) == int(s.argmax())
+    assert float((out['ref_probs'].cpu() - torch.softmax(s, 0)).abs().max()) < TOL
+    out2 = _run(gpu_model, b)                                            # deterministic: bitwise equal
+    for k in ('obj_feats', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores'):
+        assert torch.equal(out[k], out2[k]), k
+
+
+def test_forward_c4_relation_stress(gpu_model, state_dict, args):
+    """BASELINE.json configs[3] shape (64-instance scenes), reduced batch so the oracle stays fast."""
+    b = synthetic.make_batch(7, batch_size=3, num_points=12000, n_inst=64, n_cand=64, n_tokens=[8, 20, 14])
+    out = _run(gpu_model, b)
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), args)
+    for k in ('relation_scores', 'attribute_scores', 'scene_scores', 'obj_feats'):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k
