@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — referrals/sec of the InstanceRefer hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one InstanceRefer.forward (eval) over one batch of the BASELINE.json `configs[1]` workload:
+1 synthetic scene, 40k points (~28k voxels @5 cm), 32 candidate instances x 1024 points, 20-token
+utterance.  One step = one referral per GPU; scenes shard across ranks with no data-path collective
+(weak scaling).  Prints ONE JSON line on rank 0:
+  value  referrals/s with inputs resident in HBM (CUDA events around each step, L2 flushed between
+         steps outside the timed spans, max over ranks);
+  e2e    the same forward through the public module API from HOST buffers: pinned H2D of the step's
+         inputs + host packing of the instance lists + D2H of the scores, wall clock with syncs;
+  roofline  dominant kernel (tcgen05 pair-GEMM) algorithmic bytes / event-timed duration vs measured
+         HBM peak;  cpu_baseline  the oracle port (oracle/model_ref.py) timed on the host cores.
+--impl reference: the reference's CPU path.  The reference is pure Python over un-vendored torchsparse /
+PyG and cannot travel to the GPU box, so this arm times the oracle port of it (kind "port").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = dict(num_points=40000, n_inst=32, n_cand=32, n_tokens=20)
+WORKLOAD_NAME = ('configs[1]: full InstanceRefer.forward, 1 synthetic scene (40k points -> ~28k voxels @5cm, '
+                 '32 candidate instances x 1024 pts @2cm, 20-token utterance), eval mode, fp32')
+METRIC = 'referrals/sec'
+
+
+def make_args():
+    return types.SimpleNamespace(language_module='lang_module', attribute_module='attribute_module',
+                                 relation_module='relation_module', scene_module='scene_module',
+                                 num_classes=18, use_bidir=True, voxel_size_ap=0.02, voxel_size_glp=0.05,
+                                 k=8, use_gt_lang=True)
+
+
+def cpu_reference_leg(steps, warmup):
+    """Oracle port of the reference forward on the host cores (bounded sample)."""
+    import model_ref
+    import weights
+    from instancerefer_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = weights.make_state_dict(123)
+    args = make_args()
+    b = synthetic.make_batch(1000, batch_size=1, **WORKLOAD)
+    data = model_ref.data_from_batch(b)
+    for _ in range(warmup):
+        model_ref.forward(sd, data, args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model_ref.forward(sd, data, args)
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=1.0 / dt, unit=METRIC, cores=torch.get_num_threads(), kind='port',
+                sample=f'{steps} referrals of the bench workload after {warmup} warm-up, oracle/model_ref.py '
+                       f'(torch CPU fp32, {torch.get_num_threads()} threads), {dt * 1e3:.0f} ms each'), dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == 'Active'})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def load_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='no CUDA-graph replay (launch every kernel from Python)')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(a.warmup, 3)
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 8))
+        cb, dt = cpu_reference_leg(steps, min(warmup, 2))
+        print(json.dumps(dict(metric=METRIC, value=cb['value'], unit=METRIC, impl='reference', n_gpus=a.gpus,
+                              steps=steps, warmup=min(warmup, 2), ms_per_step=dt * 1e3, higher_is_better=True,
+                              scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                              config=dict(workload=WORKLOAD_NAME), cpu_baseline=cb,
+                              e2e=dict(value=cb['value'], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    import __graft_entry__ as g
+    g.build()
+    import weights
+    from instancerefer_b200 import SparseTensor, _lib, ops, synthetic
+    from instancerefer_b200.candidates import KEY, CandidatePack
+    from instancerefer_b200.instancerefer import InstanceRefer
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    ops.check_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    args = make_args()
+    model = InstanceRefer(7, args)
+    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    model = model.to(dev).eval()
+
+    # ---- this rank's stream of scenes (a few distinct scenes, cycled)
+    n_scenes = 4
+    batches = [synthetic.make_batch(1000 + 97 * rank + 7 * i, batch_size=1, **WORKLOAD) for i in range(n_scenes)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def host_dict(b):
+        """step inputs in pinned host memory, in the layout the reference's collate_fn produces"""
+        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+        return dict(lidar_F=pin(b['lidar_feats']), lidar_C=pin(b['lidar_coords']), lang_feat=pin(b['lang_feat']),
+                    lang_len=pin(b['lang_len']), object_cat=pin(b['object_cat']), point_min=pin(b['point_min']),
+                    instance_points=b['instance_points'], instance_obbs=b['instance_obbs'],
+                    instance_class=b['instance_class'])
+
+    def to_device(h):
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in h.items()}
+        d['lidar'] = SparseTensor(d.pop('lidar_F'), d.pop('lidar_C'))
+        return d
+
+    hosts = [host_dict(b) for b in batches]
+    h2d_tensor_bytes = sum(v.numel() * v.element_size() for v in hosts[0].values() if torch.is_tensor(v))
+
+    # ---- resident inputs for `value`
+    resident = []
+    for h in hosts:
+        d = to_device(h)
+        pack = CandidatePack(d, d['object_cat'], dev)
+        pack.resident = True
+        d[KEY] = pack
+        d['_ir_lang_len_max'] = int(h['lang_len'].max())
+        resident.append(d)
+    torch.cuda.synchronize()
+
+    out_keys = ('attribute_scores', 'relation_scores', 'scene_scores', 'lang_scores', 'seg_scores', 'ref_pred')
+    from instancerefer_b200.graphed import GraphedInstanceRefer
+    runner = GraphedInstanceRefer(model)
+    use_graph = not a.eager
+
+    # `value`: inputs resident in HBM -> one captured graph per resident scene, replay only
+    res_graphs = []
+    if use_graph:
+        for d in resident:
+            for _ in range(2):
+                model(dict(d))
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                o_ = model(dict(d))
+            res_graphs.append((g_, o_))
+
+    def step_resident(i):
+        if use_graph:
+            g_, o_ = res_graphs[i % n_scenes]
+            g_.replay()
+            return o_
+        d = dict(resident[i % n_scenes])
+        return model(d)
+
+    d2h_bytes = [0]
+    pinned_out = {}
+
+    def step_e2e(i):
+        if use_graph:                       # host dict in, staged + replayed by the graph runner
+            h = hosts[i % n_scenes]
+            d = dict(h)
+            d['lidar'] = SparseTensor(d.pop('lidar_F'), d.pop('lidar_C'))
+            out = runner(d)
+        else:
+            d = to_device(hosts[i % n_scenes])
+            out = model(d)
+        n = 0
+        for k in out_keys:
+            t = out[k]
+            if k not in pinned_out or pinned_out[k].shape != t.shape:
+                pinned_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            pinned_out[k].copy_(t, non_blocking=True)
+            n += t.numel() * t.element_size()
+        torch.cuda.synchronize()
+        d2h_bytes[0] = n
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: resident inputs, per-step CUDA events, L2 flush between steps
+    for i in range(warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.ir_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for i in range(a.steps):
+        flush.zero_()
+        evs[i][0].record()
+        step_resident(i)
+        evs[i][1].record()
+    barrier()
+    launches = lib.ir_launch_count() - launches0
+    if use_graph:                           # replayed kernels are not re-counted by the library: count one step
+        c0 = lib.ir_launch_count()
+        model(dict(resident[0]))
+        launches = (lib.ir_launch_count() - c0) * a.steps
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    dev_ms = max_over_ranks(dev_ms)
+    clocks = sampler.stop() if sampler else None
+    value = world * a.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers in, scores out
+    for i in range(warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = dict(value=world * a.steps / e2e_s, unit=METRIC, ms_per_step=e2e_s / a.steps * 1e3,
+               h2d_bytes_per_step=int(runner.h2d_bytes if use_graph else h2d_tensor_bytes + resident[0][KEY].h2d_bytes),
+               d2h_bytes_per_step=int(d2h_bytes[0]))
+
+    # ---- roofline pass: event-timed pair-GEMM / reduce launches of the same resident steps
+    roofline, detail = None, None
+    if rank == 0:
+        nprof = min(a.steps, 10)
+        lib.ir_profile_enable(1)
+        cap = 512
+        gm, rm = (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
+        meta, nout = (ctypes.c_int32 * (4 * cap))(), ctypes.c_int32(0)
+        acc = {}
+        for i in range(nprof):
+            flush.zero_()
+            model(dict(resident[i % n_scenes]))            # eager launches so the event hooks fire
+            torch.cuda.synchronize()
+            _lib.call('ir_profile_read', gm, rm, meta, cap, ctypes.byref(nout))
+            # pair counts of this step's rulebooks (attribute encoder first, scene encoder second)
+            kc = [model.attribute.net._ws[next(iter(model.attribute.net._ws))].kcount().cpu().numpy(),
+                  model.scene.net._ws[next(iter(model.scene.net._ws))].kcount().cpu().numpy()]
+            maps = [0, 5, 1, 1, 6, 2, 2, 7, 3, 3, 8, 4, 4]                  # layer -> kernel map id
+            for j in range(nout.value):
+                enc, layer = divmod(j, 13)
+                cin, cout, K, tc = (meta[4 * j + q] for q in range(4))
+                P = int(kc[enc][maps[layer]][:K].sum())
+                by = P * (4 * cin + 4) + P * 4 * cout + 4 * K * cin * cout     # gather + T write + weights
+                fl = 2 * P * cin * cout
+                key = ('tcgen05' if tc else 'simt', cin, cout, K)
+                e = acc.setdefault(key, [0.0, 0.0, 0, 0, 0.0, 0])
+                e[0] += gm[j]; e[1] += by; e[2] += fl; e[3] += 1; e[4] += rm[j]; e[5] += P
+        lib.ir_profile_enable(0)
+        peak, peak_src = load_peak()
+        tc_ms = sum(v[0] for k, v in acc.items() if k[0] == 'tcgen05')
+        tc_by = sum(v[1] for k, v in acc.items() if k[0] == 'tcgen05')
+        tc_n = sum(v[3] for k, v in acc.items() if k[0] == 'tcgen05')
+        all_ms = sum(v[0] + v[4] for v in acc.values())
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        if tc_ms > 0:
+            ach = tc_by / (tc_ms * 1e-3) / 1e9
+            roofline = dict(bound='hbm', kernel='k_pairgemm_tc (tcgen05 3xTF32 pair-GEMM, 24 launches/step)',
+                            achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic,
+                            peak_source=peak_src, bytes_per_launch=tc_by / tc_n, us_per_launch=tc_ms * 1e3 / tc_n,
+                            share_of_step=tc_ms / nprof / (dev_ms / a.steps),
+                            spconv_share_of_step=all_ms / nprof / (dev_ms / a.steps))
+        detail = {f'{k[0]}_{k[1]}x{k[2]}_k{k[3]}': dict(launches_per_step=v[3] / nprof, gemm_us=v[0] * 1e3 / v[3],
+                                                       reduce_us=v[4] * 1e3 / v[3], pairs=v[5] / v[3],
+                                                       gemm_GBs=v[1] / (v[0] * 1e-3) / 1e9,
+                                                       gemm_TFLOPs=v[2] / (v[0] * 1e-3) / 1e12)
+                  for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_reference_leg(5, 1)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=a.steps, warmup=warmup,
+                    ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32 (3xTF32 tcgen05 rule GEMM, fp32 accumulate)', data='synthetic',
+                    config=dict(workload=WORKLOAD_NAME, referrals_per_step_per_gpu=1,
+                                l2='flushed between steps (256 MiB write outside the timed spans)',
+                                parallelism=f'scenes sharded over {world} GPU(s), no data-path collective',
+                                launch='eager' if not use_graph else 'CUDA-graph replay, 4 streams'),
+                    e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
+                    cpu_baseline=cb, spconv_detail=detail)
+        print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -33,6 +33,14 @@ const char* ir_last_error(void);
 /* IR_OK iff `device` is compute capability 10.x (B200). */
 int ir_check_device(int device);
 
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t ir_launch_count(void);
+/* Measurement hooks: while enabled every sparse-conv layer brackets its pair-GEMM and its reduce
+ * launch with CUDA events on the launching stream; ir_profile_read synchronises, returns per-layer
+ * milliseconds and meta = (cin, cout, K, used_tcgen05) x n, and resets the record. */
+int ir_profile_enable(int on);
+int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out);
+
 /* ------------------------------------------------------------------ sparse-voxel encoder
  * SparseConvEncoder / BEVEncoder (models/basic_blocks.py:59-95,136-171): 13 sparse convs
  * (stem k3; 4 x [k2 s2 down, residual k3 k3]) with eval-mode BatchNorm, ReLU and the identity
@@ -61,8 +69,8 @@ typedef struct {
     int64_t off_keys, off_vals;            /* 5 tables: keys u64[cap]; vals {minrow,row} i32[cap]  */
     int64_t off_coords[IR_ENC_LEVELS];     /* int32 (n_max,4) [x,y,z,b] per level                 */
     int64_t off_pslot;
-    int64_t off_k3_in[IR_ENC_LEVELS], off_k3_slot[IR_ENC_LEVELS]; /* in_idx[27][n_max], slot[n_max][32] */
-    int64_t off_k2_in[4], off_k2_slot[4];                         /* in_idx[8][n_max],  slot[n_max][8]  */
+    int64_t off_k3_in[IR_ENC_LEVELS], off_k3_slot[IR_ENC_LEVELS]; /* in_idx[27][n_max], slot[27][n_max] */
+    int64_t off_k2_in[4], off_k2_slot[4];                         /* in_idx[8][n_max],  slot[8][n_max]  */
     int64_t off_feat0;                     /* fp32 (n_max, 8)  voxelised level-0 features          */
     int64_t off_feat[3];                   /* fp32 (n_max,128) rotating activations               */
     int64_t off_T;                         /* fp32 (27*n_max,128) pair products                   */
@@ -83,17 +91,19 @@ int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand, int32_t p
                 double voxel, void* ws, int64_t n_max, ir_stream_t stream);
 
 /* Builds levels 1-4 and all 9 kernel maps.  coords0==NULL: level 0 comes from ir_voxelize in
- * `ws`; otherwise coords0 (n0,4) int32 is hashed here (ir_encoder_reset is implied). */
-int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* ws, int64_t n_max,
-                          ir_stream_t stream);
+ * `ws`; otherwise coords0 (n0,4) int32 is hashed here (ir_encoder_reset is implied).  n0 is an
+ * upper bound on the row count when n0_dev (device int, e.g. inside a CUDA graph) is given. */
+int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const int32_t* n0_dev, void* ws,
+                          int64_t n_max, ir_stream_t stream);
 
 /* Feature pass over prebuilt maps.  feats0==NULL: use the voxelised features in `ws`.
  * feats_out (n_max,128) fp32; row count = nlvl[4] inside ws, coords = off_coords[4]. */
 int ir_encoder_features(const ir_encoder_params* p, const float* feats0, void* ws, int64_t n_max,
                         float* feats_out, ir_stream_t stream);
 
-/* One sparse conv layer on explicit buffers (unit tests / tracing). */
-int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K, int32_t KP,
+/* One sparse conv layer on explicit buffers (unit tests / tracing): rulebook = in_idx (K,seg_cap)
+ * [input row of pair pos], slot (K,seg_cap) [pair pos of output row o, or -1], count (K). */
+int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,
                     const int32_t* in_idx, int64_t seg_cap, const int32_t* slot,
                     const int32_t* count, const int32_t* n_out_dev, int64_t n_max,
                     const float* weight, const float* wprep, int32_t use_tc, const float* scale,
@@ -152,7 +162,8 @@ int ir_token_attention(const float* feats, const float* embed, int64_t embed_str
                        ir_stream_t stream);
 
 /* ------------------------------------------------------------------ matching heads
- * Fused 2-layer head: h = relu(norm(x W1^T + b1)); y = h W2^T + b2, then
+ * Fused 2-layer head: h = relu(norm(x W1 + b1)); y = h W2 + b2 with W1 (K,N1), W2 (N1,N2) in
+ * (in,out) layout (transposed nn.Linear weights, coalesced reads), then
  *   mode 0: write y;  1: write y/max(|y|,1e-12);
  *   2: score[r] = <y/max(|y|,1e-12), partner[seg[r]]>;  3: score[r] = cos(y, partner[seg[r]]), eps 1e-8.
  * norm 0: none, 1: per-channel affine (eval BatchNorm1d), 2: LayerNorm(eps 1e-5).
@@ -183,7 +194,8 @@ int ir_knn(const float* xyz, const int32_t* seg_ofs, const int32_t* qidx, const 
 
 /* DynamicEdgeConv message + max aggregation (models/basic_blocks.py:125-133): x (S,F) with the
  * class one-hot in the last `ncls` columns; per edge j->i: w = W2w relu(W1w [p_j-p_i, oh_i, oh_j]),
- * msg = W2m relu(W1m [x_i, w, x_j]); out[i] = max_j msg (0 if no edge).  F<=32, hidden 64/128. */
+ * msg = W2m relu(W1m [x_i, w, x_j]); out[i] = max_j msg (0 if no edge).  F<=32, hidden 64/128.
+ * All four weight matrices are passed in (in,out) layout, i.e. transposed nn.Linear weights. */
 int ir_edgeconv(const float* x, const float* xyz, const int32_t* qidx, const int32_t* nbr,
                 int32_t nq, int32_t k, int32_t F, int32_t ncls, const float* Ww1, const float* bw1,
                 const float* Ww2, const float* bw2, const float* Wm1, const float* bm1,

@@ -37,13 +37,16 @@ SIGNATURES = {
     "ir_version": (i32, []),
     "ir_last_error": (C.c_char_p, []),
     "ir_check_device": (i32, [i32]),
+    "ir_launch_count": (i64, []),
+    "ir_profile_enable": (i32, [i32]),
+    "ir_profile_read": (i32, [p, p, p, i32, p]),
     "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),
     "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),
     "ir_encoder_reset": (i32, [p, i64, p]),
     "ir_voxelize": (i32, [p, p, i32, i32, i32, f64, p, i64, p]),
-    "ir_encoder_build_maps": (i32, [p, i32, p, i64, p]),
+    "ir_encoder_build_maps": (i32, [p, i32, p, p, i64, p]),
     "ir_encoder_features": (i32, [C.POINTER(EncoderParams), p, p, i64, p, p]),
-    "ir_spconv_layer": (i32, [p, i32, i32, i32, i32, p, i64, p, p, p, i64, p, p, i32, p, p, p, i32, p, p, p]),
+    "ir_spconv_layer": (i32, [p, i32, i32, i32, p, i64, p, p, p, i64, p, p, i32, p, p, p, i32, p, p, p]),
     "ir_spconv_wprep_floats": (i64, [i32, i32, i32]),
     "ir_spconv_prepare_weights": (i32, [p, i32, i32, i32, p, p]),
     "ir_segmax": (i32, [p, p, p, i64, i32, i32, p, p, p]),

@@ -8,6 +8,7 @@ import torch.nn as nn
 
 from . import ops
 from .basic_blocks import PrepCache, SparseConvEncoder, fold_bn, require_eval
+from .candidates import KEY as _KEY
 from .candidates import get_pack
 
 
@@ -37,38 +38,44 @@ class AttributeModule(nn.Module, PrepCache):
 
     def _prepare(self):
         f = lambda t: t.detach().float().contiguous()
+        ft = lambda t: t.detach().float().t().contiguous()         # (in,out) layout for ir_mlp_head
         v, l = self.vis_emb_fc, self.lang_emb_fc
         s, b = fold_bn(l[1])
-        return dict(vw1=f(v[0].weight), vb1=f(v[0].bias), vg=f(v[1].weight), vbeta=f(v[1].bias),
-                    vw2=f(v[3].weight), vb2=f(v[3].bias),
-                    lw1=f(l[0].weight), lb1=f(l[0].bias), lg=s, lbeta=b, lw2=f(l[3].weight), lb2=f(l[3].bias))
+        return dict(vw1=ft(v[0].weight), vb1=f(v[0].bias), vg=f(v[1].weight), vbeta=f(v[1].bias),
+                    vw2=ft(v[3].weight), vb2=f(v[3].bias),
+                    lw1=ft(l[0].weight), lb1=f(l[0].bias), lg=s, lbeta=b, lw2=ft(l[3].weight), lb2=f(l[3].bias))
 
-    def _prep_key(self):            # heads only; the encoder caches its own copies
-        ts = list(self.vis_emb_fc.parameters()) + list(self.lang_emb_fc.parameters()) + list(self.lang_emb_fc.buffers())
-        return tuple((t.data_ptr(), t._version) for t in ts)
+    def _prep_tensors(self):        # heads only; the encoder caches its own copies
+        return list(self.vis_emb_fc.parameters()) + list(self.lang_emb_fc.parameters()) + list(self.lang_emb_fc.buffers())
 
-    def forward(self, data_dict):
+    def encode_candidates(self, data_dict, device, pack=None):
+        """Phase A (no language dependency): host class filter + one packed H2D (:42-81,101), GPU
+        voxelisation @2 cm, sparse encoder (:104), per-candidate max-pool (:105)."""
         require_eval(self)
-        ops.check_device()
-        p = self.prepared()
-        lang = data_dict['lang_attr_feats']
-        dev = lang.device
-        # language side: Linear-BN-ReLU-Linear, L2 normalise (:88-90)
-        lang_emb, _ = ops.mlp_head(lang.float().contiguous(), p['lw1'], p['lb1'], ops.NORM_AFFINE, p['lg'],
-                                   p['lbeta'], p['lw2'], p['lb2'], ops.MODE_L2)
-        # candidates: host class filter + one packed H2D (:42-81,101)
-        pack = get_pack(data_dict, self.args, dev, rebuild=True)
+        pack = pack or get_pack(data_dict, self.args, device, rebuild=True)
         data_dict['num_filtered_objs'] = pack.num_filtered
         ppi = pack.points.shape[1]
-        ws = self.net.workspace(pack.M * ppi, dev)
+        ws = self.net.workspace(pack.M * ppi, device)
         ops.encoder_reset(ws)
         ops.voxelize(pack.points, pack.cand_rows, float(self.voxel_size[0]), ws)
-        f4, c4, n4 = self.net.encode(ws)                                        # (:104)
-        obj = ops.segmax(f4, c4, n4, ws.n_max, pack.M)                          # (:105)
-        data_dict['obj_feats'] = obj
-        # visual side: Linear-LN-ReLU-Linear, L2 normalise, dot with the scene's language vector (:108-126)
-        _, scores = ops.mlp_head(obj, p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'], p['vw2'],
-                                 p['vb2'], ops.MODE_DOT, partner=lang_emb, seg=pack.cand_scene)
-        data_dict['attribute_scores'] = scores
+        f4, c4, n4 = self.net.encode(ws)
+        data_dict['obj_feats'] = ops.segmax(f4, c4, n4, ws.n_max, pack.M)
         data_dict['pred_obb_batch'] = pack.pred_obb_batch
         return data_dict
+
+    def match(self, data_dict):
+        """Phase B: language side Linear-BN-ReLU-Linear + L2 normalise (:88-90); visual side
+        Linear-LN-ReLU-Linear + L2 normalise, dot with the scene's language vector (:108-126)."""
+        p = self.prepared()
+        pack = data_dict[_KEY]
+        lang_emb, _ = ops.mlp_head(data_dict['lang_attr_feats'].float().contiguous(), p['lw1'], p['lb1'],
+                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_L2)
+        _, scores = ops.mlp_head(data_dict['obj_feats'], p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'],
+                                 p['vw2'], p['vb2'], ops.MODE_DOT, partner=lang_emb, seg=pack.cand_scene)
+        data_dict['attribute_scores'] = scores
+        return data_dict
+
+    def forward(self, data_dict):
+        ops.check_device()
+        data_dict = self.encode_candidates(data_dict, data_dict['lang_attr_feats'].device)
+        return self.match(data_dict)

@@ -19,9 +19,15 @@ class PrepCache:
     """Kernel-friendly copies of the parameters (folded BN, repacked weights), rebuilt only when a
     parameter/buffer changed (tensor ``_version``) or moved."""
 
+    def _prep_tensors(self):
+        return list(self.parameters()) + list(self.buffers())
+
     def _prep_key(self):
-        ts = list(self.parameters()) + list(self.buffers())
-        return tuple((t.data_ptr(), t._version) for t in ts)
+        ts = self.__dict__.get('_prep_ts')
+        if ts is None:                      # module structure is fixed after construction
+            ts = self._prep_tensors()
+            self.__dict__['_prep_ts'] = ts
+        return [(t.data_ptr(), t._version) for t in ts]
 
     def prepared(self):
         key = self._prep_key()
@@ -126,12 +132,12 @@ class SparseConvEncoder(nn.Module, PrepCache):
             self._ws = {key: ops.EncoderWorkspace(n_max, device)}      # keep only the latest bucket
         return self._ws[key]
 
-    def encode(self, ws, feats0=None, coords0=None):
+    def encode(self, ws, feats0=None, coords0=None, n0_dev=None):
         """Run maps + 13 layers.  Level 0 either comes from ``ops.voxelize`` (already in ``ws``) or
         from (feats0, coords0).  -> (F4 padded (n_max,128), C4 padded (n_max,4), n4 device int)."""
         require_eval(self)
         prep = self.prepared()
-        ops.encoder_build_maps(ws, coords0)
+        ops.encoder_build_maps(ws, coords0, n0_dev)
         out = torch.empty(ws.n_max, 128, dtype=torch.float32, device=ws.buf.device)
         ops.encoder_features(prep['params'], ws, feats0, out)
         return out, ws.coords(4), ws.nlvl()[4:5]

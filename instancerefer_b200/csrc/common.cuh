@@ -12,6 +12,7 @@
 #define IR_NUM_SMS 148
 
 void ir_set_error(const char* fmt, ...);
+void ir_count_launch(int n);
 
 #define IR_CHECK_ARG(cond)                                                        \
     do {                                                                          \
@@ -23,6 +24,7 @@ void ir_set_error(const char* fmt, ...);
 
 #define IR_CHECK_LAUNCH()                                                         \
     do {                                                                          \
+        ir_count_launch(1);                                                       \
         cudaError_t e_ = cudaGetLastError();                                      \
         if (e_ != cudaSuccess) {                                                  \
             ir_set_error("%s:%d: CUDA: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \

@@ -74,7 +74,7 @@ __device__ __forceinline__ void compact_ordered(int n, unsigned long long* state
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_set_int(int* p, int v, const int* src) { *p = src ? *src : v; }
 
 __global__ void k_hash_build(const int4* __restrict__ coords, const int* __restrict__ n_dev,
                              IrTable t) {
@@ -154,54 +154,52 @@ k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n
 // Kernel map for out[o] += F[j] @ W[k], j at C_out[o] + off_k (Appendix A offset enumeration):
 //   KS=3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
 //   KS=2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
-// Emits, per offset k: in_idx[k*seg_cap + pos] (input row of pair `pos`), count[k];
-// per output row: slot[o*KP + k] = pos or -1.  Pair order inside k is append order (unordered).
+// grid (row blocks, K): one hash probe per thread, one warp-aggregated append per warp.
+// Emits, per offset k: in_idx[k*seg_cap + pos] (input row of pair `pos`), count[k], and
+// slot[k*seg_cap + o] = pos or -1.  Pair order inside k is append order (unordered).
 template <int KS>
-__global__ void k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev,
-                       IrTable tin, int stride, int* __restrict__ in_idx, long long seg_cap,
-                       int* __restrict__ slot, int* __restrict__ count) {
-    constexpr int K = KS * KS * KS;
-    constexpr int KP = (KS == 3) ? 32 : 8;
+__global__ void __launch_bounds__(256)
+k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev, IrTable tin, int stride,
+       int* __restrict__ in_idx, long long seg_cap, int* __restrict__ slot, int* __restrict__ count) {
     const int n = *n_out_dev;
+    const int k = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int n_round = (n + 31) & ~31;
+    int dx, dy, dz;
+    if (KS == 3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
+    else         { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
+    int* in_k = in_idx + (long long)k * seg_cap;
+    int* slot_k = slot + (long long)k * seg_cap;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
         const bool live = o < n;
-        int4 c = make_int4(0, 0, 0, 0);
-        if (live) c = coords_out[o];
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            int dx, dy, dz;
-            if (KS == 3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
-            else         { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
-            int j = -1;
-            if (live) {
-                if (KS == 3 && k == 13) j = o;
-                else {
-                    const int s = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
-                    if (s >= 0) j = tin.row[s];
-                }
+        int j = -1;
+        if (live) {
+            if (KS == 3 && k == 13) j = o;
+            else {
+                const int4 c = coords_out[o];
+                const int s = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
+                if (s >= 0) j = tin.row[s];
             }
-            const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
-            int pos = -1;
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&count[k], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (j >= 0) {
-                    pos = base + __popc(m & ((1u << lane) - 1u));
-                    in_idx[(long long)k * seg_cap + pos] = j;
-                }
-            }
-            if (live) slot[(long long)o * KP + k] = pos;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+        int pos = -1;
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&count[k], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (j >= 0) {
+                pos = base + __popc(m & ((1u << lane) - 1u));
+                in_k[pos] = j;
+            }
+        }
+        if (live) slot_k[o] = pos;
     }
 }
 
 // ------------------------------------------------------------------ host launchers (internal)
-int irk_set_int(int* p, int v, cudaStream_t st) {
-    k_set_int<<<1, 1, 0, st>>>(p, v);
+int irk_set_int(int* p, int v, const int* src, cudaStream_t st) {
+    k_set_int<<<1, 1, 0, st>>>(p, v, src);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
@@ -246,9 +244,9 @@ int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdi
 int irk_kmap(int ks, const int32_t* coords_out, const int* n_out_dev, long long n_max,
              IrTable t, int stride, int* in_idx, long long seg_cap, int* slot,
              int* count, cudaStream_t st) {
-    const int g = grid_for(n_max, 128);
-    if (ks == 3) k_kmap<3><<<g, 128, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
-    else if (ks == 2) k_kmap<2><<<g, 128, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
+    const int gx = ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, 256), IR_NUM_SMS * 2);
+    if (ks == 3) k_kmap<3><<<dim3(gx, 27), 256, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
+    else if (ks == 2) k_kmap<2><<<dim3(gx, 8), 256, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
     else { ir_set_error("kmap: unsupported kernel size %d", ks); return IR_ERR_UNSUPPORTED; }
     IR_CHECK_LAUNCH();
     return IR_OK;

@@ -31,6 +31,44 @@ extern "C" int ir_check_device(int device) {
     return IR_OK;
 }
 
+// ------------------------------------------------------------------ launch counter + profiling hooks
+static long long g_launches = 0;
+void ir_count_launch(int n) { g_launches += n; }
+extern "C" int64_t ir_launch_count(void) { return g_launches; }
+
+#define IR_PROF_MAX 512
+static int g_prof_on = 0, g_prof_n = 0;
+static cudaEvent_t g_prof_ev[IR_PROF_MAX][3];
+static int g_prof_made = 0;
+static int g_prof_meta[IR_PROF_MAX][4];   // cin, cout, K, use_tc
+
+extern "C" int ir_profile_enable(int on) {
+    g_prof_on = on;
+    g_prof_n = 0;
+    return IR_OK;
+}
+// per conv layer since ir_profile_enable(1): pair-GEMM ms, reduce ms, (cin,cout,K,tc). Synchronises.
+extern "C" int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out) {
+    IR_CHECK_ARG(gemm_ms && reduce_ms && meta && n_out);
+    const int n = g_prof_n < cap ? g_prof_n : cap;
+    for (int i = 0; i < n; ++i) {
+        IR_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[i][2]));
+        IR_CHECK_CUDA(cudaEventElapsedTime(&gemm_ms[i], g_prof_ev[i][0], g_prof_ev[i][1]));
+        IR_CHECK_CUDA(cudaEventElapsedTime(&reduce_ms[i], g_prof_ev[i][1], g_prof_ev[i][2]));
+        for (int j = 0; j < 4; ++j) meta[4 * i + j] = g_prof_meta[i][j];
+    }
+    *n_out = n;
+    g_prof_n = 0;
+    return IR_OK;
+}
+static cudaEvent_t prof_event(int i, int j) {
+    while (g_prof_made <= i && g_prof_made < IR_PROF_MAX) {
+        for (int q = 0; q < 3; ++q) cudaEventCreate(&g_prof_ev[g_prof_made][q]);
+        ++g_prof_made;
+    }
+    return g_prof_ev[i][j];
+}
+
 // ------------------------------------------------------------------ layout
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -54,7 +92,7 @@ extern "C" int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* L) {
     L->off_pslot = take(n_max * 4);
     for (int l = 0; l < IR_ENC_LEVELS; ++l) {
         L->off_k3_in[l] = take(27 * n_max * 4);
-        L->off_k3_slot[l] = take(32 * n_max * 4);
+        L->off_k3_slot[l] = take(27 * n_max * 4);
     }
     for (int l = 0; l < 4; ++l) {
         L->off_k2_in[l] = take(8 * n_max * 4);
@@ -125,8 +163,8 @@ extern "C" int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand
                         w.feat0(), w.nlvl() + 0, w.scan(0), (cudaStream_t)stream);
 }
 
-extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* ws, int64_t n_max,
-                                     ir_stream_t stream) {
+extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const int32_t* n0_dev,
+                                     void* ws, int64_t n_max, ir_stream_t stream) {
     Ws w;
     int r = ws_open(ws, n_max, &w);
     if (r != IR_OK) return r;
@@ -135,7 +173,7 @@ extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* w
     if (coords0 != nullptr) {
         IR_CHECK_ARG(n0 >= 0 && n0 <= n_max);
         if ((r = ir_encoder_reset(ws, n_max, stream)) != IR_OK) return r;
-        if ((r = irk_set_int(w.nlvl() + 0, n0, st)) != IR_OK) return r;
+        if ((r = irk_set_int(w.nlvl() + 0, n0, n0_dev, st)) != IR_OK) return r;
         if ((r = irk_hash_build(coords0, w.nlvl() + 0, n0, w.table(0), st)) != IR_OK) return r;
         c0 = coords0;
     }
@@ -159,31 +197,40 @@ extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, void* w
     return IR_OK;
 }
 
-static int conv_layer(const float* fin, int cin, int cout, int K, int KP, const int* in_idx,
+static int conv_layer(const float* fin, int cin, int cout, int K, const int* in_idx,
                       long long seg_cap, const int* slot, const int* count, const int* n_out_dev,
                       long long n_max, const float* weight, const float* wprep, int use_tc,
                       const float* scale, const float* shift, const float* resid, int relu, float* T,
                       float* out, cudaStream_t st) {
     int r;
     const long long pairs_max = (long long)K * n_max;
-    if (use_tc && wprep != nullptr && cin >= 32)
+    const bool tc = use_tc && wprep != nullptr && cin >= 32;
+    const int pi = (g_prof_on && g_prof_n < IR_PROF_MAX) ? g_prof_n++ : -1;
+    if (pi >= 0) {
+        g_prof_meta[pi][0] = cin; g_prof_meta[pi][1] = cout; g_prof_meta[pi][2] = K; g_prof_meta[pi][3] = tc;
+        cudaEventRecord(prof_event(pi, 0), st);
+    }
+    if (tc)
         r = irk_pairgemm_tc(fin, cin, cout, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
     else
         r = irk_pairgemm_simt(fin, cin, cout, K, in_idx, seg_cap, count, weight, T, pairs_max, st);
     if (r != IR_OK) return r;
-    return irk_reduce_epilogue(T, cout, K, KP, slot, count, n_out_dev, n_max, scale, shift, resid,
-                               relu, out, st);
+    if (pi >= 0) cudaEventRecord(prof_event(pi, 1), st);
+    r = irk_reduce_epilogue(T, cout, K, slot, seg_cap, count, n_out_dev, n_max, scale, shift, resid,
+                            relu, out, st);
+    if (pi >= 0) cudaEventRecord(prof_event(pi, 2), st);
+    return r;
 }
 
 extern "C" int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,
-                               int32_t KP, const int32_t* in_idx, int64_t seg_cap,
+                               const int32_t* in_idx, int64_t seg_cap,
                                const int32_t* slot, const int32_t* count,
                                const int32_t* n_out_dev, int64_t n_max, const float* weight,
                                const float* wprep, int32_t use_tc, const float* scale,
                                const float* shift, const float* resid, int32_t relu, float* T,
                                float* out, ir_stream_t stream) {
     IR_CHECK_ARG(feat_in && in_idx && slot && count && n_out_dev && weight && T && out);
-    return conv_layer(feat_in, cin, cout, K, KP, in_idx, seg_cap, slot, count, n_out_dev, n_max,
+    return conv_layer(feat_in, cin, cout, K, in_idx, seg_cap, slot, count, n_out_dev, n_max,
                       weight, wprep, use_tc, scale, shift, resid, relu, T, out, (cudaStream_t)stream);
 }
 
@@ -199,20 +246,20 @@ extern "C" int ir_encoder_features(const ir_encoder_params* p, const float* feat
     float* A = w.feat(0);
     float* X = w.feat(1);
     float* Y = w.feat(2);
-#define LAYER(idx, fin, cin_, cout_, K_, KP_, in_, slot_, cnt_, nout_, resid_, out_)                      \
-    if ((r = conv_layer(fin, cin_, cout_, K_, KP_, in_, n_max, slot_, cnt_, nout_, n_max, p->weight[idx], \
+#define LAYER(idx, fin, cin_, cout_, K_, in_, slot_, cnt_, nout_, resid_, out_)                           \
+    if ((r = conv_layer(fin, cin_, cout_, K_, in_, n_max, slot_, cnt_, nout_, n_max, p->weight[idx],      \
                         p->wprep[idx], p->use_tc, p->bn_scale[idx], p->bn_shift[idx], resid_, 1, w.T(),   \
                         out_, st)) != IR_OK) return r;
     // stem: k3 at level 0
-    LAYER(0, f0, p->cin, ch[0], 27, 32, w.k3_in(0), w.k3_slot(0), w.kcount(0), w.nlvl() + 0, nullptr, A);
+    LAYER(0, f0, p->cin, ch[0], 27, w.k3_in(0), w.k3_slot(0), w.kcount(0), w.nlvl() + 0, nullptr, A);
     for (int s = 1; s <= 4; ++s) {
         const int l = s - 1, li = 1 + 3 * (s - 1);
         float* outp = (s == 4) ? feats_out : A;
         // down: k2 s2, level l -> l+1
-        LAYER(li + 0, A, ch[l], ch[s], 8, 8, w.k2_in(l), w.k2_slot(l), w.kcount(5 + l), w.nlvl() + s, nullptr, X);
+        LAYER(li + 0, A, ch[l], ch[s], 8, w.k2_in(l), w.k2_slot(l), w.kcount(5 + l), w.nlvl() + s, nullptr, X);
         // residual block at level s: relu(bn(conv(relu(bn(conv(X))))) + X)
-        LAYER(li + 1, X, ch[s], ch[s], 27, 32, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, nullptr, Y);
-        LAYER(li + 2, Y, ch[s], ch[s], 27, 32, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, X, outp);
+        LAYER(li + 1, X, ch[s], ch[s], 27, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, nullptr, Y);
+        LAYER(li + 2, Y, ch[s], ch[s], 27, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, X, outp);
     }
 #undef LAYER
     return IR_OK;

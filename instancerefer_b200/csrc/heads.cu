@@ -7,49 +7,60 @@
 
 #define MH_TM 8
 #define MH_MAXD 256
+#define MH_THREADS 1024
+#define MH_SLICES (MH_THREADS / MH_MAXD)
+#define MH_SMEM_BYTES ((2 * MH_TM * MH_MAXD + MH_SLICES * MH_TM * MH_MAXD) * 4)
 
-// rows [r0, r0+8) of x (M,K): dst[r][n] = b[n] + sum_k W[n][k] * src[r][k]   (8 warps over n)
-__device__ __forceinline__ void tile_linear(const float (*src)[MH_MAXD], int K, const float* __restrict__ W,
-                                            const float* __restrict__ b, int N, float (*dst)[MH_MAXD]) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int n = w; n < N; n += 8) {
-        float acc[MH_TM];
+// dst[r][n] = b[n] + sum_k WT[k][n] * src[r][k] for the 8 rows of the tile.  Thread = (k-slice,
+// column): coalesced weight reads (WT is (in,out)), activations broadcast from shared memory,
+// 4-way split-K combined through shared memory in a fixed order (deterministic).
+__device__ __forceinline__ void tile_linear_t(const float (*src)[MH_MAXD], int K, const float* __restrict__ WT,
+                                              const float* __restrict__ b, int N, float (*dst)[MH_MAXD],
+                                              float (*part)[MH_TM][MH_MAXD]) {
+    const int col = threadIdx.x & (MH_MAXD - 1), slice = threadIdx.x / MH_MAXD;
+    const int kper = (K + MH_SLICES - 1) / MH_SLICES;
+    const int k0 = slice * kper, k1 = min(K, k0 + kper);
+    float acc[MH_TM];
 #pragma unroll
-        for (int r = 0; r < MH_TM; ++r) acc[r] = 0.f;
-        const float* wr = W + (long long)n * K;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = wr[k];
+    for (int r = 0; r < MH_TM; ++r) acc[r] = 0.f;
+    if (col < N) {
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) {
+            const float wv = __ldg(WT + (long long)k * N + col);
 #pragma unroll
             for (int r = 0; r < MH_TM; ++r) acc[r] = fmaf(wv, src[r][k], acc[r]);
         }
-        const float bv = b ? b[n] : 0.f;
-#pragma unroll
-        for (int r = 0; r < MH_TM; ++r) {
-            const float v = warp_sum(acc[r]);
-            if (lane == r) dst[r][n] = v + bv;
-        }
     }
+#pragma unroll
+    for (int r = 0; r < MH_TM; ++r) part[slice][r][col] = acc[r];
+    __syncthreads();
+    for (int i = threadIdx.x; i < MH_TM * N; i += MH_THREADS) {
+        const int r = i / N, n = i - r * N;
+        dst[r][n] = ((part[0][r][n] + part[1][r][n]) + (part[2][r][n] + part[3][r][n])) + (b ? b[n] : 0.f);
+    }
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
-k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ W1,
+__global__ void __launch_bounds__(MH_THREADS)
+k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ W1T,
            const float* __restrict__ b1, int N1, int norm, const float* __restrict__ g,
-           const float* __restrict__ beta, const float* __restrict__ W2, const float* __restrict__ b2,
+           const float* __restrict__ beta, const float* __restrict__ W2T, const float* __restrict__ b2,
            int N2, int mode, const float* __restrict__ partner, const int* __restrict__ seg,
            float* __restrict__ y, float* __restrict__ score) {
-    __shared__ float xs[MH_TM][MH_MAXD];
-    __shared__ float hs[MH_TM][MH_MAXD];
+    extern __shared__ float mh_smem[];
+    float (*xs)[MH_MAXD] = reinterpret_cast<float (*)[MH_MAXD]>(mh_smem);
+    float (*hs)[MH_MAXD] = reinterpret_cast<float (*)[MH_MAXD]>(mh_smem + MH_TM * MH_MAXD);
+    float (*part)[MH_TM][MH_MAXD] = reinterpret_cast<float (*)[MH_TM][MH_MAXD]>(mh_smem + 2 * MH_TM * MH_MAXD);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int r0 = blockIdx.x * MH_TM;
     const int rows = min(MH_TM, M - r0);
-    for (int i = tid; i < MH_TM * K; i += 256) {
+    for (int i = tid; i < MH_TM * K; i += MH_THREADS) {
         const int r = i / K, k = i - r * K;
         xs[r][k] = (r < rows) ? x[(long long)(r0 + r) * K + k] : 0.f;
     }
     __syncthreads();
-    tile_linear(xs, K, W1, b1, N1, hs);
-    __syncthreads();
-    {   // normalisation + ReLU: warp w owns row w
+    tile_linear_t(xs, K, W1T, b1, N1, hs, part);
+    if (w < MH_TM) {   // normalisation + ReLU: warp w owns row w
         const int r = w;
         if (norm == 2) {
             float s = 0.f;
@@ -67,8 +78,7 @@ k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ 
         }
     }
     __syncthreads();
-    tile_linear(hs, N1, W2, b2, N2, xs);      // xs now holds y
-    __syncthreads();
+    tile_linear_t(hs, N1, W2T, b2, N2, xs, part);      // xs now holds y
     const int r = w;
     if (r >= rows) return;
     const long long row = r0 + r;
@@ -101,17 +111,22 @@ k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ 
     }
 }
 
-extern "C" int ir_mlp_head(const float* x, int32_t M, int32_t K, const float* W1, const float* b1,
+extern "C" int ir_mlp_head(const float* x, int32_t M, int32_t K, const float* W1T, const float* b1,
                            int32_t N1, int32_t norm, const float* g, const float* beta,
-                           const float* W2, const float* b2, int32_t N2, int32_t mode,
+                           const float* W2T, const float* b2, int32_t N2, int32_t mode,
                            const float* partner, const int32_t* seg, float* y, float* score,
                            ir_stream_t stream) {
-    IR_CHECK_ARG(x && W1 && W2 && M > 0 && K > 0 && K <= MH_MAXD && N1 > 0 && N1 <= MH_MAXD && N2 > 0 && N2 <= MH_MAXD);
+    IR_CHECK_ARG(x && W1T && W2T && M > 0 && K > 0 && K <= MH_MAXD && N1 > 0 && N1 <= MH_MAXD && N2 > 0 && N2 <= MH_MAXD);
     IR_CHECK_ARG(norm >= 0 && norm <= 2 && mode >= 0 && mode <= 3);
     IR_CHECK_ARG(norm == 0 || (g && beta));
     IR_CHECK_ARG(mode >= 2 ? (partner && seg && score) : (y != nullptr));
-    k_mlp_head<<<ir_div_up(M, MH_TM), 256, 0, (cudaStream_t)stream>>>(x, M, K, W1, b1, N1, norm, g, beta, W2, b2,
-                                                                      N2, mode, partner, seg, y, score);
+    static bool attr_done = false;
+    if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_head, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_SMEM_BYTES));
+        attr_done = true;
+    }
+    k_mlp_head<<<ir_div_up(M, MH_TM), MH_THREADS, MH_SMEM_BYTES, (cudaStream_t)stream>>>(
+        x, M, K, W1T, b1, N1, norm, g, beta, W2T, b2, N2, mode, partner, seg, y, score);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

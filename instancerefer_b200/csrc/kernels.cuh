@@ -5,7 +5,7 @@
 #include "common.cuh"
 
 // coords.cu
-int irk_set_int(int* p, int v, cudaStream_t st);
+int irk_set_int(int* p, int v, const int* src, cudaStream_t st);
 int irk_hash_build(const int32_t* coords, const int* n_dev, long long n_max, IrTable t,
                    cudaStream_t st);
 int irk_downsample(const int32_t* coords, const int* n_dev, long long n_max, int new_stride,
@@ -22,8 +22,8 @@ int irk_kmap(int ks, const int32_t* coords_out, const int* n_out_dev, long long 
 int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int* in_idx,
                       long long seg_cap, const int* count, const float* weight, float* T,
                       long long pairs_max, cudaStream_t st);
-int irk_reduce_epilogue(const float* T, int cout, int K, int KP, const int* slot, const int* count,
-                        const int* n_out_dev, long long n_max, const float* scale,
+int irk_reduce_epilogue(const float* T, int cout, int K, const int* slot, long long seg_cap,
+                        const int* count, const int* n_out_dev, long long n_max, const float* scale,
                         const float* shift, const float* resid, int relu, float* out,
                         cudaStream_t st);
 

@@ -49,59 +49,71 @@ extern "C" int ir_linear(const float* x, int32_t M, int32_t K, const float* W, c
 }
 
 // ------------------------------------------------------------------ GRU layer (both directions)
-// grid (B, 2); 3H threads; W_hh^T resident in shared memory (H*3H floats = 192 KB for H=128).
-__global__ void k_gru_layer(const float* __restrict__ xproj, const float* __restrict__ whh,
-                            const float* __restrict__ bhh, const long long* __restrict__ lengths,
-                            int L, int H, float* __restrict__ out) {
-    extern __shared__ float smem[];
-    const int G = 3 * H;
-    float* WT = smem;               // [H][G]
-    float* s_h = WT + (size_t)H * G;  // [H]
-    float* s_hp = s_h + H;          // [G]
-    const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
-    const float* Wd = whh + (size_t)dir * G * H;
-    for (int i = j; i < G * H; i += G) {
-        const int row = i / H, k = i - row * H;   // coalesced global read of W[row][k]
-        WT[(size_t)k * G + row] = Wd[i];
+// grid (B, 2 directions); 2*3H threads.  Thread (gate row j, half) keeps its 64 recurrent weights in
+// REGISTERS for the whole sequence; the hidden state lives in shared memory (padded so the two
+// halves read different banks); partial dot products are combined with one warp shuffle.
+#define GRU_H 128
+#define GRU_HALF 64
+#define GRU_PAD 4
+__global__ void __launch_bounds__(6 * GRU_H)
+k_gru_layer(const float* __restrict__ xproj, const float* __restrict__ whh, const float* __restrict__ bhh,
+            const long long* __restrict__ lengths, int L, float* __restrict__ out) {
+    constexpr int H = GRU_H, G = 3 * GRU_H;
+    __shared__ __align__(16) float s_h[2 * (GRU_HALF + GRU_PAD)];
+    __shared__ float s_hp[G];
+    const int b = blockIdx.x, dir = blockIdx.y, t = threadIdx.x;
+    const int j = t >> 1, half = t & 1;
+    float w[GRU_HALF];
+    {
+        const float4* src = reinterpret_cast<const float4*>(whh + ((size_t)dir * G + j) * H + half * GRU_HALF);
+#pragma unroll
+        for (int i = 0; i < GRU_HALF / 4; ++i) {
+            const float4 v = __ldg(src + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
     }
-    if (j < H) s_h[j] = 0.f;
     const float bj = bhh[dir * G + j];
+    if (t < H) s_h[(t / GRU_HALF) * (GRU_HALF + GRU_PAD) + (t % GRU_HALF)] = 0.f;
     int len = (int)lengths[b];
     len = max(0, min(len, L));
     __syncthreads();
+    const float4* hv = reinterpret_cast<const float4*>(s_h + half * (GRU_HALF + GRU_PAD));
     for (int s = 0; s < len; ++s) {
-        const int t = dir ? (len - 1 - s) : s;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < H; ++k) acc = fmaf(WT[(size_t)k * G + j], s_h[k], acc);
-        s_hp[j] = acc + bj;
+        const int tt = dir ? (len - 1 - s) : s;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < GRU_HALF / 4; ++i) {
+            const float4 h4 = hv[i];
+            a0 = fmaf(w[4 * i], h4.x, a0);
+            a1 = fmaf(w[4 * i + 1], h4.y, a1);
+            a0 = fmaf(w[4 * i + 2], h4.z, a0);
+            a1 = fmaf(w[4 * i + 3], h4.w, a1);
+        }
+        float acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) s_hp[j] = acc + bj;
         __syncthreads();
-        if (j < H) {
-            const float* xp = xproj + (((size_t)b * L + t) * 2 + dir) * G;
-            const float r = 1.f / (1.f + expf(-(xp[j] + s_hp[j])));
-            const float z = 1.f / (1.f + expf(-(xp[H + j] + s_hp[H + j])));
-            const float n = tanhf(xp[2 * H + j] + r * s_hp[2 * H + j]);
-            const float h = (1.f - z) * n + z * s_h[j];
-            out[((size_t)b * L + t) * (2 * H) + dir * H + j] = h;
-            s_h[j] = h;
+        if (t < H) {
+            const float* xp = xproj + (((size_t)b * L + tt) * 2 + dir) * G;
+            const int hi = (t / GRU_HALF) * (GRU_HALF + GRU_PAD) + (t % GRU_HALF);
+            const float r = 1.f / (1.f + expf(-(xp[t] + s_hp[t])));
+            const float z = 1.f / (1.f + expf(-(xp[H + t] + s_hp[H + t])));
+            const float n = tanhf(xp[2 * H + t] + r * s_hp[2 * H + t]);
+            const float h = (1.f - z) * n + z * s_h[hi];
+            out[((size_t)b * L + tt) * (2 * H) + dir * H + t] = h;
+            s_h[hi] = h;
         }
         __syncthreads();
     }
-    if (j < H)
-        for (int t = len; t < L; ++t) out[((size_t)b * L + t) * (2 * H) + dir * H + j] = 0.f;
+    if (t < H)
+        for (int tt = len; tt < L; ++tt) out[((size_t)b * L + tt) * (2 * H) + dir * H + t] = 0.f;
 }
 
 extern "C" int ir_gru_layer(const float* xproj, const float* whh, const float* bhh,
                             const int64_t* lengths, int32_t B, int32_t L, int32_t H, float* out,
                             ir_stream_t stream) {
-    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && B > 0 && L > 0 && H == 128);
-    const size_t smem = ((size_t)H * 3 * H + H + 3 * H) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        IR_CHECK_CUDA(cudaFuncSetAttribute(k_gru_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    k_gru_layer<<<dim3(B, 2), 3 * H, smem, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, L, H, out);
+    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && B > 0 && L > 0 && H == GRU_H);
+    k_gru_layer<<<dim3(B, 2), 6 * GRU_H, 0, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, L, out);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

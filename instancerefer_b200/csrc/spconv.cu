@@ -7,7 +7,7 @@
 // version in spconv_tc.cu is validated against), the reduce/epilogue, segmented max-pool.
 //
 //   T[kofs[k] + pos, :] = F[in_idx[k][pos], :] @ W[k]            (pair-GEMM, weight-stationary)
-//   out[o, :] = act( scale * sum_{k asc} T[kofs[k] + slot[o][k], :] + shift (+ resid[o, :]) )
+//   out[o, :] = act( scale * sum_{k asc} T[kofs[k] + slot[k][o], :] + shift (+ resid[o, :]) )
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -92,9 +92,9 @@ int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int*
 }
 
 // ------------------------------------------------------------------ reduce + epilogue
-template <int COUT, int KP>
+template <int COUT>
 __global__ void __launch_bounds__(256)
-k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ slot,
+k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ slot, long long seg_cap,
                   const int* __restrict__ count, const int* __restrict__ n_dev,
                   const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ resid, int relu, float* __restrict__ out) {
@@ -121,7 +121,7 @@ k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ sl
     }
     const int wpb = blockDim.x >> 5;
     for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
-        const int my = (lane < KP) ? slot[o * KP + lane] : -1;
+        const int my = (lane < K) ? slot[(long long)lane * seg_cap + o] : -1;
         float acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.f;
@@ -155,27 +155,18 @@ k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ sl
     }
 }
 
-int irk_reduce_epilogue(const float* T, int cout, int K, int KP, const int* slot, const int* count,
-                        const int* n_out_dev, long long n_max, const float* scale,
+int irk_reduce_epilogue(const float* T, int cout, int K, const int* slot, long long seg_cap,
+                        const int* count, const int* n_out_dev, long long n_max, const float* scale,
                         const float* shift, const float* resid, int relu, float* out,
                         cudaStream_t st) {
-    IR_CHECK_ARG((KP == 32 || KP == 8) && K <= KP);
+    IR_CHECK_ARG(K <= 32);
     const int grid = ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, 8), IR_NUM_SMS * 8);
-#define LAUNCH_RE(CO, KPV) k_reduce_epilogue<CO, KPV><<<grid, 256, 0, st>>>(T, K, slot, count, n_out_dev, scale, shift, resid, relu, out)
-    if (KP == 32) {
-        switch (cout) {
-            case 32: LAUNCH_RE(32, 32); break;
-            case 64: LAUNCH_RE(64, 32); break;
-            case 128: LAUNCH_RE(128, 32); break;
-            default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
-        }
-    } else {
-        switch (cout) {
-            case 32: LAUNCH_RE(32, 8); break;
-            case 64: LAUNCH_RE(64, 8); break;
-            case 128: LAUNCH_RE(128, 8); break;
-            default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
-        }
+#define LAUNCH_RE(CO) k_reduce_epilogue<CO><<<grid, 256, 0, st>>>(T, K, slot, seg_cap, count, n_out_dev, scale, shift, resid, relu, out)
+    switch (cout) {
+        case 32: LAUNCH_RE(32); break;
+        case 64: LAUNCH_RE(64); break;
+        case 128: LAUNCH_RE(128); break;
+        default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
     }
 #undef LAUNCH_RE
     IR_CHECK_LAUNCH();

@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from . import ops
 from .candidates import KEY as _PACK_KEY
+from .candidates import CandidatePack, target_classes
 
 
 def _load(name):
@@ -32,25 +33,62 @@ class InstanceRefer(nn.Module):
         if args.scene_module:
             self.scene = _load(args.scene_module).SceneModule(input_feature_dim, args)
 
+    concurrent = True      # run the three language-independent encoders on side streams
+
+    def _streams(self, device):
+        st = self.__dict__.get('_side_streams')
+        if st is None or st[0].device != device:
+            st = [torch.cuda.Stream(device=device) for _ in range(3)]
+            self.__dict__['_side_streams'] = st
+        return st
+
     def forward(self, data_dict):
-        data_dict.pop(_PACK_KEY, None)
+        ops.check_device()
+        if not getattr(data_dict.get(_PACK_KEY), 'resident', False):
+            data_dict.pop(_PACK_KEY, None)
+        a = self.args
+        full = bool(a.attribute_module and a.relation_module and a.scene_module)
         with torch.no_grad():
-            data_dict = self.lang(data_dict)
-            if self.args.attribute_module:
-                data_dict = self.attribute(data_dict)
-            if self.args.relation_module:
-                data_dict = self.relation(data_dict)
-            if self.args.scene_module:
-                data_dict = self.scene(data_dict)
-            if self.args.attribute_module and self.args.relation_module and self.args.scene_module:
+            if not (full and self.concurrent and a.use_gt_lang):
+                # plain chain, exactly the reference order (models/instancerefer.py:56-70)
+                data_dict = self.lang(data_dict)
+                if a.attribute_module:
+                    data_dict = self.attribute(data_dict)
+                if a.relation_module:
+                    data_dict = self.relation(data_dict)
+                if a.scene_module:
+                    data_dict = self.scene(data_dict)
+            else:
+                # same arithmetic, B200 schedule: the instance encoder, the scene encoder and the
+                # relation graph do not depend on the language branch, so they run on three side
+                # streams while the GRU runs on the caller's stream; the matching heads join them.
+                dev = data_dict['lang_feat'].device
+                main = torch.cuda.current_stream(dev)
+                sa, ss, sr = self._streams(dev)
+                pack = data_dict.get(_PACK_KEY)
+                if pack is None:                       # host filter + packed H2D on the caller's stream
+                    pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+                    data_dict[_PACK_KEY] = pack
+                for s_ in (sa, ss, sr):
+                    s_.wait_stream(main)
+                with torch.cuda.stream(sa):
+                    self.attribute.encode_candidates(data_dict, dev, pack)
+                with torch.cuda.stream(ss):
+                    self.scene.encode_scene(data_dict, dev)
+                with torch.cuda.stream(sr):
+                    self.relation.encode_graph(data_dict, dev)
+                data_dict = self.lang(data_dict)
+                for s_ in (sa, ss, sr):
+                    main.wait_stream(s_)
+                self.attribute.match(data_dict)
+                self.relation.match(data_dict)
+                self.scene.match(data_dict)
+            if full:
                 # extra fused output (not in the reference dict): per-scene softmax / argmax over
                 # candidates of the summed score (the reference does this on the host,
                 # lib/eval_helper.py:61-67)
                 pack = data_dict[_PACK_KEY]
-                nf = [n for n in pack.num_filtered if n >= 2]
-                ofs = torch.tensor([0] + list(torch.tensor(nf).cumsum(0).tolist()), dtype=torch.int32)
-                ofs = ofs.pin_memory().to(data_dict['attribute_scores'].device, non_blocking=True)
                 prob, arg = ops.candidate_softmax(data_dict['attribute_scores'], data_dict['relation_scores'],
-                                                  data_dict['scene_scores'], ofs)
+                                                  data_dict['scene_scores'], pack.cand_ofs)
                 data_dict['ref_probs'], data_dict['ref_pred'] = prob, arg
         return data_dict

@@ -55,10 +55,12 @@ class LangModule(nn.Module, PrepCache):
         require_eval(self)
         p = self.prepared()
         dev = embed_in.device
-        len_host = length.detach().to('cpu') if length.is_cuda else length     # one small D2H (ref: :60)
         len_dev = length.to(dev, torch.int64).contiguous()
         B = embed_in.shape[0]
-        L = int(len_host.max())
+        if data_dict.get('_ir_lang_len_max') is not None:                      # caller already knows max(len)
+            L = int(data_dict['_ir_lang_len_max'])
+        else:                                                                  # one small D2H (ref: :60)
+            L = int((length.detach().to('cpu') if length.is_cuda else length).max())
         x = embed_in[:, :L].float().contiguous().view(B * L, -1)               # only the L live tokens
         e = ops.linear(ops.linear(x, p['w0'], p['b0'], relu=True), p['w3'], p['b3'], relu=True)
         h = e

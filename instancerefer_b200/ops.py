@@ -9,7 +9,7 @@ from ._lib import EncoderLayout, EncoderParams, call
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _p(t, dtype=None):
@@ -25,11 +25,17 @@ def _p(t, dtype=None):
     return C.c_void_p(t.data_ptr())
 
 
+_checked_devices = set()
+
+
 def check_device(device_index=None):
-    if not torch.cuda.is_available():
+    """Raise unless the current device is a B200-class (sm_100) GPU.  Checked once per device."""
+    if not _checked_devices and not torch.cuda.is_available():
         raise _lib.IrError("no CUDA device: instancerefer_b200 has no CPU fallback")
     idx = torch.cuda.current_device() if device_index is None else device_index
-    call("ir_check_device", idx)
+    if idx not in _checked_devices:
+        call("ir_check_device", idx)
+        _checked_devices.add(idx)
 
 
 # ----------------------------------------------------------------------------- encoder workspace
@@ -68,12 +74,12 @@ class EncoderWorkspace:
     def k3(self, level):
         L = self.layout
         return (self._view(L.off_k3_in[level], 27 * self.n_max * 4, torch.int32).view(27, self.n_max),
-                self._view(L.off_k3_slot[level], 32 * self.n_max * 4, torch.int32).view(self.n_max, 32))
+                self._view(L.off_k3_slot[level], 27 * self.n_max * 4, torch.int32).view(27, self.n_max))
 
     def k2(self, level):
         L = self.layout
         return (self._view(L.off_k2_in[level], 8 * self.n_max * 4, torch.int32).view(8, self.n_max),
-                self._view(L.off_k2_slot[level], 8 * self.n_max * 4, torch.int32).view(self.n_max, 8))
+                self._view(L.off_k2_slot[level], 8 * self.n_max * 4, torch.int32).view(8, self.n_max))
 
     def T(self):
         return self._view(self.layout.off_T, 27 * self.n_max * 128 * 4, torch.float32)
@@ -90,11 +96,13 @@ def voxelize(pts, cand, voxel, ws):
          float(voxel), ws.ptr, ws.n_max, _stream())
 
 
-def encoder_build_maps(ws, coords0=None):
+def encoder_build_maps(ws, coords0=None, n0_dev=None):
+    """coords0 (n,4) int32; with n0_dev (device int32[1]) only the first *n0_dev rows are live."""
     if coords0 is None:
-        call("ir_encoder_build_maps", None, 0, ws.ptr, ws.n_max, _stream())
+        call("ir_encoder_build_maps", None, 0, None, ws.ptr, ws.n_max, _stream())
     else:
-        call("ir_encoder_build_maps", _p(coords0, torch.int32), coords0.shape[0], ws.ptr, ws.n_max, _stream())
+        call("ir_encoder_build_maps", _p(coords0, torch.int32), coords0.shape[0],
+             _p(n0_dev, torch.int32) if n0_dev is not None else None, ws.ptr, ws.n_max, _stream())
 
 
 def make_encoder_params(cin, weights, bn_scale, bn_shift, wprep=None, use_tc=False):
@@ -131,8 +139,7 @@ def spconv_wprep(weight):
 def spconv_layer(feat_in, in_idx, slot, count, n_out_dev, n_max, weight, scale, shift, resid, relu,
                  T, out, wprep=None, use_tc=False):
     K, cin, cout = weight.shape
-    KP = slot.shape[1]
-    call("ir_spconv_layer", _p(feat_in, torch.float32), cin, cout, K, KP, _p(in_idx, torch.int32),
+    call("ir_spconv_layer", _p(feat_in, torch.float32), cin, cout, K, _p(in_idx, torch.int32),
          in_idx.shape[1], _p(slot, torch.int32), _p(count, torch.int32), _p(n_out_dev, torch.int32),
          n_max, _p(weight, torch.float32), _p(wprep), 1 if use_tc else 0, _p(scale), _p(shift),
          _p(resid), 1 if relu else 0, _p(T, torch.float32), _p(out, torch.float32), _stream())
@@ -210,8 +217,9 @@ MODE_RAW, MODE_L2, MODE_DOT, MODE_COS = 0, 1, 2, 3
 
 
 def mlp_head(x, W1, b1, norm, g, beta, W2, b2, mode, partner=None, seg=None, want_y=False):
+    """W1 (K,N1), W2 (N1,N2): (in,out) layout, i.e. transposed nn.Linear weights."""
     M, K = x.shape
-    N1, N2 = W1.shape[0], W2.shape[0]
+    N1, N2 = W1.shape[1], W2.shape[1]
     dev = x.device
     y = torch.empty(M, N2, dtype=torch.float32, device=dev) if (mode < 2 or want_y) else None
     score = torch.empty(M, dtype=torch.float32, device=dev) if mode >= 2 else None

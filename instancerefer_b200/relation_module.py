@@ -8,6 +8,7 @@ import torch.nn as nn
 
 from . import ops
 from .basic_blocks import DynamicEdgeConv, PrepCache, fold_bn, require_eval
+from .candidates import KEY as _KEY
 from .candidates import get_pack
 
 
@@ -31,36 +32,45 @@ class RelationModule(nn.Module, PrepCache):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
-    def _prep_key(self):
-        ts = list(self.vis_emb_fc.parameters()) + list(self.lang_emb_fc.parameters()) + list(self.lang_emb_fc.buffers())
-        return tuple((t.data_ptr(), t._version) for t in ts)
+    def _prep_tensors(self):
+        return list(self.vis_emb_fc.parameters()) + list(self.lang_emb_fc.parameters()) + list(self.lang_emb_fc.buffers())
 
     def _prepare(self):
         f = lambda t: t.detach().float().contiguous()
+        ft = lambda t: t.detach().float().t().contiguous()         # (in,out) layout for ir_mlp_head
         v, l = self.vis_emb_fc, self.lang_emb_fc
         s, b = fold_bn(l[1])
-        return dict(vw1=f(v[0].weight), vb1=f(v[0].bias), vg=f(v[1].weight), vbeta=f(v[1].bias),
-                    vw2=f(v[4].weight), vb2=f(v[4].bias),
-                    lw1=f(l[0].weight), lb1=f(l[0].bias), lg=s, lbeta=b, lw2=f(l[4].weight), lb2=f(l[4].bias))
+        return dict(vw1=ft(v[0].weight), vb1=f(v[0].bias), vg=f(v[1].weight), vbeta=f(v[1].bias),
+                    vw2=ft(v[4].weight), vb2=f(v[4].bias),
+                    lw1=ft(l[0].weight), lb1=f(l[0].bias), lg=s, lbeta=b, lw2=ft(l[4].weight), lb2=f(l[4].bias))
 
-    def forward(self, data_dict):
+    def encode_graph(self, data_dict, device):
+        """Phase A (no language dependency): per-instance 25-d rows (:66-73: mean of the points with
+        xyz := OBB centre, + class one-hot), per-scene kNN, fused EdgeConv (:100)."""
         require_eval(self)
-        ops.check_device()
-        p = self.prepared()
-        lang = data_dict['lang_rel_feats']
-        dev = lang.device
-        lang_emb, _ = ops.mlp_head(lang.float().contiguous(), p['lw1'], p['lb1'], ops.NORM_AFFINE, p['lg'],
-                                   p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)                 # (:82)
-        pack = get_pack(data_dict, self.args, dev)
-        # (:66-73) mean of each instance's points with xyz := OBB centre, + class one-hot
+        pack = get_pack(data_dict, self.args, device)
         mean = ops.instance_mean(pack.points)
         ncls = self.args.num_classes
-        onehot = torch.nn.functional.one_hot(pack.centres_cls[:, 3].long(), ncls).float()
+        cls_ids = torch.arange(ncls, device=device, dtype=torch.float32)
+        onehot = (pack.centres_cls[:, 3:4] == cls_ids[None, :]).float()          # capture-safe one-hot
         xyz = pack.centres_cls[:, :3].contiguous()
         feats = torch.cat([xyz, mean[:, 3:], onehot], 1).contiguous()
-        g, nbr = self.gcn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, feats)              # (:100)
-        data_dict['_ir_knn'] = nbr
-        _, scores = ops.mlp_head(g, p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'], p['vw2'],
-                                 p['vb2'], ops.MODE_COS, partner=lang_emb, seg=pack.cand_scene)  # (:101-103)
+        g, nbr = self.gcn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, feats)
+        data_dict['_ir_gcn'], data_dict['_ir_knn'] = g, nbr
+        return data_dict
+
+    def match(self, data_dict):
+        """Phase B: language MLP (:82), visual MLP, cosine (:101-103)."""
+        p = self.prepared()
+        pack = data_dict[_KEY]
+        lang_emb, _ = ops.mlp_head(data_dict['lang_rel_feats'].float().contiguous(), p['lw1'], p['lb1'],
+                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        _, scores = ops.mlp_head(data_dict['_ir_gcn'], p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'],
+                                 p['vw2'], p['vb2'], ops.MODE_COS, partner=lang_emb, seg=pack.cand_scene)
         data_dict['relation_scores'] = scores
         return data_dict
+
+    def forward(self, data_dict):
+        ops.check_device()
+        data_dict = self.encode_graph(data_dict, data_dict['lang_rel_feats'].device)
+        return self.match(data_dict)

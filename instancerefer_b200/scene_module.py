@@ -37,13 +37,13 @@ class SceneModule(nn.Module, PrepCache):
         self.cls = nn.Sequential(nn.Linear(h_dim, h_dim), nn.BatchNorm1d(h_dim), nn.ReLU(),
                                  nn.Linear(h_dim, 9))
 
-    def _prep_key(self):
+    def _prep_tensors(self):
         mods = (self.to_bev, self.vis_emb_fc, self.vis_emb_fc1, self.lang_emb_fc, self.cls)
-        ts = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
-        return tuple((t.data_ptr(), t._version) for t in ts)
+        return [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
 
     def _prepare(self):
         f = lambda t: t.detach().float().contiguous()
+        ft = lambda t: t.detach().float().t().contiguous()         # (in,out) layout for ir_mlp_head
         pk = lambda conv: conv.weight.detach().float().permute(2, 3, 1, 0).contiguous()   # [ky][kx][Cin][Cout]
         bs, bb = fold_bn(self.to_bev[2])
         c1s, c1b = fold_bn(self.vis_emb_fc[1])
@@ -52,39 +52,50 @@ class SceneModule(nn.Module, PrepCache):
         return dict(bev_kernel=f(self.to_bev[1].kernel), bev_s=bs, bev_b=bb,
                     c1w=pk(self.vis_emb_fc[0]), c1bias=f(self.vis_emb_fc[0].bias), c1s=c1s, c1b=c1b,
                     c2w=pk(self.vis_emb_fc[4]), c2bias=f(self.vis_emb_fc[4].bias),
-                    ow1=f(v1[0].weight), ob1=f(v1[0].bias), og=f(v1[1].weight), obeta=f(v1[1].bias),
-                    ow2=f(v1[4].weight), ob2=f(v1[4].bias),
-                    lw1=f(l[0].weight), lb1=f(l[0].bias), lg=f(l[1].weight), lbeta=f(l[1].bias),
-                    lw2=f(l[4].weight), lb2=f(l[4].bias),
-                    kw1=f(self.cls[0].weight), kb1=f(self.cls[0].bias), kg=cs, kbeta=cb,
-                    kw2=f(self.cls[3].weight), kb2=f(self.cls[3].bias))
+                    ow1=ft(v1[0].weight), ob1=f(v1[0].bias), og=f(v1[1].weight), obeta=f(v1[1].bias),
+                    ow2=ft(v1[4].weight), ob2=f(v1[4].bias),
+                    lw1=ft(l[0].weight), lb1=f(l[0].bias), lg=f(l[1].weight), lbeta=f(l[1].bias),
+                    lw2=ft(l[4].weight), lb2=f(l[4].bias),
+                    kw1=ft(self.cls[0].weight), kb1=f(self.cls[0].bias), kg=cs, kbeta=cb,
+                    kw2=ft(self.cls[3].weight), kb2=f(self.cls[3].bias))
 
-    def forward(self, data_dict):
+    def encode_scene(self, data_dict, device):
+        """Phase A (no language dependency): whole-scene sparse encoder (:69), crop + dense BEV + BN +
+        ReLU (:70), Conv2d-BN-ReLU-Conv2d (:71) -> (B,11,21,128) NHWC."""
         require_eval(self)
-        ops.check_device()
         p = self.prepared()
         lidar = data_dict['lidar']
         B = data_dict['point_min'].shape[0]                                     # (:62-63)
-        lang = data_dict['lang_scene_feats']
-        dev = lang.device
-        F0 = lidar.F.to(dev, torch.float32).contiguous()
-        C0 = lidar.C.to(dev, torch.int32).contiguous()
-        ws = self.net.workspace(F0.shape[0], dev)
-        f4, c4, n4 = self.net.encode(ws, F0, C0)                                # (:69)
-        bev = ops.bev(f4, c4, n4, ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)   # (:70) NHWC
+        F0 = lidar.F.to(device, torch.float32).contiguous()
+        C0 = lidar.C.to(device, torch.int32).contiguous()
+        ws = self.net.workspace(F0.shape[0], device)
+        f4, c4, n4 = self.net.encode(ws, F0, C0, data_dict.get('_ir_lidar_rows'))
+        bev = ops.bev(f4, c4, n4, ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
         x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
-        x = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)         # (:71) (B,11,21,128)
-        h, w = x.shape[1], x.shape[2]
-        q, _ = ops.mlp_head(lang.float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER, p['lg'], p['lbeta'],
-                            p['lw2'], p['lb2'], ops.MODE_RAW)
-        atten, scene_feats = ops.scene_attention(x.view(B, h * w, -1), q)       # (:73-83)
+        data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        return data_dict
+
+    def match(self, data_dict):
+        """Phase B: language-guided attention over the 11x21 cells (:73-83), region classifier (:84),
+        cosine(vis_emb_fc1(obj_feats), scene_feat) (:89-104)."""
+        p = self.prepared()
+        x = data_dict['_ir_bev_feats']
+        B, h, w = x.shape[0], x.shape[1], x.shape[2]
+        q, _ = ops.mlp_head(data_dict['lang_scene_feats'].float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER,
+                            p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        atten, scene_feats = ops.scene_attention(x.view(B, h * w, -1), q)
         data_dict['vis_atten'] = atten.view(B, h, w)
         seg, _ = ops.mlp_head(scene_feats, p['kw1'], p['kb1'], ops.NORM_AFFINE, p['kg'], p['kbeta'],
-                              p['kw2'], p['kb2'], ops.MODE_RAW)                 # (:84)
+                              p['kw2'], p['kb2'], ops.MODE_RAW)
         data_dict['seg_scores'] = seg
-        pack = get_pack(data_dict, self.args, dev)
+        pack = get_pack(data_dict, self.args, x.device)
         _, scores = ops.mlp_head(data_dict['obj_feats'], p['ow1'], p['ob1'], ops.NORM_LAYER, p['og'],
                                  p['obeta'], p['ow2'], p['ob2'], ops.MODE_COS, partner=scene_feats,
-                                 seg=pack.cand_scene)                            # (:89-104)
+                                 seg=pack.cand_scene)
         data_dict['scene_scores'] = scores
         return data_dict
+
+    def forward(self, data_dict):
+        ops.check_device()
+        data_dict = self.encode_scene(data_dict, data_dict['lang_scene_feats'].device)
+        return self.match(data_dict)
