@@ -290,6 +290,7 @@ def main():
     roofline, detail = None, None
     if rank == 0:
         nprof = min(a.steps, 10)
+        model.concurrent = False          # serial launches: the event spans must not overlap other streams
         lib.ir_profile_enable(1)
         cap = 512
         gm, rm = (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
@@ -314,6 +315,7 @@ def main():
                 e = acc.setdefault(key, [0.0, 0.0, 0, 0, 0.0, 0])
                 e[0] += gm[j]; e[1] += by; e[2] += fl; e[3] += 1; e[4] += rm[j]; e[5] += P
         lib.ir_profile_enable(0)
+        model.concurrent = True
         peak, peak_src = load_peak()
         tc_ms = sum(v[0] for k, v in acc.items() if k[0] == 'tcgen05')
         tc_by = sum(v[1] for k, v in acc.items() if k[0] == 'tcgen05')

@@ -41,6 +41,12 @@ int64_t ir_launch_count(void);
 int ir_profile_enable(int on);
 int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out);
 
+/* Tuning aid for the tcgen05 pair-GEMM (tools/bench_spconv.py): bit0 skip gather loads, bit1 skip T
+ * stores, bit2 skip MMA issue.  0 = normal operation. */
+int ir_debug_set(int flags);
+/* Copies the kernel's 64 int64 debug counters to the host (synchronises; unused in normal builds). */
+int ir_debug_stats(long long* out64);
+
 /* ------------------------------------------------------------------ sparse-voxel encoder
  * SparseConvEncoder / BEVEncoder (models/basic_blocks.py:59-95,136-171): 13 sparse convs
  * (stem k3; 4 x [k2 s2 down, residual k3 k3]) with eval-mode BatchNorm, ReLU and the identity
@@ -51,7 +57,7 @@ int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap
 
 typedef struct {
     int32_t cin;                           /* input channels (7 = xyz+rgb+height)               */
-    int32_t use_tc;                        /* 0: SIMT fp32 pair-GEMM, 1: tcgen05 3xTF32          */
+    int32_t use_tc;                        /* 0: SIMT fp32 pair-GEMM, 1: tcgen05 split-fp16      */
     const float* weight[IR_ENC_LAYERS];    /* (K,Cin,Cout) fp32, reference `kernel` layout        */
     const float* wprep[IR_ENC_LAYERS];     /* ir_spconv_prepare_weights images (use_tc=1) or NULL */
     const float* bn_scale[IR_ENC_LAYERS];  /* gamma / sqrt(var+eps)                               */
@@ -110,9 +116,9 @@ int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,
                     const float* shift, const float* resid, int32_t relu, float* T, float* out,
                     ir_stream_t stream);
 
-/* tcgen05 operand images for one conv weight (K,Cin,Cout): per offset k the transposed weight
- * [Cout][Cin] split into tf32 hi / lo parts, stored in the 128B-swizzled K-major shared-memory
- * layout the MMA reads.  out holds ir_spconv_wprep_floats(K,cin,cout) floats. */
+/* Weight buffer the tcgen05 pair-GEMM reads: a 16-byte aligned copy of the reference layout
+ * (K,Cin,Cout); W[k] is staged by one TMA bulk copy per CTA and split into fp16 hi / lo parts on its
+ * way into TMEM.  out holds ir_spconv_wprep_floats(K,cin,cout) floats. */
 int64_t ir_spconv_wprep_floats(int32_t K, int32_t cin, int32_t cout);
 int ir_spconv_prepare_weights(const float* weight, int32_t K, int32_t cin, int32_t cout,
                               float* out, ir_stream_t stream);

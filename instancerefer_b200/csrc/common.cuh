@@ -56,8 +56,10 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------ coordinate hash table
-// keys u64[cap] (EMPTY = all ones) | minrow i32[cap] | row i32[cap]; open addressing, linear probe.
-#define IR_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+// keys u64[cap] | minrow i32[cap] | row i32[cap]; open addressing, linear probe.  EMPTY and NOROW
+// share the byte pattern 0x7F so one memset clears a whole table set; batch ids must stay < 0x7F7F.
+#define IR_EMPTY_KEY 0x7F7F7F7F7F7F7F7Full
+#define IR_MAX_BATCH 0x7F7F
 #define IR_NOROW 0x7F7F7F7F
 
 struct IrTable {

@@ -74,18 +74,7 @@ __device__ __forceinline__ void compact_ordered(int n, unsigned long long* state
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void k_set_int(int* p, int v, const int* src) { *p = src ? *src : v; }
-
-__global__ void k_hash_build(const int4* __restrict__ coords, const int* __restrict__ n_dev,
-                             IrTable t) {
-    const int n = *n_dev;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int4 c = coords[i];
-        const int s = ir_ht_insert(t, ir_pack_key(c.x, c.y, c.z, c.w));
-        atomicMin(&t.minrow[s], i);
-        atomicMin(&t.row[s], i);
-    }
-}
+typedef IrLevels LevelTables;
 
 __device__ __forceinline__ int4 parent_coord(int4 c, int new_stride) {
     // floor(c / ns) * ns for power-of-two ns, negatives included (two's complement floor)
@@ -93,28 +82,52 @@ __device__ __forceinline__ int4 parent_coord(int4 c, int new_stride) {
     return make_int4(c.x & m, c.y & m, c.z & m, c.w);
 }
 
-__global__ void k_ds_insert(const int4* __restrict__ coords, const int* __restrict__ n_dev,
-                            int new_stride, IrTable t, int* __restrict__ pslot) {
-    const int n = *n_dev;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int4 p = parent_coord(coords[i], new_stride);
-        const int s = ir_ht_insert(t, ir_pack_key(p.x, p.y, p.z, p.w));
-        atomicMin(&t.minrow[s], i);
-        pslot[i] = s;
+// every ancestor voxel (stride 2,4,8,16) of level-0 row i remembers the smallest level-0 row below it:
+// row order of level l = order of that minimum = the first-occurrence order torchsparse-style
+// repeated downsampling produces (first occurrence is transitive).
+__device__ __forceinline__ void insert_ancestors(const LevelTables& lt, int4 c, int i, int* __restrict__ pslot,
+                                                 long long n_max) {
+#pragma unroll
+    for (int l = 1; l < 5; ++l) {
+        const int4 p = parent_coord(c, 1 << l);
+        const int s = ir_ht_insert(lt.t[l], ir_pack_key(p.x, p.y, p.z, p.w));
+        atomicMin(&lt.t[l].minrow[s], i);
+        pslot[(long long)(l - 1) * n_max + i] = s;
     }
 }
 
+// level 0 from given coords: hash every row, register its ancestors; also publishes the row count
+__global__ void k_hash_build_levels(const int4* __restrict__ coords, int n_host, const int* __restrict__ n_dev,
+                                    LevelTables lt, int* __restrict__ pslot, long long n_max,
+                                    int* __restrict__ nlvl0) {
+    const int n = n_dev ? *n_dev : n_host;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nlvl0 = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = coords[i];
+        const int s = ir_ht_insert(lt.t[0], ir_pack_key(c.x, c.y, c.z, c.w));
+        atomicMin(&lt.t[0].minrow[s], i);
+        atomicMin(&lt.t[0].row[s], i);
+        insert_ancestors(lt, c, i, pslot, n_max);
+    }
+}
+
+// ordered compaction of levels 1..4 (blockIdx.y = level-1), all from the level-0 rows
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_ds_compact(const int4* __restrict__ coords, const int* __restrict__ n_dev, int new_stride,
-             IrTable t, const int* __restrict__ pslot, int4* __restrict__ coords_out,
-             int* __restrict__ n_out, unsigned long long* state) {
-    const int n = *n_dev;
+k_levels_compact(const int4* __restrict__ coords0, const int* __restrict__ nlvl, LevelTables lt,
+                 const int* __restrict__ pslot, long long n_max, int4* __restrict__ c1, int4* __restrict__ c2,
+                 int4* __restrict__ c3, int4* __restrict__ c4, int* __restrict__ nlvl_out,
+                 unsigned long long* state, long long state_stride) {
+    const int l = blockIdx.y + 1;
+    const int n = nlvl[0];
+    const IrTable t = lt.t[l];
+    const int* ps = pslot + (long long)(l - 1) * n_max;
+    int4* cout = (l == 1) ? c1 : (l == 2) ? c2 : (l == 3) ? c3 : c4;
     compact_ordered(
-        n, state, n_out,
-        [&](int i) { return t.minrow[pslot[i]] == i; },
+        n, state + (long long)l * state_stride, nlvl_out + l,
+        [&](int i) { return t.minrow[ps[i]] == i; },
         [&](int i, int r) {
-            coords_out[r] = parent_coord(coords[i], new_stride);
-            t.row[pslot[i]] = r;
+            cout[r] = parent_coord(coords0[i], 1 << l);
+            t.row[ps[i]] = r;
         });
 }
 
@@ -133,48 +146,61 @@ __global__ void k_vox_insert(const float* __restrict__ pts, const int* __restric
     }
 }
 
+// first-point-wins compaction -> level-0 rows (coords + the winning point's feature row); each new row
+// registers its ancestors for the level compaction that follows.  vslot: the insert slots above.
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n_pts, int ppi,
-              int fdim, double voxel, IrTable t, const int* __restrict__ pslot,
+              int fdim, double voxel, LevelTables lt, const int* __restrict__ vslot,
               int4* __restrict__ coords_out, float* __restrict__ feats_out, int* __restrict__ n_out,
-              unsigned long long* state) {
+              unsigned long long* state, int* __restrict__ pslot, long long n_max) {
+    const IrTable t = lt.t[0];
     compact_ordered(
         n_pts, state, n_out,
-        [&](int p) { return t.minrow[pslot[p]] == p; },
+        [&](int p) { return t.minrow[vslot[p]] == p; },
         [&](int p, int r) {
             const int m = p / ppi, j = p - m * ppi;
             const float* src = pts + ((long long)cand[m] * ppi + j) * fdim;
-            coords_out[r] = make_int4((int)floor((double)src[0] / voxel), (int)floor((double)src[1] / voxel),
-                                      (int)floor((double)src[2] / voxel), m);
-            for (int c = 0; c < fdim; ++c) feats_out[(long long)r * fdim + c] = src[c];
-            t.row[pslot[p]] = r;
+            const int4 c = make_int4((int)floor((double)src[0] / voxel), (int)floor((double)src[1] / voxel),
+                                     (int)floor((double)src[2] / voxel), m);
+            coords_out[r] = c;
+            for (int q = 0; q < fdim; ++q) feats_out[(long long)r * fdim + q] = src[q];
+            t.row[vslot[p]] = r;
+            insert_ancestors(lt, c, r, pslot, n_max);
         });
 }
 
-// Kernel map for out[o] += F[j] @ W[k], j at C_out[o] + off_k (Appendix A offset enumeration):
-//   KS=3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
-//   KS=2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
-// grid (row blocks, K): one hash probe per thread, one warp-aggregated append per warp.
-// Emits, per offset k: in_idx[k*seg_cap + pos] (input row of pair `pos`), count[k], and
-// slot[k*seg_cap + o] = pos or -1.  Pair order inside k is append order (unordered).
-template <int KS>
+// All nine kernel maps of an encoder in one launch.  blockIdx.y < 135: k3 map of level y/27, offset
+// y%27; else k2s2 map from level l=(y-135)/8 to l+1, offset (y-135)%8.  Appendix-A enumeration:
+//   k3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
+//   k2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
+// One hash probe per thread, one warp-aggregated append per warp.  Emits per offset k:
+// in_idx[k*n_max + pos] (input row of pair pos), count[k], slot[k*n_max + o] = pos or -1.
+typedef IrKmapArgs KmapArgs;
+
 __global__ void __launch_bounds__(256)
-k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev, IrTable tin, int stride,
-       int* __restrict__ in_idx, long long seg_cap, int* __restrict__ slot, int* __restrict__ count) {
-    const int n = *n_out_dev;
-    const int k = blockIdx.y;
+k_kmap_all(KmapArgs a) {
+    const int y = blockIdx.y;
+    const bool is3 = y < 135;
+    const int l = is3 ? y / 27 : (y - 135) / 8;
+    const int k = is3 ? y % 27 : (y - 135) % 8;
+    const int lo = is3 ? l : l + 1;                       // output level
+    const int stride = 1 << l;
+    const int n = a.nlvl[lo];
+    const int4* __restrict__ coords_out = a.coords[lo];
+    const IrTable tin = a.lt.t[l];
+    int* __restrict__ in_k = (is3 ? a.k3_in[l] : a.k2_in[l]) + (long long)k * a.n_max;
+    int* __restrict__ slot_k = (is3 ? a.k3_slot[l] : a.k2_slot[l]) + (long long)k * a.n_max;
+    int* __restrict__ cnt = a.kcount + (is3 ? l : 5 + l) * 32 + k;
+    int dx, dy, dz;
+    if (is3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
+    else     { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
     const int lane = threadIdx.x & 31;
     const int n_round = (n + 31) & ~31;
-    int dx, dy, dz;
-    if (KS == 3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
-    else         { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
-    int* in_k = in_idx + (long long)k * seg_cap;
-    int* slot_k = slot + (long long)k * seg_cap;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
         const bool live = o < n;
         int j = -1;
         if (live) {
-            if (KS == 3 && k == 13) j = o;
+            if (is3 && k == 13) j = o;
             else {
                 const int4 c = coords_out[o];
                 const int s = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
@@ -186,7 +212,7 @@ k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev, I
         if (m) {
             const int leader = __ffs(m) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(&count[k], __popc(m));
+            if (lane == leader) base = atomicAdd(cnt, __popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (j >= 0) {
                 pos = base + __popc(m & ((1u << lane) - 1u));
@@ -198,56 +224,48 @@ k_kmap(const int4* __restrict__ coords_out, const int* __restrict__ n_out_dev, I
 }
 
 // ------------------------------------------------------------------ host launchers (internal)
-int irk_set_int(int* p, int v, const int* src, cudaStream_t st) {
-    k_set_int<<<1, 1, 0, st>>>(p, v, src);
-    IR_CHECK_LAUNCH();
-    return IR_OK;
-}
-
-
 static inline int grid_for(long long n, int threads) {
     int g = ir_div_up(n > 0 ? n : 1, threads);
     const int cap = IR_NUM_SMS * 8;
     return g < cap ? g : cap;
 }
+static inline int scan_grid(long long n) {
+    return ir_min_i(ir_div_up(n > 0 ? n : 1, SCAN_TILE), IR_NUM_SMS * 2);
+}
 
-int irk_hash_build(const int32_t* coords, const int* n_dev, long long n_max, IrTable t,
-                   cudaStream_t st) {
-    k_hash_build<<<grid_for(n_max, 256), 256, 0, st>>>((const int4*)coords, n_dev, t);
+int irk_levels_from_coords(const int32_t* coords0, int n0, const int* n0_dev, IrLevels lt, int* pslot,
+                           long long n_max, int* nlvl, cudaStream_t st) {
+    k_hash_build_levels<<<grid_for(n0, 256), 256, 0, st>>>((const int4*)coords0, n0, n0_dev, lt, pslot, n_max, nlvl);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
 
-int irk_downsample(const int32_t* coords, const int* n_dev, long long n_max, int new_stride,
-                   IrTable t, int* pslot, int32_t* coords_out, int* n_out_dev,
-                   unsigned long long* scan_state, cudaStream_t st) {
-    k_ds_insert<<<grid_for(n_max, 256), 256, 0, st>>>((const int4*)coords, n_dev, new_stride, t, pslot);
-    IR_CHECK_LAUNCH();
-    k_ds_compact<<<ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, SCAN_TILE), IR_NUM_SMS * 4), SCAN_THREADS, 0, st>>>(
-        (const int4*)coords, n_dev, new_stride, t, pslot, (int4*)coords_out, n_out_dev, scan_state);
+int irk_levels_compact(const int32_t* coords0, long long n0_max, int* nlvl, IrLevels lt, const int* pslot,
+                       long long n_max, int32_t* c1, int32_t* c2, int32_t* c3, int32_t* c4,
+                       unsigned long long* scan_state, long long scan_stride, cudaStream_t st) {
+    k_levels_compact<<<dim3(scan_grid(n0_max), 4), SCAN_THREADS, 0, st>>>(
+        (const int4*)coords0, nlvl, lt, pslot, n_max, (int4*)c1, (int4*)c2, (int4*)c3, (int4*)c4, nlvl,
+        scan_state, scan_stride);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
 
 int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdim, double voxel,
-                 IrTable t, int* pslot, int32_t* coords_out, float* feats_out,
-                 int* n_out_dev, unsigned long long* scan_state, cudaStream_t st) {
+                 IrLevels lt, int* vslot, int32_t* coords_out, float* feats_out, int* nlvl,
+                 unsigned long long* scan_state, int* pslot, long long n_max, cudaStream_t st) {
     const long long n_pts = (long long)n_cand * ppi;
-    k_vox_insert<<<grid_for(n_pts, 256), 256, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, t, pslot);
+    k_vox_insert<<<grid_for(n_pts, 256), 256, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, lt.t[0], vslot);
     IR_CHECK_LAUNCH();
-    k_vox_compact<<<ir_min_i(ir_div_up(n_pts > 0 ? n_pts : 1, SCAN_TILE), IR_NUM_SMS * 4), SCAN_THREADS, 0, st>>>(
-        pts, cand, (int)n_pts, ppi, fdim, voxel, t, pslot, (int4*)coords_out, feats_out, n_out_dev, scan_state);
+    k_vox_compact<<<scan_grid(n_pts), SCAN_THREADS, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, lt, vslot,
+                                                            (int4*)coords_out, feats_out, nlvl, scan_state,
+                                                            pslot, n_max);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
 
-int irk_kmap(int ks, const int32_t* coords_out, const int* n_out_dev, long long n_max,
-             IrTable t, int stride, int* in_idx, long long seg_cap, int* slot,
-             int* count, cudaStream_t st) {
-    const int gx = ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, 256), IR_NUM_SMS * 2);
-    if (ks == 3) k_kmap<3><<<dim3(gx, 27), 256, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
-    else if (ks == 2) k_kmap<2><<<dim3(gx, 8), 256, 0, st>>>((const int4*)coords_out, n_out_dev, t, stride, in_idx, seg_cap, slot, count);
-    else { ir_set_error("kmap: unsupported kernel size %d", ks); return IR_ERR_UNSUPPORTED; }
+int irk_kmap_all(const IrKmapArgs& a, long long rows_max, cudaStream_t st) {
+    const int gx = ir_min_i(ir_div_up(rows_max > 0 ? rows_max : 1, 256), IR_NUM_SMS);
+    k_kmap_all<<<dim3(gx, 5 * 27 + 4 * 8), 256, 0, st>>>(a);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

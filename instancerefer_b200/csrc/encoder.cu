@@ -89,7 +89,7 @@ extern "C" int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* L) {
     L->off_keys = take(5 * cap * 8);
     L->off_vals = take(5 * cap * 8);
     for (int l = 0; l < IR_ENC_LEVELS; ++l) L->off_coords[l] = take(n_max * 16);
-    L->off_pslot = take(n_max * 4);
+    L->off_pslot = take(5 * n_max * 4);
     for (int l = 0; l < IR_ENC_LEVELS; ++l) {
         L->off_k3_in[l] = take(27 * n_max * 4);
         L->off_k3_slot[l] = take(27 * n_max * 4);
@@ -122,7 +122,9 @@ struct Ws {
                               base + L.off_vals + (int64_t)l * L.cap * 8, L.cap);
     }
     int32_t* coords(int l) const { return (int32_t*)(base + L.off_coords[l]); }
-    int* pslot() const { return (int*)(base + L.off_pslot); }
+    int* vslot() const { return (int*)(base + L.off_pslot); }                       // voxelize insert slots
+    int* pslot() const { return (int*)(base + L.off_pslot) + L.n_max; }             // ancestor slots [4][n_max]
+    IrLevels levels() const { IrLevels lt; for (int l = 0; l < 5; ++l) lt.t[l] = table(l); return lt; }
     int* k3_in(int l) const { return (int*)(base + L.off_k3_in[l]); }
     int* k3_slot(int l) const { return (int*)(base + L.off_k3_slot[l]); }
     int* k2_in(int l) const { return (int*)(base + L.off_k2_in[l]); }
@@ -146,8 +148,8 @@ extern "C" int ir_encoder_reset(void* ws, int64_t n_max, ir_stream_t stream) {
     if (r != IR_OK) return r;
     cudaStream_t st = (cudaStream_t)stream;
     IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_nlvl, 0, (size_t)w.L.zero_bytes, st));
-    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_keys, 0xFF, (size_t)(5 * w.L.cap * 8), st));
-    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_vals, 0x7F, (size_t)(5 * w.L.cap * 8), st));
+    // keys (EMPTY) and {minrow,row} (NOROW) share the 0x7F byte pattern and are contiguous
+    IR_CHECK_CUDA(cudaMemsetAsync(w.base + w.L.off_keys, 0x7F, (size_t)(w.L.off_vals - w.L.off_keys + 5 * w.L.cap * 8), st));
     return IR_OK;
 }
 
@@ -158,9 +160,9 @@ extern "C" int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand
     int r = ws_open(ws, n_max, &w);
     if (r != IR_OK) return r;
     IR_CHECK_ARG(pts && cand && n_cand > 0 && ppi > 0 && fdim >= 3 && fdim <= 8 && voxel > 0);
-    IR_CHECK_ARG((int64_t)n_cand * ppi <= n_max && n_cand < 65536);
-    return irk_voxelize(pts, cand, n_cand, ppi, fdim, voxel, w.table(0), w.pslot(), w.coords(0),
-                        w.feat0(), w.nlvl() + 0, w.scan(0), (cudaStream_t)stream);
+    IR_CHECK_ARG((int64_t)n_cand * ppi <= n_max && n_cand < IR_MAX_BATCH);
+    return irk_voxelize(pts, cand, n_cand, ppi, fdim, voxel, w.levels(), w.vslot(), w.coords(0),
+                        w.feat0(), w.nlvl() + 0, w.scan(0), w.pslot(), n_max, (cudaStream_t)stream);
 }
 
 extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const int32_t* n0_dev,
@@ -170,31 +172,30 @@ extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const i
     if (r != IR_OK) return r;
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t* c0 = w.coords(0);
+    long long rows0 = n_max;
     if (coords0 != nullptr) {
         IR_CHECK_ARG(n0 >= 0 && n0 <= n_max);
         if ((r = ir_encoder_reset(ws, n_max, stream)) != IR_OK) return r;
-        if ((r = irk_set_int(w.nlvl() + 0, n0, n0_dev, st)) != IR_OK) return r;
-        if ((r = irk_hash_build(coords0, w.nlvl() + 0, n0, w.table(0), st)) != IR_OK) return r;
+        if ((r = irk_levels_from_coords(coords0, n0, n0_dev, w.levels(), w.pslot(), n_max, w.nlvl(), st)) != IR_OK) return r;
         c0 = coords0;
+        rows0 = n0;
     }
-    // levels 1..4 (stride 2,4,8,16)
-    const int32_t* cprev = c0;
-    for (int l = 0; l < 4; ++l) {
-        if ((r = irk_downsample(cprev, w.nlvl() + l, n_max, 2 << l, w.table(l + 1), w.pslot(),
-                                w.coords(l + 1), w.nlvl() + l + 1, w.scan(l + 1), st)) != IR_OK) return r;
-        cprev = w.coords(l + 1);
-    }
-    // kernel maps: k3 at every level, k2s2 between levels
+    // levels 1..4 (stride 2,4,8,16): one ordered compaction per level, all from the level-0 rows
+    if ((r = irk_levels_compact(c0, rows0, w.nlvl(), w.levels(), w.pslot(), n_max, w.coords(1), w.coords(2),
+                                w.coords(3), w.coords(4), w.scan(0), w.L.scan_stride, st)) != IR_OK) return r;
+    // kernel maps: k3 at every level, k2s2 between levels — one launch
+    IrKmapArgs ka;
+    ka.nlvl = w.nlvl();
+    ka.lt = w.levels();
+    ka.kcount = w.kcount(0);
+    ka.n_max = n_max;
     for (int l = 0; l < IR_ENC_LEVELS; ++l) {
-        const int32_t* cl = (l == 0) ? c0 : w.coords(l);
-        if ((r = irk_kmap(3, cl, w.nlvl() + l, n_max, w.table(l), 1 << l, w.k3_in(l), n_max,
-                          w.k3_slot(l), w.kcount(l), st)) != IR_OK) return r;
+        ka.coords[l] = (const int4*)((l == 0) ? c0 : w.coords(l));
+        ka.k3_in[l] = w.k3_in(l);
+        ka.k3_slot[l] = w.k3_slot(l);
     }
-    for (int l = 0; l < 4; ++l) {
-        if ((r = irk_kmap(2, w.coords(l + 1), w.nlvl() + l + 1, n_max, w.table(l), 1 << l, w.k2_in(l),
-                          n_max, w.k2_slot(l), w.kcount(5 + l), st)) != IR_OK) return r;
-    }
-    return IR_OK;
+    for (int l = 0; l < 4; ++l) { ka.k2_in[l] = w.k2_in(l); ka.k2_slot[l] = w.k2_slot(l); }
+    return irk_kmap_all(ka, rows0, st);
 }
 
 static int conv_layer(const float* fin, int cin, int cout, int K, const int* in_idx,

@@ -25,24 +25,27 @@ k_pairgemm_simt(const float* __restrict__ F, int cin, int K, const int* __restri
     __shared__ __align__(16) float As[PG_TP][PG_MAXC];
     __shared__ int s_kofs[33], s_tofs[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        int a = 0, t = 0;
-        for (int k = 0; k < K; ++k) {
-            s_kofs[k] = a; s_tofs[k] = t;
-            const int c = count[k];
-            a += c; t += (c + PG_TP - 1) / PG_TP;
+    if (warp == 0) {                     // pair / tile prefixes, one lane per kernel offset
+        const int c = (lane < K) ? count[lane] : 0;
+        const int t = (c + PG_TP - 1) / PG_TP;
+        int cinc = c, tinc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int c2 = __shfl_up_sync(0xffffffffu, cinc, o), t2 = __shfl_up_sync(0xffffffffu, tinc, o);
+            if (lane >= o) { cinc += c2; tinc += t2; }
         }
-        s_kofs[K] = a; s_tofs[K] = t;
+        s_kofs[lane] = cinc - c; s_tofs[lane] = tinc - t;
+        if (lane == 31) { s_kofs[32] = cinc; s_tofs[32] = tinc; }
     }
     __syncthreads();
-    const int ntiles = s_tofs[K];
+    const int ntiles = s_tofs[32];
     const int cp = (cin + 3) & ~3;
     const int co = tid % COUT, g = tid / COUT;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int k = 0;
-        while (tile >= s_tofs[k + 1]) ++k;
+        while (k + 1 < K && tile >= s_tofs[k + 1]) ++k;
         const int p0 = (tile - s_tofs[k]) * PG_TP;
-        const int np = min(PG_TP, (s_kofs[k + 1] - s_kofs[k]) - p0);
+        const int np = min(PG_TP, ((k + 1 < 32 ? s_kofs[k + 1] : s_kofs[32]) - s_kofs[k]) - p0);
         for (int r = warp; r < PG_TP; r += PG_THREADS / 32) {
             const int j = (r < np) ? in_idx[(long long)k * seg_cap + p0 + r] : -1;
             for (int c = lane; c < cp; c += 32)
