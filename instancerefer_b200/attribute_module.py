@@ -63,13 +63,21 @@ class AttributeModule(nn.Module, PrepCache):
         data_dict['pred_obb_batch'] = pack.pred_obb_batch
         return data_dict
 
+    def embed_language(self, data_dict):
+        """Language side only (needs nothing from the encoder): Linear-BN-ReLU-Linear + L2 norm."""
+        p = self.prepared()
+        lang_emb, _ = ops.mlp_head(data_dict['lang_attr_feats'].float().contiguous(), p['lw1'], p['lb1'],
+                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_L2)
+        return lang_emb
+
     def match(self, data_dict):
         """Phase B: language side Linear-BN-ReLU-Linear + L2 normalise (:88-90); visual side
         Linear-LN-ReLU-Linear + L2 normalise, dot with the scene's language vector (:108-126)."""
         p = self.prepared()
         pack = data_dict[_KEY]
-        lang_emb, _ = ops.mlp_head(data_dict['lang_attr_feats'].float().contiguous(), p['lw1'], p['lb1'],
-                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_L2)
+        lang_emb = data_dict.pop('_ir_attr_lang', None)
+        if lang_emb is None:
+            lang_emb = self.embed_language(data_dict)
         _, scores = ops.mlp_head(data_dict['obj_feats'], p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'],
                                  p['vw2'], p['vb2'], ops.MODE_DOT, partner=lang_emb, seg=pack.cand_scene)
         data_dict['attribute_scores'] = scores

@@ -82,32 +82,28 @@ __device__ __forceinline__ int4 parent_coord(int4 c, int new_stride) {
     return make_int4(c.x & m, c.y & m, c.z & m, c.w);
 }
 
-// every ancestor voxel (stride 2,4,8,16) of level-0 row i remembers the smallest level-0 row below it:
-// row order of level l = order of that minimum = the first-occurrence order torchsparse-style
-// repeated downsampling produces (first occurrence is transitive).
-__device__ __forceinline__ void insert_ancestors(const LevelTables& lt, int4 c, int i, int* __restrict__ pslot,
-                                                 long long n_max) {
-#pragma unroll
-    for (int l = 1; l < 5; ++l) {
-        const int4 p = parent_coord(c, 1 << l);
-        const int s = ir_ht_insert(lt.t[l], ir_pack_key(p.x, p.y, p.z, p.w));
-        atomicMin(&lt.t[l].minrow[s], i);
-        pslot[(long long)(l - 1) * n_max + i] = s;
-    }
-}
-
-// level 0 from given coords: hash every row, register its ancestors; also publishes the row count
-__global__ void k_hash_build_levels(const int4* __restrict__ coords, int n_host, const int* __restrict__ n_dev,
-                                    LevelTables lt, int* __restrict__ pslot, long long n_max,
-                                    int* __restrict__ nlvl0) {
+// Level registration, one thread per (row, level): level 0 hashes the row itself; level l >= 1 makes
+// the ancestor voxel (stride 2^l) of level-0 row i remember the smallest level-0 row below it.  Row
+// order of level l = order of that minimum = the first-occurrence order that repeated torchsparse-
+// style downsampling produces (first occurrence is transitive).  grid.y = level - first_level.
+__global__ void k_insert_levels(const int4* __restrict__ coords, int n_host, const int* __restrict__ n_dev,
+                                IrLevels lt, int* __restrict__ pslot, long long n_max, int first_level,
+                                int* __restrict__ nlvl0) {
     const int n = n_dev ? *n_dev : n_host;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *nlvl0 = n;
+    const int l = blockIdx.y + first_level;
+    if (nlvl0 != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *nlvl0 = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 c = coords[i];
-        const int s = ir_ht_insert(lt.t[0], ir_pack_key(c.x, c.y, c.z, c.w));
-        atomicMin(&lt.t[0].minrow[s], i);
-        atomicMin(&lt.t[0].row[s], i);
-        insert_ancestors(lt, c, i, pslot, n_max);
+        if (l == 0) {
+            const int s = ir_ht_insert(lt.t[0], ir_pack_key(c.x, c.y, c.z, c.w));
+            atomicMin(&lt.t[0].minrow[s], i);
+            atomicMin(&lt.t[0].row[s], i);
+        } else {
+            const int4 p = parent_coord(c, 1 << l);
+            const int s = ir_ht_insert(lt.t[l], ir_pack_key(p.x, p.y, p.z, p.w));
+            atomicMin(&lt.t[l].minrow[s], i);
+            pslot[(long long)(l - 1) * n_max + i] = s;
+        }
     }
 }
 
@@ -146,14 +142,13 @@ __global__ void k_vox_insert(const float* __restrict__ pts, const int* __restric
     }
 }
 
-// first-point-wins compaction -> level-0 rows (coords + the winning point's feature row); each new row
-// registers its ancestors for the level compaction that follows.  vslot: the insert slots above.
+// first-point-wins compaction -> level-0 rows (coords + the winning point's feature row).
+// vslot: the insert slots above.
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n_pts, int ppi,
-              int fdim, double voxel, LevelTables lt, const int* __restrict__ vslot,
+              int fdim, double voxel, IrTable t, const int* __restrict__ vslot,
               int4* __restrict__ coords_out, float* __restrict__ feats_out, int* __restrict__ n_out,
-              unsigned long long* state, int* __restrict__ pslot, long long n_max) {
-    const IrTable t = lt.t[0];
+              unsigned long long* state) {
     compact_ordered(
         n_pts, state, n_out,
         [&](int p) { return t.minrow[vslot[p]] == p; },
@@ -165,7 +160,6 @@ k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n
             coords_out[r] = c;
             for (int q = 0; q < fdim; ++q) feats_out[(long long)r * fdim + q] = src[q];
             t.row[vslot[p]] = r;
-            insert_ancestors(lt, c, r, pslot, n_max);
         });
 }
 
@@ -235,7 +229,7 @@ static inline int scan_grid(long long n) {
 
 int irk_levels_from_coords(const int32_t* coords0, int n0, const int* n0_dev, IrLevels lt, int* pslot,
                            long long n_max, int* nlvl, cudaStream_t st) {
-    k_hash_build_levels<<<grid_for(n0, 256), 256, 0, st>>>((const int4*)coords0, n0, n0_dev, lt, pslot, n_max, nlvl);
+    k_insert_levels<<<dim3(grid_for(n0, 256), 5), 256, 0, st>>>((const int4*)coords0, n0, n0_dev, lt, pslot, n_max, 0, nlvl);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
@@ -256,9 +250,11 @@ int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdi
     const long long n_pts = (long long)n_cand * ppi;
     k_vox_insert<<<grid_for(n_pts, 256), 256, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, lt.t[0], vslot);
     IR_CHECK_LAUNCH();
-    k_vox_compact<<<scan_grid(n_pts), SCAN_THREADS, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, lt, vslot,
-                                                            (int4*)coords_out, feats_out, nlvl, scan_state,
-                                                            pslot, n_max);
+    k_vox_compact<<<scan_grid(n_pts), SCAN_THREADS, 0, st>>>(pts, cand, (int)n_pts, ppi, fdim, voxel, lt.t[0], vslot,
+                                                            (int4*)coords_out, feats_out, nlvl, scan_state);
+    IR_CHECK_LAUNCH();
+    // ancestors of the new level-0 rows (levels 1..4), one thread per (row, level)
+    k_insert_levels<<<dim3(grid_for(n_pts, 256), 4), 256, 0, st>>>((const int4*)coords_out, 0, nlvl, lt, pslot, n_max, 1, nullptr);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -128,20 +128,31 @@ k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ sl
         float acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const int pos = __shfl_sync(0xffffffffu, my, k);
-            if (pos >= 0) {
-                const float* row = T + (long long)(s_kofs[k] + pos) * COUT + lane * V;
+        // batches of up to 9 independent row loads (missing pairs contribute +0), then a fixed-order
+        // accumulation over k ascending: deterministic and latency-tolerant
+        constexpr int U = 9;
+        for (int k0 = 0; k0 < K; k0 += U) {
+            float t[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + u;
+                const int pos = __shfl_sync(0xffffffffu, my, k & 31);
+                const bool ok = (k < K) && (pos >= 0);
+                const float* row = T + (long long)(s_kofs[k & 31] + (ok ? pos : 0)) * COUT + lane * V;
                 if (V == 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(row);
-                    acc[0] += t.x; acc[1 % V] += t.y; acc[2 % V] += t.z; acc[3 % V] += t.w;
+                    const float4 q = ok ? *reinterpret_cast<const float4*>(row) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    t[u][0] = q.x; t[u][1 % V] = q.y; t[u][2 % V] = q.z; t[u][3 % V] = q.w;
                 } else if (V == 2) {
-                    const float2 t = *reinterpret_cast<const float2*>(row);
-                    acc[0] += t.x; acc[1 % V] += t.y;
+                    const float2 q = ok ? *reinterpret_cast<const float2*>(row) : make_float2(0.f, 0.f);
+                    t[u][0] = q.x; t[u][1 % V] = q.y;
                 } else {
-                    acc[0] += row[0];
+                    t[u][0] = ok ? row[0] : 0.f;
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] += t[u][v];
         }
         float* orow = out + o * COUT + lane * V;
         const float* rrow = resid ? resid + o * COUT + lane * V : nullptr;

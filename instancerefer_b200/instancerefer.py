@@ -78,6 +78,10 @@ class InstanceRefer(nn.Module):
                 with torch.cuda.stream(sr):
                     self.relation.encode_graph(data_dict, dev)
                 data_dict = self.lang(data_dict)
+                # language-side embeddings need nothing from the encoders: run them before the join
+                data_dict['_ir_attr_lang'] = self.attribute.embed_language(data_dict)
+                data_dict['_ir_rel_lang'] = self.relation.embed_language(data_dict)
+                data_dict['_ir_scene_lang'] = self.scene.embed_language(data_dict)
                 for s_ in (sa, ss, sr):
                     main.wait_stream(s_)
                 self.attribute.match(data_dict)

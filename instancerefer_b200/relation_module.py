@@ -59,12 +59,19 @@ class RelationModule(nn.Module, PrepCache):
         data_dict['_ir_gcn'], data_dict['_ir_knn'] = g, nbr
         return data_dict
 
+    def embed_language(self, data_dict):
+        p = self.prepared()
+        lang_emb, _ = ops.mlp_head(data_dict['lang_rel_feats'].float().contiguous(), p['lw1'], p['lb1'],
+                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        return lang_emb
+
     def match(self, data_dict):
         """Phase B: language MLP (:82), visual MLP, cosine (:101-103)."""
         p = self.prepared()
         pack = data_dict[_KEY]
-        lang_emb, _ = ops.mlp_head(data_dict['lang_rel_feats'].float().contiguous(), p['lw1'], p['lb1'],
-                                   ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        lang_emb = data_dict.pop('_ir_rel_lang', None)
+        if lang_emb is None:
+            lang_emb = self.embed_language(data_dict)
         _, scores = ops.mlp_head(data_dict['_ir_gcn'], p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'],
                                  p['vw2'], p['vb2'], ops.MODE_COS, partner=lang_emb, seg=pack.cand_scene)
         data_dict['relation_scores'] = scores

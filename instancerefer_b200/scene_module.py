@@ -75,14 +75,21 @@ class SceneModule(nn.Module, PrepCache):
         data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
         return data_dict
 
+    def embed_language(self, data_dict):
+        p = self.prepared()
+        q, _ = ops.mlp_head(data_dict['lang_scene_feats'].float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER,
+                            p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        return q
+
     def match(self, data_dict):
         """Phase B: language-guided attention over the 11x21 cells (:73-83), region classifier (:84),
         cosine(vis_emb_fc1(obj_feats), scene_feat) (:89-104)."""
         p = self.prepared()
         x = data_dict['_ir_bev_feats']
         B, h, w = x.shape[0], x.shape[1], x.shape[2]
-        q, _ = ops.mlp_head(data_dict['lang_scene_feats'].float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER,
-                            p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_RAW)
+        q = data_dict.pop('_ir_scene_lang', None)
+        if q is None:
+            q = self.embed_language(data_dict)
         atten, scene_feats = ops.scene_attention(x.view(B, h * w, -1), q)
         data_dict['vis_atten'] = atten.view(B, h, w)
         seg, _ = ops.mlp_head(scene_feats, p['kw1'], p['kb1'], ops.NORM_AFFINE, p['kg'], p['kbeta'],
