@@ -327,7 +327,7 @@ def main():
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
         if tc_ms > 0:
             ach = tc_by / (tc_ms * 1e-3) / 1e9
-            roofline = dict(bound='hbm', kernel='k_pairgemm_tc (tcgen05 3xTF32 pair-GEMM, 24 launches/step)',
+            roofline = dict(bound='hbm', kernel='k_pairgemm_tc (tcgen05 split-fp16 pair-GEMM, 24 launches/step)',
                             achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic,
                             peak_source=peak_src, bytes_per_launch=tc_by / tc_n, us_per_launch=tc_ms * 1e3 / tc_n,
                             share_of_step=tc_ms / nprof / (dev_ms / a.steps),
@@ -348,7 +348,7 @@ def main():
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=a.steps, warmup=warmup,
                     ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f32 (3xTF32 tcgen05 rule GEMM, fp32 accumulate)', data='synthetic',
+                    dtype='f32 (rule GEMM on tcgen05 as split-fp16 hi/lo, fp32 accumulate)', data='synthetic',
                     config=dict(workload=WORKLOAD_NAME, referrals_per_step_per_gpu=1,
                                 l2='flushed between steps (256 MiB write outside the timed spans)',
                                 parallelism=f'scenes sharded over {world} GPU(s), no data-path collective',

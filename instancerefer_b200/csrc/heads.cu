@@ -1,66 +1,88 @@
 // Matching heads: fused Linear -> {BN-affine | LayerNorm} -> ReLU -> Linear -> {L2-normalise, dot,
-// cosine} with warp-shuffle reductions, plus the per-scene softmax/argmax over candidates.
+// cosine}.  A thread-block CLUSTER of 8 CTAs serves 8 rows: each CTA computes 1/8 of a layer's output
+// columns and broadcasts them through distributed shared memory; warp-shuffle reductions for the
+// norms / dots; plus the per-scene softmax/argmax over candidates.
 // Reference: models/attribute_module.py:88-90,108-126; models/relation_module.py:82,101-103;
 // models/scene_module.py:44-57,84-104; lib/eval_helper.py:61-67 (host argmax of summed scores).
 #include "../../include/instancerefer_b200.h"
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
-#define MH_TM 8
+#define MH_TM 8          // rows per cluster
 #define MH_MAXD 256
-#define MH_THREADS 1024
-#define MH_SLICES (MH_THREADS / MH_MAXD)
-#define MH_SMEM_BYTES ((2 * MH_TM * MH_MAXD + MH_SLICES * MH_TM * MH_MAXD) * 4)
+#define MH_CL 8          // CTAs per cluster: each owns 1/8 of a layer's output columns
+#define MH_THREADS 256
+#define MH_MAXSL 32      // max K slices per CTA
 
-// dst[r][n] = b[n] + sum_k WT[k][n] * src[r][k] for the 8 rows of the tile.  Thread = (k-slice,
-// column): coalesced weight reads (WT is (in,out)), activations broadcast from shared memory,
-// 4-way split-K combined through shared memory in a fixed order (deterministic).
-__device__ __forceinline__ void tile_linear_t(const float (*src)[MH_MAXD], int K, const float* __restrict__ WT,
-                                              const float* __restrict__ b, int N, float (*dst)[MH_MAXD],
-                                              float (*part)[MH_TM][MH_MAXD]) {
-    const int col = threadIdx.x & (MH_MAXD - 1), slice = threadIdx.x / MH_MAXD;
-    const int kper = (K + MH_SLICES - 1) / MH_SLICES;
-    const int k0 = slice * kper, k1 = min(K, k0 + kper);
-    float acc[MH_TM];
+namespace cg = cooperative_groups;
+
+// One layer for the 8 rows of the tile, columns split over the 8 CTAs of the cluster:
+// dst[r][n] = b[n] + sum_k WT[k][n] * src[r][k].  Inside a CTA: thread = (K slice, local column),
+// coalesced weight reads (WT is (in,out)), activations broadcast from shared memory, slices combined
+// in a fixed order; the finished column block is written into the `dst` buffer of EVERY CTA of the
+// cluster through distributed shared memory, so after cluster.sync() each CTA holds the full rows.
+__device__ __forceinline__ void cluster_linear(cg::cluster_group& cluster, int rank,
+                                               const float (*src)[MH_MAXD], int K,
+                                               const float* __restrict__ WT, const float* __restrict__ b, int N,
+                                               float (*dst)[MH_MAXD], float (*part)[MH_TM][32]) {
+    const bool split = N >= 64;                       // tiny layers (e.g. 9 logits) stay on rank 0
+    const int nc = split ? N / MH_CL : N;             // columns owned by this CTA (<= 32)
+    const int c0 = split ? rank * nc : 0;
+    const bool active = split || rank == 0;
+    const int nsl = min(MH_THREADS / nc, MH_MAXSL);
+    const int col = threadIdx.x % nc, slice = threadIdx.x / nc;
+    if (active && slice < nsl) {
+        const int kper = (K + nsl - 1) / nsl;
+        const int k0 = slice * kper, k1 = min(K, k0 + kper);
+        float acc[MH_TM];
 #pragma unroll
-    for (int r = 0; r < MH_TM; ++r) acc[r] = 0.f;
-    if (col < N) {
+        for (int r = 0; r < MH_TM; ++r) acc[r] = 0.f;
+        const float* w = WT + c0 + col;
 #pragma unroll 8
         for (int k = k0; k < k1; ++k) {
-            const float wv = __ldg(WT + (long long)k * N + col);
+            const float wv = __ldg(w + (long long)k * N);
 #pragma unroll
             for (int r = 0; r < MH_TM; ++r) acc[r] = fmaf(wv, src[r][k], acc[r]);
         }
-    }
 #pragma unroll
-    for (int r = 0; r < MH_TM; ++r) part[slice][r][col] = acc[r];
-    __syncthreads();
-    for (int i = threadIdx.x; i < MH_TM * N; i += MH_THREADS) {
-        const int r = i / N, n = i - r * N;
-        dst[r][n] = ((part[0][r][n] + part[1][r][n]) + (part[2][r][n] + part[3][r][n])) + (b ? b[n] : 0.f);
+        for (int r = 0; r < MH_TM; ++r) part[slice][r][col] = acc[r];
     }
     __syncthreads();
+    if (active) {
+        for (int i = threadIdx.x; i < MH_TM * nc; i += MH_THREADS) {
+            const int r = i / nc, c = i - r * nc;
+            float v = b ? b[c0 + c] : 0.f;
+            for (int sl = 0; sl < nsl; ++sl) v += part[sl][r][c];
+            float* cell = &dst[r][c0 + c];
+#pragma unroll
+            for (int q = 0; q < MH_CL; ++q) *cluster.map_shared_rank(cell, q) = v;
+        }
+    }
+    cluster.sync();
 }
 
-__global__ void __launch_bounds__(MH_THREADS)
+__global__ void __cluster_dims__(MH_CL, 1, 1) __launch_bounds__(MH_THREADS)
 k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ W1T,
            const float* __restrict__ b1, int N1, int norm, const float* __restrict__ g,
            const float* __restrict__ beta, const float* __restrict__ W2T, const float* __restrict__ b2,
            int N2, int mode, const float* __restrict__ partner, const int* __restrict__ seg,
            float* __restrict__ y, float* __restrict__ score) {
-    extern __shared__ float mh_smem[];
-    float (*xs)[MH_MAXD] = reinterpret_cast<float (*)[MH_MAXD]>(mh_smem);
-    float (*hs)[MH_MAXD] = reinterpret_cast<float (*)[MH_MAXD]>(mh_smem + MH_TM * MH_MAXD);
-    float (*part)[MH_TM][MH_MAXD] = reinterpret_cast<float (*)[MH_TM][MH_MAXD]>(mh_smem + 2 * MH_TM * MH_MAXD);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ float xs[MH_TM][MH_MAXD];
+    __shared__ float hs[MH_TM][MH_MAXD];
+    __shared__ float part[MH_MAXSL][MH_TM][32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int r0 = blockIdx.x * MH_TM;
+    const int r0 = (blockIdx.x / MH_CL) * MH_TM;
     const int rows = min(MH_TM, M - r0);
     for (int i = tid; i < MH_TM * K; i += MH_THREADS) {
         const int r = i / K, k = i - r * K;
         xs[r][k] = (r < rows) ? x[(long long)(r0 + r) * K + k] : 0.f;
     }
     __syncthreads();
-    tile_linear_t(xs, K, W1T, b1, N1, hs, part);
-    if (w < MH_TM) {   // normalisation + ReLU: warp w owns row w
+    cluster_linear(cluster, rank, xs, K, W1T, b1, N1, hs, part);
+    {   // normalisation + ReLU on the full rows (every CTA, redundantly): warp w owns row w
         const int r = w;
         if (norm == 2) {
             float s = 0.f;
@@ -78,7 +100,8 @@ k_mlp_head(const float* __restrict__ x, int M, int K, const float* __restrict__ 
         }
     }
     __syncthreads();
-    tile_linear_t(hs, N1, W2T, b2, N2, xs, part);      // xs now holds y
+    cluster_linear(cluster, rank, hs, N1, W2T, b2, N2, xs, part);      // xs now holds y (all CTAs)
+    if (rank != 0) return;
     const int r = w;
     if (r >= rows) return;
     const long long row = r0 + r;
@@ -117,15 +140,11 @@ extern "C" int ir_mlp_head(const float* x, int32_t M, int32_t K, const float* W1
                            const float* partner, const int32_t* seg, float* y, float* score,
                            ir_stream_t stream) {
     IR_CHECK_ARG(x && W1T && W2T && M > 0 && K > 0 && K <= MH_MAXD && N1 > 0 && N1 <= MH_MAXD && N2 > 0 && N2 <= MH_MAXD);
+    IR_CHECK_ARG((N1 < 64 ? N1 <= 32 : N1 % MH_CL == 0) && (N2 < 64 ? N2 <= 32 : N2 % MH_CL == 0));
     IR_CHECK_ARG(norm >= 0 && norm <= 2 && mode >= 0 && mode <= 3);
     IR_CHECK_ARG(norm == 0 || (g && beta));
     IR_CHECK_ARG(mode >= 2 ? (partner && seg && score) : (y != nullptr));
-    static bool attr_done = false;
-    if (!attr_done) {
-        IR_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_head, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_SMEM_BYTES));
-        attr_done = true;
-    }
-    k_mlp_head<<<ir_div_up(M, MH_TM), MH_THREADS, MH_SMEM_BYTES, (cudaStream_t)stream>>>(
+    k_mlp_head<<<ir_div_up(M, MH_TM) * MH_CL, MH_THREADS, 0, (cudaStream_t)stream>>>(
         x, M, K, W1T, b1, N1, norm, g, beta, W2T, b2, N2, mode, partner, seg, y, score);
     IR_CHECK_LAUNCH();
     return IR_OK;

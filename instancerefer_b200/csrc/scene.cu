@@ -91,13 +91,18 @@ extern "C" int ir_bev(const float* feats, const int32_t* coords, const int32_t* 
 }
 
 // ------------------------------------------------------------------ conv2d 3x3 (valid), NHWC, C=128
+// CTA = 4 output pixels x 128 output channels x 8 K-slices (1024 threads): every thread walks 144 of
+// the 1152 (ky,kx,cin) taps with 8 independent coalesced weight loads in flight; slices are combined
+// through shared memory in a fixed order (deterministic).
 #define C2_TPX 4
-#define C2_KS 4   // cin slices
+#define C2_KS 8   // K slices
 __global__ void __launch_bounds__(BEV_C * C2_KS)
 k_conv2d_3x3(const float* __restrict__ in, int H, int W, const float* __restrict__ wpack,
              const float* __restrict__ bias, const float* __restrict__ scale,
              const float* __restrict__ shift, int relu, float* __restrict__ out) {
     constexpr int C = BEV_C;
+    constexpr int TAPS = 9 * C;                 // 1152 taps, tap t = (ky*3+kx)*C + cin
+    constexpr int PER = TAPS / C2_KS;           // 144 taps per slice
     __shared__ float patch[3][C2_TPX + 2][C];
     __shared__ float red[C2_KS][C2_TPX][C];
     const int Ho = H - 2, Wo = W - 2;
@@ -112,30 +117,30 @@ k_conv2d_3x3(const float* __restrict__ in, int H, int W, const float* __restrict
     float acc[C2_TPX];
 #pragma unroll
     for (int p = 0; p < C2_TPX; ++p) acc[p] = 0.f;
-    const int c_lo = ks * (C / C2_KS), c_hi = c_lo + C / C2_KS;
-    for (int kk = 0; kk < 9; ++kk) {
-        const int ky = kk / 3, kx = kk % 3;
-        const float* wk = wpack + ((long long)kk * C + c_lo) * C + co;
-#pragma unroll 4
-        for (int ci = c_lo; ci < c_hi; ++ci) {
-            const float wv = wk[(long long)(ci - c_lo) * C];
+    const int t0 = ks * PER;
+    const float* wk = wpack + (long long)t0 * C + co;
+#pragma unroll 8
+    for (int i = 0; i < PER; ++i) {
+        const int t = t0 + i;
+        const int kk = t / C, ci = t - kk * C;
+        const int ky = kk / 3, kx = kk - ky * 3;
+        const float wv = __ldg(wk + (long long)i * C);
 #pragma unroll
-            for (int p = 0; p < C2_TPX; ++p) acc[p] = fmaf(wv, patch[ky][p + kx][ci], acc[p]);
-        }
+        for (int p = 0; p < C2_TPX; ++p) acc[p] = fmaf(wv, patch[ky][p + kx][ci], acc[p]);
     }
 #pragma unroll
     for (int p = 0; p < C2_TPX; ++p) red[ks][p][co] = acc[p];
     __syncthreads();
-    if (ks == 0) {
+    if (ks < C2_TPX) {                          // slice index reused as the pixel this thread finalises
+        const int p = ks;
+        if (x0 + p < Wo) {
+            float v = 0.f;
 #pragma unroll
-        for (int p = 0; p < C2_TPX; ++p) {
-            if (x0 + p < Wo) {
-                float v = ((red[0][p][co] + red[1][p][co]) + red[2][p][co]) + red[3][p][co];
-                v += bias ? bias[co] : 0.f;
-                if (scale) v = fmaf(v, scale[co], shift[co]);
-                if (relu) v = fmaxf(v, 0.f);
-                out[(((long long)b * Ho + y) * Wo + (x0 + p)) * C + co] = v;
-            }
+            for (int q = 0; q < C2_KS; ++q) v += red[q][p][co];
+            v += bias ? bias[co] : 0.f;
+            if (scale) v = fmaf(v, scale[co], shift[co]);
+            if (relu) v = fmaxf(v, 0.f);
+            out[(((long long)b * Ho + y) * Wo + (x0 + p)) * C + co] = v;
         }
     }
 }

@@ -111,6 +111,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -216,7 +230,7 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
         for (int s = 0; s < NS; ++s) { mbar_init(bar_full(s), WARPS_PER_GROUP); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 4); }
         mbar_init(bar_wfull, 1);
-        mbar_init(bar_wdone, 4);           // weights resident in TMEM (one arrival per epilogue warp)
+        mbar_init(bar_wdone, 16);          // weights resident in TMEM (one arrival per staging warp)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -233,6 +247,35 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
     const int kk = s_sched[0];
     const int t_begin = s_sched[1], t_end = (kk >= 0) ? s_sched[2] : 0;
     const int kofs = s_sched[3], kcount = s_sched[4];
+
+    // W[k] (Cin,Cout) fp32 is staged in shared memory by one TMA bulk-copy chain (issued by thread 0);
+    // 16 warps (4 per TMEM sub-partition) then scale it by 2^8, split it into fp16 hi/lo and park it in
+    // TMEM as packed pairs, where it stays for the whole kernel: the MMA reads its weight operand from
+    // TMEM, not from shared memory.  A warp's TMEM lanes are fixed by warp%4 (lanes = output channels);
+    // `quarter` selects its share of the packed K columns.
+    auto weights_to_tmem = [&](int quarter) {
+        constexpr int NCOL = C::CINP / 2 / 4;                      // packed columns per warp (8 or 16)
+        mbar_wait(bar_wfull, 0u);
+        const int sp = warp & 3;
+        if (sp * 32 < COUT) {
+            const float* ws = reinterpret_cast<const float*>(sm + C::OFF_STAGE) + sp * 32 + lane;
+            const uint32_t tw = tmem_base + ((uint32_t)(sp * 32) << 16) + quarter * NCOL;
+            uint32_t hi[NCOL], lo[NCOL];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) {
+                const int c = 2 * (quarter * NCOL + q);
+                const float w0 = (c < CIN) ? ws[c * COUT] * W_SCALE : 0.f;
+                const float w1 = (c + 1 < CIN) ? ws[(c + 1) * COUT] * W_SCALE : 0.f;
+                split2(w0, w1, hi[q], lo[q]);
+            }
+            if constexpr (NCOL == 16) { tmem_st16(tw + C::COL_W_HI, hi); tmem_st16(tw + C::COL_W_LO, lo); }
+            else                      { tmem_st8(tw + C::COL_W_HI, hi);  tmem_st8(tw + C::COL_W_LO, lo); }
+            tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_wdone);
+    };
 
     if (warp >= 5) {
         // ===================== gather producers: NS independent groups of 128 threads ==========
@@ -270,8 +313,9 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
                 }
             }
         };
+        if (grp < n_items) load_idx(grp);
+        if (t_end > t_begin) weights_to_tmem(1 + pw / 4);       // this warp's share of the weight columns
         if (grp < n_items) {
-            load_idx(grp);
             load_rows(grp);
             load_idx(grp + NS);
         }
@@ -342,38 +386,13 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
     } else {
         // ===================== epilogue (warps 0-3: TMEM lanes 32*warp ..) =====================
         if (t_end > t_begin) {
-            // W[k] (Cin,Cout) fp32 -> shared memory by one TMA bulk copy chain, then each thread
-            // (= output channel) scales its column by 2^8, splits it into fp16 hi/lo and parks it in
-            // TMEM as packed pairs, where it stays for the whole kernel: the MMA reads the weight
-            // operand from TMEM, not from shared memory.
             if (tid == 0) {
                 mbar_expect_tx(bar_wfull, (uint32_t)C::W_RAW_BYTES);
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(weight) + (size_t)kk * C::W_RAW_BYTES;
                 for (int o = 0; o < C::W_RAW_BYTES; o += 16384)
                     bulk_g2s(s_stage + o, src + o, (uint32_t)min(16384, C::W_RAW_BYTES - o), bar_wfull);
             }
-            mbar_wait(bar_wfull, 0u);
-            if (warp * 32 < COUT) {
-                const float* ws = reinterpret_cast<const float*>(sm + C::OFF_STAGE) + warp * 32 + lane;
-                const uint32_t tw = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-                for (int c0 = 0; c0 < C::CINP; c0 += 64) {       // 64 channels -> 32 packed columns
-                    uint32_t hi[32], lo[32];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int c = c0 + 2 * q;
-                        const float w0 = (c < CIN) ? ws[c * COUT] * W_SCALE : 0.f;
-                        const float w1 = (c + 1 < CIN) ? ws[(c + 1) * COUT] * W_SCALE : 0.f;
-                        split2(w0, w1, hi[q], lo[q]);
-                    }
-                    tmem_st32(tw + C::COL_W_HI + c0 / 2, hi);
-                    tmem_st32(tw + C::COL_W_LO + c0 / 2, lo);
-                }
-                tmem_wait_st();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_wdone);
+            weights_to_tmem(0);
         }
         uint32_t acc_it = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {

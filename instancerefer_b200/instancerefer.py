@@ -71,22 +71,34 @@ class InstanceRefer(nn.Module):
                     data_dict[_PACK_KEY] = pack
                 for s_ in (sa, ss, sr):
                     s_.wait_stream(main)
+                ev_obj = torch.cuda.Event()
                 with torch.cuda.stream(sa):
                     self.attribute.encode_candidates(data_dict, dev, pack)
+                    ev_obj.record(sa)                                  # obj_feats ready (scene head needs it)
                 with torch.cuda.stream(ss):
                     self.scene.encode_scene(data_dict, dev)
                 with torch.cuda.stream(sr):
                     self.relation.encode_graph(data_dict, dev)
                 data_dict = self.lang(data_dict)
-                # language-side embeddings need nothing from the encoders: run them before the join
+                # language-side embeddings need nothing from the encoders
                 data_dict['_ir_attr_lang'] = self.attribute.embed_language(data_dict)
                 data_dict['_ir_rel_lang'] = self.relation.embed_language(data_dict)
                 data_dict['_ir_scene_lang'] = self.scene.embed_language(data_dict)
+                ev_lang = torch.cuda.Event()
+                ev_lang.record(main)
+                # each branch finishes with its own matching head on its own stream
+                with torch.cuda.stream(sa):
+                    sa.wait_event(ev_lang)
+                    self.attribute.match(data_dict)
+                with torch.cuda.stream(sr):
+                    sr.wait_event(ev_lang)
+                    self.relation.match(data_dict)
+                with torch.cuda.stream(ss):
+                    ss.wait_event(ev_lang)
+                    ss.wait_event(ev_obj)
+                    self.scene.match(data_dict)
                 for s_ in (sa, ss, sr):
                     main.wait_stream(s_)
-                self.attribute.match(data_dict)
-                self.relation.match(data_dict)
-                self.scene.match(data_dict)
             if full:
                 # extra fused output (not in the reference dict): per-scene softmax / argmax over
                 # candidates of the summed score (the reference does this on the host,
