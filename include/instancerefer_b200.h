@@ -107,6 +107,14 @@ int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const int32_t* n0_
 int ir_encoder_features(const ir_encoder_params* p, const float* feats0, void* ws, int64_t n_max,
                         float* feats_out, ir_stream_t stream);
 
+/* The same feature pass for TWO encoders with identical topology (InstanceRefer: the candidate
+ * encoder and the scene encoder) sharing every launch: each pair-GEMM / reduce kernel serves both
+ * problems, halving the dependent-launch chain. */
+int ir_encoder_features_pair(const ir_encoder_params* pa, const float* feats0a, void* wsa,
+                             int64_t n_max_a, float* out_a, const ir_encoder_params* pb,
+                             const float* feats0b, void* wsb, int64_t n_max_b, float* out_b,
+                             ir_stream_t stream);
+
 /* One sparse conv layer on explicit buffers (unit tests / tracing): rulebook = in_idx (K,seg_cap)
  * [input row of pair pos], slot (K,seg_cap) [pair pos of output row o, or -1], count (K). */
 int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,

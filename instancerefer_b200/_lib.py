@@ -48,6 +48,7 @@ SIGNATURES = {
     "ir_voxelize": (i32, [p, p, i32, i32, i32, f64, p, i64, p]),
     "ir_encoder_build_maps": (i32, [p, i32, p, p, i64, p]),
     "ir_encoder_features": (i32, [C.POINTER(EncoderParams), p, p, i64, p, p]),
+    "ir_encoder_features_pair": (i32, [C.POINTER(EncoderParams), p, p, i64, p, C.POINTER(EncoderParams), p, p, i64, p, p]),
     "ir_spconv_layer": (i32, [p, i32, i32, i32, p, i64, p, p, p, i64, p, p, i32, p, p, p, i32, p, p, p]),
     "ir_spconv_wprep_floats": (i64, [i32, i32, i32]),
     "ir_spconv_prepare_weights": (i32, [p, i32, i32, i32, p, p]),

@@ -70,6 +70,23 @@ class AttributeModule(nn.Module, PrepCache):
                                    ops.NORM_AFFINE, p['lg'], p['lbeta'], p['lw2'], p['lb2'], ops.MODE_L2)
         return lang_emb
 
+    def prepare_maps(self, data_dict, device, pack=None):
+        """Phase A1: host class filter + packed H2D, GPU voxelisation, levels + kernel maps."""
+        require_eval(self)
+        pack = pack or get_pack(data_dict, self.args, device, rebuild=True)
+        data_dict['num_filtered_objs'] = pack.num_filtered
+        data_dict['pred_obb_batch'] = pack.pred_obb_batch
+        ws = self.net.workspace(pack.M * pack.points.shape[1], device)
+        ops.encoder_reset(ws)
+        ops.voxelize(pack.points, pack.cand_rows, float(self.voxel_size[0]), ws)
+        self.net.build_maps(ws)
+        return ws, pack
+
+    def pool(self, data_dict, ws, f4, pack):
+        """Phase A3: per-candidate max-pool of the stride-16 features (:105)."""
+        data_dict['obj_feats'] = ops.segmax(f4, ws.coords(4), ws.nlvl()[4:5], ws.n_max, pack.M)
+        return data_dict
+
     def match(self, data_dict):
         """Phase B: language side Linear-BN-ReLU-Linear + L2 normalise (:88-90); visual side
         Linear-LN-ReLU-Linear + L2 normalise, dot with the scene's language vector (:108-126)."""

@@ -142,6 +142,11 @@ class SparseConvEncoder(nn.Module, PrepCache):
         ops.encoder_features(prep['params'], ws, feats0, out)
         return out, ws.coords(4), ws.nlvl()[4:5]
 
+    def build_maps(self, ws, coords0=None, n0_dev=None):
+        """Coordinate half of ``encode``: levels 1-4 and the nine kernel maps."""
+        require_eval(self)
+        ops.encoder_build_maps(ws, coords0, n0_dev)
+
     def forward(self, x):
         """SparseTensor -> SparseTensor at stride 16 (API fidelity; synchronises to size the result)."""
         F = x.F.float().contiguous()

@@ -198,27 +198,26 @@ extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const i
     return irk_kmap_all(ka, rows0, st);
 }
 
-static int conv_layer(const float* fin, int cin, int cout, int K, const int* in_idx,
-                      long long seg_cap, const int* slot, const int* count, const int* n_out_dev,
-                      long long n_max, const float* weight, const float* wprep, int use_tc,
-                      const float* scale, const float* shift, const float* resid, int relu, float* T,
-                      float* out, cudaStream_t st) {
+static int conv_layer(const IrConvBatch& b, int cin, int cout, int K, const float* const* wprep, int use_tc,
+                      cudaStream_t st) {
     int r;
-    const long long pairs_max = (long long)K * n_max;
-    const bool tc = use_tc && wprep != nullptr && cin >= 32;
+    bool tc = use_tc && cin >= 32;
+    for (int g = 0; g < b.G; ++g) tc = tc && wprep[g] != nullptr;
     const int pi = (g_prof_on && g_prof_n < IR_PROF_MAX) ? g_prof_n++ : -1;
     if (pi >= 0) {
         g_prof_meta[pi][0] = cin; g_prof_meta[pi][1] = cout; g_prof_meta[pi][2] = K; g_prof_meta[pi][3] = tc;
         cudaEventRecord(prof_event(pi, 0), st);
     }
-    if (tc)
-        r = irk_pairgemm_tc(fin, cin, cout, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
-    else
-        r = irk_pairgemm_simt(fin, cin, cout, K, in_idx, seg_cap, count, weight, T, pairs_max, st);
+    if (tc) {
+        IrConvBatch bt = b;
+        for (int g = 0; g < b.G; ++g) bt.p[g].weight = wprep[g];      // 16-byte aligned copy for the TMA bulk copy
+        r = irk_pairgemm_tc(bt, cin, cout, K, st);
+    } else {
+        r = irk_pairgemm_simt(b, cin, cout, K, st);
+    }
     if (r != IR_OK) return r;
     if (pi >= 0) cudaEventRecord(prof_event(pi, 1), st);
-    r = irk_reduce_epilogue(T, cout, K, slot, seg_cap, count, n_out_dev, n_max, scale, shift, resid,
-                            relu, out, st);
+    r = irk_reduce_epilogue(b, cout, K, st);
     if (pi >= 0) cudaEventRecord(prof_event(pi, 2), st);
     return r;
 }
@@ -231,39 +230,90 @@ extern "C" int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, 
                                const float* shift, const float* resid, int32_t relu, float* T,
                                float* out, ir_stream_t stream) {
     IR_CHECK_ARG(feat_in && in_idx && slot && count && n_out_dev && weight && T && out);
-    return conv_layer(feat_in, cin, cout, K, in_idx, seg_cap, slot, count, n_out_dev, n_max,
-                      weight, wprep, use_tc, scale, shift, resid, relu, T, out, (cudaStream_t)stream);
+    IrConvBatch b;
+    memset(&b, 0, sizeof(b));
+    b.G = 1;
+    b.p[0] = IrConvProblem{feat_in, in_idx, slot, count, n_out_dev, weight, scale, shift, resid, T, out,
+                           (long long)seg_cap, (long long)n_max, relu};
+    return conv_layer(b, cin, cout, K, &wprep, use_tc, (cudaStream_t)stream);
+}
+
+// The 13-layer feature pass for one or two encoders (same topology) with shared launches.
+static int encoder_features_multi(int G, const ir_encoder_params* const* ps, const float* const* feats0,
+                                  void* const* wss, const int64_t* n_maxs, float* const* outs, cudaStream_t st) {
+    Ws w[IR_MAX_GROUPS];
+    int r;
+    for (int g = 0; g < G; ++g) {
+        if ((r = ws_open(wss[g], n_maxs[g], &w[g])) != IR_OK) return r;
+        IR_CHECK_ARG(ps[g] != nullptr && outs[g] != nullptr && ps[g]->cin >= 1 && ps[g]->cin <= 128);
+        IR_CHECK_ARG(ps[g]->cin == ps[0]->cin && ps[g]->use_tc == ps[0]->use_tc);
+    }
+    static const int ch[5] = {32, 64, 128, 128, 128};
+    // per problem: fin, map (in/slot/count), output level, residual, destination, for layer `idx`
+    auto run = [&](int idx, int cin, int cout, int K, auto&& fill) -> int {
+        IrConvBatch b;
+        memset(&b, 0, sizeof(b));
+        b.G = G;
+        const float* wp[IR_MAX_GROUPS] = {nullptr, nullptr};
+        for (int g = 0; g < G; ++g) {
+            IrConvProblem& P = b.p[g];
+            fill(g, P);
+            P.weight = ps[g]->weight[idx];
+            P.scale = ps[g]->bn_scale[idx];
+            P.shift = ps[g]->bn_shift[idx];
+            P.T = w[g].T();
+            P.seg_cap = n_maxs[g];
+            P.n_max = n_maxs[g];
+            P.relu = 1;
+            wp[g] = ps[g]->wprep[idx];
+        }
+        return conv_layer(b, cin, cout, K, wp, ps[0]->use_tc, st);
+    };
+    // stem: k3 at level 0
+    if ((r = run(0, ps[0]->cin, ch[0], 27, [&](int g, IrConvProblem& P) {
+             P.fin = feats0[g] ? feats0[g] : w[g].feat0();
+             P.in_idx = w[g].k3_in(0); P.slot = w[g].k3_slot(0); P.count = w[g].kcount(0);
+             P.n_out_dev = w[g].nlvl() + 0; P.resid = nullptr; P.out = w[g].feat(0);
+         })) != IR_OK) return r;
+    for (int s = 1; s <= 4; ++s) {
+        const int l = s - 1, li = 1 + 3 * (s - 1);
+        // down: k2 s2, level l -> l+1
+        if ((r = run(li + 0, ch[l], ch[s], 8, [&](int g, IrConvProblem& P) {
+                 P.fin = w[g].feat(0);
+                 P.in_idx = w[g].k2_in(l); P.slot = w[g].k2_slot(l); P.count = w[g].kcount(5 + l);
+                 P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(1);
+             })) != IR_OK) return r;
+        // residual block at level s: relu(bn(conv(relu(bn(conv(X))))) + X)
+        if ((r = run(li + 1, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
+                 P.fin = w[g].feat(1);
+                 P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
+                 P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(2);
+             })) != IR_OK) return r;
+        if ((r = run(li + 2, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
+                 P.fin = w[g].feat(2);
+                 P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
+                 P.n_out_dev = w[g].nlvl() + s; P.resid = w[g].feat(1);
+                 P.out = (s == 4) ? outs[g] : w[g].feat(0);
+             })) != IR_OK) return r;
+    }
+    return IR_OK;
 }
 
 extern "C" int ir_encoder_features(const ir_encoder_params* p, const float* feats0, void* ws,
                                    int64_t n_max, float* feats_out, ir_stream_t stream) {
-    Ws w;
-    int r = ws_open(ws, n_max, &w);
-    if (r != IR_OK) return r;
-    IR_CHECK_ARG(p != nullptr && feats_out != nullptr && p->cin >= 1 && p->cin <= 128);
-    cudaStream_t st = (cudaStream_t)stream;
-    const float* f0 = feats0 ? feats0 : w.feat0();
-    static const int ch[5] = {32, 64, 128, 128, 128};
-    float* A = w.feat(0);
-    float* X = w.feat(1);
-    float* Y = w.feat(2);
-#define LAYER(idx, fin, cin_, cout_, K_, in_, slot_, cnt_, nout_, resid_, out_)                           \
-    if ((r = conv_layer(fin, cin_, cout_, K_, in_, n_max, slot_, cnt_, nout_, n_max, p->weight[idx],      \
-                        p->wprep[idx], p->use_tc, p->bn_scale[idx], p->bn_shift[idx], resid_, 1, w.T(),   \
-                        out_, st)) != IR_OK) return r;
-    // stem: k3 at level 0
-    LAYER(0, f0, p->cin, ch[0], 27, w.k3_in(0), w.k3_slot(0), w.kcount(0), w.nlvl() + 0, nullptr, A);
-    for (int s = 1; s <= 4; ++s) {
-        const int l = s - 1, li = 1 + 3 * (s - 1);
-        float* outp = (s == 4) ? feats_out : A;
-        // down: k2 s2, level l -> l+1
-        LAYER(li + 0, A, ch[l], ch[s], 8, w.k2_in(l), w.k2_slot(l), w.kcount(5 + l), w.nlvl() + s, nullptr, X);
-        // residual block at level s: relu(bn(conv(relu(bn(conv(X))))) + X)
-        LAYER(li + 1, X, ch[s], ch[s], 27, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, nullptr, Y);
-        LAYER(li + 2, Y, ch[s], ch[s], 27, w.k3_in(s), w.k3_slot(s), w.kcount(s), w.nlvl() + s, X, outp);
-    }
-#undef LAYER
-    return IR_OK;
+    return encoder_features_multi(1, &p, &feats0, &ws, &n_max, &feats_out, (cudaStream_t)stream);
+}
+
+extern "C" int ir_encoder_features_pair(const ir_encoder_params* pa, const float* feats0a, void* wsa,
+                                        int64_t n_max_a, float* out_a, const ir_encoder_params* pb,
+                                        const float* feats0b, void* wsb, int64_t n_max_b, float* out_b,
+                                        ir_stream_t stream) {
+    const ir_encoder_params* ps[2] = {pa, pb};
+    const float* f0[2] = {feats0a, feats0b};
+    void* wss[2] = {wsa, wsb};
+    const int64_t nm[2] = {n_max_a, n_max_b};
+    float* outs[2] = {out_a, out_b};
+    return encoder_features_multi(2, ps, f0, wss, nm, outs, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ segmented max (GlobalMaxPooling)

@@ -27,16 +27,33 @@ int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdi
                  unsigned long long* scan_state, int* pslot, long long n_max, cudaStream_t st);
 int irk_kmap_all(const IrKmapArgs& a, long long rows_max, cudaStream_t st);
 
-// spconv.cu  (SIMT fp32 pair-GEMM + deterministic reduce/epilogue)
-int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int* in_idx,
-                      long long seg_cap, const int* count, const float* weight, float* T,
-                      long long pairs_max, cudaStream_t st);
-int irk_reduce_epilogue(const float* T, int cout, int K, const int* slot, long long seg_cap,
-                        const int* count, const int* n_out_dev, long long n_max, const float* scale,
-                        const float* shift, const float* resid, int relu, float* out,
-                        cudaStream_t st);
+// A sparse-conv launch serves up to two independent problems with identical layer shapes (the
+// instance encoder and the scene encoder run the same 13 layers): one launch, CTAs dealt to both.
+#define IR_MAX_GROUPS 2
+struct IrConvProblem {
+    const float* fin;        // (rows_in, Cin)
+    const int* in_idx;       // [K][seg_cap]
+    const int* slot;         // [K][seg_cap]
+    const int* count;        // [K]
+    const int* n_out_dev;    // device row count of the output level
+    const float* weight;     // (K,Cin,Cout) fp32 (16-byte aligned)
+    const float* scale;      // folded BN (or NULL)
+    const float* shift;
+    const float* resid;      // (rows_out, Cout) or NULL
+    float* T;                // pair products
+    float* out;              // (rows_out, Cout)
+    long long seg_cap;
+    long long n_max;
+    int relu;
+};
+struct IrConvBatch {
+    IrConvProblem p[IR_MAX_GROUPS];
+    int G;
+};
 
-// spconv_tc.cu  (tcgen05 / TMEM / TMA pair-GEMM, 3xTF32)
-int irk_pairgemm_tc(const float* feat_in, int cin, int cout, int K, const int* in_idx,
-                    long long seg_cap, const int* count, const float* wprep, float* T,
-                    long long pairs_max, cudaStream_t st);
+// spconv.cu  (SIMT fp32 pair-GEMM + deterministic reduce/epilogue)
+int irk_pairgemm_simt(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);
+int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st);
+
+// spconv_tc.cu  (tcgen05 / TMEM / TMA pair-GEMM, split-fp16)
+int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);

@@ -17,9 +17,14 @@
 
 template <int COUT>
 __global__ void __launch_bounds__(PG_THREADS)
-k_pairgemm_simt(const float* __restrict__ F, int cin, int K, const int* __restrict__ in_idx,
-                long long seg_cap, const int* __restrict__ count, const float* __restrict__ W,
-                float* __restrict__ T) {
+k_pairgemm_simt(IrConvBatch b, int cin, int K) {
+    const IrConvProblem& P = b.p[blockIdx.y];
+    const float* __restrict__ F = P.fin;
+    const int* __restrict__ in_idx = P.in_idx;
+    const long long seg_cap = P.seg_cap;
+    const int* __restrict__ count = P.count;
+    const float* __restrict__ W = P.weight;
+    float* __restrict__ T = P.T;
     constexpr int G = PG_THREADS / COUT;      // pair groups per block
     constexpr int PPT = PG_TP / G;            // pairs per thread
     __shared__ __align__(16) float As[PG_TP][PG_MAXC];
@@ -78,16 +83,15 @@ k_pairgemm_simt(const float* __restrict__ F, int cin, int K, const int* __restri
     }
 }
 
-int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int* in_idx,
-                      long long seg_cap, const int* count, const float* weight, float* T,
-                      long long pairs_max, cudaStream_t st) {
-    IR_CHECK_ARG(cin >= 1 && cin <= PG_MAXC && K <= 32);
-    long long tiles = pairs_max / PG_TP + K;
-    const int grid = ir_min_i(tiles > 0 ? tiles : 1, IR_NUM_SMS * 16);
+int irk_pairgemm_simt(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
+    IR_CHECK_ARG(cin >= 1 && cin <= PG_MAXC && K <= 32 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
+    long long tiles = 0;
+    for (int g = 0; g < b.G; ++g) tiles = tiles > ((long long)K * b.p[g].n_max / PG_TP + K) ? tiles : ((long long)K * b.p[g].n_max / PG_TP + K);
+    const dim3 grid(ir_min_i(tiles > 0 ? tiles : 1, IR_NUM_SMS * 16), b.G);
     switch (cout) {
-        case 32:  k_pairgemm_simt<32><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
-        case 64:  k_pairgemm_simt<64><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
-        case 128: k_pairgemm_simt<128><<<grid, PG_THREADS, 0, st>>>(feat_in, cin, K, in_idx, seg_cap, count, weight, T); break;
+        case 32:  k_pairgemm_simt<32><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
+        case 64:  k_pairgemm_simt<64><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
+        case 128: k_pairgemm_simt<128><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
         default: ir_set_error("pairgemm_simt: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
     }
     IR_CHECK_LAUNCH();
@@ -97,10 +101,18 @@ int irk_pairgemm_simt(const float* feat_in, int cin, int cout, int K, const int*
 // ------------------------------------------------------------------ reduce + epilogue
 template <int COUT>
 __global__ void __launch_bounds__(256)
-k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ slot, long long seg_cap,
-                  const int* __restrict__ count, const int* __restrict__ n_dev,
-                  const float* __restrict__ scale, const float* __restrict__ shift,
-                  const float* __restrict__ resid, int relu, float* __restrict__ out) {
+k_reduce_epilogue(IrConvBatch b, int K) {
+    const IrConvProblem& P = b.p[blockIdx.y];
+    const float* __restrict__ T = P.T;
+    const int* __restrict__ slot = P.slot;
+    const long long seg_cap = P.seg_cap;
+    const int* __restrict__ count = P.count;
+    const int* __restrict__ n_dev = P.n_out_dev;
+    const float* __restrict__ scale = P.scale;
+    const float* __restrict__ shift = P.shift;
+    const float* __restrict__ resid = P.resid;
+    const int relu = P.relu;
+    float* __restrict__ out = P.out;
     constexpr int V = COUT / 32;
     __shared__ int s_kofs[32];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -169,20 +181,17 @@ k_reduce_epilogue(const float* __restrict__ T, int K, const int* __restrict__ sl
     }
 }
 
-int irk_reduce_epilogue(const float* T, int cout, int K, const int* slot, long long seg_cap,
-                        const int* count, const int* n_out_dev, long long n_max, const float* scale,
-                        const float* shift, const float* resid, int relu, float* out,
-                        cudaStream_t st) {
-    IR_CHECK_ARG(K <= 32);
-    const int grid = ir_min_i(ir_div_up(n_max > 0 ? n_max : 1, 8), IR_NUM_SMS * 8);
-#define LAUNCH_RE(CO) k_reduce_epilogue<CO><<<grid, 256, 0, st>>>(T, K, slot, seg_cap, count, n_out_dev, scale, shift, resid, relu, out)
+int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) {
+    IR_CHECK_ARG(K <= 32 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
+    long long rows = 1;
+    for (int g = 0; g < b.G; ++g) rows = rows > b.p[g].n_max ? rows : b.p[g].n_max;
+    const dim3 grid(ir_min_i(ir_div_up(rows, 8), IR_NUM_SMS * 8), b.G);
     switch (cout) {
-        case 32: LAUNCH_RE(32); break;
-        case 64: LAUNCH_RE(64); break;
-        case 128: LAUNCH_RE(128); break;
+        case 32: k_reduce_epilogue<32><<<grid, 256, 0, st>>>(b, K); break;
+        case 64: k_reduce_epilogue<64><<<grid, 256, 0, st>>>(b, K); break;
+        case 128: k_reduce_epilogue<128><<<grid, 256, 0, st>>>(b, K); break;
         default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
     }
-#undef LAUNCH_RE
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -169,8 +169,7 @@ struct Cfg {
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(N_THREADS, 1)
-k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx, long long seg_cap,
-              const int* __restrict__ count, const float* __restrict__ weight, float* __restrict__ T) {
+k_pairgemm_tc(IrConvBatch batch, int K) {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -190,40 +189,65 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (warp == 0) {
-        // pair / tile prefixes and the CTA <-> offset assignment, one lane per kernel offset.
-        // Every CTA serves ONE offset k (weights are staged once); CTAs are dealt to offsets in
+        // Pair / tile prefixes and the CTA <-> offset assignment.  Virtual offset v = g*K + k runs over
+        // the (up to two) problems of this launch; lane handles v = lane and v = lane + 32.  Every CTA
+        // serves ONE virtual offset (its weights are staged once); CTAs are dealt to offsets in
         // proportion to their tile counts, each offset with work gets at least one.
-        const int c = (lane < K) ? __ldg(count + lane) : 0;
-        const int t = (c + TILE_M - 1) / TILE_M;
-        int cinc = c, tinc = t;
+        const int V = batch.G * K;
+        int c[2], t[2];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int c2 = __shfl_up_sync(0xffffffffu, cinc, o), t2 = __shfl_up_sync(0xffffffffu, tinc, o);
-            if (lane >= o) { cinc += c2; tinc += t2; }
+        for (int h = 0; h < 2; ++h) {
+            const int v = lane + 32 * h;
+            c[h] = 0;
+            if (v < V) c[h] = __ldg(((v < K) ? batch.p[0].count : batch.p[1].count) + ((v < K) ? v : v - K));
+            t[h] = (c[h] + TILE_M - 1) / TILE_M;
         }
-        const int T_all = __shfl_sync(0xffffffffu, tinc, 31);
-        const int nonempty = __popc(__ballot_sync(0xffffffffu, t > 0));
+        int cinc[2] = {c[0], c[1]}, tinc[2] = {t[0], t[1]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int c2 = __shfl_up_sync(0xffffffffu, cinc[h], o), t2 = __shfl_up_sync(0xffffffffu, tinc[h], o);
+                if (lane >= o) { cinc[h] += c2; tinc[h] += t2; }
+            }
+        }
+        const int csum0 = __shfl_sync(0xffffffffu, cinc[0], 31), tsum0 = __shfl_sync(0xffffffffu, tinc[0], 31);
+        cinc[1] += csum0; tinc[1] += tsum0;
+        const int T_all = __shfl_sync(0xffffffffu, tinc[1], 31);
+        // exclusive pair prefix at the start of problem 1 (v == K): pairs of problem 0
+        const int cbase1 = __shfl_sync(0xffffffffu, cinc[0] - c[0], K & 31);      // K < 32 always
+        const int nonempty = __popc(__ballot_sync(0xffffffffu, t[0] > 0)) + __popc(__ballot_sync(0xffffffffu, t[1] > 0));
         const int spare = max(0, (int)gridDim.x - nonempty);
-        int g = 0;
-        if (t > 0) g = 1 + (int)(((long long)spare * t) / max(T_all, 1));
-        g = min(g, t);
-        int ginc = g;
+        int g[2], ginc[2];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int g2 = __shfl_up_sync(0xffffffffu, ginc, o);
-            if (lane >= o) ginc += g2;
+        for (int h = 0; h < 2; ++h) {
+            g[h] = 0;
+            if (t[h] > 0) g[h] = min(t[h], 1 + (int)(((long long)spare * t[h]) / max(T_all, 1)));
+            ginc[h] = g[h];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int g2 = __shfl_up_sync(0xffffffffu, ginc[h], o);
+                if (lane >= o) ginc[h] += g2;
+            }
         }
-        const int cta_lo = ginc - g;
-        if (lane == 0) { s_sched[0] = -1; s_sched[1] = 0; s_sched[2] = 0; s_sched[3] = 0; s_sched[4] = 0; }
+        ginc[1] += __shfl_sync(0xffffffffu, ginc[0], 31);
+        if (lane == 0) { s_sched[0] = -1; s_sched[1] = 0; s_sched[2] = 0; s_sched[3] = 0; s_sched[4] = 0; s_sched[5] = 0; }
         __syncwarp();
         const int bx = (int)blockIdx.x;
-        if (g > 0 && bx >= cta_lo && bx < ginc) {
-            const int r = bx - cta_lo;
-            s_sched[0] = lane;                                        // offset k served by this CTA
-            s_sched[1] = (int)(((long long)r * t) / g);               // first tile (within k)
-            s_sched[2] = (int)(((long long)(r + 1) * t) / g);         // end tile (within k)
-            s_sched[3] = cinc - c;                                    // kofs[k]: first T row of this offset
-            s_sched[4] = c;                                           // pairs of this offset
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cta_lo = ginc[h] - g[h];
+            if (g[h] > 0 && bx >= cta_lo && bx < ginc[h]) {
+                const int v = lane + 32 * h;
+                const int grp_id = (v < K) ? 0 : 1;
+                const int r = bx - cta_lo;
+                s_sched[0] = v - grp_id * K;                                    // offset k served by this CTA
+                s_sched[1] = (int)(((long long)r * t[h]) / g[h]);               // first tile (within k)
+                s_sched[2] = (int)(((long long)(r + 1) * t[h]) / g[h]);         // end tile (within k)
+                s_sched[3] = (cinc[h] - c[h]) - (grp_id ? cbase1 : 0);          // kofs[k] inside this problem's T
+                s_sched[4] = c[h];                                              // pairs of this offset
+                s_sched[5] = grp_id;                                            // which problem
+            }
         }
     }
     if (tid == 32) {
@@ -247,6 +271,12 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
     const int kk = s_sched[0];
     const int t_begin = s_sched[1], t_end = (kk >= 0) ? s_sched[2] : 0;
     const int kofs = s_sched[3], kcount = s_sched[4];
+    const IrConvProblem& P = batch.p[s_sched[5]];
+    const float* __restrict__ F = P.fin;
+    const int* __restrict__ in_idx = P.in_idx;
+    const long long seg_cap = P.seg_cap;
+    const float* __restrict__ weight = P.weight;
+    float* __restrict__ T = P.T;
 
     // W[k] (Cin,Cout) fp32 is staged in shared memory by one TMA bulk-copy chain (issued by thread 0);
     // 16 warps (4 per TMEM sub-partition) then scale it by 2^8, split it into fp16 hi/lo and park it in
@@ -434,30 +464,30 @@ k_pairgemm_tc(const float* __restrict__ F, int K, const int* __restrict__ in_idx
 }
 
 template <int CIN, int COUT>
-int launch(const float* F, int K, const int* in_idx, long long seg_cap, const int* count, const float* weight,
-           float* T, long long pairs_max, cudaStream_t st) {
+int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     static bool attr_done = false;
     if (!attr_done) {
         IR_CHECK_CUDA(cudaFuncSetAttribute(k_pairgemm_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_done = true;
     }
-    const long long tiles_max = pairs_max / TILE_M + K;
+    long long tiles_max = 0;
+    for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
     const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, IR_NUM_SMS);
-    k_pairgemm_tc<CIN, COUT><<<grid, N_THREADS, C::SMEM_BYTES, st>>>(F, K, in_idx, seg_cap, count, weight, T);
+    k_pairgemm_tc<CIN, COUT><<<grid, N_THREADS, C::SMEM_BYTES, st>>>(b, K);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
 
 }  // namespace tc
 
-int irk_pairgemm_tc(const float* feat_in, int cin, int cout, int K, const int* in_idx, long long seg_cap,
-                    const int* count, const float* wprep, float* T, long long pairs_max, cudaStream_t st) {
-    IR_CHECK_ARG(K <= 32 && wprep != nullptr);
-    if (cin == 32 && cout == 64) return tc::launch<32, 64>(feat_in, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
-    if (cin == 64 && cout == 64) return tc::launch<64, 64>(feat_in, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
-    if (cin == 64 && cout == 128) return tc::launch<64, 128>(feat_in, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
-    if (cin == 128 && cout == 128) return tc::launch<128, 128>(feat_in, K, in_idx, seg_cap, count, wprep, T, pairs_max, st);
+int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
+    IR_CHECK_ARG(K <= 27 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
+    for (int g = 0; g < b.G; ++g) IR_CHECK_ARG(b.p[g].weight != nullptr && (reinterpret_cast<uintptr_t>(b.p[g].weight) & 15) == 0);
+    if (cin == 32 && cout == 64) return tc::launch<32, 64>(b, K, st);
+    if (cin == 64 && cout == 64) return tc::launch<64, 64>(b, K, st);
+    if (cin == 64 && cout == 128) return tc::launch<64, 128>(b, K, st);
+    if (cin == 128 && cout == 128) return tc::launch<128, 128>(b, K, st);
     ir_set_error("pairgemm_tc: unsupported channels %d -> %d", cin, cout);
     return IR_ERR_UNSUPPORTED;
 }

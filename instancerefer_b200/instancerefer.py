@@ -34,6 +34,7 @@ class InstanceRefer(nn.Module):
             self.scene = _load(args.scene_module).SceneModule(input_feature_dim, args)
 
     concurrent = True      # run the three language-independent encoders on side streams
+    pair_encoders = False  # run both sparse encoders through shared launches (ir_encoder_features_pair)
 
     def _streams(self, device):
         st = self.__dict__.get('_side_streams')
@@ -72,11 +73,32 @@ class InstanceRefer(nn.Module):
                 for s_ in (sa, ss, sr):
                     s_.wait_stream(main)
                 ev_obj = torch.cuda.Event()
-                with torch.cuda.stream(sa):
-                    self.attribute.encode_candidates(data_dict, dev, pack)
-                    ev_obj.record(sa)                                  # obj_feats ready (scene head needs it)
-                with torch.cuda.stream(ss):
-                    self.scene.encode_scene(data_dict, dev)
+                if self.pair_encoders:
+                    # both encoders through shared launches (measured slower than two overlapping chains
+                    # at the bench size: kept as an option for small scenes)
+                    ev_maps, ev_feat = torch.cuda.Event(), torch.cuda.Event()
+                    with torch.cuda.stream(ss):
+                        ws_s, F0 = self.scene.prepare_maps(data_dict, dev)
+                        ev_maps.record(ss)
+                    with torch.cuda.stream(sa):
+                        ws_a, _ = self.attribute.prepare_maps(data_dict, dev, pack)
+                        sa.wait_event(ev_maps)
+                        pa, ps_ = self.attribute.net.prepared(), self.scene.net.prepared()
+                        f4a = torch.empty(ws_a.n_max, 128, dtype=torch.float32, device=dev)
+                        f4s = torch.empty(ws_s.n_max, 128, dtype=torch.float32, device=dev)
+                        ops.encoder_features_pair(pa['params'], ws_a, None, f4a, ps_['params'], ws_s, F0, f4s)
+                        ev_feat.record(sa)
+                        self.attribute.pool(data_dict, ws_a, f4a, pack)
+                        ev_obj.record(sa)
+                    with torch.cuda.stream(ss):
+                        ss.wait_event(ev_feat)
+                        self.scene.bev_convs(data_dict, ws_s, f4s)
+                else:
+                    with torch.cuda.stream(sa):
+                        self.attribute.encode_candidates(data_dict, dev, pack)
+                        ev_obj.record(sa)                              # obj_feats ready (scene head needs it)
+                    with torch.cuda.stream(ss):
+                        self.scene.encode_scene(data_dict, dev)
                 with torch.cuda.stream(sr):
                     self.relation.encode_graph(data_dict, dev)
                 data_dict = self.lang(data_dict)

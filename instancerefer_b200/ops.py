@@ -127,6 +127,12 @@ def encoder_features(params, ws, feats0, out):
          _p(out, torch.float32), _stream())
 
 
+def encoder_features_pair(pa, wsa, feats0a, outa, pb, wsb, feats0b, outb):
+    """Both encoders of the model through shared launches (see ir_encoder_features_pair)."""
+    call("ir_encoder_features_pair", C.byref(pa), _p(feats0a, torch.float32), wsa.ptr, wsa.n_max, _p(outa, torch.float32),
+         C.byref(pb), _p(feats0b, torch.float32), wsb.ptr, wsb.n_max, _p(outb, torch.float32), _stream())
+
+
 def spconv_wprep(weight):
     """(K,Cin,Cout) fp32 -> tcgen05 operand image tensor (see ir_spconv_prepare_weights)."""
     K, cin, cout = weight.shape

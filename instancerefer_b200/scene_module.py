@@ -75,6 +75,25 @@ class SceneModule(nn.Module, PrepCache):
         data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
         return data_dict
 
+    def prepare_maps(self, data_dict, device):
+        """Phase A1: hash the loader's 5 cm voxels, levels + kernel maps."""
+        require_eval(self)
+        lidar = data_dict['lidar']
+        F0 = lidar.F.to(device, torch.float32).contiguous()
+        C0 = lidar.C.to(device, torch.int32).contiguous()
+        ws = self.net.workspace(F0.shape[0], device)
+        self.net.build_maps(ws, C0, data_dict.get('_ir_lidar_rows'))
+        return ws, F0
+
+    def bev_convs(self, data_dict, ws, f4):
+        """Phase A3: crop + dense BEV + BN + ReLU (:70), Conv2d-BN-ReLU-Conv2d (:71)."""
+        p = self.prepared()
+        B = data_dict['point_min'].shape[0]
+        bev = ops.bev(f4, ws.coords(4), ws.nlvl()[4:5], ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
+        x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
+        data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        return data_dict
+
     def embed_language(self, data_dict):
         p = self.prepared()
         q, _ = ops.mlp_head(data_dict['lang_scene_feats'].float().contiguous(), p['lw1'], p['lb1'], ops.NORM_LAYER,

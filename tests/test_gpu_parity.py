@@ -383,6 +383,11 @@ def test_streams_and_graph_replay_bitwise(gpu_model):
         seq = _run(gpu_model, b)
         gpu_model.concurrent = True
         con = _run(gpu_model, b)
+        gpu_model.pair_encoders = True                 # both encoders through shared launches
+        pair = _run(gpu_model, b)
+        gpu_model.pair_encoders = False
+        for k in keys:
+            assert torch.equal(seq[k], pair[k]), ('paired encoders', k)
         gr = runner(synthetic.to_data_dict(b, SparseTensor, 'cpu'))      # host inputs, staged by the runner
         torch.cuda.synchronize()
         for k in keys:
