@@ -11,7 +11,7 @@ import torch
 KEY = '_ir_candidates'
 
 _pinned = {}
-_last_h2d = [None]          # event recorded after the latest staging copies (guards pinned-buffer reuse)
+_last_h2d = {}              # tag -> event recorded after the latest copies out of that tag's staging buffers
 
 
 def _pinned_buf(name, shape, dtype):
@@ -36,9 +36,9 @@ class CandidatePack:
     cand_scene    : (M,) original scene index of each candidate;  cand_seg: index into `active`
     cand_ofs      : (len(active)+1,) candidate offsets per active scene
     ``static``: dict of preallocated device buffers (CUDA-graph replay) to copy into instead of
-    allocating."""
+    allocating; ``tag`` selects a private set of pinned staging buffers (one per in-flight slot)."""
 
-    def __init__(self, data_dict, lang_cls_pred, device, static=None):
+    def __init__(self, data_dict, lang_cls_pred, device, static=None, tag=''):
         classes = data_dict['instance_class']
         pred = lang_cls_pred.detach().to('cpu').tolist() if torch.is_tensor(lang_cls_pred) else list(lang_cls_pred)
         self.cands, self.pred_obb_batch, self.num_filtered = [], [], []
@@ -66,16 +66,16 @@ class CandidatePack:
         self.n_inst, self.M = inst_ofs[-1], len(cand_rows)
         ppi, fdim = pts[0].shape
         cand_ofs = np.concatenate([[0], np.cumsum([len(self.cands[i]) for i in self.active])])
-        if _last_h2d[0] is not None:
-            _last_h2d[0].synchronize()                 # previous copies out of the staging buffers are done
-        h_points = _pinned_buf('points', (self.n_inst, ppi, fdim), torch.float32)
+        if _last_h2d.get(tag) is not None:
+            _last_h2d[tag].synchronize()               # previous copies out of these staging buffers are done
+        h_points = _pinned_buf('points' + tag, (self.n_inst, ppi, fdim), torch.float32)
         np.stack(pts, 0, out=h_points.numpy())
-        h_meta = _pinned_buf('meta', (self.n_inst, 4), torch.float32)
+        h_meta = _pinned_buf('meta' + tag, (self.n_inst, 4), torch.float32)
         m = h_meta.numpy()
         m[:, :3] = np.asarray(centres, np.float64)
         m[:, 3] = cls
         a = len(inst_ofs)
-        h_ints = _pinned_buf('ints', (2 * a + 3 * self.M,), torch.int32)
+        h_ints = _pinned_buf('ints' + tag, (2 * a + 3 * self.M,), torch.int32)
         h_ints.numpy()[:] = np.concatenate([inst_ofs, cand_rows, cand_scene, cand_seg, cand_ofs])
         if static is None:
             self.points = h_points.to(device, non_blocking=True)                # one H2D for all instances
@@ -88,7 +88,7 @@ class CandidatePack:
             ints.copy_(h_ints, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        _last_h2d[0] = ev
+        _last_h2d[tag] = ev
         self.ints = ints
         self.inst_ofs = ints[:a]
         self.cand_rows = ints[a:a + self.M]

@@ -1,127 +1,186 @@
-"""CUDA-graph replay of the whole forward (B200-first: no tracing compiler, explicit stream capture).
+"""CUDA-graph replay of the whole forward (B200-first: no tracing compiler, explicit stream capture),
+double-buffered so the host side of step i+1 overlaps the GPU side of step i.
 
 ``GraphedInstanceRefer(model)(data_dict)`` has the contract of ``InstanceRefer.forward`` (eval mode,
 ``use_gt_lang: True``).  Per step the host does what cannot be captured — the class filter over the
-Python lists, packing every instance into one pinned buffer, async H2D copies into STATIC device
-buffers — and then replays one captured graph: ~120 kernels on four streams (language branch,
-instance encoder, scene encoder, relation graph) with every row / pair count kept on the device.
+Python lists, packing every instance into one pinned buffer, async H2D copies into STATIC device buffers
+on a copy stream — and then replays one captured graph: ~85 kernels on four streams (language branch,
+instance encoder, scene encoder, relation graph) with every row / pair count kept on the device.  The
+score tensors are concatenated inside the graph and read back with ONE D2H copy.
+
+``submit()`` is the asynchronous form: it returns a handle at once; ``handle.result()`` waits for that
+step only.  Two slots (static inputs + graph + outputs) alternate per shape signature, so while the GPU
+replays step i the host already filters / packs / uploads step i+1.
 
 Graphs are cached by shape signature (B, max tokens, #instances, #candidates, #active scenes, lidar
-row bucket).  Outputs are views of static buffers: they stay valid until the next call with the same
-signature (clone them to keep them)."""
+row bucket).  Device outputs are views of a slot's static buffers: valid until that slot is reused
+(two submits later); host copies of the score tensors are owned by the handle."""
 import torch
 
 from . import ops
-from .candidates import KEY, CandidatePack, target_classes
+from .candidates import KEY, CandidatePack
 from .sparse_tensor import SparseTensor
 
 OUT_KEYS = ('lang_feat', 'atten_attr', 'atten_rel', 'atten_scene', 'lang_cls_feats', 'lang_attr_feats',
             'lang_rel_feats', 'lang_scene_feats', 'lang_scores', 'obj_feats', 'attribute_scores',
             'relation_scores', 'scene_scores', 'seg_scores', 'vis_atten', 'ref_probs', 'ref_pred')
+HOST_KEYS = ('attribute_scores', 'relation_scores', 'scene_scores', 'lang_scores', 'seg_scores', 'ref_probs',
+             'ref_pred')
 
 
-class _Entry:
+class _Slot:
     pass
 
 
+class Handle:
+    """One in-flight forward.  ``result()`` blocks until this step's scores reached the host."""
+
+    def __init__(self, slot, pack, data_dict):
+        self.slot, self.pack, self.data_dict = slot, pack, data_dict
+
+    def result(self):
+        s = self.slot
+        s.done.synchronize()
+        d = self.data_dict
+        for k in OUT_KEYS:
+            if k in s.out:
+                d[k] = s.out[k]                                  # device views (static buffers of the slot)
+        host, off = {}, 0
+        flat = s.host_flat.clone()                               # owned by this handle (the slot is reused)
+        for k, shape, n, is_int in s.flat_layout:
+            v = flat[off:off + n].view(shape)
+            host[k] = v.to(torch.int32) if is_int else v
+            off += n
+        d['host_scores'] = host                                  # pinned host copies of the score tensors
+        d['num_filtered_objs'] = self.pack.num_filtered
+        d['pred_obb_batch'] = self.pack.pred_obb_batch
+        return d
+
+
 class GraphedInstanceRefer:
-    def __init__(self, model, max_graphs=8):
+    def __init__(self, model, max_graphs=8, depth=2):
         if model.training:
             raise NotImplementedError("graph replay is an eval-mode path")
         self.model = model
         self.max_graphs = max_graphs
+        self.depth = depth
         self.cache = {}
         self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._copy_stream = None
 
-    # --- static input staging ------------------------------------------------------------
-    def _stage(self, e, data_dict, lmax_host):
-        m = self.model
-        dev = e.device
-        pack = CandidatePack(data_dict, data_dict['_ir_target_host'], dev, static=e.pack_static)
-        e.lang_feat.copy_(data_dict['lang_feat'], non_blocking=True)
-        e.lang_len.copy_(data_dict['lang_len'], non_blocking=True)
-        e.point_min.copy_(data_dict['point_min'], non_blocking=True)
-        lid = data_dict['lidar']
-        n0 = lid.F.shape[0]
-        e.lidar_F[:n0].copy_(lid.F, non_blocking=True)
-        e.lidar_C[:n0].copy_(lid.C, non_blocking=True)
-        e.n0_host[0] = n0
-        e.n0_dev.copy_(e.n0_host, non_blocking=True)
-        self.h2d_bytes = (pack.h2d_bytes + e.lang_feat.numel() * 4 + e.lang_len.numel() * 8 +
-                          e.point_min.numel() * e.point_min.element_size() + n0 * (lid.F.shape[1] + 4) * 4 + 4)
+    # --- static input staging (copy stream) ------------------------------------------------
+    def _stage(self, s, data_dict, target_host):
+        cs = self._copy_stream
+        s.done.synchronize()                       # slot's previous result was read back -> buffers reusable
+        with torch.cuda.stream(cs):
+            cs.wait_event(s.graph_done)            # previous replay of this slot no longer reads its inputs
+            pack = CandidatePack(data_dict, target_host, s.device, static=s.pack_static, tag=s.tag)
+            s.lang_feat.copy_(data_dict['lang_feat'], non_blocking=True)
+            s.lang_len.copy_(data_dict['lang_len'], non_blocking=True)
+            s.point_min.copy_(data_dict['point_min'], non_blocking=True)
+            lid = data_dict['lidar']
+            n0 = lid.F.shape[0]
+            s.lidar_F[:n0].copy_(lid.F, non_blocking=True)
+            s.lidar_C[:n0].copy_(lid.C, non_blocking=True)
+            s.n0_host[0] = n0
+            s.n0_dev.copy_(s.n0_host, non_blocking=True)
+            s.staged.record(cs)
+        self.h2d_bytes = (pack.h2d_bytes + s.lang_feat.numel() * 4 + s.lang_len.numel() * 8 +
+                          s.point_min.numel() * s.point_min.element_size() + n0 * (lid.F.shape[1] + 4) * 4 + 4)
         return pack
 
-    def _new_entry(self, data_dict, pack, lmax, key):
-        m = self.model
-        dev = pack.points.device
-        e = _Entry()
-        e.device = dev
+    def _new_slot(self, data_dict, pack0, lmax, tag):
+        dev = pack0.points.device
+        s = _Slot()
+        s.device, s.tag, s.lmax = dev, tag, lmax
         B = data_dict['lang_feat'].shape[0]
         lid = data_dict['lidar']
         rows = ops.round_rows(lid.F.shape[0])
-        e.pack_static = {k: torch.empty_like(v) for k, v in pack.static_buffers().items()}
-        e.lang_feat = torch.empty(data_dict['lang_feat'].shape, dtype=torch.float32, device=dev)
-        e.lang_len = torch.empty(B, dtype=torch.int64, device=dev)
-        e.point_min = torch.empty(tuple(data_dict['point_min'].shape), dtype=data_dict['point_min'].dtype, device=dev)
-        e.lidar_F = torch.zeros(rows, lid.F.shape[1], dtype=torch.float32, device=dev)
-        e.lidar_C = torch.zeros(rows, 4, dtype=torch.int32, device=dev)
-        e.n0_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        e.n0_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        e.lmax = lmax
-        return e
+        s.pack_static = {k: torch.empty_like(v) for k, v in pack0.static_buffers().items()}
+        s.lang_feat = torch.empty(data_dict['lang_feat'].shape, dtype=torch.float32, device=dev)
+        s.lang_len = torch.empty(B, dtype=torch.int64, device=dev)
+        s.point_min = torch.empty(tuple(data_dict['point_min'].shape), dtype=data_dict['point_min'].dtype, device=dev)
+        s.lidar_F = torch.zeros(rows, lid.F.shape[1], dtype=torch.float32, device=dev)
+        s.lidar_C = torch.zeros(rows, 4, dtype=torch.int32, device=dev)
+        s.n0_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        s.n0_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        s.staged, s.graph_done, s.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        s.graph_done.record()
+        s.done.record()
+        return s
 
-    def _static_dict(self, e, pack):
-        d = dict(lang_feat=e.lang_feat, lang_len=e.lang_len, point_min=e.point_min,
-                 lidar=SparseTensor(e.lidar_F, e.lidar_C), _ir_lidar_rows=e.n0_dev, _ir_lang_len_max=e.lmax)
+    def _static_dict(self, s, pack):
+        d = dict(lang_feat=s.lang_feat, lang_len=s.lang_len, point_min=s.point_min,
+                 lidar=SparseTensor(s.lidar_F, s.lidar_C), _ir_lidar_rows=s.n0_dev, _ir_lang_len_max=s.lmax)
         pack.resident = True
         d[KEY] = pack
         return d
 
-    def __call__(self, data_dict):
+    def _forward_flat(self, s, pack):
+        out = self.model(self._static_dict(s, pack))
+        flat = torch.cat([out[k].reshape(-1).to(torch.float32) for k in HOST_KEYS])   # one D2H per step
+        return out, flat
+
+    def _capture(self, s, pack):
+        m, dev = self.model, s.device
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(s.staged)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(main)
+        with torch.cuda.stream(warm):             # warm-up (allocations, lazy attribute sets), then capture
+            for _ in range(2):
+                self._forward_flat(s, pack)
+        main.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        s.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(s.graph):
+            s.out, s.flat = self._forward_flat(s, pack)
+        s.flat_layout = [(k, tuple(s.out[k].shape), s.out[k].numel(), s.out[k].dtype in (torch.int32, torch.int64))
+                         for k in HOST_KEYS]
+        s.host_flat = torch.empty(s.flat.shape, dtype=torch.float32).pin_memory()
+        self.d2h_bytes = s.flat.numel() * 4
+
+    # --- public API ---------------------------------------------------------------------------
+    def submit(self, data_dict):
         m = self.model
-        a = m.args
-        if not a.use_gt_lang:
+        if not m.args.use_gt_lang:
             raise NotImplementedError("graph replay needs use_gt_lang: True (the class filter runs on the host "
                                       "before the language branch)")
-        # the two tiny D2H reads the host-side filter / shapes need (object_cat, max token count)
-        tgt = data_dict['object_cat']
-        ln = data_dict['lang_len']
-        data_dict['_ir_target_host'] = tgt.detach().to('cpu') if tgt.is_cuda else tgt
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        # the two tiny host reads the filter / shapes need (object_cat, max token count)
+        tgt, ln = data_dict['object_cat'], data_dict['lang_len']
+        target_host = tgt.detach().to('cpu') if tgt.is_cuda else tgt
         lmax = int((ln.detach().to('cpu') if ln.is_cuda else ln).max())
         lid = data_dict['lidar']
         B = data_dict['lang_feat'].shape[0]
-        # peek at the candidate structure for the signature (cheap: class lists only)
-        pred = data_dict['_ir_target_host'].tolist()
+        pred = target_host.tolist()
         n_c = [sum(1 for c in cl if int(c) == int(pred[i])) for i, cl in enumerate(data_dict['instance_class'])]
         act = [i for i, n in enumerate(n_c) if n >= 2]
         key = (B, lmax, sum(len(data_dict['instance_class'][i]) for i in act), sum(n_c[i] for i in act), len(act),
-               ops.round_rows(lid.F.shape[0]), torch.cuda.current_device())
+               ops.round_rows(lid.F.shape[0]), dev.index)
         e = self.cache.get(key)
-        dev = torch.device('cuda', torch.cuda.current_device())
         if e is None:
             if len(self.cache) >= self.max_graphs:
                 self.cache.pop(next(iter(self.cache)))
-            pack0 = CandidatePack(data_dict, data_dict['_ir_target_host'], dev)
-            e = self._new_entry(data_dict, pack0, lmax, key)
-            pack = self._stage(e, data_dict, lmax)
-            # warm-up on a side stream (allocations, lazy attribute sets), then capture
-            s = torch.cuda.Stream(device=dev)
-            s.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    m(self._static_dict(e, pack))
-            torch.cuda.current_stream(dev).wait_stream(s)
-            torch.cuda.synchronize(dev)
-            e.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(e.graph):
-                e.out = m(self._static_dict(e, pack))
+            pack0 = CandidatePack(data_dict, target_host, dev)
+            e = dict(slots=[self._new_slot(data_dict, pack0, lmax, f'g{len(self.cache)}s{j}')
+                            for j in range(self.depth)], i=0)
+            for s in e['slots']:
+                self._capture(s, self._stage(s, data_dict, target_host))
             self.cache[key] = e
-        else:
-            pack = self._stage(e, data_dict, lmax)
-        e.graph.replay()
-        for k in OUT_KEYS:
-            if k in e.out:
-                data_dict[k] = e.out[k]
-        data_dict['num_filtered_objs'] = pack.num_filtered
-        data_dict['pred_obb_batch'] = pack.pred_obb_batch
-        return data_dict
+        s = e['slots'][e['i'] % self.depth]
+        e['i'] += 1
+        pack = self._stage(s, data_dict, target_host)
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(s.staged)
+        s.graph.replay()
+        s.graph_done.record(main)
+        s.host_flat.copy_(s.flat, non_blocking=True)
+        s.done.record(main)
+        return Handle(s, pack, data_dict)
+
+    def __call__(self, data_dict):
+        return self.submit(data_dict).result()

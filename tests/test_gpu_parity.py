@@ -395,3 +395,17 @@ def test_streams_and_graph_replay_bitwise(gpu_model):
             assert torch.equal(seq[k], gr[k]), ('graph', k)
         assert gr['num_filtered_objs'] == seq['num_filtered_objs']
     assert len(runner.cache) == 1
+    # asynchronous double-buffered form: two steps in flight, host score copies owned by the handle
+    bs = [synthetic.make_batch(s_, batch_size=2, num_points=9000, n_inst=12, n_cand=[5, 4], n_tokens=[9, 6])
+          for s_ in (311, 312, 313)]
+    hs = [runner.submit(synthetic.to_data_dict(b, SparseTensor, 'cpu')) for b in bs[:2]]
+    res = [hs[0].result()]
+    hs.append(runner.submit(synthetic.to_data_dict(bs[2], SparseTensor, 'cpu')))
+    res += [hs[1].result(), hs[2].result()]
+    gpu_model.concurrent = False
+    for b, r in zip(bs, res):
+        want = _run(gpu_model, b)
+        for k in ('attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'lang_scores', 'ref_probs'):
+            assert torch.equal(r['host_scores'][k], want[k].cpu()), ('pipelined', k)
+        assert torch.equal(r['host_scores']['ref_pred'], want['ref_pred'].cpu())
+    gpu_model.concurrent = True
