@@ -41,6 +41,28 @@ void ir_count_launch(int n);
         }                                                                         \
     } while (0)
 
+// Programmatic dependent launch (PDL): the kernel may begin while its stream predecessor is still
+// running; it must execute ir_pdl_wait() before touching anything the predecessor writes.  Kernels
+// call ir_pdl_trigger() early to let their successor start its own independent prologue.
+__device__ __forceinline__ void ir_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ir_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ir_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int ir_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int ir_min_i(long long a, long long b) { return (int)(a < b ? a : b); }
 

@@ -43,6 +43,8 @@ k_pairgemm_simt(IrConvBatch b, int cin, int K) {
         if (lane == 31) { s_kofs[32] = cinc; s_tofs[32] = tinc; }
     }
     __syncthreads();
+    ir_pdl_trigger();
+    ir_pdl_wait();                        // the input features come from the previous kernel
     const int ntiles = s_tofs[32];
     const int cp = (cin + 3) & ~3;
     const int co = tid % COUT, g = tid / COUT;
@@ -89,9 +91,9 @@ int irk_pairgemm_simt(const IrConvBatch& b, int cin, int cout, int K, cudaStream
     for (int g = 0; g < b.G; ++g) tiles = tiles > ((long long)K * b.p[g].n_max / PG_TP + K) ? tiles : ((long long)K * b.p[g].n_max / PG_TP + K);
     const dim3 grid(ir_min_i(tiles > 0 ? tiles : 1, IR_NUM_SMS * 16), b.G);
     switch (cout) {
-        case 32:  k_pairgemm_simt<32><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
-        case 64:  k_pairgemm_simt<64><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
-        case 128: k_pairgemm_simt<128><<<grid, PG_THREADS, 0, st>>>(b, cin, K); break;
+        case 32:  IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_simt<32>, grid, dim3(PG_THREADS), 0, st, b, cin, K)); break;
+        case 64:  IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_simt<64>, grid, dim3(PG_THREADS), 0, st, b, cin, K)); break;
+        case 128: IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_simt<128>, grid, dim3(PG_THREADS), 0, st, b, cin, K)); break;
         default: ir_set_error("pairgemm_simt: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
     }
     IR_CHECK_LAUNCH();
@@ -127,6 +129,8 @@ k_reduce_epilogue(IrConvBatch b, int K) {
         s_kofs[lane] = inc - v;
     }
     __syncthreads();
+    ir_pdl_trigger();                     // the next layer's pair-GEMM may start staging its weights
+    ir_pdl_wait();                        // T comes from the pair-GEMM launched just before
     const int n = *n_dev;
     float sc[V], sh[V];
 #pragma unroll
@@ -187,9 +191,9 @@ int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) 
     for (int g = 0; g < b.G; ++g) rows = rows > b.p[g].n_max ? rows : b.p[g].n_max;
     const dim3 grid(ir_min_i(ir_div_up(rows, 8), IR_NUM_SMS * 8), b.G);
     switch (cout) {
-        case 32: k_reduce_epilogue<32><<<grid, 256, 0, st>>>(b, K); break;
-        case 64: k_reduce_epilogue<64><<<grid, 256, 0, st>>>(b, K); break;
-        case 128: k_reduce_epilogue<128><<<grid, 256, 0, st>>>(b, K); break;
+        case 32: IR_CHECK_CUDA(ir_launch_pdl(k_reduce_epilogue<32>, grid, dim3(256), 0, st, b, K)); break;
+        case 64: IR_CHECK_CUDA(ir_launch_pdl(k_reduce_epilogue<64>, grid, dim3(256), 0, st, b, K)); break;
+        case 128: IR_CHECK_CUDA(ir_launch_pdl(k_reduce_epilogue<128>, grid, dim3(256), 0, st, b, K)); break;
         default: ir_set_error("reduce: unsupported cout %d", cout); return IR_ERR_UNSUPPORTED;
     }
     IR_CHECK_LAUNCH();

@@ -267,6 +267,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
+    ir_pdl_trigger();                      // the reduce kernel behind us may be scheduled as SMs free up
     const int dbg = g_tc_debug;
     const int kk = s_sched[0];
     const int t_begin = s_sched[1], t_end = (kk >= 0) ? s_sched[2] : 0;
@@ -343,8 +344,9 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
                 }
             }
         };
-        if (grp < n_items) load_idx(grp);
+        if (grp < n_items) load_idx(grp);                       // the rulebook is final long before this launch
         if (t_end > t_begin) weights_to_tmem(1 + pw / 4);       // this warp's share of the weight columns
+        ir_pdl_wait();                                          // feature rows come from the previous kernel
         if (grp < n_items) {
             load_rows(grp);
             load_idx(grp + NS);
@@ -424,6 +426,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
             }
             weights_to_tmem(0);
         }
+        ir_pdl_wait();                                          // T is still being read by the previous reduce
         uint32_t acc_it = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int p0 = tile * TILE_M;
@@ -474,7 +477,7 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     long long tiles_max = 0;
     for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
     const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, IR_NUM_SMS);
-    k_pairgemm_tc<CIN, COUT><<<grid, N_THREADS, C::SMEM_BYTES, st>>>(b, K);
+    IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
