@@ -302,7 +302,7 @@ def main():
     if rank == 0:
         nprof = min(a.steps, 10)
         model.concurrent = False          # serial launches: the event spans must not overlap other streams
-        lib.ir_profile_enable(1)
+        lib.ir_profile_enable(8)          # each timed kernel 8x back to back inside its event span (per-launch average)
         cap = 512
         gm, rm = (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
         meta, nout = (ctypes.c_int32 * (4 * cap))(), ctypes.c_int32(0)
@@ -345,8 +345,8 @@ def main():
                             spconv_share_of_step=all_ms / nprof / (dev_ms / a.steps))
         detail = {f'{k[0]}_{k[1]}x{k[2]}_k{k[3]}': dict(launches_per_step=v[3] / nprof, gemm_us=v[0] * 1e3 / v[3],
                                                        reduce_us=v[4] * 1e3 / v[3], pairs=v[5] / v[3],
-                                                       gemm_GBs=v[1] / (v[0] * 1e-3) / 1e9,
-                                                       gemm_TFLOPs=v[2] / (v[0] * 1e-3) / 1e12)
+                                                       gemm_GBs=v[1] / (max(v[0], 1e-4) * 1e-3) / 1e9,
+                                                       gemm_TFLOPs=v[2] / (max(v[0], 1e-4) * 1e-3) / 1e12)
                   for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
 
     cb = None

@@ -37,7 +37,9 @@ int ir_check_device(int device);
 int64_t ir_launch_count(void);
 /* Measurement hooks: while enabled every sparse-conv layer brackets its pair-GEMM and its reduce
  * launch with CUDA events on the launching stream; ir_profile_read synchronises, returns per-layer
- * milliseconds and meta = (cin, cout, K, used_tcgen05) x n, and resets the record. */
+ * per-launch milliseconds and meta = (cin, cout, K, used_tcgen05) x n, and resets the record.
+ * on = N > 1 launches each timed kernel N times back to back (idempotent) inside its event span so the
+ * host launch gap of an eager launch is amortised; the reported time is the per-launch average. */
 int ir_profile_enable(int on);
 int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out);
 

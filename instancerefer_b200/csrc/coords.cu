@@ -167,7 +167,7 @@ k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n
 // y%27; else k2s2 map from level l=(y-135)/8 to l+1, offset (y-135)%8.  Appendix-A enumeration:
 //   k3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
 //   k2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
-// One hash probe per thread, one warp-aggregated append per warp.  Emits per offset k:
+// One hash probe per thread, one block-aggregated append per CTA.  Emits per offset k:
 // in_idx[k*n_max + pos] (input row of pair pos), count[k], slot[k*n_max + o] = pos or -1.
 typedef IrKmapArgs KmapArgs;
 
@@ -188,8 +188,10 @@ k_kmap_all(KmapArgs a) {
     int dx, dy, dz;
     if (is3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
     else     { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
-    const int lane = threadIdx.x & 31;
-    const int n_round = (n + 31) & ~31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ int s_wcnt[8];
+    __shared__ int s_base;
+    const int n_round = (n + 255) & ~255;                  // whole CTAs iterate together (block-level scan)
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
         const bool live = o < n;
         int j = -1;
@@ -201,19 +203,25 @@ k_kmap_all(KmapArgs a) {
                 if (s >= 0) j = tin.row[s];
             }
         }
+        // one atomicAdd per CTA and offset (the 27 / 8 counters are hot): ballot inside the warp,
+        // 8-entry scan across warps, thread 0 claims the block's range
         const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+        if (lane == 0) s_wcnt[wid] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(cnt, tot) : 0;
+        }
+        __syncthreads();
         int pos = -1;
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(cnt, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (j >= 0) {
-                pos = base + __popc(m & ((1u << lane) - 1u));
-                in_k[pos] = j;
-            }
+        if (j >= 0) {
+            pos = s_base + s_wcnt[wid] + __popc(m & ((1u << lane) - 1u));
+            in_k[pos] = j;
         }
         if (live) slot_k[o] = pos;
+        __syncthreads();
     }
 }
 

@@ -54,6 +54,7 @@ struct IrConvBatch {
 // spconv.cu  (SIMT fp32 pair-GEMM + deterministic reduce/epilogue)
 int irk_pairgemm_simt(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);
 int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st);
+int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st);   // fused k3 conv for Cin <= 8 -> 32
 
 // spconv_tc.cu  (tcgen05 / TMEM / TMA pair-GEMM, split-fp16)
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);

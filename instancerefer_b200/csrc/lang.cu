@@ -78,8 +78,20 @@ k_gru_layer(const float* __restrict__ xproj, const float* __restrict__ whh, cons
     len = max(0, min(len, L));
     __syncthreads();
     const float4* hv = reinterpret_cast<const float4*>(s_h + half * (GRU_HALF + GRU_PAD));
+    // input projections of the current step live in registers; the next step's are prefetched while the
+    // recurrent matvec runs (they do not depend on h)
+    float xr = 0.f, xz = 0.f, xn = 0.f;
+    if (t < H && len > 0) {
+        const float* xp = xproj + (((size_t)b * L + (dir ? len - 1 : 0)) * 2 + dir) * G;
+        xr = xp[t]; xz = xp[H + t]; xn = xp[2 * H + t];
+    }
     for (int s = 0; s < len; ++s) {
         const int tt = dir ? (len - 1 - s) : s;
+        float nr = 0.f, nz = 0.f, nn = 0.f;
+        if (t < H && s + 1 < len) {
+            const float* xp = xproj + (((size_t)b * L + (dir ? tt - 1 : tt + 1)) * 2 + dir) * G;
+            nr = xp[t]; nz = xp[H + t]; nn = xp[2 * H + t];
+        }
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < GRU_HALF / 4; ++i) {
@@ -94,14 +106,14 @@ k_gru_layer(const float* __restrict__ xproj, const float* __restrict__ whh, cons
         if (half == 0) s_hp[j] = acc + bj;
         __syncthreads();
         if (t < H) {
-            const float* xp = xproj + (((size_t)b * L + tt) * 2 + dir) * G;
             const int hi = (t / GRU_HALF) * (GRU_HALF + GRU_PAD) + (t % GRU_HALF);
-            const float r = 1.f / (1.f + expf(-(xp[t] + s_hp[t])));
-            const float z = 1.f / (1.f + expf(-(xp[H + t] + s_hp[H + t])));
-            const float n = tanhf(xp[2 * H + t] + r * s_hp[2 * H + t]);
+            const float r = 1.f / (1.f + expf(-(xr + s_hp[t])));
+            const float z = 1.f / (1.f + expf(-(xz + s_hp[H + t])));
+            const float n = tanhf(xn + r * s_hp[2 * H + t]);
             const float h = (1.f - z) * n + z * s_h[hi];
             out[((size_t)b * L + tt) * (2 * H) + dir * H + t] = h;
             s_h[hi] = h;
+            xr = nr; xz = nz; xn = nn;
         }
         __syncthreads();
     }

@@ -199,3 +199,55 @@ int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) 
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ fused stem (Cin <= 8 -> 32, k3)
+// The stem has 7 input channels: a pair-GEMM + reduce round trip through T costs more than the
+// arithmetic.  Direct output-stationary form instead: one warp per output row, lane = output channel,
+// the 27 x Cin x 32 weights in shared memory, neighbours resolved through the same rulebook
+// (slot -> in_idx), folded BN + ReLU in the epilogue.  Replaces stem.0 of models/basic_blocks.py:64-66.
+#define STEM_COUT 32
+#define STEM_MAXCIN 8
+__global__ void __launch_bounds__(256)
+k_stem_direct(IrConvBatch b, int cin) {
+    const IrConvProblem& P = b.p[blockIdx.y];
+    __shared__ float Ws[27 * STEM_MAXCIN * STEM_COUT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 27 * cin * STEM_COUT; i += 256) Ws[i] = P.weight[i];     // (27, cin, 32), constant
+    __syncthreads();
+    ir_pdl_trigger();
+    ir_pdl_wait();
+    const int n = *P.n_out_dev;
+    const float sc = P.scale ? P.scale[lane] : 1.f, sh = P.shift ? P.shift[lane] : 0.f;
+    const int wpb = blockDim.x >> 5;
+    for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
+        int my_j = -1;
+        if (lane < 27) {
+            const int pos = P.slot[(long long)lane * P.seg_cap + o];
+            if (pos >= 0) my_j = P.in_idx[(long long)lane * P.seg_cap + pos];
+        }
+        float acc = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < 27; ++k) {
+            const int j = __shfl_sync(0xffffffffu, my_j, k);
+            if (j >= 0) {                                                   // warp-uniform
+                const float* f = P.fin + (long long)j * cin;
+                const float* w = Ws + (k * cin) * STEM_COUT + lane;
+                for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(f + ci), w[ci * STEM_COUT], acc);
+            }
+        }
+        float y = fmaf(acc, sc, sh);
+        if (P.resid) y += P.resid[o * STEM_COUT + lane];
+        if (P.relu) y = fmaxf(y, 0.f);
+        P.out[o * STEM_COUT + lane] = y;
+    }
+}
+
+int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st) {
+    IR_CHECK_ARG(cin >= 1 && cin <= STEM_MAXCIN && b.G >= 1 && b.G <= IR_MAX_GROUPS);
+    long long rows = 1;
+    for (int g = 0; g < b.G; ++g) rows = rows > b.p[g].n_max ? rows : b.p[g].n_max;
+    const dim3 grid(ir_min_i(ir_div_up(rows, 8), IR_NUM_SMS * 8), b.G);
+    IR_CHECK_CUDA(ir_launch_pdl(k_stem_direct, grid, dim3(256), 0, st, b, cin));
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

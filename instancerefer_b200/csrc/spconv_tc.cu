@@ -35,7 +35,8 @@ extern "C" int ir_debug_stats(long long* out64) {
 
 namespace tc {
 
-constexpr int TILE_M = 128;          // pairs per tile (UMMA N)
+constexpr int TILE_M = 64;           // pairs per tile (UMMA N); 64 keeps a CTA at half an SM's TMEM / registers
+constexpr int TASKS = TILE_M / 16;   // (row, chunk) tasks per producer thread and item
 constexpr int PANEL = 64;            // fp16 channels per 128-byte swizzle row = channels per stage
 constexpr int PANEL_BYTES = TILE_M * 128;          // one operand panel (hi or lo) of the gathered tile
 constexpr int STAGE_BYTES = 2 * PANEL_BYTES;       // hi + lo
@@ -154,7 +155,8 @@ struct Cfg {
     static constexpr int KP = CINP / PANEL;                      // K panels (= pipeline items) per tile
     static constexpr int W_RAW_BYTES = CIN * COUT * 4;           // W[k] (Cin,Cout) fp32, staged once by TMA
     static constexpr int OFF_STAGE = 0;
-    static constexpr int OFF_BAR = OFF_STAGE + NS * STAGE_BYTES;
+    static constexpr int STAGE_AREA = (NS * STAGE_BYTES > W_RAW_BYTES) ? NS * STAGE_BYTES : W_RAW_BYTES;
+    static constexpr int OFF_BAR = OFF_STAGE + STAGE_AREA;
     static constexpr int N_BAR = 2 * NS + 6;
     static constexpr int OFF_MISC = OFF_BAR + N_BAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 16 * 4 + 1024;   // + alignment slack
@@ -162,13 +164,13 @@ struct Cfg {
     // pairs (Cin/2 columns each)
     static constexpr int COL_W_HI = 2 * TILE_M;
     static constexpr int COL_W_LO = COL_W_HI + CINP / 2;
-    static constexpr int TMEM_COLS = 512;
-    static_assert(W_RAW_BYTES <= NS * STAGE_BYTES, "raw weight tile must fit the stage area");
+    static constexpr int TMEM_COLS = (COL_W_LO + CINP / 2 <= 256) ? 256 : 512;
     static_assert(COL_W_LO + CINP / 2 <= 512, "TMEM column budget");
+    static_assert(STAGE_AREA % 1024 == 0, "barriers follow the stage area");
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(N_THREADS, 1)
+__global__ void __launch_bounds__(N_THREADS, 2)
 k_pairgemm_tc(IrConvBatch batch, int K) {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
@@ -311,22 +313,22 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     if (warp >= 5) {
         // ===================== gather producers: NS independent groups of 128 threads ==========
         // Work items = (tile, 64-channel panel) in order; group g owns stage g and the items
-        // it = g, g+NS, ...  A thread owns 8 (row, 8-channel chunk) tasks per item: two 16-byte loads,
+        // it = g, g+NS, ...  A thread owns TILE_M/16 (row, 8-channel chunk) tasks per item: two 16-byte loads,
         // fp32 -> fp16 hi/lo split, two 16-byte swizzled shared-memory stores.  The loads of the group's
         // next item are issued right after the current item was handed to the tensor core.
         const int pw = warp - 5;
         const int grp = pw / WARPS_PER_GROUP;
         const int gt = (pw % WARPS_PER_GROUP) * 32 + lane;     // thread inside the group (0..127)
         const int j = gt & 7;                  // 16-byte (8 x fp16) chunk inside the 128-byte panel row
-        const int rbase = gt >> 3;             // rows rbase + 16*i, i < 8
+        const int rbase = gt >> 3;             // rows rbase + 16*i, i < TASKS
         const int* idx_k = in_idx + (long long)kk * seg_cap;
         const int n_items = (t_end - t_begin) * C::KP;
-        int idx[8];
-        float4 va[8], vb[8];
+        int idx[TASKS];
+        float4 va[TASKS], vb[TASKS];
         auto load_idx = [&](int it) {
             const int p0 = (t_begin + it / C::KP) * TILE_M;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TASKS; ++i) {
                 const int r = p0 + rbase + 16 * i;
                 idx[i] = (it < n_items && r < kcount) ? __ldg(idx_k + r) : -1;
             }
@@ -334,7 +336,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
         auto load_rows = [&](int it) {
             const int ch = (it % C::KP) * PANEL + j * 8;           // first channel of this thread's chunk
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TASKS; ++i) {
                 va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (idx[i] >= 0 && ch < CIN && !(dbg & 1)) {
@@ -359,7 +361,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
         for (int it = grp; it < n_items; it += NS, ++round) {
             mbar_wait(bar_empty(grp), (round & 1u) ^ 1u);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TASKS; ++i) {
                 const int r = rbase + 16 * i;
                 const int off = r * 128 + ((j ^ (r & 7)) << 4);
                 uint4 h, l;
@@ -476,7 +478,7 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     }
     long long tiles_max = 0;
     for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
-    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, IR_NUM_SMS);
+    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, 2 * IR_NUM_SMS);       // two CTAs per SM
     IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
     IR_CHECK_LAUNCH();
     return IR_OK;

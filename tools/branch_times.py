@@ -56,3 +56,37 @@ ws = m.scene.net.workspace(d0['lidar'].F.shape[0], 'cuda')
 timeit(lambda: ops.encoder_build_maps(ws, d0['lidar'].C), 'scene maps only')
 prep = m.scene.net.prepared(); out = torch.empty(ws.n_max, 128, device='cuda')
 timeit(lambda: ops.encoder_features(prep['params'], ws, d0['lidar'].F, out), 'scene 13 conv layers only')
+
+# two encoders concurrently on two streams (how much do they overlap?)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def both():
+    cur = torch.cuda.current_stream()
+    s1.wait_stream(cur); s2.wait_stream(cur)
+    with torch.cuda.stream(s1):
+        d = dict(d0); m.attribute.encode_candidates(d, 'cuda', pack)
+    with torch.cuda.stream(s2):
+        d = dict(d0); m.scene.encode_scene(d, torch.device('cuda'))
+    cur.wait_stream(s1); cur.wait_stream(s2)
+timeit(both, 'attr || scene (2 streams)')
+def three():
+    cur = torch.cuda.current_stream()
+    s1.wait_stream(cur); s2.wait_stream(cur)
+    with torch.cuda.stream(s1):
+        d = dict(d0); m.attribute.encode_candidates(d, 'cuda', pack)
+    with torch.cuda.stream(s2):
+        d = dict(d0); m.scene.encode_scene(d, torch.device('cuda'))
+    m.lang(dict(d0))
+    cur.wait_stream(s1); cur.wait_stream(s2)
+timeit(three, 'attr || scene || lang')
+ws_a = m.attribute.net.workspace(32 * 1024, 'cuda')
+prep_a = m.attribute.net.prepared(); out_a = torch.empty(ws_a.n_max, 128, device='cuda')
+def convs2():
+    cur = torch.cuda.current_stream()
+    s1.wait_stream(cur); s2.wait_stream(cur)
+    with torch.cuda.stream(s1):
+        ops.encoder_features(prep_a['params'], ws_a, None, out_a)
+    with torch.cuda.stream(s2):
+        ops.encoder_features(prep['params'], ws, d0['lidar'].F, out)
+    cur.wait_stream(s1); cur.wait_stream(s2)
+timeit(lambda: ops.encoder_features(prep_a['params'], ws_a, None, out_a), 'attr 13 conv layers only')
+timeit(convs2, '13 convs attr || 13 convs scene')
