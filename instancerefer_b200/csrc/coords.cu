@@ -163,64 +163,88 @@ k_vox_compact(const float* __restrict__ pts, const int* __restrict__ cand, int n
         });
 }
 
-// All nine kernel maps of an encoder in one launch.  blockIdx.y < 135: k3 map of level y/27, offset
-// y%27; else k2s2 map from level l=(y-135)/8 to l+1, offset (y-135)%8.  Appendix-A enumeration:
+// All nine kernel maps of an encoder in one launch (grid.y walks map x offset group).  Appendix-A
+// offset enumeration:
 //   k3: k = (dz+1)*9 + (dy+1)*3 + (dx+1), offsets {-1,0,1}*stride
 //   k2: k = 4*bx + 2*by + bz,            offsets {0,1}*stride   (stride = INPUT level stride)
 // One hash probe per thread, one block-aggregated append per CTA.  Emits per offset k:
 // in_idx[k*n_max + pos] (input row of pair pos), count[k], slot[k*n_max + o] = pos or -1.
 typedef IrKmapArgs KmapArgs;
 
+#define KM_K3_GROUPS 9          // 27 offsets = 9 groups of 3 per thread
+#define KM_NY (5 * KM_K3_GROUPS + 4 * 2)   // + 4 k2 maps x 2 groups of 4
 __global__ void __launch_bounds__(256)
 k_kmap_all(KmapArgs a) {
+    // blockIdx.y < 45: k3 map of level y/9, offsets 3*(y%9) .. +2;  else k2s2 map l=(y-45)/2, offsets
+    // 4*((y-45)%2) .. +3.  A thread probes its 3-4 offsets back to back (independent L2 latencies).
     const int y = blockIdx.y;
-    const bool is3 = y < 135;
-    const int l = is3 ? y / 27 : (y - 135) / 8;
-    const int k = is3 ? y % 27 : (y - 135) % 8;
+    const bool is3 = y < 5 * KM_K3_GROUPS;
+    const int l = is3 ? y / KM_K3_GROUPS : (y - 5 * KM_K3_GROUPS) / 2;
+    const int k0 = is3 ? 3 * (y % KM_K3_GROUPS) : 4 * ((y - 5 * KM_K3_GROUPS) % 2);
+    const int NK = is3 ? 3 : 4;
     const int lo = is3 ? l : l + 1;                       // output level
     const int stride = 1 << l;
     const int n = a.nlvl[lo];
     const int4* __restrict__ coords_out = a.coords[lo];
     const IrTable tin = a.lt.t[l];
-    int* __restrict__ in_k = (is3 ? a.k3_in[l] : a.k2_in[l]) + (long long)k * a.n_max;
-    int* __restrict__ slot_k = (is3 ? a.k3_slot[l] : a.k2_slot[l]) + (long long)k * a.n_max;
-    int* __restrict__ cnt = a.kcount + (is3 ? l : 5 + l) * 32 + k;
-    int dx, dy, dz;
-    if (is3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
-    else     { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
+    int* __restrict__ in_base = is3 ? a.k3_in[l] : a.k2_in[l];
+    int* __restrict__ slot_base = is3 ? a.k3_slot[l] : a.k2_slot[l];
+    int* __restrict__ cnt = a.kcount + (is3 ? l : 5 + l) * 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ int s_wcnt[8];
-    __shared__ int s_base;
+    __shared__ int s_wcnt[4][8];
+    __shared__ int s_base[4];
     const int n_round = (n + 255) & ~255;                  // whole CTAs iterate together (block-level scan)
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_round; o += gridDim.x * blockDim.x) {
         const bool live = o < n;
-        int j = -1;
-        if (live) {
-            if (is3 && k == 13) j = o;
-            else {
-                const int4 c = coords_out[o];
-                const int s = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
-                if (s >= 0) j = tin.row[s];
+        int4 c = make_int4(0, 0, 0, 0);
+        if (live) c = coords_out[o];
+        int sl[4], j[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            sl[u] = -1;
+            j[u] = -1;
+            const int k = k0 + u;
+            if (live && u < NK && !(is3 && k == 13)) {
+                int dx, dy, dz;
+                if (is3) { dx = (k % 3 - 1) * stride; dy = ((k / 3) % 3 - 1) * stride; dz = (k / 9 - 1) * stride; }
+                else     { dx = (k >> 2) * stride; dy = ((k >> 1) & 1) * stride; dz = (k & 1) * stride; }
+                sl[u] = ir_ht_find(tin, ir_pack_key(c.x + dx, c.y + dy, c.z + dz, c.w));
             }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (sl[u] >= 0) j[u] = tin.row[sl[u]];
+            if (live && u < NK && is3 && k0 + u == 13) j[u] = o;       // centre offset: the row itself
+        }
         // one atomicAdd per CTA and offset (the 27 / 8 counters are hot): ballot inside the warp,
-        // 8-entry scan across warps, thread 0 claims the block's range
-        const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
-        if (lane == 0) s_wcnt[wid] = __popc(m);
+        // 8-entry scan across warps, threads 0..3 claim the block's ranges
+        unsigned m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            m[u] = __ballot_sync(0xffffffffu, j[u] >= 0);
+            if (lane == 0) s_wcnt[u][wid] = __popc(m[u]);
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < NK) {
+            const int u = threadIdx.x;
             int tot = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { const int c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
-            s_base = tot ? atomicAdd(cnt, tot) : 0;
+            for (int w = 0; w < 8; ++w) { const int cc = s_wcnt[u][w]; s_wcnt[u][w] = tot; tot += cc; }
+            s_base[u] = tot ? atomicAdd(cnt + k0 + u, tot) : 0;
         }
         __syncthreads();
-        int pos = -1;
-        if (j >= 0) {
-            pos = s_base + s_wcnt[wid] + __popc(m & ((1u << lane) - 1u));
-            in_k[pos] = j;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < NK) {
+                const long long seg = (long long)(k0 + u) * a.n_max;
+                int pos = -1;
+                if (j[u] >= 0) {
+                    pos = s_base[u] + s_wcnt[u][wid] + __popc(m[u] & ((1u << lane) - 1u));
+                    in_base[seg + pos] = j[u];
+                }
+                if (live) slot_base[seg + o] = pos;
+            }
         }
-        if (live) slot_k[o] = pos;
         __syncthreads();
     }
 }
@@ -269,7 +293,7 @@ int irk_voxelize(const float* pts, const int* cand, int n_cand, int ppi, int fdi
 
 int irk_kmap_all(const IrKmapArgs& a, long long rows_max, cudaStream_t st) {
     const int gx = ir_min_i(ir_div_up(rows_max > 0 ? rows_max : 1, 256), IR_NUM_SMS);
-    k_kmap_all<<<dim3(gx, 5 * 27 + 4 * 8), 256, 0, st>>>(a);
+    k_kmap_all<<<dim3(gx, KM_NY), 256, 0, st>>>(a);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -225,6 +225,8 @@ k_stem_direct(IrConvBatch b, int cin) {
             const int pos = P.slot[(long long)lane * P.seg_cap + o];
             if (pos >= 0) my_j = P.in_idx[(long long)lane * P.seg_cap + pos];
         }
+        // (a shuffle-broadcast variant with all 27 rows prefetched was measured slower in the pipeline:
+        //  it is instruction-bound, while this form hides its load latency behind the other warps)
         float acc = 0.f;
 #pragma unroll 1
         for (int k = 0; k < 27; ++k) {
