@@ -46,8 +46,6 @@ int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap
 /* Tuning aid for the tcgen05 pair-GEMM (tools/bench_spconv.py): bit0 skip gather loads, bit1 skip T
  * stores, bit2 skip MMA issue.  0 = normal operation. */
 int ir_debug_set(int flags);
-/* Copies the kernel's 64 int64 debug counters to the host (synchronises; unused in normal builds). */
-int ir_debug_stats(long long* out64);
 
 /* ------------------------------------------------------------------ sparse-voxel encoder
  * SparseConvEncoder / BEVEncoder (models/basic_blocks.py:59-95,136-171): 13 sparse convs

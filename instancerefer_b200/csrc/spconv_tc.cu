@@ -25,12 +25,8 @@
 
 // tuning aid (tools/bench_spconv.py): bit0 skip gather loads, bit1 skip T stores, bit2 skip MMA issue
 __device__ int g_tc_debug = 0;
-__device__ long long g_tc_stats[64];
 extern "C" int ir_debug_set(int flags) {
     return cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? IR_OK : IR_ERR_CUDA;
-}
-extern "C" int ir_debug_stats(long long* out64) {
-    return cudaMemcpyFromSymbol(out64, g_tc_stats, sizeof(long long) * 64) == cudaSuccess ? IR_OK : IR_ERR_CUDA;
 }
 
 namespace tc {

@@ -409,3 +409,49 @@ def test_streams_and_graph_replay_bitwise(gpu_model):
             assert torch.equal(r['host_scores'][k], want[k].cpu()), ('pipelined', k)
         assert torch.equal(r['host_scores']['ref_pred'], want['ref_pred'].cpu())
     gpu_model.concurrent = True
+
+
+def test_forward_predicted_language_class(lib_built, state_dict):
+    """use_gt_lang: False — candidates filtered by argmax(lang_scores) (models/attribute_module.py:93-97)."""
+    from conftest import make_args
+    from instancerefer_b200.instancerefer import InstanceRefer
+    a = make_args(use_gt_lang=False)
+    m = InstanceRefer(7, a)
+    m.load_state_dict(state_dict, strict=True)
+    m = m.cuda().eval()
+    b = synthetic.make_batch(61, batch_size=2, num_points=5000, n_inst=18, n_cand=3, n_tokens=[6, 8])
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), a)
+    pred = ref['lang_scores'].argmax(1).tolist()
+    for i in range(2):                       # make the predicted class own >= 2 instances in every scene
+        b['instance_class'][i][:3] = [pred[i]] * 3
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), a)
+    out = _run(m, b)
+    assert out['num_filtered_objs'] == ref['num_filtered_objs']
+    for k in ('lang_scores', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores'):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k
+
+
+def test_forward_c5_large_scene(gpu_model, state_dict, args):
+    """BASELINE.json configs[4] sweep point: 120k points, 64 instances (two row buckets above the bench)."""
+    b = synthetic.make_batch(77, batch_size=1, num_points=120000, n_inst=64, n_cand=64, n_tokens=20,
+                             room=(11.5, 14.0, 3.0))
+    out = _run(gpu_model, b)
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), args)
+    for k in ('obj_feats', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'vis_atten'):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k
+
+
+def test_encoder_sparse_tensor_api(ops, state_dict):
+    """SparseConvEncoder.forward(SparseTensor) -> SparseTensor at stride 16 (API fidelity)."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.basic_blocks import SparseConvEncoder
+    b = synthetic.make_batch(5, batch_size=1, num_points=3000, n_inst=4, n_cand=2, n_tokens=4)
+    enc = SparseConvEncoder(7)
+    enc.load_state_dict({k[len('attribute.net.'):]: v for k, v in state_dict.items() if k.startswith('attribute.net.')})
+    enc = enc.cuda().eval()
+    y = enc(SparseTensor(torch.from_numpy(b['lidar_feats']), torch.from_numpy(b['lidar_coords'])).cuda())
+    sd = {k: v.float() for k, v in state_dict.items()}
+    Fr, Cr, s = model_ref.encoder_forward(sd, 'attribute.net', torch.from_numpy(b['lidar_feats']),
+                                          torch.from_numpy(b['lidar_coords']))
+    assert y.s == 16 and np.array_equal(y.C.cpu().numpy(), Cr.numpy())
+    assert float((y.F.cpu() - Fr).abs().max()) < TOL
