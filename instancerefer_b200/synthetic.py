@@ -16,6 +16,8 @@ import numpy as np
 
 MAX_DES_LEN = 126          # lib/config.py:74
 NUM_CLASSES = 18           # config/InstanceRefer.yaml:8
+LABEL_KEYS = ('ref_center_label', 'ref_size_residual_label', 'ref_heading_class_label',
+              'ref_heading_residual_label', 'ref_size_class_label')
 
 
 def quantize_first(xyz, feats, voxel):
@@ -99,10 +101,21 @@ def make_scene(seed, num_points=40000, n_inst=32, n_cand=32, n_tokens=20,
 
     lang = np.zeros((MAX_DES_LEN, 300), np.float32)
     lang[:n_tokens] = rng.normal(0.0, 0.4, (n_tokens, 300)).astype(np.float32)
+    # training labels (lib/dataset.py:263-298): the referred object is one of the target-class
+    # instances; its box is the instance OBB, slightly perturbed so the IoU argmax is non-trivial.
+    # Drawn last so the forward inputs above are unchanged for a given seed.
+    cand_ids = [j for j in range(n_inst) if cls[j] == target_class]
+    ref_j = cand_ids[int(rng.integers(0, len(cand_ids)))] if cand_ids else 0
+    ref_obb = inst_obbs[ref_j] if n_inst else np.zeros(7)
+    ref_center = (ref_obb[:3] + rng.normal(0.0, 0.03, 3)).astype(np.float32)
+    ref_size = (ref_obb[3:6] * rng.uniform(0.9, 1.1, 3)).astype(np.float32)
     return dict(point_cloud=pc, instance_points=inst_pts, instance_obbs=inst_obbs,
                 instance_class=[int(c) for c in cls], object_cat=np.int64(target_class),
                 lang_feat=lang, lang_len=np.int64(n_tokens),
-                point_min=pc[:, :3].min(0), point_max=pc[:, :3].max(0))
+                point_min=pc[:, :3].min(0), point_max=pc[:, :3].max(0),
+                ref_center_label=ref_center, ref_size_residual_label=ref_size,
+                ref_heading_class_label=np.int64(0), ref_heading_residual_label=np.float32(0),
+                ref_size_class_label=np.int64(0), ref_obj_index=np.int64(ref_j))
 
 
 def make_batch(seed, batch_size=1, voxel_size_glp=0.05, n_cand=32, n_tokens=20, **kw):
@@ -126,6 +139,7 @@ def make_batch(seed, batch_size=1, voxel_size_glp=0.05, n_cand=32, n_tokens=20, 
         object_cat=np.stack([s['object_cat'] for s in scenes], 0),
         point_min=np.stack([s['point_min'] for s in scenes], 0),
         point_max=np.stack([s['point_max'] for s in scenes], 0),
+        **{k: np.stack([s[k] for s in scenes], 0) for k in LABEL_KEYS},
         instance_points=[s['instance_points'] for s in scenes],
         instance_obbs=[s['instance_obbs'] for s in scenes],
         instance_class=[s['instance_class'] for s in scenes],
@@ -148,6 +162,8 @@ def shift_batch(batch, shift):
     out['lidar_coords'], out['lidar_feats'] = c, f
     out['point_min'] = batch['point_min'] + shift
     out['point_max'] = batch['point_max'] + shift
+    if 'ref_center_label' in batch:
+        out['ref_center_label'] = batch['ref_center_label'] + shift
     return out
 
 
@@ -164,6 +180,7 @@ def to_data_dict(batch, sparse_tensor_cls, device='cpu'):
         object_cat=torch.from_numpy(batch['object_cat']).to(device),
         point_min=torch.from_numpy(batch['point_min']).to(device),
         point_max=torch.from_numpy(batch['point_max']).to(device),
+        **{k: torch.from_numpy(np.asarray(batch[k])).to(device) for k in LABEL_KEYS if k in batch},
         instance_points=batch['instance_points'],
         instance_obbs=batch['instance_obbs'],
         instance_class=batch['instance_class'],

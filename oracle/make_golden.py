@@ -71,5 +71,44 @@ def main():
         print(name, {k: arrs[k].shape for k in ('attribute_scores', 'obj_feats')})
 
 
+TRAIN_CASES = {
+    'train_b2': dict(seed=5, batch_size=2, num_points=6000, n_inst=8, n_cand=[4, 3], n_tokens=[6, 9]),
+    'train_ragged_b3': dict(seed=21, batch_size=3, num_points=6000, n_inst=10, n_cand=[4, 1, 3], n_tokens=[7, 12, 3]),
+}
+
+
+def main_train():
+    """Golden fixtures of one training iteration (reference models + lib/loss_helper.get_loss run
+    verbatim, Dropout p=0, oracle/train_ref.SyntheticConfig as the dataset config): loss terms, the
+    L2 norm of every parameter gradient, full gradients of the small tensors, updated BN statistics."""
+    import train_ref as T
+    spec = W.load_spec()
+    ST = H.shim_sparse_tensor()
+    for name, cfg in TRAIN_CASES.items():
+        model, args = H.build_reference_model()
+        model.load_state_dict(W.make_state_dict(123, spec), strict=True)
+        b = make_case_batch(cfg)
+        out = H.run_reference_train_step(model, S.to_data_dict(b, ST), T.SyntheticConfig())
+        arrs = {k: out[k].detach().numpy().reshape(-1) for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss')}
+        names, norms = [], []
+        for k, p in model.named_parameters():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            names.append(k)
+            norms.append(float(g.double().norm()))
+            if g.numel() <= 4096:
+                arrs['grad/' + k] = g.numpy()
+        arrs['grad_names'] = np.frombuffer(json.dumps(names).encode(), dtype=np.uint8)
+        arrs['grad_norms'] = np.asarray(norms, np.float64)
+        for k, v in model.state_dict().items():
+            if k.endswith(('running_mean', 'running_var')) and v.numel() <= 64:
+                arrs['bn/' + k] = v.numpy()
+        arrs['config_json'] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(GOLD, f'golden_{name}.npz'), **arrs)
+        print(name, float(out['loss']), len(names))
+
+
 if __name__ == '__main__':
+    if '--train' in sys.argv:
+        main_train()
+        sys.exit(0)
     main()

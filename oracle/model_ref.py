@@ -30,6 +30,9 @@ def _lin(sd, p, x):
     return Fn.linear(x, sd[p + '.weight'], sd[p + '.bias'])
 
 
+BN_RECORD = None      # dict -> train-mode forwards store {prefix: (batch mean, unbiased var)} for the running-stat update
+
+
 def _bn(sd, p, x, train, eps=1e-5):
     """nn.BatchNorm{1d,2d} forward on (N,C) or (B,C,H,W); batch stats (biased var) in train."""
     w, b = sd[p + '.weight'], sd[p + '.bias']
@@ -37,6 +40,9 @@ def _bn(sd, p, x, train, eps=1e-5):
         dims = [0] if x.dim() == 2 else [0, 2, 3]
         mean = x.mean(dims)
         var = x.var(dims, unbiased=False)
+        if BN_RECORD is not None:
+            n = x.numel() // x.shape[1]
+            BN_RECORD[p] = (mean.detach().clone(), (var.detach() * (n / max(n - 1, 1))).clone())
     else:
         mean, var = sd[p + '.running_mean'], sd[p + '.running_var']
     shp = (1, -1) if x.dim() == 2 else (1, -1, 1, 1)
@@ -311,11 +317,12 @@ def scene_forward(sd, data, lang, attr, cands, args, train=False, trace=None):
 
 # ----------------------------------------------------------------------------- whole forward
 
-def forward(sd, data, args, train=False, trace=None):
+def forward(sd, data, args, train=False, trace=None, keep_grad=False):
     """InstanceRefer.forward (models/instancerefer.py:56-70).  ``data``: lang_feat (B,126,300),
     lang_len (B,), object_cat (B,), lidar_F (N,7), lidar_C (N,4), point_min (B,3), and the host
     lists instance_points / instance_obbs / instance_class.  Returns the written dict entries."""
-    sd = {k: (v.detach().float() if v.is_floating_point() else v) for k, v in sd.items()}
+    if not keep_grad:
+        sd = {k: (v.detach().float() if v.is_floating_point() else v) for k, v in sd.items()}
     out = {}
     lang = lang_forward(sd, data, train)
     out.update(lang)

@@ -126,3 +126,26 @@ def run_reference(model, data_dict, train=False):
         model.train(train)
         with torch.set_grad_enabled(train):
             return model(data_dict)
+
+
+def run_reference_train_step(model, data_dict, config):
+    """Reference forward in train mode (Dropout p forced to 0: torch's mask stream cannot be
+    reproduced elsewhere), the reference's own lib/loss_helper.get_loss VERBATIM, backward.
+    -> data_dict with 'loss', 'ref_loss', 'lang_loss', 'seg_loss'; grads sit on model params."""
+    _setup_paths()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.zero_grad()
+    out = run_reference(model, data_dict, train=True)
+    with cpu_patches():
+        orig_ones, orig_zeros = torch.ones, torch.zeros
+        torch.ones = lambda *a, **k: (k.pop('device', None), orig_ones(*a, **k))[1]      # lib/loss_helper.py:140
+        torch.zeros = lambda *a, **k: (k.pop('device', None), orig_zeros(*a, **k))[1]
+        try:
+            lh = importlib.import_module('lib.loss_helper')
+            out = lh.get_loss(out, config)
+        finally:
+            torch.ones, torch.zeros = orig_ones, orig_zeros
+    out['loss'].backward()
+    return out
