@@ -215,6 +215,68 @@ int ir_edgeconv(const float* x, const float* xyz, const int32_t* qidx, const int
                 const float* Ww2, const float* bw2, const float* Wm1, const float* bm1,
                 const float* Wm2, const float* bm2, int32_t Fout, float* out, ir_stream_t stream);
 
+/* ================================================================== training step
+ * Backward of the sparse encoders, train-mode BatchNorm, loss and optimiser.  What torchsparse's
+ * sparseconv_backward, torch autograd and torch.optim.Adam do for lib/solver.py:196-205.          */
+
+/* Transposed rulebook of one kernel map: out_idx[k][pos] = output row of pair pos,
+ * slot_in[k][i] = pair of input row i (or -1).  dgrad of a sparse conv is ir_spconv_layer run on
+ * (out_idx, slot_in) with the weight transposed to (K,Cout,Cin): dX = sum_k dY[o] @ W[k]^T.       */
+int ir_rulebook_transpose(const int32_t* in_idx, const int32_t* slot, int32_t K, int64_t seg_cap,
+                          const int32_t* n_out_dev, int64_t n_max, int32_t* out_idx, int32_t* slot_in,
+                          ir_stream_t stream);
+
+/* dW[k] = sum over pairs of offset k of x[in_idx]^T dy[out_idx]   (K,Cin,Cout), overwritten.      */
+int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int32_t cout, int32_t K,
+                    const int32_t* in_idx, const int32_t* out_idx, const int32_t* count,
+                    int64_t seg_cap, float* dW, ir_stream_t stream);
+
+/* Train-mode BatchNorm over the rows of a (n, C) matrix (spnn.BatchNorm over voxels, BatchNorm1d,
+ * BatchNorm2d on NHWC cells): batch mean / biased variance, y = act((x-mean)*rstd*gamma + beta
+ * (+resid)); running statistics updated with `momentum` (unbiased variance) when given.
+ * n_dev (optional) = device row count bounded by n.  scratch: double[2*C].  C divides 256.        */
+int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, int32_t C, const float* gamma,
+                    const float* beta, const float* resid, int32_t relu, float eps, float momentum,
+                    float* running_mean, float* running_var, double* scratch, float* mean,
+                    float* rstd, float* y, ir_stream_t stream);
+/* g = dy*[y>0] (relu); dbeta = sum g; dgamma = sum g*xhat; dx; dresid = g (optional).             */
+int ir_bn_train_bwd(const float* dy, const float* y, const float* x, const int32_t* n_dev, int32_t n,
+                    int32_t C, const float* mean, const float* rstd, const float* gamma, int32_t relu,
+                    double* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
+                    ir_stream_t stream);
+
+/* Backward of ir_segmax: the gradient of out[b,c] goes to the first row attaining the maximum.
+ * arg_scratch: int32 (n_seg, C). */
+int ir_segmax_bwd(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
+                  int32_t C, int32_t n_seg, const float* pooled, const float* dpooled,
+                  int32_t* arg_scratch, float* dfeats, ir_stream_t stream);
+
+/* Mean cross-entropy over B rows and its gradient (lib/loss_helper.py:155,189-193). B <= 1024.    */
+int ir_cross_entropy(const float* logits, const int64_t* labels, int32_t B, int32_t N, float* loss,
+                     float* dlogits, ir_stream_t stream);
+
+/* 9-way region label of compute_scene_mask_loss (lib/loss_helper.py:131-153); (B,3) fp64 inputs,
+ * inputs_were_f32 keeps fp32 rounding of the thirds when every operand was fp32 in the caller.    */
+int ir_region_label(const double* ref_center, const double* point_min, const double* point_max,
+                    int32_t B, int32_t inputs_were_f32, int64_t* label, ir_stream_t stream);
+
+/* Reference loss of get_loss (lib/loss_helper.py:225-260): per scene b, IoU of its candidate boxes
+ * pred_obb[obb_ofs[b]:obb_ofs[b+1]] (7 doubles each) with gt_obb[b] (utils/box_util.py:154-198,
+ * 310-333), label = one-hot of the first maximal IoU; when the scene has >= 2 candidates
+ * (score_ofs[b] >= 0 = its offset in the score vectors) and max IoU >= iou_thresh:
+ * loss_scene[b] = ContrastiveLoss(margin, gamma)(s_attr+s_rel+s_scene, label) (:93-107) and
+ * dscore = d loss_scene / d score.  ref_loss = sum(loss_scene) / B.                               */
+int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
+                const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
+                const float* s_scene, float margin, float gamma, float iou_thresh, float* label,
+                float* loss_scene, float* dscore, float* iou_max, ir_stream_t stream);
+
+/* torch.optim.Adam (amsgrad off) on one flat fp32 buffer; gradient = grad_scale*g + weight_decay*p
+ * (grad_scale = 1/world_size after a sum all-reduce).  `step` counts from 1.                      */
+int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                 float grad_scale, ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ p = C.c_void_p
 i32 = C.c_int32
 i64 = C.c_int64
 f64 = C.c_double
+f32 = C.c_float
 
 
 class EncoderParams(C.Structure):
@@ -63,6 +64,16 @@ SIGNATURES = {
     "ir_instance_mean": (i32, [p, i32, i32, i32, p, p]),
     "ir_knn": (i32, [p, p, p, p, i32, i32, p, p]),
     "ir_edgeconv": (i32, [p, p, p, p, i32, i32, i32, i32, p, p, p, p, p, p, p, p, i32, p, p]),
+    # training step
+    "ir_rulebook_transpose": (i32, [p, p, i32, i64, p, i64, p, p, p]),
+    "ir_spconv_wgrad": (i32, [p, i32, p, i32, i32, p, p, p, i64, p, p]),
+    "ir_bn_train_fwd": (i32, [p, p, i32, i32, p, p, p, i32, f32, f32, p, p, p, p, p, p, p]),
+    "ir_bn_train_bwd": (i32, [p, p, p, p, i32, i32, p, p, p, i32, p, p, p, p, p, p]),
+    "ir_segmax_bwd": (i32, [p, p, p, i64, i32, i32, p, p, p, p, p]),
+    "ir_cross_entropy": (i32, [p, p, i32, i32, p, p, p]),
+    "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
+    "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
+    "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p]),
 }
 
 _lib = None

@@ -1,0 +1,212 @@
+// Loss and optimiser kernels of the training step:
+//   get_loss (lib/loss_helper.py:131-161,189-269): language / region cross-entropy, axis-aligned box
+//   IoU -> one-hot cluster label -> ContrastiveLoss, each fused with its own gradient;
+//   torch.optim.Adam over ONE flat parameter buffer (scripts/train.py:93, lib/solver.py:200-205).
+#include <math.h>
+
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+
+// ------------------------------------------------------------------ cross entropy (mean) + gradient
+// single CTA: warp per row, per-row losses summed in row order (deterministic)
+#define CE_MAXROWS 1024
+__global__ void __launch_bounds__(256)
+k_cross_entropy(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int N,
+                float* __restrict__ loss, float* __restrict__ dlogits) {
+    __shared__ float s_loss[CE_MAXROWS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float invB = 1.f / B;
+    for (int r = w; r < B; r += 8) {
+        const float* z = logits + (long long)r * N;
+        float m = -INFINITY;
+        for (int j = lane; j < N; j += 32) m = fmaxf(m, z[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < N; j += 32) s += expf(z[j] - m);
+        s = warp_sum(s);
+        const float lse = m + logf(s);
+        const int y = (int)labels[r];
+        for (int j = lane; j < N; j += 32)
+            dlogits[(long long)r * N + j] = (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * invB;
+        if (lane == 0) s_loss[r] = lse - z[y];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int r = 0; r < B; ++r) t += s_loss[r];
+        loss[0] = t * invB;
+    }
+}
+
+extern "C" int ir_cross_entropy(const float* logits, const int64_t* labels, int32_t B, int32_t N,
+                                float* loss, float* dlogits, ir_stream_t stream) {
+    IR_CHECK_ARG(logits && labels && loss && dlogits && B > 0 && B <= CE_MAXROWS && N > 0);
+    k_cross_entropy<<<1, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)labels, B, N, loss, dlogits);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ 9-way region label
+// compute_scene_mask_loss (lib/loss_helper.py:131-153): thirds of the scene's xy extent.
+__global__ void k_region_label(const double* __restrict__ center, const double* __restrict__ pmin,
+                               const double* __restrict__ pmax, int B, int f32, long long* __restrict__ label) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    bool f[2], s[2];
+    for (int a = 0; a < 2; ++a) {
+        const double lo = pmin[b * 3 + a], hi = pmax[b * 3 + a], c = center[b * 3 + a];
+        if (f32) {           // all operands were fp32 in the caller: keep fp32 rounding of the thirds
+            const float lof = (float)lo, hif = (float)hi;
+            f[a] = (float)c <= lof + (hif - lof) / 3.f;
+            s[a] = (float)c <= lof + (hif - lof) / 3.f * 2.f;
+        } else {
+            f[a] = c <= lo + (hi - lo) / 3;
+            s[a] = c <= lo + (hi - lo) / 3 * 2;
+        }
+    }
+    int l = (f[0] && f[1]) ? 0 : 4;
+    if (!f[0] && s[0] && f[1]) l = 1;
+    if (!s[0] && f[1]) l = 2;
+    if (f[0] && !f[1] && s[0]) l = 3;       // (the reference's condition, lib/loss_helper.py:148)
+    if (!s[0] && !f[1] && s[1]) l = 5;
+    if (f[0] && !s[1]) l = 6;
+    if (!f[0] && s[0] && !s[1]) l = 7;
+    if (!s[0] && !s[1]) l = 8;
+    label[b] = l;
+}
+
+extern "C" int ir_region_label(const double* ref_center, const double* point_min, const double* point_max,
+                               int32_t B, int32_t inputs_were_f32, int64_t* label, ir_stream_t stream) {
+    IR_CHECK_ARG(ref_center && point_min && point_max && label && B > 0);
+    k_region_label<<<ir_div_up(B, 128), 128, 0, (cudaStream_t)stream>>>(ref_center, point_min, point_max, B,
+                                                                        inputs_were_f32, (long long*)label);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ reference loss
+// One warp per scene.  Boxes: obb = [cx,cy,cz, l,w,h, heading]; corners (+-l/2,+-w/2,+-h/2) rotated by
+// roty(heading)^T and translated (utils/box_util.py:310-333), min/max per axis, axis-aligned IoU
+// (:154-179) in fp64 like the reference's numpy.  label = one-hot of the FIRST maximal IoU.
+// For scenes with >= 2 candidates and max IoU >= 0.2: ContrastiveLoss(margin .2, gamma 5) on
+// score = attr + rel + scene, and its gradient w.r.t. every score entry.
+__device__ void box_min_max(const double* o, double mn[3], double mx[3]) {
+    const double c = cos(o[6]), s = sin(o[6]);
+    mn[0] = mn[1] = mn[2] = 1e300;
+    mx[0] = mx[1] = mx[2] = -1e300;
+    for (int q = 0; q < 8; ++q) {
+        const double x = ((q & 3) < 2 ? 0.5 : -0.5) * o[3];                 // l/2, l/2,-l/2,-l/2, ...
+        const double y = ((q & 3) == 0 || (q & 3) == 3 ? 0.5 : -0.5) * o[4]; // w/2,-w/2,-w/2, w/2, ...
+        const double z = (q < 4 ? 0.5 : -0.5) * o[5];
+        const double p[3] = {c * x + s * z + o[0], y + o[1], -s * x + c * z + o[2]};
+        for (int a = 0; a < 3; ++a) { mn[a] = fmin(mn[a], p[a]); mx[a] = fmax(mx[a], p[a]); }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_ref_loss(const double* __restrict__ pred_obb, const int* __restrict__ obb_ofs, const double* __restrict__ gt_obb,
+           const int* __restrict__ score_ofs, const float* __restrict__ sa, const float* __restrict__ sr,
+           const float* __restrict__ ss, float margin, float gamma, float iou_thresh,
+           float* __restrict__ label, float* __restrict__ loss_scene, float* __restrict__ dscore,
+           float* __restrict__ iou_max_out) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int o0 = obb_ofs[b], n = obb_ofs[b + 1] - o0;
+    if (lane == 0) { loss_scene[b] = 0.f; iou_max_out[b] = 0.f; }
+    if (n == 0) return;
+    double gmn[3], gmx[3];
+    box_min_max(gt_obb + (long long)b * 7, gmn, gmx);
+    const double gvol = (gmx[0] - gmn[0]) * (gmx[1] - gmn[1]) * (gmx[2] - gmn[2]);
+    double best = -1.0;
+    int best_j = 0x7fffffff;
+    for (int j = lane; j < n; j += 32) {
+        double mn[3], mx[3];
+        box_min_max(pred_obb + (long long)(o0 + j) * 7, mn, mx);
+        double inter = 1.0;
+        for (int a = 0; a < 3; ++a) inter *= fmax(fmin(mx[a], gmx[a]) - fmax(mn[a], gmn[a]), 0.0);
+        const double vol = (mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]);
+        const double iou = inter / (vol + gvol - inter + 1e-8);
+        if (iou > best) { best = iou; best_j = j; }          // strided scan keeps the lowest j per lane
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+    }
+    for (int j = lane; j < n; j += 32) label[o0 + j] = (j == best_j) ? 1.f : 0.f;
+    if (lane == 0) iou_max_out[b] = (float)best;
+    const int s0 = score_ofs[b];
+    if (s0 < 0 || n < 2) return;
+    if (best < (double)iou_thresh) {
+        for (int j = lane; j < n; j += 32) dscore[s0 + j] = 0.f;
+        return;
+    }
+    // t_j = gamma*score_j for negatives, 0 at the positive (score*label.logical_not()); lse over all j
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        const float t = (j == best_j) ? 0.f : gamma * (sa[s0 + j] + sr[s0 + j] + ss[s0 + j]);
+        m = fmaxf(m, t);
+    }
+    m = warp_max(m);
+    float e = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float t = (j == best_j) ? 0.f : gamma * (sa[s0 + j] + sr[s0 + j] + ss[s0 + j]);
+        e += expf(t - m);
+    }
+    e = warp_sum(e);
+    const float lse = m + logf(e);
+    const float sim = gamma * (sa[s0 + best_j] + sr[s0 + best_j] + ss[s0 + best_j]);
+    const float l = lse - sim + margin;
+    const bool active = l > 0.f;
+    if (lane == 0) loss_scene[b] = active ? l : 0.f;
+    for (int j = lane; j < n; j += 32) {
+        float g = 0.f;
+        if (active) {
+            if (j == best_j) g = -gamma;
+            else g = gamma * expf(gamma * (sa[s0 + j] + sr[s0 + j] + ss[s0 + j]) - lse);
+        }
+        dscore[s0 + j] = g;
+    }
+}
+
+extern "C" int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
+                           const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
+                           const float* s_scene, float margin, float gamma, float iou_thresh, float* label,
+                           float* loss_scene, float* dscore, float* iou_max, ir_stream_t stream) {
+    IR_CHECK_ARG(pred_obb && obb_ofs && gt_obb && score_ofs && s_attr && s_rel && s_scene && label &&
+                 loss_scene && dscore && iou_max && B > 0);
+    k_ref_loss<<<B, 32, 0, (cudaStream_t)stream>>>(pred_obb, obb_ofs, gt_obb, score_ofs, s_attr, s_rel, s_scene,
+                                                   margin, gamma, iou_thresh, label, loss_scene, dscore, iou_max);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ Adam over a flat buffer
+// g <- grad_scale*g + wd*p;  m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2;
+// p <- p - (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)          (torch.optim.Adam, amsgrad off)
+__global__ void __launch_bounds__(256)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+       long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    const float step = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float pv = p[i];
+        const float gv = fmaf(wd, pv, grad_scale * g[i]);
+        const float mv = b1 * m[i] + (1.f - b1) * gv;
+        const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+        m[i] = mv;
+        v[i] = vv;
+        p[i] = pv - step * mv / (sqrtf(vv) / bc2_sqrt + eps);
+    }
+}
+
+extern "C" int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                            float grad_scale, ir_stream_t stream) {
+    IR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1);
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+    const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
+    k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                   weight_decay, bc1, sqrtf(bc2), grad_scale);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

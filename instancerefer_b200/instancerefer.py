@@ -43,8 +43,29 @@ class InstanceRefer(nn.Module):
             self.__dict__['_side_streams'] = st
         return st
 
+    def forward_train(self, data_dict):
+        """Train mode (lib/solver.py:196): batch-statistics BatchNorm, Dropout, outputs with autograd
+        history; same chain and dict keys as the reference (models/instancerefer.py:56-70)."""
+        from . import training as T
+        a = self.args
+        torch.backends.cudnn.allow_tf32 = False      # the dense parts still on cuDNN must stay fp32 (1e-4 parity)
+        data_dict.pop(_PACK_KEY, None)
+        data_dict = T.lang_forward_train(self.lang, data_dict)
+        dev = data_dict['lang_feat'].device
+        pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+        data_dict[_PACK_KEY] = pack
+        if a.attribute_module:
+            data_dict = T.attribute_forward_train(self.attribute, data_dict, pack)
+        if a.relation_module:
+            data_dict = T.relation_forward_train(self.relation, data_dict, pack)
+        if a.scene_module:
+            data_dict = T.scene_forward_train(self.scene, data_dict, pack)
+        return data_dict
+
     def forward(self, data_dict):
         ops.check_device()
+        if self.training:
+            return self.forward_train(data_dict)
         if not getattr(data_dict.get(_PACK_KEY), 'resident', False):
             data_dict.pop(_PACK_KEY, None)
         a = self.args

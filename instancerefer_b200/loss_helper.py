@@ -1,0 +1,91 @@
+"""Device-side ``get_loss``, drop-in for the reference's ``lib/loss_helper.get_loss(data_dict,
+config)`` (lib/loss_helper.py:196-269): same signature, same dict keys written
+(``loss``, ``ref_loss``, ``lang_loss``, ``seg_loss``, ``seg_acc``, ``cluster_label``).
+
+The reference loops over scenes on the host (numpy corner boxes, IoU, argmax, per-scene
+ContrastiveLoss) with five ``.cpu()`` round trips; here the candidate boxes go to the device in one
+copy and three kernels (``ir_cross_entropy`` x2, ``ir_region_label``, ``ir_ref_loss``) produce every
+loss term together with its gradient, so the backward of the loss is a multiply by precomputed
+gradients (no graph of small torch ops)."""
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+
+class _CrossEntropy(Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, dl = ops.cross_entropy(logits.contiguous(), labels.contiguous())
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None
+
+
+class _RefLoss(Function):
+    """sum_b ContrastiveLoss_b / B with the one-hot labels from the IoU arg-max."""
+
+    @staticmethod
+    def forward(ctx, sa, sr, ss, pred_obb, obb_ofs, gt_obb, score_ofs):
+        B = gt_obb.shape[0]
+        label, loss_scene, dscore, iou_max = ops.ref_loss(pred_obb, obb_ofs, gt_obb, score_ofs, sa.contiguous(),
+                                                          sr.contiguous(), ss.contiguous())
+        ctx.save_for_backward(dscore)
+        ctx.B = B
+        ctx.mark_non_differentiable(label, iou_max)
+        return loss_scene.sum().reshape(1) / B, label, iou_max
+
+    @staticmethod
+    def backward(ctx, g, _gl, _gi):
+        (dscore,) = ctx.saved_tensors
+        d = dscore * (g / ctx.B)
+        return d, d, d, None, None, None, None
+
+
+def _gt_obb(data_dict, config):
+    """config.param2obb_batch on the label tensors (lib/loss_helper.py:212-219), host numpy like the
+    reference (five tiny D2H copies of (B,) / (B,3) labels)."""
+    t = lambda k: data_dict[k].detach().cpu().numpy()
+    return np.asarray(config.param2obb_batch(t('ref_center_label'), t('ref_heading_class_label'),
+                                             t('ref_heading_residual_label'), t('ref_size_class_label'),
+                                             t('ref_size_residual_label')), np.float64)
+
+
+def get_loss(data_dict, config):
+    dev = data_dict['lang_scores'].device
+    lang_loss = _CrossEntropy.apply(data_dict['lang_scores'], data_dict['object_cat'].to(dev).long())[0]
+    data_dict['lang_loss'] = lang_loss
+    seg_label = ops.region_label(data_dict['ref_center_label'].to(dev), data_dict['point_min'].to(dev),
+                                 data_dict['point_max'].to(dev))
+    seg_scores = data_dict['seg_scores']
+    seg_loss = _CrossEntropy.apply(seg_scores, seg_label)[0]
+    seg_acc = (seg_scores.detach().argmax(1) == seg_label).sum() / float(seg_label.numel())
+
+    pred = data_dict['pred_obb_batch']
+    B = len(pred)
+    counts = [int(np.asarray(p).reshape(-1, 7).shape[0]) if len(p) else 0 for p in pred]
+    obb_ofs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    score_ofs, s = [], 0
+    for c in counts:
+        score_ofs.append(s if c >= 2 else -1)
+        s += c if c >= 2 else 0
+    allobb = np.concatenate([np.asarray(p, np.float64).reshape(-1, 7) for p in pred if len(p)] or [np.zeros((1, 7))], 0)
+    host = torch.from_numpy(np.concatenate([allobb.reshape(-1), _gt_obb(data_dict, config).reshape(-1)]))
+    devbuf = host.to(dev)
+    pred_d = devbuf[:allobb.size].view(-1, 7)
+    gt_d = devbuf[allobb.size:].view(B, 7)
+    ints = torch.from_numpy(np.concatenate([obb_ofs, np.asarray(score_ofs, np.int32)])).to(dev)
+    ref_loss, label, iou_max = _RefLoss.apply(data_dict['attribute_scores'], data_dict['relation_scores'],
+                                              data_dict['scene_scores'], pred_d, ints[:B + 1], gt_d, ints[B + 1:])
+    data_dict['ref_loss'] = ref_loss
+    data_dict['loss'] = 10 * ref_loss + lang_loss + seg_loss                    # (lib/loss_helper.py:263)
+    data_dict['seg_loss'] = seg_loss
+    data_dict['seg_acc'] = seg_acc
+    data_dict['cluster_label'] = [label[obb_ofs[i]:obb_ofs[i + 1]] for i in range(B)]
+    data_dict['ref_iou_max'] = iou_max
+    return data_dict

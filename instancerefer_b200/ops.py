@@ -269,3 +269,98 @@ def edgeconv(x, xyz, qidx, nbr, ncls, Ww1, bw1, Ww2, bw2, Wm1, bm1, Wm2, bm2):
          _p(nbr, torch.int32), nq, k, F, ncls, _p(Ww1), _p(bw1), _p(Ww2), _p(bw2), _p(Wm1), _p(bm1),
          _p(Wm2), _p(bm2), Fout, _p(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- training step
+
+def rulebook_transpose(in_idx, slot, n_out_dev, n_rows_out):
+    """(K,seg_cap) forward rulebook -> (out_idx, slot_in) of the transposed map (dgrad / wgrad)."""
+    K, seg_cap = in_idx.shape
+    out_idx = torch.empty_like(in_idx)
+    slot_in = torch.empty_like(slot)
+    call("ir_rulebook_transpose", _p(in_idx, torch.int32), _p(slot, torch.int32), K, seg_cap,
+         _p(n_out_dev, torch.int32), int(n_rows_out), _p(out_idx), _p(slot_in), _stream())
+    return out_idx, slot_in
+
+
+def spconv_wgrad(x, dy, in_idx, out_idx, count):
+    K, seg_cap = in_idx.shape
+    cin, cout = x.shape[1], dy.shape[1]
+    dW = torch.empty(K, cin, cout, dtype=torch.float32, device=x.device)
+    call("ir_spconv_wgrad", _p(x, torch.float32), cin, _p(dy, torch.float32), cout, K, _p(in_idx, torch.int32),
+         _p(out_idx, torch.int32), _p(count, torch.int32), seg_cap, _p(dW), _stream())
+    return dW
+
+
+def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, running_var):
+    """x (n,C) fp32 -> (y, mean, rstd); running statistics are updated in place."""
+    n, Cc = x.shape
+    dev = x.device
+    scratch = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+    mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+    rstd = torch.empty(Cc, dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    call("ir_bn_train_fwd", _p(x, torch.float32), None, n, Cc, _p(gamma, torch.float32), _p(beta, torch.float32),
+         _p(resid), 1 if relu else 0, float(eps), float(momentum), _p(running_mean), _p(running_var),
+         _p(scratch), _p(mean), _p(rstd), _p(y), _stream())
+    return y, mean, rstd
+
+
+def bn_train_bwd(dy, y, x, mean, rstd, gamma, relu, want_resid):
+    n, Cc = x.shape
+    dev = x.device
+    scratch = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_resid else None
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
+    call("ir_bn_train_bwd", _p(dy, torch.float32), _p(y), _p(x, torch.float32), None, n, Cc, _p(mean), _p(rstd),
+         _p(gamma, torch.float32), 1 if relu else 0, _p(scratch), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _stream())
+    return dx, dres, dgamma, dbeta
+
+
+def segmax_bwd(feats, coords, n_dev, n_rows, n_seg, pooled, dpooled):
+    Cc = feats.shape[1]
+    arg = torch.empty(n_seg * Cc, dtype=torch.int32, device=feats.device)
+    dfeats = torch.empty_like(feats)
+    call("ir_segmax_bwd", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), int(n_rows),
+         Cc, n_seg, _p(pooled, torch.float32), _p(dpooled, torch.float32), _p(arg), _p(dfeats), _stream())
+    return dfeats
+
+
+def cross_entropy(logits, labels):
+    """-> (loss (1,), dlogits) : mean CE over rows and its gradient."""
+    B, N = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits)
+    call("ir_cross_entropy", _p(logits, torch.float32), _p(labels, torch.int64), B, N, _p(loss), _p(dl), _stream())
+    return loss, dl
+
+
+def region_label(ref_center, point_min, point_max):
+    f32 = all(t.dtype == torch.float32 for t in (ref_center, point_min, point_max))
+    B = ref_center.shape[0]
+    label = torch.empty(B, dtype=torch.int64, device=ref_center.device)
+    c, lo, hi = (t.to(torch.float64).contiguous() for t in (ref_center, point_min, point_max))   # kept alive
+    call("ir_region_label", _p(c), _p(lo), _p(hi), B, 1 if f32 else 0, _p(label), _stream())
+    return label
+
+
+def ref_loss(pred_obb, obb_ofs, gt_obb, score_ofs, sa, sr, ss, margin=0.2, gamma=5.0, iou_thresh=0.2):
+    """-> (label (Nc,), loss_scene (B,), dscore (M,), iou_max (B,))."""
+    B = gt_obb.shape[0]
+    dev = sa.device
+    label = torch.empty(pred_obb.shape[0], dtype=torch.float32, device=dev)
+    loss_scene = torch.empty(B, dtype=torch.float32, device=dev)
+    dscore = torch.zeros_like(sa)
+    iou_max = torch.empty(B, dtype=torch.float32, device=dev)
+    call("ir_ref_loss", _p(pred_obb, torch.float64), _p(obb_ofs, torch.int32), _p(gt_obb, torch.float64),
+         _p(score_ofs, torch.int32), B, _p(sa, torch.float32), _p(sr, torch.float32), _p(ss, torch.float32),
+         float(margin), float(gamma), float(iou_thresh), _p(label), _p(loss_scene), _p(dscore), _p(iou_max), _stream())
+    return label, loss_scene, dscore, iou_max
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    call("ir_adam_step", _p(params, torch.float32), _p(grads, torch.float32), _p(exp_avg, torch.float32),
+         _p(exp_avg_sq, torch.float32), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step), float(grad_scale), _stream())

@@ -1,0 +1,60 @@
+"""Optimiser side of the training step (scripts/train.py:93, lib/solver.py:200-205) for one process
+per GPU: all parameters live in ONE flat fp32 buffer (each tensor a 256-byte-aligned view), so
+
+  * ``zero_grad``      is one memset,
+  * the data-parallel gradient reduction is ONE NCCL all-reduce over 8.02 M floats,
+  * ``step``           is one fused Adam kernel (``ir_adam_step``) with the 1/world_size average
+                       folded into its gradient read.
+
+``torch.distributed`` is plumbing only (process group + all-reduce call)."""
+import torch
+
+from . import ops
+
+ALIGN = 64          # floats (256 B): keeps every parameter 16-byte aligned for TMA bulk copies
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (amsgrad off) on a flat buffer."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        assert all(p.dtype == torch.float32 for p in self.params)
+        dev = self.params[0].device
+        ofs, total = [], 0
+        for p in self.params:
+            ofs.append(total)
+            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, ofs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view_as(p)              # parameters become views of the flat buffer
+            p.grad = self.flat_grad[o:o + n].view_as(p)         # autograd accumulates straight into it
+        self.offsets, self.numel = ofs, total
+        self.step_count = 0
+        self.group = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):             # re-attach if something replaced .grad
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+    def allreduce(self):
+        """Sum over ranks (the mean is folded into the Adam kernel)."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+
+    def step(self):
+        self.allreduce()
+        self.step_count += 1
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
+                      self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / self.world)

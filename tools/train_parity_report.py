@@ -1,0 +1,41 @@
+"""Prints forward / gradient errors of one training iteration against the CPU oracle (dev aid).
+usage: [IR_SPCONV=simt] python tools/train_parity_report.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')]
+import torch
+import __graft_entry__ as g
+g.build()
+import model_ref, train_ref, weights
+from conftest import make_args
+from instancerefer_b200 import synthetic
+from test_gpu_train import make_train_model, run_train_step
+
+args = make_args()
+torch.backends.cudnn.allow_tf32 = False
+sd = weights.make_state_dict(123)
+b = synthetic.make_batch(41, batch_size=4, num_points=8000, n_inst=12, n_cand=[6, 2, 1, 5], n_tokens=[9, 14, 3, 20])
+model = make_train_model(sd, args)
+dd, grads = run_train_step(model, b)
+r = train_ref.train_step(sd, model_ref.data_from_batch(b), args)
+for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss'):
+    print(k, float(dd[k].reshape(-1)[0]), float(r[k].reshape(-1)[0]))
+for k in ('lang_scores', 'obj_feats', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores'):
+    print('fwd', k, float((dd[k].detach().cpu() - r['outputs'][k]).abs().max()))
+scale = max(float(v.abs().max()) for v in r['grads'].values())
+rows = []
+for k, v in r['grads'].items():
+    e = float((grads[k] - v).abs().max())
+    rows.append((e / max(float(v.abs().max()), 1e-3 * scale), k, e, float(v.abs().max())))
+rows.sort(reverse=True)
+for x in rows[:12]:
+    print('grad rel %.2e  %s  err %.2e  max %.2e' % x)
+for x in sorted(rows, key=lambda t: t[1]):
+    if x[1].startswith('attribute.net') and x[1].endswith('kernel'):
+        print('grad rel %.2e  %s  err %.2e  max %.2e' % x)
+k = 'attribute.net.stage2.0.net.0.kernel'
+d = (grads[k] - r['grads'][k]).abs()
+print('per-k err', d.amax((1, 2)).tolist())
+print('per-k max', r['grads'][k].abs().amax((1, 2)).tolist())
+print('per-ci err', d.amax((0, 2)).tolist()[:16])
+print('per-co err', d.amax((0, 1)).tolist()[:16])
