@@ -277,6 +277,76 @@ int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                  float grad_scale, ir_stream_t stream);
 
+/* ------------------------------------------------------------------ dense training-step operators
+ * (nn.Linear / LayerNorm / Dropout / F.normalize / cosine heads, Conv2d as im2col + GEMM, and the
+ * backward passes of ir_bev, ir_scene_attention, ir_token_attention, ir_gru_layer, ir_edgeconv.)   */
+
+/* C (M,N) = op(A) op(B) [+ bias(N)] [+ C] [relu];  A(m,k) = trans_a ? A[k*lda+m] : A[m*lda+k],
+ * B(k,n) = trans_b ? B[n*ldb+k] : B[k*ldb+n].  fp32 SIMT (latency-bound sizes).                  */
+int ir_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
+            const float* B, int32_t ldb, int32_t trans_b, float* C, int32_t ldc, const float* bias,
+            int32_t relu, int32_t accumulate, ir_stream_t stream);
+/* out[c] = sum_r x[r,c]  (bias gradients; fixed summation order). */
+int ir_colsum(const float* x, int32_t M, int32_t N, float* out, ir_stream_t stream);
+/* dx = dy * [y > 0]. */
+int ir_relu_bwd(const float* dy, const float* y, int64_t n, float* dx, ir_stream_t stream);
+/* nn.Dropout(p) in train mode with a counter-based generator: mask[i] = u(seed,i) >= p,
+ * y = x*mask/(1-p); backward applies the stored mask. */
+int ir_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, float* y, uint8_t* mask,
+                   ir_stream_t stream);
+int ir_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, ir_stream_t stream);
+/* nn.LayerNorm(N) (+ReLU) over the rows of (M,N) and its backward (dgamma/dbeta overwritten). */
+int ir_layernorm_fwd(const float* x, int32_t M, int32_t N, const float* gamma, const float* beta, float eps,
+                     int32_t relu, float* y, float* mean, float* rstd, ir_stream_t stream);
+int ir_layernorm_bwd(const float* dy, const float* y, const float* x, int32_t M, int32_t N, const float* gamma,
+                     const float* mean, const float* rstd, int32_t relu, float* dx, float* dgamma,
+                     float* dbeta, ir_stream_t stream);
+/* F.normalize(x, p=2, dim=1) and its backward. */
+int ir_l2norm_fwd(const float* x, int32_t M, int32_t N, float* y, ir_stream_t stream);
+int ir_l2norm_bwd(const float* dy, const float* x, int32_t M, int32_t N, float* dx, ir_stream_t stream);
+/* score[r] vs partner[seg[r]]: mode 0 <a/max(|a|,1e-12), p> (models/attribute_module.py:113,126),
+ * mode 1 cosine_similarity eps 1e-8 (relation_module.py:103, scene_module.py:104).  Backward: da and
+ * dpartner (n_partner,N); row_ofs (n_partner+1) = contiguous row range of every partner row. */
+int ir_match_fwd(const float* a, const float* partner, const int32_t* seg, int32_t M, int32_t N, int32_t mode,
+                 float* score, ir_stream_t stream);
+int ir_match_bwd(const float* dscore, const float* a, const float* partner, const int32_t* seg,
+                 const int32_t* row_ofs, int32_t M, int32_t N, int32_t n_partner, int32_t mode, float* da,
+                 float* dpartner, ir_stream_t stream);
+/* Conv2d 3x3 (valid, NHWC) as GEMM: col (B*(H-2)*(W-2), 9*C) with column (ky,kx,c); col2im is the
+ * adjoint (gradient w.r.t. the input image). */
+int ir_im2col_3x3(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, float* col, ir_stream_t stream);
+int ir_col2im_3x3(const float* dcol, int32_t B, int32_t H, int32_t W, int32_t C, float* din, ir_stream_t stream);
+/* Backward of ir_bev in raw mode (bn_scale = bn_shift = NULL: plain sums, no BN/ReLU): ddense
+ * (B*375,128) -> dfeats (n,128), dkernel (n_z,128,128).  cell = the buffer ir_bev filled. */
+int ir_bev_bwd(const float* ddense, const float* feats, const int32_t* coords, const int32_t* cell,
+               const int32_t* n_dev, int64_t n_max, int32_t stride, const float* kernel, int32_t n_z,
+               float* dfeats, float* dkernel, ir_stream_t stream);
+/* Backward of ir_scene_attention: dscene (B,C) [+ datten (B,ncell) or NULL] -> dfeats, dq. */
+int ir_scene_attention_bwd(const float* feats, const float* q, const float* atten, const float* dscene,
+                           const float* datten, int32_t B, int32_t ncell, int32_t C, float* dfeats, float* dq,
+                           ir_stream_t stream);
+/* Backward of ir_token_attention w.r.t. feats, embed and the four fc layers; dfcw_part (B,4,D) and
+ * dfcb_part (B,4) are per-sample partials (sum over B with ir_colsum). */
+int ir_token_attention_bwd(const float* feats, const float* embed, int64_t embed_stride, const int64_t* lengths,
+                           const float* fcw, const float* fcb, const float* atten, const float* dpooled,
+                           int32_t B, int32_t L, int32_t D, int32_t E, float* dfeats, float* dembed,
+                           float* dfcw_part, float* dfcb_part, ir_stream_t stream);
+/* Backward through time of ir_gru_layer: dout (B,L,2H) -> dxproj (B,L,2,3H) and per-sample partials
+ * dwhh_part (B,2,3H,H), dbhh_part (B,2,3H) (sum over B with ir_colsum). */
+int ir_gru_layer_bwd(const float* xproj, const float* whh, const float* bhh, const int64_t* lengths,
+                     const float* out, const float* dout, int32_t B, int32_t L, int32_t H, float* dxproj,
+                     float* dwhh_part, float* dbhh_part, ir_stream_t stream);
+/* Train-mode EdgeConv pieces (models/basic_blocks.py:125-133): w == NULL builds w_in (E, 3+2*ncls) =
+ * [xyz_j - xyz_i, onehot_i, onehot_j]; otherwise e_in (E, 3F) = [x_i, w, x_j]; E = nq*k, rows of
+ * missing neighbours (nbr < 0) are zero.  ir_edge_max_*: max over the valid edges of a query. */
+int ir_edge_inputs(const float* x, const float* xyz, const int32_t* qidx, const int32_t* nbr, int32_t nq,
+                   int32_t k, int32_t F, int32_t ncls, const float* w, float* w_in, float* e_in,
+                   ir_stream_t stream);
+int ir_edge_max_fwd(const float* msg, const int32_t* nbr, int32_t nq, int32_t k, int32_t C, float* out,
+                    int32_t* arg, ir_stream_t stream);
+int ir_edge_max_bwd(const float* dout, const int32_t* arg, int32_t nq, int32_t k, int32_t C, float* dmsg,
+                    ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,26 @@ SIGNATURES = {
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
     "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
     "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p]),
+    "ir_gemm": (i32, [i32, i32, i32, p, i32, i32, p, i32, i32, p, i32, p, i32, i32, p]),
+    "ir_colsum": (i32, [p, i32, i32, p, p]),
+    "ir_relu_bwd": (i32, [p, p, i64, p, p]),
+    "ir_dropout_fwd": (i32, [p, i64, f32, C.c_uint64, p, p, p]),
+    "ir_dropout_bwd": (i32, [p, p, i64, f32, p, p]),
+    "ir_layernorm_fwd": (i32, [p, i32, i32, p, p, f32, i32, p, p, p, p]),
+    "ir_layernorm_bwd": (i32, [p, p, p, i32, i32, p, p, p, i32, p, p, p, p]),
+    "ir_l2norm_fwd": (i32, [p, i32, i32, p, p]),
+    "ir_l2norm_bwd": (i32, [p, p, i32, i32, p, p]),
+    "ir_match_fwd": (i32, [p, p, p, i32, i32, i32, p, p]),
+    "ir_match_bwd": (i32, [p, p, p, p, p, i32, i32, i32, i32, p, p, p]),
+    "ir_im2col_3x3": (i32, [p, i32, i32, i32, i32, p, p]),
+    "ir_col2im_3x3": (i32, [p, i32, i32, i32, i32, p, p]),
+    "ir_bev_bwd": (i32, [p, p, p, p, p, i64, i32, p, i32, p, p, p]),
+    "ir_scene_attention_bwd": (i32, [p, p, p, p, p, i32, i32, i32, p, p, p]),
+    "ir_token_attention_bwd": (i32, [p, p, i64, p, p, p, p, p, i32, i32, i32, i32, p, p, p, p, p]),
+    "ir_gru_layer_bwd": (i32, [p, p, p, p, p, p, i32, i32, i32, p, p, p, p]),
+    "ir_edge_inputs": (i32, [p, p, p, p, i32, i32, i32, i32, p, p, p, p]),
+    "ir_edge_max_fwd": (i32, [p, p, i32, i32, i32, p, p, p]),
+    "ir_edge_max_bwd": (i32, [p, p, i32, i32, i32, p, p]),
 }
 
 _lib = None

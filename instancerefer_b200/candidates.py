@@ -98,6 +98,16 @@ class CandidatePack:
         self.h2d_bytes = h_points.numel() * 4 + h_meta.numel() * 4 + h_ints.numel() * 4
         self.resident = False      # True: inputs pre-staged in HBM, reuse across forwards (bench `value`)
 
+    def scene_ofs(self):
+        """(B+1,) int32 device offsets of every scene's candidates in the score vectors (scenes with
+        < 2 candidates own an empty range) — the contiguous row range of each partner row in the
+        matching heads' backward."""
+        if getattr(self, '_scene_ofs', None) is None:
+            counts = [len(ids) if len(ids) >= 2 else 0 for ids in self.cands]
+            self._scene_ofs = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32,
+                                           device=self.points.device)
+        return self._scene_ofs
+
     def signature(self):
         return (self.n_inst, self.M, len(self.active), tuple(self.points.shape[1:]))
 

@@ -72,14 +72,15 @@ k_bev_cell(const float* __restrict__ tmp, const int* __restrict__ cell, const in
     const int cnt = min(s_total, 16);
     float acc = 0.f;
     for (int i = 0; i < cnt; ++i) acc += tmp[(long long)s_list[i] * BEV_C + tid];
-    out[(long long)me * BEV_C + tid] = fmaxf(fmaf(acc, scale[tid], shift[tid]), 0.f);
+    // scale == NULL: raw sums (train mode: batch-statistics BN2d + ReLU follow as their own kernel)
+    out[(long long)me * BEV_C + tid] = scale ? fmaxf(fmaf(acc, scale[tid], shift[tid]), 0.f) : acc;
 }
 
 extern "C" int ir_bev(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
                       int32_t stride, const float* kernel, const float* bn_scale,
                       const float* bn_shift, int32_t B, float* tmp, int32_t* cell, float* out,
                       ir_stream_t stream) {
-    IR_CHECK_ARG(feats && coords && n_dev && kernel && bn_scale && bn_shift && tmp && cell && out);
+    IR_CHECK_ARG(feats && coords && n_dev && kernel && tmp && cell && out && ((bn_scale == nullptr) == (bn_shift == nullptr)));
     IR_CHECK_ARG(stride == 16 && B > 0 && n_max > 0);
     cudaStream_t st = (cudaStream_t)stream;
     k_bev_matvec<<<ir_min_i(n_max, IR_NUM_SMS * 16), BEV_C, 0, st>>>(feats, (const int4*)coords, n_dev, stride,

@@ -1,0 +1,789 @@
+// Dense training-step kernels: everything the reference's train-mode forward
+// and torch autograd do outside the sparse encoders — Linear / LayerNorm / Dropout / normalise-and-match
+// heads (models/attribute_module.py:88-126, relation_module.py:82-103, scene_module.py:44-104), the
+// Conv2d pair as im2col + GEMM (scene_module.py:33-38), BEV densification backward
+// (basic_blocks.py:195-243), language-guided attention backward (scene_module.py:73-83), the packed
+// biGRU and token-attention backward (lang_module.py:51-93) and the EdgeConv edge gather / max
+// (basic_blocks.py:98-133).  All fp32 SIMT: these operators are a few MFLOP each and latency-bound.
+#include <math.h>
+
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+
+// ------------------------------------------------------------------ GEMM  C = op(A) op(B) (+bias)(relu)(+C)
+// A(m,k) = ta ? A[k*lda+m] : A[m*lda+k];   B(k,n) = tb ? B[n*ldb+k] : B[k*ldb+n].
+// 64x64x16 tiles, 256 threads, thread (ty,tx) owns rows ty+16i, cols tx+16j (conflict-free smem reads,
+// 64-byte coalesced stores).
+#define GM_BM 64
+#define GM_BN 64
+#define GM_BK 16
+__global__ void __launch_bounds__(256)
+k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const float* __restrict__ B, int ldb,
+       int tb, float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu, int accumulate) {
+    __shared__ float As[GM_BK][GM_BM + 1];
+    __shared__ float Bs[GM_BK][GM_BN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += GM_BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + q * 256;
+            int m, k;
+            if (ta) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < K) v = ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+            As[k][m] = v;
+            int n, kb;
+            if (tb) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            float u = 0.f;
+            if (gn < N && gkb < K) u = tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn];
+            Bs[kb][n] = u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty + 16 * i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx + 16 * j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[gn];
+            if (accumulate) v += C[(long long)gm * ldc + gn];
+            if (relu) v = fmaxf(v, 0.f);
+            C[(long long)gm * ldc + gn] = v;
+        }
+    }
+}
+
+extern "C" int ir_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
+                       const float* B, int32_t ldb, int32_t trans_b, float* C, int32_t ldc, const float* bias,
+                       int32_t relu, int32_t accumulate, ir_stream_t stream) {
+    IR_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
+    const dim3 grid(ir_div_up(N, GM_BN), ir_div_up(M, GM_BM));
+    k_gemm<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients), deterministic
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+    __shared__ float sh[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (c < N)
+        for (int r = w; r < M; r += 8) s += x[(long long)r * N + c];
+    sh[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += sh[q][lane];
+        out[c] = t;
+    }
+}
+extern "C" int ir_colsum(const float* x, int32_t M, int32_t N, float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(x && out && M > 0 && N > 0);
+    k_colsum<<<ir_div_up(N, 32), 256, 0, (cudaStream_t)stream>>>(x, M, N, out);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ elementwise: ReLU mask, dropout
+__global__ void k_relu_bwd(const float* __restrict__ dy, const float* __restrict__ y, long long n, float* __restrict__ dx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+extern "C" int ir_relu_bwd(const float* dy, const float* y, int64_t n, float* dx, ir_stream_t stream) {
+    IR_CHECK_ARG(dy && y && dx && n > 0);
+    k_relu_bwd<<<ir_min_i(ir_div_up(n, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(dy, y, n, dx);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// counter-based generator (murmur-style finaliser of seed ^ index): keep with prob 1-p, scale 1/(1-p)
+__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long i) {
+    unsigned long long k = seed + i * 0x9E3779B97F4A7C15ull;
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (float)(k >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void k_dropout(const float* __restrict__ x, long long n, float p, unsigned long long seed,
+                          float* __restrict__ y, unsigned char* __restrict__ mask) {
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const bool keep = u01(seed, (unsigned long long)i) >= p;
+        mask[i] = keep;
+        y[i] = keep ? x[i] * scale : 0.f;
+    }
+}
+__global__ void k_dropout_bwd(const float* __restrict__ dy, const unsigned char* __restrict__ mask, long long n,
+                              float scale, float* __restrict__ dx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = mask[i] ? dy[i] * scale : 0.f;
+}
+extern "C" int ir_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, float* y, uint8_t* mask,
+                              ir_stream_t stream) {
+    IR_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f);
+    k_dropout<<<ir_min_i(ir_div_up(n, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, y, mask);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, ir_stream_t stream) {
+    IR_CHECK_ARG(dy && mask && dx && n > 0 && p >= 0.f && p < 1.f);
+    k_dropout_bwd<<<ir_min_i(ir_div_up(n, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(dy, mask, n, 1.f / (1.f - p), dx);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ LayerNorm (+ReLU), warp per row
+__global__ void __launch_bounds__(256)
+k_layernorm_fwd(const float* __restrict__ x, int M, int N, const float* __restrict__ g, const float* __restrict__ b,
+                float eps, int relu, float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* xr = x + (long long)r * N;
+    float s = 0.f;
+    for (int c = lane; c < N; c += 32) s += xr[c];
+    const float mu = warp_sum(s) / N;
+    float v = 0.f;
+    for (int c = lane; c < N; c += 32) { const float d = xr[c] - mu; v = fmaf(d, d, v); }
+    const float rs = rsqrtf(warp_sum(v) / N + eps);
+    for (int c = lane; c < N; c += 32) {
+        float o = (xr[c] - mu) * rs * g[c] + b[c];
+        if (relu) o = fmaxf(o, 0.f);
+        y[(long long)r * N + c] = o;
+    }
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+}
+// dgamma / dbeta are accumulated with atomics into zeroed arrays (<= a few thousand rows)
+__global__ void __launch_bounds__(256)
+k_layernorm_bwd(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, int M, int N,
+                const float* __restrict__ g, const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
+                float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const long long o = (long long)r * N;
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < N; c += 32) {
+        float gv = dy[o + c];
+        if (relu && !(y[o + c] > 0.f)) gv = 0.f;
+        const float xh = (x[o + c] - mu) * rs;
+        const float t = gv * g[c];
+        s1 += t;
+        s2 = fmaf(t, xh, s2);
+        atomicAdd(&dgamma[c], gv * xh);
+        atomicAdd(&dbeta[c], gv);
+    }
+    s1 = warp_sum(s1) / N;
+    s2 = warp_sum(s2) / N;
+    for (int c = lane; c < N; c += 32) {
+        float gv = dy[o + c];
+        if (relu && !(y[o + c] > 0.f)) gv = 0.f;
+        const float xh = (x[o + c] - mu) * rs;
+        dx[o + c] = rs * (gv * g[c] - s1 - xh * s2);
+    }
+}
+extern "C" int ir_layernorm_fwd(const float* x, int32_t M, int32_t N, const float* gamma, const float* beta, float eps,
+                                int32_t relu, float* y, float* mean, float* rstd, ir_stream_t stream) {
+    IR_CHECK_ARG(x && gamma && beta && y && mean && rstd && M > 0 && N > 0);
+    k_layernorm_fwd<<<ir_div_up(M, 8), 256, 0, (cudaStream_t)stream>>>(x, M, N, gamma, beta, eps, relu, y, mean, rstd);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_layernorm_bwd(const float* dy, const float* y, const float* x, int32_t M, int32_t N, const float* gamma,
+                                const float* mean, const float* rstd, int32_t relu, float* dx, float* dgamma,
+                                float* dbeta, ir_stream_t stream) {
+    IR_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0 && N > 0 && (!relu || y));
+    cudaStream_t st = (cudaStream_t)stream;
+    IR_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)N * 4, st));
+    IR_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)N * 4, st));
+    k_layernorm_bwd<<<ir_div_up(M, 8), 256, 0, st>>>(dy, y, x, M, N, gamma, mean, rstd, relu, dx, dgamma, dbeta);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ match scores
+// mode 0: score[r] = <l2n(a_r), p_r>, l2n(a) = a / max(|a|, 1e-12)          (attribute: F.normalize + dot)
+// mode 1: score[r] = <a_r, p_r> / max(|a_r| |p_r|, 1e-8)                     (relation / scene: cosine_similarity)
+// with p_r = partner[seg[r]].  Backward gives da and (deterministically, one CTA per partner row) dpartner.
+__global__ void __launch_bounds__(256)
+k_match_fwd(const float* __restrict__ a, const float* __restrict__ partner, const int* __restrict__ seg, int M, int N,
+            int mode, float* __restrict__ score) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* ar = a + (long long)r * N;
+    const float* pr = partner + (long long)seg[r] * N;
+    float ab = 0.f, aa = 0.f, pp = 0.f;
+    for (int c = lane; c < N; c += 32) { ab = fmaf(ar[c], pr[c], ab); aa = fmaf(ar[c], ar[c], aa); pp = fmaf(pr[c], pr[c], pp); }
+    ab = warp_sum(ab); aa = warp_sum(aa); pp = warp_sum(pp);
+    if (lane == 0) score[r] = mode == 0 ? ab / fmaxf(sqrtf(aa), 1e-12f) : ab / fmaxf(sqrtf(aa) * sqrtf(pp), 1e-8f);
+}
+__global__ void __launch_bounds__(256)
+k_match_bwd_a(const float* __restrict__ ds, const float* __restrict__ a, const float* __restrict__ partner,
+              const int* __restrict__ seg, int M, int N, int mode, float* __restrict__ da) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* ar = a + (long long)r * N;
+    const float* pr = partner + (long long)seg[r] * N;
+    float ab = 0.f, aa = 0.f, pp = 0.f;
+    for (int c = lane; c < N; c += 32) { ab = fmaf(ar[c], pr[c], ab); aa = fmaf(ar[c], ar[c], aa); pp = fmaf(pr[c], pr[c], pp); }
+    ab = warp_sum(ab); aa = warp_sum(aa); pp = warp_sum(pp);
+    const float na = sqrtf(aa), np_ = sqrtf(pp), g = ds[r];
+    for (int c = lane; c < N; c += 32) {
+        float d;
+        if (mode == 0) {
+            const float den = fmaxf(na, 1e-12f);            // s = ab/na : ds/da = p/na - ab a / na^3
+            d = pr[c] / den - (na > 1e-12f ? ab * ar[c] / (den * den * den) : 0.f);
+        } else {
+            const float den = fmaxf(na * np_, 1e-8f);       // s = ab/(na np): ds/da = p/den - s a/na^2
+            d = pr[c] / den - (na * np_ > 1e-8f ? (ab / den) * ar[c] / aa : 0.f);
+        }
+        da[(long long)r * N + c] = g * d;
+    }
+}
+// one CTA per partner row b: sums over the rows r in [ofs[b], ofs[b+1]) (candidates of a scene are contiguous)
+__global__ void __launch_bounds__(256)
+k_match_bwd_p(const float* __restrict__ ds, const float* __restrict__ a, const float* __restrict__ partner,
+              const int* __restrict__ row_ofs, int N, int mode, float* __restrict__ dpartner) {
+    __shared__ float red[8];
+    __shared__ float s_coef[2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int r0 = row_ofs[b], r1 = row_ofs[b + 1];
+    const float* pr = partner + (long long)b * N;
+    float pp = 0.f;
+    for (int c = tid; c < N; c += 256) pp = fmaf(pr[c], pr[c], pp);
+    pp = warp_sum(pp);
+    if (lane == 0) red[w] = pp;
+    __syncthreads();
+    pp = 0.f;
+    for (int q = 0; q < 8; ++q) pp += red[q];
+    const float np_ = sqrtf(pp);
+    float acc[2] = {0.f, 0.f};                                // N <= 512
+    for (int r = r0; r < r1; ++r) {
+        const float* ar = a + (long long)r * N;
+        __syncthreads();
+        float ab = 0.f, aa = 0.f;
+        for (int c = tid; c < N; c += 256) { ab = fmaf(ar[c], pr[c], ab); aa = fmaf(ar[c], ar[c], aa); }
+        ab = warp_sum(ab); aa = warp_sum(aa);
+        __shared__ float r2[2][8];
+        if (lane == 0) { r2[0][w] = ab; r2[1][w] = aa; }
+        __syncthreads();
+        if (tid == 0) {
+            float sab = 0.f, saa = 0.f;
+            for (int q = 0; q < 8; ++q) { sab += r2[0][q]; saa += r2[1][q]; }
+            s_coef[0] = sab; s_coef[1] = sqrtf(saa);
+        }
+        __syncthreads();
+        ab = s_coef[0];
+        const float na = s_coef[1], g = ds[r];
+        int i = 0;
+        for (int c = tid; c < N; c += 256, ++i) {
+            float d;
+            if (mode == 0) d = ar[c] / fmaxf(na, 1e-12f);
+            else {
+                const float den = fmaxf(na * np_, 1e-8f);
+                d = ar[c] / den - (na * np_ > 1e-8f ? (ab / den) * pr[c] / pp : 0.f);
+            }
+            acc[i] = fmaf(g, d, acc[i]);
+        }
+    }
+    int i = 0;
+    for (int c = tid; c < N; c += 256, ++i) dpartner[(long long)b * N + c] = acc[i];
+}
+extern "C" int ir_match_fwd(const float* a, const float* partner, const int32_t* seg, int32_t M, int32_t N, int32_t mode,
+                            float* score, ir_stream_t stream) {
+    IR_CHECK_ARG(a && partner && seg && score && M > 0 && N > 0 && (mode == 0 || mode == 1));
+    k_match_fwd<<<ir_div_up(M, 8), 256, 0, (cudaStream_t)stream>>>(a, partner, seg, M, N, mode, score);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_match_bwd(const float* dscore, const float* a, const float* partner, const int32_t* seg,
+                            const int32_t* row_ofs, int32_t M, int32_t N, int32_t n_partner, int32_t mode, float* da,
+                            float* dpartner, ir_stream_t stream) {
+    IR_CHECK_ARG(dscore && a && partner && seg && row_ofs && da && dpartner && M > 0 && N > 0 && N <= 512 && n_partner > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_match_bwd_a<<<ir_div_up(M, 8), 256, 0, st>>>(dscore, a, partner, seg, M, N, mode, da);
+    IR_CHECK_LAUNCH();
+    k_match_bwd_p<<<n_partner, 256, 0, st>>>(dscore, a, partner, row_ofs, N, mode, dpartner);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// L2 row normalisation y = x / max(|x|, 1e-12) (F.normalize) and its backward
+__global__ void __launch_bounds__(256)
+k_l2norm(const float* __restrict__ x, const float* __restrict__ dy, int M, int N, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const float* xr = x + (long long)r * N;
+    float xx = 0.f, xd = 0.f;
+    for (int c = lane; c < N; c += 32) { xx = fmaf(xr[c], xr[c], xx); if (dy) xd = fmaf(xr[c], dy[(long long)r * N + c], xd); }
+    xx = warp_sum(xx); xd = warp_sum(xd);
+    const float n = sqrtf(xx), den = fmaxf(n, 1e-12f);
+    for (int c = lane; c < N; c += 32) {
+        if (!dy) out[(long long)r * N + c] = xr[c] / den;
+        else out[(long long)r * N + c] = dy[(long long)r * N + c] / den - (n > 1e-12f ? xr[c] * xd / (den * den * den) : 0.f);
+    }
+}
+extern "C" int ir_l2norm_fwd(const float* x, int32_t M, int32_t N, float* y, ir_stream_t stream) {
+    IR_CHECK_ARG(x && y && M > 0 && N > 0);
+    k_l2norm<<<ir_div_up(M, 8), 256, 0, (cudaStream_t)stream>>>(x, nullptr, M, N, y);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_l2norm_bwd(const float* dy, const float* x, int32_t M, int32_t N, float* dx, ir_stream_t stream) {
+    IR_CHECK_ARG(dy && x && dx && M > 0 && N > 0);
+    k_l2norm<<<ir_div_up(M, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, M, N, dx);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ Conv2d 3x3 (valid) as im2col + GEMM, NHWC
+// col[(b,y,x), (ky,kx,c)] = in[b, y+ky, x+kx, c];   col2im is the gather-form adjoint.
+__global__ void k_im2col3(const float* __restrict__ in, int B, int H, int W, int C, float* __restrict__ col) {
+    const int Ho = H - 2, Wo = W - 2;
+    const long long total = (long long)B * Ho * Wo * 9 * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int tap = (int)(t % 9); t /= 9;
+        const int x = (int)(t % Wo); t /= Wo;
+        const int y = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        col[i] = in[(((long long)b * H + y + tap / 3) * W + x + tap % 3) * C + c];
+    }
+}
+__global__ void k_col2im3(const float* __restrict__ dcol, int B, int H, int W, int C, float* __restrict__ din) {
+    const int Ho = H - 2, Wo = W - 2;
+    const long long total = (long long)B * H * W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int x = (int)(t % W); t /= W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int oy = y - ky, ox = x - kx;
+                if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo)
+                    s += dcol[((((long long)b * Ho + oy) * Wo + ox) * 9 + ky * 3 + kx) * C + c];
+            }
+        din[i] = s;
+    }
+}
+extern "C" int ir_im2col_3x3(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, float* col, ir_stream_t stream) {
+    IR_CHECK_ARG(in && col && B > 0 && H > 2 && W > 2 && C > 0);
+    const long long total = (long long)B * (H - 2) * (W - 2) * 9 * C;
+    k_im2col3<<<ir_min_i(ir_div_up(total, 256), IR_NUM_SMS * 16), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, col);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_col2im_3x3(const float* dcol, int32_t B, int32_t H, int32_t W, int32_t C, float* din, ir_stream_t stream) {
+    IR_CHECK_ARG(dcol && din && B > 0 && H > 2 && W > 2 && C > 0);
+    const long long total = (long long)B * H * W * C;
+    k_col2im3<<<ir_min_i(ir_div_up(total, 256), IR_NUM_SMS * 16), 256, 0, (cudaStream_t)stream>>>(dcol, B, H, W, C, din);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ BEV densification backward
+// forward (ir_bev, raw mode): tmp[r] = F[r] @ kern[z_r]; dense[cell_r] += tmp[r] for kept rows.
+// dF[r] = d dense[cell_r] @ kern[z_r]^T ;  dkern[z] = sum_{r: z_r = z} F[r]^T d dense[cell_r].
+#define BV_C 128
+__global__ void __launch_bounds__(BV_C)
+k_bev_bwd_feats(const float* __restrict__ ddense, const int4* __restrict__ coords, const int* __restrict__ cell,
+                const int* __restrict__ n_dev, int stride, const float* __restrict__ kern, float* __restrict__ dF) {
+    __shared__ float g[BV_C];
+    const int n = *n_dev, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const int cl = cell[r];
+        if (cl < 0) { dF[(long long)r * BV_C + threadIdx.x] = 0.f; continue; }
+        __syncthreads();
+        g[threadIdx.x] = ddense[(long long)cl * BV_C + threadIdx.x];
+        __syncthreads();
+        const float* kz = kern + (long long)(coords[r].z / stride) * BV_C * BV_C;
+        for (int ci = w; ci < BV_C; ci += BV_C / 32) {           // warp per input channel: coalesced kernel row
+            const float* kr = kz + (long long)ci * BV_C;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < BV_C / 32; ++q) s = fmaf(g[lane + 32 * q], kr[lane + 32 * q], s);
+            s = warp_sum(s);
+            if (lane == 0) dF[(long long)r * BV_C + ci] = s;
+        }
+    }
+}
+// grid (BV_C/8, n_z): CTA owns dkern[z][ci0..ci0+7][:], thread = output channel, rows scanned in order
+__global__ void __launch_bounds__(BV_C)
+k_bev_bwd_kernel(const float* __restrict__ ddense, const float* __restrict__ F, const int4* __restrict__ coords,
+                 const int* __restrict__ cell, const int* __restrict__ n_dev, int stride, float* __restrict__ dkern) {
+    const int n = *n_dev, z = blockIdx.y, ci0 = blockIdx.x * 8, co = threadIdx.x;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int r = 0; r < n; ++r) {
+        const int cl = cell[r];
+        if (cl < 0 || coords[r].z / stride != z) continue;         // CTA-uniform
+        const float gv = ddense[(long long)cl * BV_C + co];
+        const float4 f0 = *reinterpret_cast<const float4*>(F + (long long)r * BV_C + ci0);
+        const float4 f1 = *reinterpret_cast<const float4*>(F + (long long)r * BV_C + ci0 + 4);
+        acc[0] = fmaf(f0.x, gv, acc[0]); acc[1] = fmaf(f0.y, gv, acc[1]);
+        acc[2] = fmaf(f0.z, gv, acc[2]); acc[3] = fmaf(f0.w, gv, acc[3]);
+        acc[4] = fmaf(f1.x, gv, acc[4]); acc[5] = fmaf(f1.y, gv, acc[5]);
+        acc[6] = fmaf(f1.z, gv, acc[6]); acc[7] = fmaf(f1.w, gv, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dkern[((long long)z * BV_C + ci0 + i) * BV_C + co] = acc[i];
+}
+extern "C" int ir_bev_bwd(const float* ddense, const float* feats, const int32_t* coords, const int32_t* cell,
+                          const int32_t* n_dev, int64_t n_max, int32_t stride, const float* kernel, int32_t n_z,
+                          float* dfeats, float* dkernel, ir_stream_t stream) {
+    IR_CHECK_ARG(ddense && feats && coords && cell && n_dev && kernel && dfeats && dkernel && n_max > 0 && n_z > 0 && stride > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_bev_bwd_feats<<<ir_min_i(n_max, IR_NUM_SMS * 16), BV_C, 0, st>>>(ddense, (const int4*)coords, cell, n_dev, stride, kernel, dfeats);
+    IR_CHECK_LAUNCH();
+    k_bev_bwd_kernel<<<dim3(BV_C / 8, n_z), BV_C, 0, st>>>(ddense, feats, (const int4*)coords, cell, n_dev, stride, dkernel);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ scene attention backward
+// forward: l_i = <f_i, q>/sqrt(C); a = softmax(l); s = sum_i a_i f_i.   One CTA per scene, thread = channel.
+__global__ void __launch_bounds__(128)
+k_scene_attention_bwd(const float* __restrict__ feats, const float* __restrict__ q, const float* __restrict__ atten,
+                      const float* __restrict__ ds, const float* __restrict__ datten_in, int ncell, int C,
+                      float* __restrict__ dfeats, float* __restrict__ dq) {
+    extern __shared__ float sm[];
+    float* da = sm;                 // [ncell]
+    float* dl = sm + ncell;         // [ncell]
+    __shared__ float s_dot;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    const float* f = feats + (long long)b * ncell * C;
+    const float* a = atten + (long long)b * ncell;
+    const float inv = rsqrtf((float)C);
+    for (int i = w; i < ncell; i += nw) {                      // da_i = <ds, f_i> (+ upstream d atten)
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(ds[(long long)b * C + c], f[(long long)i * C + c], s);
+        s = warp_sum(s);
+        if (lane == 0) da[i] = s + (datten_in ? datten_in[(long long)b * ncell + i] : 0.f);
+    }
+    __syncthreads();
+    if (w == 0) {
+        float s = 0.f;
+        for (int i = lane; i < ncell; i += 32) s = fmaf(a[i], da[i], s);
+        s = warp_sum(s);
+        if (lane == 0) s_dot = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < ncell; i += blockDim.x) dl[i] = a[i] * (da[i] - s_dot);
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        const float qc = q[(long long)b * C + c] * inv, dsc = ds[(long long)b * C + c];
+        float dqc = 0.f;
+        for (int i = 0; i < ncell; ++i) {
+            const float fv = f[(long long)i * C + c];
+            dfeats[((long long)b * ncell + i) * C + c] = a[i] * dsc + dl[i] * qc;
+            dqc = fmaf(dl[i], fv, dqc);
+        }
+        dq[(long long)b * C + c] = dqc * inv;
+    }
+}
+extern "C" int ir_scene_attention_bwd(const float* feats, const float* q, const float* atten, const float* dscene,
+                                      const float* datten, int32_t B, int32_t ncell, int32_t C, float* dfeats, float* dq,
+                                      ir_stream_t stream) {
+    IR_CHECK_ARG(feats && q && atten && dscene && dfeats && dq && B > 0 && ncell > 0 && ncell <= 4096 && C > 0);
+    k_scene_attention_bwd<<<B, 128, (size_t)2 * ncell * 4, (cudaStream_t)stream>>>(feats, q, atten, dscene, datten, ncell, C, dfeats, dq);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ token attention backward
+// forward (ir_token_attention): l = feats . fcw_h + fcb_h; s = softmax_L(l); u = s*mask; a = u / sum u;
+// pooled_h = a @ embed.   One CTA per sample; the four heads are accumulated in registers / smem, so
+// dfeats and dembed need no atomics; dfcw / dfcb are written per sample (B,4,D)/(B,4) and summed by ir_colsum.
+#define TAB_MAXL 128
+__global__ void __launch_bounds__(256)
+k_token_attention_bwd(const float* __restrict__ feats, const float* __restrict__ embed, long long embed_stride,
+                      const long long* __restrict__ lengths, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                      const float* __restrict__ atten, const float* __restrict__ dpooled, int B, int L, int D, int E,
+                      float* __restrict__ dfeats, float* __restrict__ dembed, float* __restrict__ dfcw_part,
+                      float* __restrict__ dfcb_part) {
+    __shared__ float s_a[4][TAB_MAXL], s_dl[4][TAB_MAXL], s_s[4][TAB_MAXL];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int len = max(0, min((int)lengths[b], L));
+    // recompute the un-normalised softmax s (needed for d softmax) and load a
+    for (int p = w; p < 4 * L; p += 8) {
+        const int h = p / L, t = p - h * L;
+        const float* f = feats + ((long long)b * L + t) * D;
+        float v = 0.f;
+        for (int d = lane; d < D; d += 32) v = fmaf(f[d], fcw[h * D + d], v);
+        v = warp_sum(v);
+        if (lane == 0) { s_s[h][t] = v + fcb[h]; s_a[h][t] = atten[((long long)h * B + b) * L + t]; }
+    }
+    __syncthreads();
+    if (w < 4) {
+        const int h = w;
+        float m = -INFINITY;
+        for (int t = lane; t < L; t += 32) m = fmaxf(m, s_s[h][t]);
+        m = warp_max(m);
+        float z = 0.f;
+        for (int t = lane; t < L; t += 32) { const float e = expf(s_s[h][t] - m); s_s[h][t] = e; z += e; }
+        z = warp_sum(z);
+        float su = 0.f;
+        for (int t = lane; t < L; t += 32) { s_s[h][t] /= z; if (t < len) su += s_s[h][t]; }
+        su = warp_sum(su);                                     // sum of masked softmax
+        // da_t = <dpooled_h, embed_t>
+        float dot_a = 0.f;
+        for (int t = 0; t < L; ++t) {
+            float v = 0.f;
+            for (int e = lane; e < E; e += 32)
+                v = fmaf(dpooled[((long long)h * B + b) * E + e], embed[(long long)b * embed_stride + (long long)t * E + e], v);
+            v = warp_sum(v);
+            if (lane == 0) s_dl[h][t] = v;
+            dot_a = fmaf(v, s_a[h][t], dot_a);                 // a_t is 0 on pads
+        }
+        __syncwarp();
+        // a = u/su: du_t = (da_t - sum_j da_j a_j)/su; ds_t = du_t * mask_t; dl = s*(ds - sum_j s_j ds_j)
+        float sd = 0.f;
+        for (int t = lane; t < L; t += 32) {
+            const float dsv = (t < len) ? (s_dl[h][t] - dot_a) / su : 0.f;
+            s_dl[h][t] = dsv;
+            sd = fmaf(s_s[h][t], dsv, sd);
+        }
+        sd = warp_sum(sd);
+        float db = 0.f;
+        for (int t = lane; t < L; t += 32) { const float v = s_s[h][t] * (s_dl[h][t] - sd); s_dl[h][t] = v; db += v; }
+        db = warp_sum(db);
+        if (lane == 0) dfcb_part[b * 4 + h] = db;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += 256) {                        // dfeats += dl (x) fcw ; dfcw_part = sum_t dl_t f_t
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        const float w0 = fcw[d], w1 = fcw[D + d], w2 = fcw[2 * D + d], w3 = fcw[3 * D + d];
+        for (int t = 0; t < L; ++t) {
+            const long long o = ((long long)b * L + t) * D + d;
+            const float fv = feats[o];
+            dfeats[o] = s_dl[0][t] * w0 + s_dl[1][t] * w1 + s_dl[2][t] * w2 + s_dl[3][t] * w3;
+            g0 = fmaf(s_dl[0][t], fv, g0); g1 = fmaf(s_dl[1][t], fv, g1);
+            g2 = fmaf(s_dl[2][t], fv, g2); g3 = fmaf(s_dl[3][t], fv, g3);
+        }
+        dfcw_part[((long long)b * 4 + 0) * D + d] = g0; dfcw_part[((long long)b * 4 + 1) * D + d] = g1;
+        dfcw_part[((long long)b * 4 + 2) * D + d] = g2; dfcw_part[((long long)b * 4 + 3) * D + d] = g3;
+    }
+    for (int e = tid; e < E; e += 256) {                        // dembed_t = sum_h a_h,t dpooled_h
+        const float p0 = dpooled[((long long)0 * B + b) * E + e], p1 = dpooled[((long long)1 * B + b) * E + e];
+        const float p2 = dpooled[((long long)2 * B + b) * E + e], p3 = dpooled[((long long)3 * B + b) * E + e];
+        for (int t = 0; t < L; ++t)
+            dembed[((long long)b * L + t) * E + e] = s_a[0][t] * p0 + s_a[1][t] * p1 + s_a[2][t] * p2 + s_a[3][t] * p3;
+    }
+}
+extern "C" int ir_token_attention_bwd(const float* feats, const float* embed, int64_t embed_stride, const int64_t* lengths,
+                                      const float* fcw, const float* fcb, const float* atten, const float* dpooled,
+                                      int32_t B, int32_t L, int32_t D, int32_t E, float* dfeats, float* dembed,
+                                      float* dfcw_part, float* dfcb_part, ir_stream_t stream) {
+    IR_CHECK_ARG(feats && embed && lengths && fcw && fcb && atten && dpooled && dfeats && dembed && dfcw_part && dfcb_part);
+    IR_CHECK_ARG(B > 0 && L > 0 && L <= TAB_MAXL && D > 0 && E > 0);
+    k_token_attention_bwd<<<B, 256, 0, (cudaStream_t)stream>>>(feats, embed, embed_stride, (const long long*)lengths, fcw, fcb,
+                                                              atten, dpooled, B, L, D, E, dfeats, dembed, dfcw_part, dfcb_part);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ GRU layer backward (BPTT)
+// grid (B, 2 directions), 384 threads (one per gate row).  Per step, from dh (upstream d out[t] + carry):
+//   recompute r,z,n from xproj[t] and h_prev (= out of the previous step of this direction);
+//   dn = dh (1-z) (1-n^2); dz = dh (h_prev - n) z (1-z); dr = dn (W_hn h_prev + b_hn) r (1-r);
+//   dxproj[t] = [dr, dz, dn]; dhp = [dr, dz, dn*r]; dh_prev = dh z + W_hh^T dhp;
+//   dW_hh += dhp (x) h_prev, db_hh += dhp  — accumulated per (sample, direction) into a per-CTA global
+//   partial (B,2,3H,H) / (B,2,3H), summed over B afterwards by ir_colsum (deterministic, no atomics).
+#define GB_H 128
+__global__ void __launch_bounds__(3 * GB_H)
+k_gru_layer_bwd(const float* __restrict__ xproj, const float* __restrict__ whh, const float* __restrict__ bhh,
+                const long long* __restrict__ lengths, const float* __restrict__ out, const float* __restrict__ dout,
+                int L, float* __restrict__ dxproj, float* __restrict__ dwhh_part, float* __restrict__ dbhh_part) {
+    constexpr int H = GB_H, G = 3 * GB_H;
+    __shared__ float s_hprev[H], s_hp[G], s_dhp[G], s_dh[H];
+    const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
+    const int len = max(0, min((int)lengths[b], L));
+    const float* W = whh + (size_t)dir * G * H;
+    const float bj = bhh[dir * G + j];
+    // this CTA's (3H,H) partial of dW_hh lives in global memory (L2): thread t updates column t%H of
+    // rows t/H, t/H+3, ... so every update is a coalesced 512-byte row segment
+    float* dWp = dwhh_part + (size_t)(b * 2 + dir) * G * H;
+    const int wc = j & (H - 1), wi0 = j >> 7;
+    for (int q = 0; q < H; ++q) dWp[(size_t)(wi0 + 3 * q) * H + wc] = 0.f;
+    float dbj = 0.f;
+    if (j < H) s_dh[j] = 0.f;
+    // zero dxproj on pads
+    for (int t = len; t < L; ++t) dxproj[(((size_t)b * L + t) * 2 + dir) * G + j] = 0.f;
+    __syncthreads();
+    for (int s = len - 1; s >= 0; --s) {
+        const int tt = dir ? (len - 1 - s) : s;                           // time index of step s
+        const int tp = dir ? tt + 1 : tt - 1;                             // previous step's time index
+        if (j < H) {
+            s_hprev[j] = (s > 0) ? out[((size_t)b * L + tp) * (2 * H) + dir * H + j] : 0.f;
+            s_dh[j] += dout[((size_t)b * L + tt) * (2 * H) + dir * H + j];
+        }
+        __syncthreads();
+        {   // hp_j = W_hh[j,:] . h_prev + b_j
+            const float4* wr = reinterpret_cast<const float4*>(W + (size_t)j * H);
+            float a = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < H / 4; ++c) {
+                const float4 wv = __ldg(wr + c);
+                a = fmaf(wv.x, s_hprev[4 * c], a); a = fmaf(wv.y, s_hprev[4 * c + 1], a);
+                a = fmaf(wv.z, s_hprev[4 * c + 2], a); a = fmaf(wv.w, s_hprev[4 * c + 3], a);
+            }
+            s_hp[j] = a + bj;
+        }
+        __syncthreads();
+        if (j < H) {
+            const float* xp = xproj + (((size_t)b * L + tt) * 2 + dir) * G;
+            const float r = 1.f / (1.f + expf(-(xp[j] + s_hp[j])));
+            const float z = 1.f / (1.f + expf(-(xp[H + j] + s_hp[H + j])));
+            const float n = tanhf(xp[2 * H + j] + r * s_hp[2 * H + j]);
+            const float dh = s_dh[j];
+            const float dn = dh * (1.f - z) * (1.f - n * n);
+            const float dz = dh * (s_hprev[j] - n) * z * (1.f - z);
+            const float dr = dn * s_hp[2 * H + j] * r * (1.f - r);
+            float* dx = dxproj + (((size_t)b * L + tt) * 2 + dir) * G;
+            dx[j] = dr; dx[H + j] = dz; dx[2 * H + j] = dn;
+            s_dhp[j] = dr; s_dhp[H + j] = dz; s_dhp[2 * H + j] = dn * r;
+            s_dh[j] = dh * z;                                             // carry through the z gate
+        }
+        __syncthreads();
+        {   // dW_hh += dhp (x) h_prev ; db_hh[j] += dhp_j
+            dbj += s_dhp[j];
+            const float hv = s_hprev[wc];
+            for (int q = 0; q < H; ++q) {
+                const int i = wi0 + 3 * q;
+                float* d = dWp + (size_t)i * H + wc;
+                *d = fmaf(s_dhp[i], hv, *d);
+            }
+        }
+        if (j < H) {  // dh_prev[j] += sum_i W_hh[i, j] * dhp_i   (column j: coalesced across threads)
+            float a = 0.f;
+            for (int i = 0; i < G; ++i) a = fmaf(__ldg(W + (size_t)i * H + j), s_dhp[i], a);
+            s_dh[j] += a;
+        }
+        __syncthreads();
+    }
+    dbhh_part[(size_t)(b * 2 + dir) * G + j] = dbj;
+}
+extern "C" int ir_gru_layer_bwd(const float* xproj, const float* whh, const float* bhh, const int64_t* lengths,
+                                const float* out, const float* dout, int32_t B, int32_t L, int32_t H, float* dxproj,
+                                float* dwhh_part, float* dbhh_part, ir_stream_t stream) {
+    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && dout && dxproj && dwhh_part && dbhh_part && B > 0 && L > 0 && H == GB_H);
+    k_gru_layer_bwd<<<dim3(B, 2), 3 * GB_H, 0, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, out, dout, L,
+                                                                      dxproj, dwhh_part, dbhh_part);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// ------------------------------------------------------------------ EdgeConv pieces (train mode)
+// edge e = (query m, slot s) with neighbour j = nbr[m][s] (or -1).  Inputs of the two edge MLPs:
+//   w_in[e] = [xyz_j - xyz_i, onehot_i, onehot_j]          (3 + 2*ncls)
+//   e_in[e] = [x_i, w[e], x_j]                              (3*F)      (models/basic_blocks.py:131-132)
+// x carries no gradient (instance statistics); only w does, so the backward of the concat is a slice.
+__global__ void k_edge_inputs(const float* __restrict__ x, const float* __restrict__ xyz, const int* __restrict__ qidx,
+                              const int* __restrict__ nbr, int nq, int k, int F, int ncls, const float* __restrict__ w,
+                              float* __restrict__ w_in, float* __restrict__ e_in) {
+    const int E = nq * k, Dw = 3 + 2 * ncls, De = 3 * F;
+    const int D = w ? De : Dw;
+    const long long total = (long long)E * D;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(t / D), c = (int)(t - (long long)e * D);
+        const int i = qidx[e / k], j = nbr[e];
+        float v = 0.f;
+        if (j >= 0) {
+            if (!w) {
+                if (c < 3) v = xyz[(long long)j * 3 + c] - xyz[(long long)i * 3 + c];
+                else if (c < 3 + ncls) v = x[(long long)i * F + (F - ncls) + (c - 3)];
+                else v = x[(long long)j * F + (F - ncls) + (c - 3 - ncls)];
+            } else {
+                if (c < F) v = x[(long long)i * F + c];
+                else if (c < 2 * F) v = w[(long long)e * F + (c - F)];
+                else v = x[(long long)j * F + (c - 2 * F)];
+            }
+        }
+        if (w) e_in[t] = v; else w_in[t] = v;
+    }
+}
+extern "C" int ir_edge_inputs(const float* x, const float* xyz, const int32_t* qidx, const int32_t* nbr, int32_t nq,
+                              int32_t k, int32_t F, int32_t ncls, const float* w, float* w_in, float* e_in,
+                              ir_stream_t stream) {
+    IR_CHECK_ARG(x && xyz && qidx && nbr && nq > 0 && k > 0 && F > ncls && ncls > 0 && (w ? e_in != nullptr : w_in != nullptr));
+    const long long total = (long long)nq * k * (w ? 3 * F : 3 + 2 * ncls);
+    k_edge_inputs<<<ir_min_i(ir_div_up(total, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(x, xyz, qidx, nbr, nq, k, F, ncls, w, w_in, e_in);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+// out[m,c] = max over valid slots of msg[m,s,c] (0 if none), arg = winning slot (first on ties); backward scatters.
+__global__ void k_edge_max(const float* __restrict__ msg, const int* __restrict__ nbr, int nq, int k, int C,
+                           float* __restrict__ out, int* __restrict__ arg) {
+    const long long total = (long long)nq * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(t / C), c = (int)(t - (long long)m * C);
+        float best = -INFINITY;
+        int bs = -1;
+        for (int s = 0; s < k; ++s) {
+            if (nbr[m * k + s] < 0) continue;
+            const float v = msg[((long long)m * k + s) * C + c];
+            if (v > best) { best = v; bs = s; }
+        }
+        out[t] = bs >= 0 ? best : 0.f;
+        arg[t] = bs;
+    }
+}
+__global__ void k_edge_max_bwd(const float* __restrict__ dout, const int* __restrict__ arg, int nq, int k, int C,
+                               float* __restrict__ dmsg) {
+    const long long total = (long long)nq * k * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const long long e = t / C;
+        const int m = (int)(e / k), s = (int)(e - (long long)m * k);
+        dmsg[t] = (arg[(long long)m * C + c] == s) ? dout[(long long)m * C + c] : 0.f;
+    }
+}
+extern "C" int ir_edge_max_fwd(const float* msg, const int32_t* nbr, int32_t nq, int32_t k, int32_t C, float* out,
+                               int32_t* arg, ir_stream_t stream) {
+    IR_CHECK_ARG(msg && nbr && out && arg && nq > 0 && k > 0 && C > 0);
+    k_edge_max<<<ir_min_i(ir_div_up((long long)nq * C, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(msg, nbr, nq, k, C, out, arg);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+extern "C" int ir_edge_max_bwd(const float* dout, const int32_t* arg, int32_t nq, int32_t k, int32_t C, float* dmsg,
+                               ir_stream_t stream) {
+    IR_CHECK_ARG(dout && arg && dmsg && nq > 0 && k > 0 && C > 0);
+    k_edge_max_bwd<<<ir_min_i(ir_div_up((long long)nq * k * C, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(dout, arg, nq, k, C, dmsg);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

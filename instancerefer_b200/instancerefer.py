@@ -48,7 +48,6 @@ class InstanceRefer(nn.Module):
         history; same chain and dict keys as the reference (models/instancerefer.py:56-70)."""
         from . import training as T
         a = self.args
-        torch.backends.cudnn.allow_tf32 = False      # the dense parts still on cuDNN must stay fp32 (1e-4 parity)
         data_dict.pop(_PACK_KEY, None)
         data_dict = T.lang_forward_train(self.lang, data_dict)
         dev = data_dict['lang_feat'].device

@@ -364,3 +364,183 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
     call("ir_adam_step", _p(params, torch.float32), _p(grads, torch.float32), _p(exp_avg, torch.float32),
          _p(exp_avg_sq, torch.float32), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
          float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+# ----------------------------------------------------------------------------- dense training-step operators
+
+def gemm(A, B, ta=False, tb=False, bias=None, relu=False, out=None, accumulate=False):
+    """out (M,N) = op(A) op(B) [+bias] [+out] [relu]; A, B 2-D fp32 with unit inner stride."""
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    N = B.shape[0] if tb else B.shape[1]
+    assert (B.shape[1] if tb else B.shape[0]) == K and A.stride(1) == 1 and B.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    call("ir_gemm", M, N, K, C.c_void_p(A.data_ptr()), A.stride(0), 1 if ta else 0, C.c_void_p(B.data_ptr()),
+         B.stride(0), 1 if tb else 0, _p(out, torch.float32), N, _p(bias), 1 if relu else 0,
+         1 if accumulate else 0, _stream())
+    return out
+
+
+def colsum(x):
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    call("ir_colsum", _p(x, torch.float32), M, N, _p(out), _stream())
+    return out
+
+
+def relu_bwd(dy, y):
+    dx = torch.empty_like(dy)
+    call("ir_relu_bwd", _p(dy, torch.float32), _p(y, torch.float32), dy.numel(), _p(dx), _stream())
+    return dx
+
+
+def dropout_fwd(x, p, seed):
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    call("ir_dropout_fwd", _p(x, torch.float32), x.numel(), float(p), C.c_uint64(seed & (2 ** 64 - 1)), _p(y), _p(mask), _stream())
+    return y, mask
+
+
+def dropout_bwd(dy, mask, p):
+    dx = torch.empty_like(dy)
+    call("ir_dropout_bwd", _p(dy, torch.float32), _p(mask, torch.uint8), dy.numel(), float(p), _p(dx), _stream())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps, relu):
+    M, N = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    call("ir_layernorm_fwd", _p(x, torch.float32), M, N, _p(gamma, torch.float32), _p(beta, torch.float32), float(eps),
+         1 if relu else 0, _p(y), _p(mean), _p(rstd), _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, y, x, gamma, mean, rstd, relu):
+    M, N = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.empty(N, dtype=torch.float32, device=x.device)
+    db = torch.empty(N, dtype=torch.float32, device=x.device)
+    call("ir_layernorm_bwd", _p(dy, torch.float32), _p(y), _p(x, torch.float32), M, N, _p(gamma, torch.float32), _p(mean),
+         _p(rstd), 1 if relu else 0, _p(dx), _p(dg), _p(db), _stream())
+    return dx, dg, db
+
+
+def l2norm_fwd(x):
+    y = torch.empty_like(x)
+    call("ir_l2norm_fwd", _p(x, torch.float32), x.shape[0], x.shape[1], _p(y), _stream())
+    return y
+
+
+def l2norm_bwd(dy, x):
+    dx = torch.empty_like(x)
+    call("ir_l2norm_bwd", _p(dy, torch.float32), _p(x, torch.float32), x.shape[0], x.shape[1], _p(dx), _stream())
+    return dx
+
+
+def match_fwd(a, partner, seg, mode):
+    M, N = a.shape
+    score = torch.empty(M, dtype=torch.float32, device=a.device)
+    call("ir_match_fwd", _p(a, torch.float32), _p(partner, torch.float32), _p(seg, torch.int32), M, N, mode, _p(score), _stream())
+    return score
+
+
+def match_bwd(dscore, a, partner, seg, row_ofs, mode):
+    M, N = a.shape
+    da = torch.empty_like(a)
+    dp = torch.empty_like(partner)
+    call("ir_match_bwd", _p(dscore, torch.float32), _p(a, torch.float32), _p(partner, torch.float32), _p(seg, torch.int32),
+         _p(row_ofs, torch.int32), M, N, partner.shape[0], mode, _p(da), _p(dp), _stream())
+    return da, dp
+
+
+def im2col_3x3(x):
+    B, H, W, Cc = x.shape
+    col = torch.empty(B * (H - 2) * (W - 2), 9 * Cc, dtype=torch.float32, device=x.device)
+    call("ir_im2col_3x3", _p(x, torch.float32), B, H, W, Cc, _p(col), _stream())
+    return col
+
+
+def col2im_3x3(dcol, B, H, W, Cc):
+    din = torch.empty(B, H, W, Cc, dtype=torch.float32, device=dcol.device)
+    call("ir_col2im_3x3", _p(dcol, torch.float32), B, H, W, Cc, _p(din), _stream())
+    return din
+
+
+def bev_raw(feats, coords, n_dev, n_rows, stride, kernel, B):
+    """ir_bev without BN/ReLU (train mode) -> (dense (B*375,128), cell (n_rows,))."""
+    dev = feats.device
+    tmp = torch.empty(max(n_rows, 1), 128, dtype=torch.float32, device=dev)
+    cell = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+    out = torch.empty(B * 375, 128, dtype=torch.float32, device=dev)
+    call("ir_bev", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), n_rows, stride,
+         _p(kernel, torch.float32), None, None, B, _p(tmp), _p(cell), _p(out), _stream())
+    return out, cell
+
+
+def bev_bwd(ddense, feats, coords, cell, n_dev, n_rows, stride, kernel):
+    df = torch.empty_like(feats)
+    dk = torch.empty_like(kernel)
+    call("ir_bev_bwd", _p(ddense, torch.float32), _p(feats, torch.float32), _p(coords, torch.int32), _p(cell, torch.int32),
+         _p(n_dev, torch.int32), n_rows, stride, _p(kernel, torch.float32), kernel.shape[0], _p(df), _p(dk), _stream())
+    return df, dk
+
+
+def scene_attention_bwd(feats, q, atten, dscene):
+    B, ncell, Cc = feats.shape
+    df = torch.empty_like(feats)
+    dq = torch.empty_like(q)
+    call("ir_scene_attention_bwd", _p(feats, torch.float32), _p(q, torch.float32), _p(atten, torch.float32),
+         _p(dscene, torch.float32), None, B, ncell, Cc, _p(df), _p(dq), _stream())
+    return df, dq
+
+
+def token_attention_bwd(feats, embed, lengths, fcw, fcb, atten, dpooled):
+    B, L, D = feats.shape
+    E = embed.shape[-1]
+    dev = feats.device
+    dfeats = torch.empty_like(feats)
+    dembed = torch.empty(B, L, E, dtype=torch.float32, device=dev)
+    dw = torch.empty(B, 4 * D, dtype=torch.float32, device=dev)
+    db = torch.empty(B, 4, dtype=torch.float32, device=dev)
+    call("ir_token_attention_bwd", _p(feats, torch.float32), _p(embed, torch.float32), embed.shape[1] * E,
+         _p(lengths, torch.int64), _p(fcw, torch.float32), _p(fcb, torch.float32), _p(atten, torch.float32),
+         _p(dpooled, torch.float32), B, L, D, E, _p(dfeats), _p(dembed), _p(dw), _p(db), _stream())
+    return dfeats, dembed, colsum(dw).view(4, D), colsum(db)
+
+
+def gru_layer_bwd(xproj, whh, bhh, lengths, out, dout, B, L, H=128):
+    dev = xproj.device
+    dxp = torch.empty_like(xproj)
+    dw = torch.empty(B, 2 * 3 * H * H, dtype=torch.float32, device=dev)
+    db = torch.empty(B, 2 * 3 * H, dtype=torch.float32, device=dev)
+    call("ir_gru_layer_bwd", _p(xproj, torch.float32), _p(whh, torch.float32), _p(bhh, torch.float32),
+         _p(lengths, torch.int64), _p(out, torch.float32), _p(dout, torch.float32), B, L, H, _p(dxp), _p(dw), _p(db), _stream())
+    return dxp, colsum(dw).view(2, 3 * H, H), colsum(db).view(2, 3 * H)
+
+
+def edge_inputs(x, xyz, qidx, nbr, ncls, w=None):
+    nq, k = nbr.shape
+    F = x.shape[1]
+    D = 3 * F if w is not None else 3 + 2 * ncls
+    out = torch.empty(nq * k, D, dtype=torch.float32, device=x.device)
+    call("ir_edge_inputs", _p(x, torch.float32), _p(xyz, torch.float32), _p(qidx, torch.int32), _p(nbr, torch.int32),
+         nq, k, F, ncls, _p(w), None if w is not None else _p(out), _p(out) if w is not None else None, _stream())
+    return out
+
+
+def edge_max_fwd(msg, nbr):
+    nq, k = nbr.shape
+    Cc = msg.shape[1]
+    out = torch.empty(nq, Cc, dtype=torch.float32, device=msg.device)
+    arg = torch.empty(nq, Cc, dtype=torch.int32, device=msg.device)
+    call("ir_edge_max_fwd", _p(msg, torch.float32), _p(nbr, torch.int32), nq, k, Cc, _p(out), _p(arg), _stream())
+    return out, arg
+
+
+def edge_max_bwd(dout, arg, k):
+    nq, Cc = dout.shape
+    dmsg = torch.empty(nq * k, Cc, dtype=torch.float32, device=dout.device)
+    call("ir_edge_max_bwd", _p(dout, torch.float32), _p(arg, torch.int32), nq, k, Cc, _p(dmsg), _stream())
+    return dmsg

@@ -4,7 +4,8 @@ statistics BatchNorm everywhere, Dropout, and outputs that carry autograd histor
 ``loss.backward()`` / optimiser step work unchanged.
 
 Every differentiable operator is a ``torch.autograd.Function`` whose forward AND backward are calls
-into the CUDA library (ops.*); torch only chains them (plumbing).  Sparse encoders:
+into the CUDA library (ops.*); torch only chains them (plumbing: views, cat/stack of parameters,
+gradient accumulation).  Sparse encoders:
 conv = pair-GEMM + reduce (the eval kernels, identity epilogue) -> train-mode BN kernel (+ residual,
 ReLU); backward = BN backward, dgrad (the same pair-GEMM/reduce on the transposed rulebook with
 W^T) and wgrad (per-offset gathered outer products).
@@ -133,53 +134,314 @@ def encoder_forward_train(net, ws, feats0=None, coords0=None):
     return x, G
 
 
-# ----------------------------------------------------------------------------- helpers (heads)
+# ----------------------------------------------------------------------------- dense operators
+
+class Linear(Function):
+    """nn.Linear (+ReLU): y = act(x W^T + b), W (N,K) in the reference layout."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu=False):
+        x = x.contiguous()
+        y = ops.gemm(x, W.detach(), tb=True, bias=None if b is None else b.detach(), relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, W.detach(), y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        g = ops.relu_bwd(dy.contiguous(), y) if ctx.relu else dy.contiguous()
+        dx = ops.gemm(g, W) if ctx.needs_input_grad[0] else None          # (M,N) @ (N,K)
+        dW = ops.gemm(g, x, ta=True)                                      # g^T @ x -> (N,K)
+        db = ops.colsum(g) if ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+class LayerNormAct(Function):
+    """nn.LayerNorm (+ReLU)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, relu):
+        x = x.contiguous()
+        y, mean, rstd = ops.layernorm_fwd(x, gamma.detach(), beta.detach(), eps, relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, gamma.detach(), y, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, y, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous(), y, x, gamma, mean, rstd, ctx.relu)
+        return dx, dg, db, None, None
+
+
+class BatchNormAct(Function):
+    """nn.BatchNorm1d / BatchNorm2d (NHWC rows) in train mode (+ReLU): batch statistics, running
+    statistics updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu):
+        x = x.contiguous()
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        y, mean, rstd = ops.bn_train_fwd(x, gamma.detach(), beta.detach(), None, relu, bn.eps, mom,
+                                         bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+        ctx.relu = relu
+        ctx.save_for_backward(x, gamma.detach(), y, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, y, mean, rstd = ctx.saved_tensors
+        dx, _, dg, db = ops.bn_train_bwd(dy.contiguous(), y, x, mean, rstd, gamma, ctx.relu, False)
+        return dx, dg, db, None, None
+
+
+_dropout_calls = [0]
+
+
+class Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        _dropout_calls[0] += 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + _dropout_calls[0] * 0x85EBCA6B) & (2 ** 63 - 1)
+        y, mask = ops.dropout_fwd(x.contiguous(), p, seed)
+        ctx.p = p
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        return ops.dropout_bwd(dy.contiguous(), mask, ctx.p), None
+
 
 def dropout(x, module):
-    """nn.Dropout in train mode (p may be patched to 0 for parity tests)."""
-    return torch.nn.functional.dropout(x, module.p, True) if module.p > 0 else x
+    """nn.Dropout in train mode (p = 0, as parity tests set it, is the identity)."""
+    return Dropout.apply(x, float(module.p)) if module.p > 0 else x
 
 
-def repeat_by_scene(x, pack):
-    """row i of the per-scene matrix repeated for each of that scene's candidates
-    (models/attribute_module.py:116-125)."""
-    return x.index_select(0, pack.cand_scene.long())
+class L2Norm(Function):
+    """F.normalize(x, p=2, dim=1)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.l2norm_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.l2norm_bwd(dy.contiguous(), x)
+
+
+class Match(Function):
+    """score[r] of candidate row r against its scene's partner row: mode 0 = normalise + dot
+    (models/attribute_module.py:113-126), mode 1 = cosine similarity (relation_module.py:103,
+    scene_module.py:104)."""
+
+    @staticmethod
+    def forward(ctx, a, partner, seg, row_ofs, mode):
+        a, partner = a.contiguous(), partner.contiguous()
+        ctx.mode = mode
+        ctx.save_for_backward(a, partner, seg, row_ofs)
+        return ops.match_fwd(a, partner, seg, mode)
+
+    @staticmethod
+    def backward(ctx, ds):
+        a, partner, seg, row_ofs = ctx.saved_tensors
+        da, dp = ops.match_bwd(ds.contiguous(), a, partner, seg, row_ofs, ctx.mode)
+        return da, dp, None, None, None
+
+
+class Conv3x3(Function):
+    """nn.Conv2d(C, Cout, 3) (valid) on NHWC activations as im2col + GEMM; weight in the reference
+    layout (Cout, Cin, 3, 3)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        B, H, W, Cc = x.shape
+        wp = weight.detach().permute(2, 3, 1, 0).reshape(9 * Cc, -1).contiguous()      # [ky][kx][Cin] x Cout
+        col = ops.im2col_3x3(x)
+        y = ops.gemm(col, wp, bias=bias.detach())
+        ctx.shape = (B, H, W, Cc)
+        ctx.save_for_backward(col, wp)
+        return y.view(B, H - 2, W - 2, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, wp = ctx.saved_tensors
+        B, H, W, Cc = ctx.shape
+        g = dy.contiguous().view(-1, wp.shape[1])
+        dx = ops.col2im_3x3(ops.gemm(g, wp, tb=True), B, H, W, Cc) if ctx.needs_input_grad[0] else None
+        dwp = ops.gemm(col, g, ta=True)                                               # (9C, Cout)
+        dW = dwp.view(3, 3, Cc, -1).permute(3, 2, 0, 1).contiguous()
+        return dx, dW, ops.colsum(g)
+
+
+class BEV(Function):
+    """SparseCrop + ToDenseBEVConvolution (models/basic_blocks.py:174-243) -> (B*375, 128) raw sums."""
+
+    @staticmethod
+    def forward(ctx, f4, kernel, coords, n_dev, n_rows, B):
+        f4 = f4.contiguous()
+        k = kernel.detach().contiguous()
+        dense, cell = ops.bev_raw(f4, coords, n_dev, n_rows, 16, k, B)
+        ctx.n_rows = n_rows
+        ctx.save_for_backward(f4, k, coords, n_dev, cell)
+        return dense
+
+    @staticmethod
+    def backward(ctx, dd):
+        f4, k, coords, n_dev, cell = ctx.saved_tensors
+        df, dk = ops.bev_bwd(dd.contiguous(), f4, coords, cell, n_dev, ctx.n_rows, 16, k)
+        return df, dk, None, None, None, None
+
+
+class SceneAttention(Function):
+    """softmax_cells(<f, q>/sqrt(C)) weighted sum (models/scene_module.py:73-83) -> (scene_feats, atten)."""
+
+    @staticmethod
+    def forward(ctx, feats, q):
+        feats, q = feats.contiguous(), q.contiguous()
+        atten, sf = ops.scene_attention(feats, q)
+        ctx.save_for_backward(feats, q, atten)
+        ctx.mark_non_differentiable(atten)
+        return sf, atten
+
+    @staticmethod
+    def backward(ctx, dsf, _da):
+        feats, q, atten = ctx.saved_tensors
+        return ops.scene_attention_bwd(feats, q, atten, dsf.contiguous())
+
+
+class TokenAttention(Function):
+    """Four masked attention poolings (models/lang_module.py:60-83) -> (pooled (4,B,E), atten (4,B,L))."""
+
+    @staticmethod
+    def forward(ctx, feats, embed, lengths, fcw, fcb):
+        feats, embed = feats.contiguous(), embed.contiguous()
+        atten, pooled = ops.token_attention(feats, embed, lengths, fcw.detach().contiguous(), fcb.detach().contiguous())
+        ctx.save_for_backward(feats, embed, lengths, fcw.detach().contiguous(), fcb.detach().contiguous(), atten)
+        ctx.mark_non_differentiable(atten)
+        return pooled, atten
+
+    @staticmethod
+    def backward(ctx, dpooled, _da):
+        feats, embed, lengths, fcw, fcb, atten = ctx.saved_tensors
+        df, de, dw, db = ops.token_attention_bwd(feats, embed, lengths, fcw, fcb, atten, dpooled.contiguous())
+        return df, de, None, dw, db
+
+
+class GRULayer(Function):
+    """One packed bidirectional GRU layer (models/lang_module.py:53-57): xproj (B*L, 2*3H) hoisted input
+    projections, whh (2,3H,H), bhh (2,3H) -> out (B*L, 2H)."""
+
+    @staticmethod
+    def forward(ctx, xproj, whh, bhh, lengths, B, L):
+        xproj = xproj.contiguous()
+        w, b = whh.detach().contiguous(), bhh.detach().contiguous()
+        out = ops.gru_layer(xproj, w, b, lengths, B, L)
+        ctx.BL = (B, L)
+        ctx.save_for_backward(xproj, w, b, lengths, out)
+        return out.view(B * L, -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xproj, w, b, lengths, out = ctx.saved_tensors
+        B, L = ctx.BL
+        dxp, dw, db = ops.gru_layer_bwd(xproj, w, b, lengths, out, dout.contiguous(), B, L)
+        return dxp, dw, db, None, None, None
+
+
+class EdgeConcat(Function):
+    """e_in = [x_i, w, x_j] per edge (models/basic_blocks.py:132); only w carries a gradient."""
+
+    @staticmethod
+    def forward(ctx, w, x, xyz, qidx, nbr, ncls):
+        ctx.F = x.shape[1]
+        ctx.save_for_backward(nbr)
+        return ops.edge_inputs(x, xyz, qidx, nbr, ncls, w=w.contiguous())
+
+    @staticmethod
+    def backward(ctx, de):
+        F = ctx.F
+        (nbr,) = ctx.saved_tensors
+        return de[:, F:2 * F] * (nbr.reshape(-1, 1) >= 0), None, None, None, None, None
+
+
+class EdgeMax(Function):
+    """max aggregation over the incoming edges of each query (MessagePassing aggr='max')."""
+
+    @staticmethod
+    def forward(ctx, msg, nbr):
+        out, arg = ops.edge_max_fwd(msg.contiguous(), nbr)
+        ctx.k = nbr.shape[1]
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        return ops.edge_max_bwd(dout.contiguous(), arg, ctx.k), None
+
+
+def mlp_head(seq, x, norm_idx, last_idx, drop_idx=None):
+    """Linear -> {BatchNorm1d | LayerNorm} -> ReLU [-> Dropout] -> Linear of the reference's
+    nn.Sequential heads (e.g. models/relation_module.py:13-25), every stage a CUDA-library kernel."""
+    h = Linear.apply(x, seq[0].weight, seq[0].bias, False)
+    nm = seq[norm_idx]
+    if isinstance(nm, torch.nn.LayerNorm):
+        h = LayerNormAct.apply(h, nm.weight, nm.bias, nm.eps, True)
+    else:
+        h = BatchNormAct.apply(h, nm.weight, nm.bias, nm, True)
+    if drop_idx is not None:
+        h = dropout(h, seq[drop_idx])
+    return Linear.apply(h, seq[last_idx].weight, seq[last_idx].bias, False)
 
 
 # ----------------------------------------------------------------------------- module forwards
-# Dense parts below marked (torch) still run on torch/cuBLAS/cuDNN kernels under autograd in this
-# round; DESIGN.md §0 lists them.  The sparse encoders, pooling, loss and optimiser are CUDA-library
-# kernels in both directions.
 
 def lang_forward_train(m, data_dict):
-    """models/lang_module.py:51-108 in train mode."""
-    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    """models/lang_module.py:51-108 in train mode: word MLP (+Dropout), 2-layer packed biGRU, four
+    masked attention pools over the PROJECTED embeddings, classifier."""
     x, length = data_dict['lang_feat'], data_dict['lang_len']
-    len_cpu = length.detach().to('cpu')
-    L = int(len_cpu.max())
+    dev = x.device
+    L = int(length.detach().to('cpu').max())
     B = x.shape[0]
-    e = m.word_projection(x[:, :L].float())                                     # (torch)
-    packed = pack_padded_sequence(e, len_cpu, batch_first=True, enforce_sorted=False)
-    feats, _ = pad_packed_sequence(m.gru(packed)[0], batch_first=True)          # (torch, cuDNN GRU)
+    len_dev = length.to(dev, torch.int64).contiguous()
+    wp = m.word_projection
+    h = Linear.apply(x[:, :L].float().reshape(B * L, -1), wp[0].weight, wp[0].bias, True)
+    h = dropout(h, wp[2])
+    e = Linear.apply(h, wp[3].weight, wp[3].bias, True)                                     # (B*L, 256)
+    g = m.gru
+    h = e
+    for l in (0, 1):
+        wih = torch.cat([getattr(g, f'weight_ih_l{l}'), getattr(g, f'weight_ih_l{l}_reverse')], 0)
+        bih = torch.cat([getattr(g, f'bias_ih_l{l}'), getattr(g, f'bias_ih_l{l}_reverse')], 0)
+        whh = torch.stack([getattr(g, f'weight_hh_l{l}'), getattr(g, f'weight_hh_l{l}_reverse')], 0)
+        bhh = torch.stack([getattr(g, f'bias_hh_l{l}'), getattr(g, f'bias_hh_l{l}_reverse')], 0)
+        xp = Linear.apply(h, wih, bih, False)                                               # hoisted input GEMM
+        h = GRULayer.apply(xp, whh, bhh, len_dev, B, L)
+    feats = h.view(B, L, -1)
     data_dict['lang_feat'] = feats
-    mask = (torch.arange(L, device=x.device)[None, :] < length.to(x.device)[:, None]).float()
-    fcw = torch.cat([m.fc_a.weight, m.fc_cls.weight, m.fc_rel.weight, m.fc_scene.weight], 0)   # (4,256)
+    fcw = torch.cat([m.fc_a.weight, m.fc_cls.weight, m.fc_rel.weight, m.fc_scene.weight], 0)
     fcb = torch.cat([m.fc_a.bias, m.fc_cls.bias, m.fc_rel.bias, m.fc_scene.bias], 0)
-    a = torch.softmax(feats @ fcw.t() + fcb, dim=1) * mask[:, :, None]          # (B,L,4)
-    a = a / a.sum(1, keepdim=True)
-    pooled = torch.einsum('blh,bld->hbd', a, e)                                 # (4,B,256)
-    data_dict['atten_attr'], data_dict['atten_rel'], data_dict['atten_scene'] = a[..., 0], a[..., 2], a[..., 3]
+    pooled, atten = TokenAttention.apply(feats, e.view(B, L, -1), len_dev, fcw, fcb)
+    data_dict['atten_attr'], data_dict['atten_rel'], data_dict['atten_scene'] = atten[0], atten[2], atten[3]
     data_dict['lang_attr_feats'], data_dict['lang_cls_feats'] = pooled[0], pooled[1]
     data_dict['lang_rel_feats'], data_dict['lang_scene_feats'] = pooled[2], pooled[3]
     if m.use_lang_classifier:
-        data_dict['lang_scores'] = m.lang_cls(data_dict['lang_cls_feats'])
+        data_dict['lang_scores'] = Linear.apply(pooled[1], m.lang_cls[0].weight, m.lang_cls[0].bias, False)
     return data_dict
 
 
 def attribute_forward_train(m, data_dict, pack):
     """models/attribute_module.py:83-131 in train mode."""
     dev = pack.points.device
-    lang = torch.nn.functional.normalize(m.lang_emb_fc(data_dict['lang_attr_feats']), p=2, dim=1)   # (torch)
+    lang = L2Norm.apply(mlp_head(m.lang_emb_fc, data_dict['lang_attr_feats'], 1, 3))
     data_dict['num_filtered_objs'] = pack.num_filtered
     data_dict['pred_obb_batch'] = pack.pred_obb_batch
     ws = m.net.workspace(pack.M * pack.points.shape[1], dev)
@@ -188,34 +450,32 @@ def attribute_forward_train(m, data_dict, pack):
     f4, G = encoder_forward_train(m.net, ws)
     obj = SegMax.apply(f4, ws.coords(4), G.nlvl_dev[4:5], G.n[4], pack.M)
     data_dict['obj_feats'] = obj
-    vis = torch.nn.functional.normalize(m.vis_emb_fc(obj), p=2, dim=1)                               # (torch)
-    data_dict['attribute_scores'] = (vis * repeat_by_scene(lang, pack)).sum(1)
+    vis = mlp_head(m.vis_emb_fc, obj, 1, 3)
+    data_dict['attribute_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 0)
     return data_dict
 
 
 def relation_forward_train(m, data_dict, pack):
-    """models/relation_module.py:80-107 in train mode; the graph (kNN) comes from the CUDA library,
-    the edge MLPs run under autograd (torch)."""
+    """models/relation_module.py:80-107 in train mode: kNN graph, edge MLPs as edge-batched GEMMs,
+    max aggregation, cosine match."""
     dev = pack.points.device
-    lang = m.lang_emb_fc(data_dict['lang_rel_feats'])
+    lang = mlp_head(m.lang_emb_fc, data_dict['lang_rel_feats'], 1, 4, 3)
     mean = ops.instance_mean(pack.points)
     ncls = m.args.num_classes
     onehot = (pack.centres_cls[:, 3:4] == torch.arange(ncls, device=dev, dtype=torch.float32)[None, :]).float()
     xyz = pack.centres_cls[:, :3].contiguous()
     feats = torch.cat([xyz, mean[:, 3:], onehot], 1).contiguous()
-    nbr = ops.knn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, m.gcn.k)              # (M,k), -1 padded
-    q = pack.cand_rows.long()
-    valid = nbr >= 0
-    j = nbr.clamp(min=0).long()
-    x_i = feats[q][:, None, :].expand(-1, nbr.shape[1], -1)
-    x_j = feats[j]
-    w_in = torch.cat([xyz[j] - xyz[q][:, None, :], x_i[..., -ncls:], x_j[..., -ncls:]], -1)
-    w = m.gcn.weight(w_in)
-    msg = m.gcn.mlp(torch.cat([x_i, w, x_j], -1))                                           # (M,k,128)
-    msg = torch.where(valid[..., None], msg, torch.full_like(msg, float('-inf')))
-    g = msg.max(1)[0]
-    vis = m.vis_emb_fc(g)
-    data_dict['relation_scores'] = torch.nn.functional.cosine_similarity(vis, repeat_by_scene(lang, pack), dim=1)
+    gcn = m.gcn
+    nbr = ops.knn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, gcn.k)                  # (M,k), -1 padded
+    w_in = ops.edge_inputs(feats, xyz, pack.cand_rows, nbr, ncls)
+    w = Linear.apply(Linear.apply(w_in, gcn.weight[0].weight, gcn.weight[0].bias, True),
+                     gcn.weight[2].weight, gcn.weight[2].bias, False)
+    e_in = EdgeConcat.apply(w, feats, xyz, pack.cand_rows, nbr, ncls)
+    msg = Linear.apply(Linear.apply(e_in, gcn.mlp[0].weight, gcn.mlp[0].bias, True),
+                       gcn.mlp[2].weight, gcn.mlp[2].bias, False)
+    g = EdgeMax.apply(msg, nbr)
+    vis = mlp_head(m.vis_emb_fc, g, 1, 4, 3)
+    data_dict['relation_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 1)
     return data_dict
 
 
@@ -228,26 +488,19 @@ def scene_forward_train(m, data_dict, pack):
     C0 = lidar.C.to(dev, torch.int32).contiguous()
     ws = m.net.workspace(F0.shape[0], dev)
     f4, G = encoder_forward_train(m.net, ws, F0, C0)
-    c4 = ws.coords(4)[:G.n[4]].long()
-    # SparseCrop + ToDenseBEVConvolution (models/basic_blocks.py:174-243)                   (torch)
-    keep = ((c4[:, 0] >= 0) & (c4[:, 0] < 240) & (c4[:, 1] >= 0) & (c4[:, 1] < 400) & (c4[:, 2] >= 0) & (c4[:, 2] < 80))
-    kern = m.to_bev[1].kernel
-    z = (c4[:, 2] // 16).clamp(0, kern.shape[0] - 1)
-    fz = torch.zeros(f4.shape[0], kern.shape[2], device=dev)
-    for zi in range(kern.shape[0]):
-        sel = (z == zi) & keep
-        fz = fz + torch.where(sel[:, None], f4 @ kern[zi], torch.zeros_like(fz))
-    flat = (c4[:, 3] * 375 + (c4[:, 0] // 16).clamp(0, 14) * 25 + (c4[:, 1] // 16).clamp(0, 24)).clamp(0, B * 375 - 1)
-    dense = torch.zeros(B * 375, kern.shape[2], device=dev).index_add(0, flat, fz * keep[:, None].float())
-    bev = dense.view(B, 15, 25, -1).permute(0, 3, 1, 2)
-    bev = torch.relu(m.to_bev[2](bev))
-    x = m.vis_emb_fc(bev)                                                                   # (torch, cuDNN)
-    feats = x.reshape(B, m.h_dim, -1).permute(0, 2, 1)
-    lang = m.lang_emb_fc(data_dict['lang_scene_feats']).unsqueeze(2)
-    atten = torch.softmax((torch.bmm(feats, lang) / math.sqrt(feats.shape[2])).squeeze(2), dim=1)
-    data_dict['vis_atten'] = atten.reshape(B, x.shape[2], x.shape[3])
-    scene_feats = (feats * atten.unsqueeze(2)).sum(1)
-    data_dict['seg_scores'] = m.cls(scene_feats)
-    obj = m.vis_emb_fc1(data_dict['obj_feats'])
-    data_dict['scene_scores'] = torch.nn.functional.cosine_similarity(obj, repeat_by_scene(scene_feats, pack), dim=1)
+    dense = BEV.apply(f4, m.to_bev[1].kernel, ws.coords(4), G.nlvl_dev[4:5], G.n[4], B)     # (B*375,128)
+    bn = m.to_bev[2]
+    x = BatchNormAct.apply(dense, bn.weight, bn.bias, bn, True).view(B, 15, 25, -1)          # NHWC
+    ve = m.vis_emb_fc
+    x = Conv3x3.apply(x, ve[0].weight, ve[0].bias)
+    x = BatchNormAct.apply(x.reshape(-1, x.shape[-1]), ve[1].weight, ve[1].bias, ve[1], True).view(x.shape)
+    x = dropout(x, ve[3])
+    x = Conv3x3.apply(x, ve[4].weight, ve[4].bias)                                           # (B,11,21,128)
+    h, w = x.shape[1], x.shape[2]
+    q = mlp_head(m.lang_emb_fc, data_dict['lang_scene_feats'], 1, 4, 3)
+    scene_feats, atten = SceneAttention.apply(x.view(B, h * w, -1), q)
+    data_dict['vis_atten'] = atten.view(B, h, w)
+    data_dict['seg_scores'] = mlp_head(m.cls, scene_feats, 1, 3)
+    obj = mlp_head(m.vis_emb_fc1, data_dict['obj_feats'], 1, 4, 3)
+    data_dict['scene_scores'] = Match.apply(obj, scene_feats, pack.cand_scene, pack.scene_ofs(), 1)
     return data_dict
