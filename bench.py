@@ -112,8 +112,167 @@ def load_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+TRAIN_WORKLOAD_NAME = ('configs[2]: ScanRefer-train-shaped training step — 2 scenes per GPU (16 on 8 GPUs), 40k points, '
+                       '32 instances x 1024 pts, 2..8 target-class candidates per scene, 20-token utterances; train-mode '
+                       'forward + get_loss + backward + flat gradient all-reduce + Adam, fp32')
+
+
+def train_batches(rank, n=4, per_gpu=2):
+    from instancerefer_b200 import synthetic
+    out = []
+    for i in range(n):
+        rng = np.random.default_rng(5000 + 131 * rank + i)
+        out.append(synthetic.make_batch(3000 + 977 * rank + 13 * i, batch_size=per_gpu, num_points=40000, n_inst=32,
+                                        n_cand=[int(c) for c in rng.integers(2, 9, per_gpu)], n_tokens=20))
+    return out
+
+
+def cpu_train_leg(steps, warmup, per_gpu=2):
+    """Oracle port of one training iteration (forward + loss + backward, torch CPU autograd)."""
+    import model_ref
+    import train_ref
+    import weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = weights.make_state_dict(123)
+    data = model_ref.data_from_batch(train_batches(0, 1, per_gpu)[0])
+    for _ in range(warmup):
+        train_ref.train_step(sd, data, make_args())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_ref.train_step(sd, data, make_args())
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=per_gpu / dt, unit=METRIC, cores=torch.get_num_threads(), kind='port',
+                sample=f'{steps} training iterations of {per_gpu} scenes after {warmup} warm-up, oracle/train_ref.py '
+                       f'(torch CPU fp32 autograd, {torch.get_num_threads()} threads, no optimiser step), {dt * 1e3:.0f} ms each'), dt
+
+
+def main_train(a):
+    """--workload train: BASELINE.json configs[2].  One step = train-mode forward + get_loss + backward +
+    ONE flat NCCL all-reduce of the 8.02 M gradients + fused Adam, inputs from HOST buffers every step
+    (so `value` is already end to end); phases are CUDA-event timed."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(a.warmup, 3)
+    per_gpu = 2
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 4))
+        cb, dt = cpu_train_leg(steps, 1, per_gpu)
+        print(json.dumps(dict(metric=METRIC, value=cb['value'], unit=METRIC, impl='reference', n_gpus=a.gpus, steps=steps,
+                              warmup=1, ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                              dtype='f32', data='synthetic', config=dict(workload=TRAIN_WORKLOAD_NAME), cpu_baseline=cb,
+                              e2e=dict(value=cb['value'], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    import __graft_entry__ as g
+    g.build()
+    import train_ref
+    import weights
+    from instancerefer_b200 import SparseTensor, _lib, ops
+    from instancerefer_b200.instancerefer import InstanceRefer
+    from instancerefer_b200.loss_helper import get_loss
+    from instancerefer_b200.optim import FlatAdam
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    ops.check_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    model = InstanceRefer(7, make_args())
+    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    model = model.to(dev).train()
+    opt = FlatAdam(model, lr=1e-3, weight_decay=1e-5)          # config/InstanceRefer.yaml:48,53
+    cfg = train_ref.SyntheticConfig()                          # dataset-config stand-in (label -> GT box), not on the timed path's arithmetic
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hosts = []
+    for b in train_batches(rank):
+        h = {k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+        hosts.append(h)
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values() if torch.is_tensor(v))
+    h2d += sum(p.nbytes for sc in hosts[0]['instance_points'] for p in sc)
+    ph = {k: 0.0 for k in ('forward', 'loss', 'backward', 'allreduce+adam')}
+
+    def step(i, timed):
+        h = hosts[i % len(hosts)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in h.items()}
+        d['lidar'] = SparseTensor(d.pop('lidar_feats'), d.pop('lidar_coords'))
+        opt.zero_grad()
+        d = model(d)
+        ev[1].record()
+        d = get_loss(d, cfg)
+        ev[2].record()
+        d['loss'].backward()
+        ev[3].record()
+        opt.step()
+        ev[4].record()
+        loss = float(d['loss'])                                # D2H of the step's result
+        if timed:
+            for j, k in enumerate(ph):
+                ph[k] += ev[j].elapsed_time(ev[j + 1])
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i, False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    c0 = lib.ir_launch_count()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = [step(i, True) for i in range(a.steps)]
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(t[0]), float(t[1])
+    launches = lib.ir_launch_count() - c0
+    clocks = sampler.stop() if sampler else None
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_train_leg(2, 1, per_gpu)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        value = world * per_gpu * a.steps / (dev_ms * 1e-3)
+        print(json.dumps(dict(
+            metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=a.steps, warmup=warmup,
+            ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='f32 (forward rule GEMM on tcgen05 split-fp16; dgrad/wgrad fp32 SIMT)', data='synthetic',
+            config=dict(workload=TRAIN_WORKLOAD_NAME, scenes_per_gpu=per_gpu, global_batch=world * per_gpu,
+                        l2='inputs (2.6 MB) and activations change every step; working set > L2 over a step',
+                        parallelism=f'dp{world}: scenes sharded, one flat all-reduce of 8.02 M fp32 grads, Adam replicated'),
+            e2e=dict(value=world * per_gpu * a.steps / wall, unit=METRIC, ms_per_step=wall / a.steps * 1e3,
+                     h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
+            phases_ms={k: v / a.steps for k, v in ph.items()}, gpu_launches=int(launches), clocks=clocks,
+            final_loss=losses[-1], first_loss=losses[0], cpu_baseline=cb)))
+
+
 def main():
+    if '--workload' in sys.argv and sys.argv[sys.argv.index('--workload') + 1] == 'train':
+        ap = argparse.ArgumentParser()
+        ap.add_argument('--workload')
+        ap.add_argument('--gpus', type=int, default=1)
+        ap.add_argument('--steps', type=int, default=20)
+        ap.add_argument('--warmup', type=int, default=3)
+        ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+        ap.add_argument('--no-cpu-baseline', action='store_true')
+        return main_train(ap.parse_args())
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='forward', choices=['forward', 'train'])
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
