@@ -234,15 +234,17 @@ int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int32_t cout, 
 /* Train-mode BatchNorm over the rows of a (n, C) matrix (spnn.BatchNorm over voxels, BatchNorm1d,
  * BatchNorm2d on NHWC cells): batch mean / biased variance, y = act((x-mean)*rstd*gamma + beta
  * (+resid)); running statistics updated with `momentum` (unbiased variance) when given.
- * n_dev (optional) = device row count bounded by n.  scratch: double[2*C].  C divides 256.        */
+ * n_dev (optional) = device row count bounded by n.  scratch: float[ir_bn_scratch_floats(C)]
+ * (per-CTA partial sums; deterministic, no atomics).  C divides 256, C >= 4.                     */
+int64_t ir_bn_scratch_floats(int32_t C);
 int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, int32_t C, const float* gamma,
                     const float* beta, const float* resid, int32_t relu, float eps, float momentum,
-                    float* running_mean, float* running_var, double* scratch, float* mean,
+                    float* running_mean, float* running_var, float* scratch, float* mean,
                     float* rstd, float* y, ir_stream_t stream);
 /* g = dy*[y>0] (relu); dbeta = sum g; dgamma = sum g*xhat; dx; dresid = g (optional).             */
 int ir_bn_train_bwd(const float* dy, const float* y, const float* x, const int32_t* n_dev, int32_t n,
                     int32_t C, const float* mean, const float* rstd, const float* gamma, int32_t relu,
-                    double* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
+                    float* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
                     ir_stream_t stream);
 
 /* Backward of ir_segmax: the gradient of out[b,c] goes to the first row attaining the maximum.
@@ -276,6 +278,47 @@ int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt
 int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                  float grad_scale, ir_stream_t stream);
+
+/* ------------------------------------------------------------------ one-call encoder training passes
+ * All 13 [conv -> train-mode BN (-> + skip) -> ReLU] layers forward, and their backward, as one chain
+ * of launches each.  Activations (pre-BN y, post-activation out, batch mean / rstd per layer), the
+ * transposed rulebooks and gradient scratch live in a caller-owned arena.  n_lvl = HOST row counts of
+ * the five levels (read back once from the workspace after ir_encoder_build_maps).               */
+typedef struct {
+    int32_t cin, use_tc;                      /* use_tc: forward pair-GEMM on tcgen05 (weights 16-B aligned) */
+    const float* weight[IR_ENC_LAYERS];       /* (K,Cin,Cout)                                          */
+    const float* gamma[IR_ENC_LAYERS];
+    const float* beta[IR_ENC_LAYERS];
+    float* running_mean[IR_ENC_LAYERS];       /* updated in place by the forward (or NULL)             */
+    float* running_var[IR_ENC_LAYERS];
+    float momentum[IR_ENC_LAYERS];
+    float eps;
+} ir_encoder_train_params;
+
+typedef struct {                              /* outputs of the backward, caller-owned                  */
+    float* dweight[IR_ENC_LAYERS];
+    float* dgamma[IR_ENC_LAYERS];
+    float* dbeta[IR_ENC_LAYERS];
+} ir_encoder_train_grads;
+
+typedef struct {
+    int64_t total_bytes;
+    int64_t off_y[IR_ENC_LAYERS], off_out[IR_ENC_LAYERS];      /* fp32 (n_lvl[level], Cout)              */
+    int64_t off_mean[IR_ENC_LAYERS], off_rstd[IR_ENC_LAYERS];
+    int64_t off_bn_scratch;
+    int64_t off_tr_out[9], off_tr_slot[9];                     /* transposed rulebooks, int32 [K][n_max]  */
+    int64_t off_grad[4];                                       /* fp32 (max rows, 128) gradient buffers   */
+    int64_t off_wt;                                            /* fp32 (27,128,128) transposed weight      */
+} ir_encoder_train_layout_t;
+
+int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int32_t cin, ir_encoder_train_layout_t* out);
+/* feats0 == NULL: level-0 features voxelised into `ws`.  The encoder output is arena + off_out[12]. */
+int ir_encoder_train_forward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                             const int32_t* n_lvl, void* arena, ir_stream_t stream);
+/* dout (n_lvl[4],128) = gradient w.r.t. the encoder output; same arena as the forward call.          */
+int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                              const int32_t* n_lvl, void* arena, const float* dout,
+                              const ir_encoder_train_grads* g, ir_stream_t stream);
 
 /* ------------------------------------------------------------------ dense training-step operators
  * (nn.Linear / LayerNorm / Dropout / F.normalize / cosine heads, Conv2d as im2col + GEMM, and the
@@ -331,11 +374,12 @@ int ir_token_attention_bwd(const float* feats, const float* embed, int64_t embed
                            const float* fcw, const float* fcb, const float* atten, const float* dpooled,
                            int32_t B, int32_t L, int32_t D, int32_t E, float* dfeats, float* dembed,
                            float* dfcw_part, float* dfcb_part, ir_stream_t stream);
-/* Backward through time of ir_gru_layer: dout (B,L,2H) -> dxproj (B,L,2,3H) and per-sample partials
- * dwhh_part (B,2,3H,H), dbhh_part (B,2,3H) (sum over B with ir_colsum). */
+/* Backward through time of ir_gru_layer: dout (B,L,2H) -> dxproj (B,L,2,3H), plus per step
+ * dhp (B,L,2,3H) = gradient w.r.t. W_hh h + b_hh and hprev (B,L,2,H) = the step's input state, so that
+ * dW_hh[d] = dhp[:,:,d,:]^T @ hprev[:,:,d,:] (ir_gemm) and db_hh = column sums of dhp (ir_colsum). */
 int ir_gru_layer_bwd(const float* xproj, const float* whh, const float* bhh, const int64_t* lengths,
                      const float* out, const float* dout, int32_t B, int32_t L, int32_t H, float* dxproj,
-                     float* dwhh_part, float* dbhh_part, ir_stream_t stream);
+                     float* dhp, float* hprev, ir_stream_t stream);
 /* Train-mode EdgeConv pieces (models/basic_blocks.py:125-133): w == NULL builds w_in (E, 3+2*ncls) =
  * [xyz_j - xyz_i, onehot_i, onehot_j]; otherwise e_in (E, 3F) = [x_i, w, x_j]; E = nq*k, rows of
  * missing neighbours (nbr < 0) are zero.  ir_edge_max_*: max over the valid edges of a query. */

@@ -33,6 +33,23 @@ class EncoderLayout(C.Structure):
                 ("off_feat0", i64), ("off_feat", i64 * 3), ("off_T", i64)]
 
 
+class EncoderTrainParams(C.Structure):
+    _fields_ = [("cin", i32), ("use_tc", i32),
+                ("weight", p * ENC_LAYERS), ("gamma", p * ENC_LAYERS), ("beta", p * ENC_LAYERS),
+                ("running_mean", p * ENC_LAYERS), ("running_var", p * ENC_LAYERS),
+                ("momentum", f32 * ENC_LAYERS), ("eps", f32)]
+
+
+class EncoderTrainGrads(C.Structure):
+    _fields_ = [("dweight", p * ENC_LAYERS), ("dgamma", p * ENC_LAYERS), ("dbeta", p * ENC_LAYERS)]
+
+
+class EncoderTrainLayout(C.Structure):
+    _fields_ = [("total_bytes", i64), ("off_y", i64 * ENC_LAYERS), ("off_out", i64 * ENC_LAYERS),
+                ("off_mean", i64 * ENC_LAYERS), ("off_rstd", i64 * ENC_LAYERS), ("off_bn_scratch", i64),
+                ("off_tr_out", i64 * 9), ("off_tr_slot", i64 * 9), ("off_grad", i64 * 4), ("off_wt", i64)]
+
+
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
 SIGNATURES = {
     "ir_version": (i32, []),
@@ -67,6 +84,7 @@ SIGNATURES = {
     # training step
     "ir_rulebook_transpose": (i32, [p, p, i32, i64, p, i64, p, p, p]),
     "ir_spconv_wgrad": (i32, [p, i32, p, i32, i32, p, p, p, i64, p, p]),
+    "ir_bn_scratch_floats": (i64, [i32]),
     "ir_bn_train_fwd": (i32, [p, p, i32, i32, p, p, p, i32, f32, f32, p, p, p, p, p, p, p]),
     "ir_bn_train_bwd": (i32, [p, p, p, p, i32, i32, p, p, p, i32, p, p, p, p, p, p]),
     "ir_segmax_bwd": (i32, [p, p, p, i64, i32, i32, p, p, p, p, p]),
@@ -74,6 +92,9 @@ SIGNATURES = {
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
     "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
     "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p]),
+    "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),
+    "ir_encoder_train_forward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p]),
+    "ir_encoder_train_backward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p, C.POINTER(EncoderTrainGrads), p]),
     "ir_gemm": (i32, [i32, i32, i32, p, i32, i32, p, i32, i32, p, i32, p, i32, i32, p]),
     "ir_colsum": (i32, [p, i32, i32, p, p]),
     "ir_relu_bwd": (i32, [p, p, i64, p, p]),

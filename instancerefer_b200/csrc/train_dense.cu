@@ -618,55 +618,61 @@ extern "C" int ir_token_attention_bwd(const float* feats, const float* embed, in
 }
 
 // ------------------------------------------------------------------ GRU layer backward (BPTT)
-// grid (B, 2 directions), 384 threads (one per gate row).  Per step, from dh (upstream d out[t] + carry):
+// grid (B, 2 directions), 384 threads (one per gate row), W_hh of the direction resident in shared
+// memory (384 x 129 floats, padded rows: row-wise AND column-wise reads are conflict-free).
+// Per step, from dh (upstream d out[t] + carry):
 //   recompute r,z,n from xproj[t] and h_prev (= out of the previous step of this direction);
 //   dn = dh (1-z) (1-n^2); dz = dh (h_prev - n) z (1-z); dr = dn (W_hn h_prev + b_hn) r (1-r);
-//   dxproj[t] = [dr, dz, dn]; dhp = [dr, dz, dn*r]; dh_prev = dh z + W_hh^T dhp;
-//   dW_hh += dhp (x) h_prev, db_hh += dhp  — accumulated per (sample, direction) into a per-CTA global
-//   partial (B,2,3H,H) / (B,2,3H), summed over B afterwards by ir_colsum (deterministic, no atomics).
+//   dxproj[t] = [dr, dz, dn]; dhp[t] = [dr, dz, dn*r]; dh_prev = dh z + W_hh^T dhp.
+// dhp and h_prev are written out per step: dW_hh = dhp^T @ h_prev and db_hh = colsum(dhp) are then ONE
+// GEMM / column sum per direction over all (sample, step) rows instead of a serial rank-1 update chain.
 #define GB_H 128
+#define GB_LD 129
 __global__ void __launch_bounds__(3 * GB_H)
 k_gru_layer_bwd(const float* __restrict__ xproj, const float* __restrict__ whh, const float* __restrict__ bhh,
                 const long long* __restrict__ lengths, const float* __restrict__ out, const float* __restrict__ dout,
-                int L, float* __restrict__ dxproj, float* __restrict__ dwhh_part, float* __restrict__ dbhh_part) {
+                int L, float* __restrict__ dxproj, float* __restrict__ dhp_out, float* __restrict__ hprev_out) {
     constexpr int H = GB_H, G = 3 * GB_H;
-    __shared__ float s_hprev[H], s_hp[G], s_dhp[G], s_dh[H];
+    extern __shared__ float Wsm[];                                        // [G][GB_LD]
+    __shared__ float s_hprev[H], s_hp[G], s_dhp[G], s_dh[H], s_part[3][H];
     const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
     const int len = max(0, min((int)lengths[b], L));
-    const float* W = whh + (size_t)dir * G * H;
+    {
+        const float* W = whh + (size_t)dir * G * H;
+        for (int i = j; i < G * H; i += G) Wsm[(i >> 7) * GB_LD + (i & (H - 1))] = __ldg(W + i);
+    }
     const float bj = bhh[dir * G + j];
-    // this CTA's (3H,H) partial of dW_hh lives in global memory (L2): thread t updates column t%H of
-    // rows t/H, t/H+3, ... so every update is a coalesced 512-byte row segment
-    float* dWp = dwhh_part + (size_t)(b * 2 + dir) * G * H;
-    const int wc = j & (H - 1), wi0 = j >> 7;
-    for (int q = 0; q < H; ++q) dWp[(size_t)(wi0 + 3 * q) * H + wc] = 0.f;
-    float dbj = 0.f;
     if (j < H) s_dh[j] = 0.f;
-    // zero dxproj on pads
-    for (int t = len; t < L; ++t) dxproj[(((size_t)b * L + t) * 2 + dir) * G + j] = 0.f;
+    for (int t = len; t < L; ++t) {                                       // pads carry no gradient
+        const size_t o = (((size_t)b * L + t) * 2 + dir);
+        dxproj[o * G + j] = 0.f;
+        dhp_out[o * G + j] = 0.f;
+        if (j < H) hprev_out[o * H + j] = 0.f;
+    }
     __syncthreads();
+    const int pc = j & (H - 1), part = j >> 7;
     for (int s = len - 1; s >= 0; --s) {
         const int tt = dir ? (len - 1 - s) : s;                           // time index of step s
         const int tp = dir ? tt + 1 : tt - 1;                             // previous step's time index
+        const size_t o = (((size_t)b * L + tt) * 2 + dir);
         if (j < H) {
-            s_hprev[j] = (s > 0) ? out[((size_t)b * L + tp) * (2 * H) + dir * H + j] : 0.f;
+            const float hv = (s > 0) ? out[((size_t)b * L + tp) * (2 * H) + dir * H + j] : 0.f;
+            s_hprev[j] = hv;
+            hprev_out[o * H + j] = hv;
             s_dh[j] += dout[((size_t)b * L + tt) * (2 * H) + dir * H + j];
         }
         __syncthreads();
         {   // hp_j = W_hh[j,:] . h_prev + b_j
-            const float4* wr = reinterpret_cast<const float4*>(W + (size_t)j * H);
-            float a = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < H / 4; ++c) {
-                const float4 wv = __ldg(wr + c);
-                a = fmaf(wv.x, s_hprev[4 * c], a); a = fmaf(wv.y, s_hprev[4 * c + 1], a);
-                a = fmaf(wv.z, s_hprev[4 * c + 2], a); a = fmaf(wv.w, s_hprev[4 * c + 3], a);
-            }
-            s_hp[j] = a + bj;
+            const float* wr = Wsm + j * GB_LD;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 16
+            for (int c = 0; c < H; c += 2) { a0 = fmaf(wr[c], s_hprev[c], a0); a1 = fmaf(wr[c + 1], s_hprev[c + 1], a1); }
+            s_hp[j] = a0 + a1 + bj;
         }
         __syncthreads();
+        float dhz = 0.f;
         if (j < H) {
-            const float* xp = xproj + (((size_t)b * L + tt) * 2 + dir) * G;
+            const float* xp = xproj + o * G;
             const float r = 1.f / (1.f + expf(-(xp[j] + s_hp[j])));
             const float z = 1.f / (1.f + expf(-(xp[H + j] + s_hp[H + j])));
             const float n = tanhf(xp[2 * H + j] + r * s_hp[2 * H + j]);
@@ -674,36 +680,38 @@ k_gru_layer_bwd(const float* __restrict__ xproj, const float* __restrict__ whh, 
             const float dn = dh * (1.f - z) * (1.f - n * n);
             const float dz = dh * (s_hprev[j] - n) * z * (1.f - z);
             const float dr = dn * s_hp[2 * H + j] * r * (1.f - r);
-            float* dx = dxproj + (((size_t)b * L + tt) * 2 + dir) * G;
+            float* dx = dxproj + o * G;
             dx[j] = dr; dx[H + j] = dz; dx[2 * H + j] = dn;
             s_dhp[j] = dr; s_dhp[H + j] = dz; s_dhp[2 * H + j] = dn * r;
-            s_dh[j] = dh * z;                                             // carry through the z gate
+            dhz = dh * z;                                                 // carry through the z gate
         }
         __syncthreads();
-        {   // dW_hh += dhp (x) h_prev ; db_hh[j] += dhp_j
-            dbj += s_dhp[j];
-            const float hv = s_hprev[wc];
-            for (int q = 0; q < H; ++q) {
-                const int i = wi0 + 3 * q;
-                float* d = dWp + (size_t)i * H + wc;
-                *d = fmaf(s_dhp[i], hv, *d);
-            }
+        dhp_out[o * G + j] = s_dhp[j];
+        {   // W_hh^T dhp, split over the three gate blocks: thread (part, pc) sums rows part*H .. +H of column pc
+            const float* wc = Wsm + (size_t)part * H * GB_LD + pc;
+            const float* dp = s_dhp + part * H;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 16
+            for (int i = 0; i < H; i += 2) { a0 = fmaf(wc[i * GB_LD], dp[i], a0); a1 = fmaf(wc[(i + 1) * GB_LD], dp[i + 1], a1); }
+            s_part[part][pc] = a0 + a1;
         }
-        if (j < H) {  // dh_prev[j] += sum_i W_hh[i, j] * dhp_i   (column j: coalesced across threads)
-            float a = 0.f;
-            for (int i = 0; i < G; ++i) a = fmaf(__ldg(W + (size_t)i * H + j), s_dhp[i], a);
-            s_dh[j] += a;
-        }
+        __syncthreads();
+        if (j < H) s_dh[j] = dhz + s_part[0][j] + s_part[1][j] + s_part[2][j];
         __syncthreads();
     }
-    dbhh_part[(size_t)(b * 2 + dir) * G + j] = dbj;
 }
 extern "C" int ir_gru_layer_bwd(const float* xproj, const float* whh, const float* bhh, const int64_t* lengths,
                                 const float* out, const float* dout, int32_t B, int32_t L, int32_t H, float* dxproj,
-                                float* dwhh_part, float* dbhh_part, ir_stream_t stream) {
-    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && dout && dxproj && dwhh_part && dbhh_part && B > 0 && L > 0 && H == GB_H);
-    k_gru_layer_bwd<<<dim3(B, 2), 3 * GB_H, 0, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, out, dout, L,
-                                                                      dxproj, dwhh_part, dbhh_part);
+                                float* dhp, float* hprev, ir_stream_t stream) {
+    IR_CHECK_ARG(xproj && whh && bhh && lengths && out && dout && dxproj && dhp && hprev && B > 0 && L > 0 && H == GB_H);
+    const size_t smem = (size_t)3 * GB_H * GB_LD * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_gru_layer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_gru_layer_bwd<<<dim3(B, 2), 3 * GB_H, smem, (cudaStream_t)stream>>>(xproj, whh, bhh, (const long long*)lengths, out, dout, L,
+                                                                         dxproj, dhp, hprev);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -1,0 +1,162 @@
+// One-call training passes of a sparse encoder (SURVEY.md §8 rows a7 + a14): all 13
+// [conv -> train-mode BN (-> + skip) -> ReLU] layers of SparseConvEncoder / BEVEncoder
+// (models/basic_blocks.py:59-95,136-171) forward, and their backward (BN backward, wgrad, dgrad on the
+// transposed rulebooks, skip-gradient folded into the dgrad epilogue), as ONE chain of asynchronous
+// launches per direction: the host issues two library calls per encoder and training step instead of
+// ~200 per-operator calls.  Activations live in a caller-owned arena (ir_encoder_train_layout).
+#include <string.h>
+
+#include "../../include/instancerefer_b200.h"
+#include "common.cuh"
+
+static const int kCh[5] = {32, 64, 128, 128, 128};
+// layer -> (input level, output level, K, map id in kcount: 0-4 = k3 at level l, 5-8 = k2 l->l+1)
+struct LayerInfo { int lin, lout, K, map, cin, cout, resid_from; };
+static LayerInfo layer_info(int idx, int cin0) {
+    LayerInfo li;
+    if (idx == 0) { li.lin = 0; li.lout = 0; li.K = 27; li.map = 0; li.cin = cin0; li.cout = kCh[0]; li.resid_from = -1; return li; }
+    const int s = (idx - 1) / 3 + 1, r = (idx - 1) % 3;
+    if (r == 0) { li.lin = s - 1; li.lout = s; li.K = 8; li.map = 5 + s - 1; li.cin = kCh[s - 1]; li.cout = kCh[s]; li.resid_from = -1; }
+    else { li.lin = s; li.lout = s; li.K = 27; li.map = s; li.cin = kCh[s]; li.cout = kCh[s]; li.resid_from = (r == 2) ? idx - 2 : -1; }
+    return li;
+}
+
+static inline int64_t al(int64_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int32_t cin, ir_encoder_train_layout_t* L) {
+    IR_CHECK_ARG(n_max > 0 && n_lvl && L && cin >= 1 && cin <= 128);
+    memset(L, 0, sizeof(*L));
+    int64_t off = 0, rows_max = 1;
+    auto take = [&](int64_t bytes) { int64_t o = off; off = al(off + bytes); return o; };
+    for (int l = 0; l < 5; ++l) { IR_CHECK_ARG(n_lvl[l] >= 0 && n_lvl[l] <= n_max); if (n_lvl[l] > rows_max) rows_max = n_lvl[l]; }
+    for (int i = 0; i < IR_ENC_LAYERS; ++i) {
+        const LayerInfo li = layer_info(i, cin);
+        const int64_t rows = n_lvl[li.lout] > 0 ? n_lvl[li.lout] : 1;
+        L->off_y[i] = take(rows * li.cout * 4);
+        L->off_out[i] = take(rows * li.cout * 4);
+        L->off_mean[i] = take(li.cout * 4);
+        L->off_rstd[i] = take(li.cout * 4);
+    }
+    L->off_bn_scratch = take(ir_bn_scratch_floats(256) * 4);
+    for (int m = 0; m < 9; ++m) {
+        const int K = m < 5 ? 27 : 8;
+        L->off_tr_out[m] = take((int64_t)K * n_max * 4);
+        L->off_tr_slot[m] = take((int64_t)K * n_max * 4);
+    }
+    for (int i = 0; i < 4; ++i) L->off_grad[i] = take(rows_max * 128 * 4);
+    L->off_wt = take((int64_t)27 * 128 * 128 * 4);
+    L->total_bytes = off;
+    return IR_OK;
+}
+
+__global__ void k_transpose_w(const float* __restrict__ w, int K, int cin, int cout, float* __restrict__ wt) {
+    const long long total = (long long)K * cin * cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const long long t = i / cin;
+        const int co = (int)(t % cout), k = (int)(t / cout);
+        wt[i] = w[((long long)k * cin + ci) * cout + co];                  // wt[k][co][ci]
+    }
+}
+
+struct Tr {
+    ir_encoder_layout_t W;          // encoder workspace (rulebooks)
+    ir_encoder_train_layout_t A;    // arena
+    char *ws, *ar;
+    int64_t n_max;
+    const int32_t* n;
+    const int* nlvl_dev() const { return (const int*)(ws + W.off_nlvl); }
+    const int* kcount(int map) const { return (const int*)(ws + W.off_kcount) + map * 32; }
+    const int* in_idx(int map) const { return (const int*)(ws + (map < 5 ? W.off_k3_in[map] : W.off_k2_in[map - 5])); }
+    const int* slot(int map) const { return (const int*)(ws + (map < 5 ? W.off_k3_slot[map] : W.off_k2_slot[map - 5])); }
+    float* T() const { return (float*)(ws + W.off_T); }
+    float* y(int i) const { return (float*)(ar + A.off_y[i]); }
+    float* out(int i) const { return (float*)(ar + A.off_out[i]); }
+    float* mean(int i) const { return (float*)(ar + A.off_mean[i]); }
+    float* rstd(int i) const { return (float*)(ar + A.off_rstd[i]); }
+    float* bn_scratch() const { return (float*)(ar + A.off_bn_scratch); }
+    int* tr_out(int map) const { return (int*)(ar + A.off_tr_out[map]); }
+    int* tr_slot(int map) const { return (int*)(ar + A.off_tr_slot[map]); }
+    float* grad(int i) const { return (float*)(ar + A.off_grad[i]); }
+    float* wt() const { return (float*)(ar + A.off_wt); }
+};
+
+static int tr_open(const ir_encoder_train_params* p, void* ws, int64_t n_max, const int32_t* n_lvl, void* arena, Tr* t) {
+    IR_CHECK_ARG(p && ws && arena && n_lvl);
+    int r;
+    if ((r = ir_encoder_layout(n_max, &t->W)) != IR_OK) return r;
+    if ((r = ir_encoder_train_layout(n_max, n_lvl, p->cin, &t->A)) != IR_OK) return r;
+    t->ws = (char*)ws; t->ar = (char*)arena; t->n_max = n_max; t->n = n_lvl;
+    for (int l = 0; l < 5; ++l) IR_CHECK_ARG(n_lvl[l] > 0);
+    return IR_OK;
+}
+
+extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                                        const int32_t* n_lvl, void* arena, ir_stream_t stream) {
+    Tr t;
+    int r;
+    if ((r = tr_open(p, ws, n_max, n_lvl, arena, &t)) != IR_OK) return r;
+    const float* f0 = feats0 ? feats0 : (const float*)(t.ws + t.W.off_feat0);
+    for (int i = 0; i < IR_ENC_LAYERS; ++i) {
+        const LayerInfo li = layer_info(i, p->cin);
+        const float* fin = (i == 0) ? f0 : t.out(i - 1);
+        const int tc = p->use_tc && li.cin >= 32 && ((reinterpret_cast<uintptr_t>(p->weight[i]) & 15) == 0);
+        if ((r = ir_spconv_layer(fin, li.cin, li.cout, li.K, t.in_idx(li.map), n_max, t.slot(li.map), t.kcount(li.map),
+                                 t.nlvl_dev() + li.lout, t.n[li.lout], p->weight[i], tc ? p->weight[i] : nullptr, tc,
+                                 nullptr, nullptr, nullptr, 0, t.T(), t.y(i), stream)) != IR_OK) return r;
+        if ((r = ir_bn_train_fwd(t.y(i), nullptr, t.n[li.lout], li.cout, p->gamma[i], p->beta[i],
+                                 li.resid_from >= 0 ? t.out(li.resid_from) : nullptr, 1, p->eps, p->momentum[i],
+                                 p->running_mean[i], p->running_var[i], t.bn_scratch(), t.mean(i), t.rstd(i), t.out(i),
+                                 stream)) != IR_OK) return r;
+    }
+    return IR_OK;
+}
+
+extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                                         const int32_t* n_lvl, void* arena, const float* dout,
+                                         const ir_encoder_train_grads* g, ir_stream_t stream) {
+    Tr t;
+    int r;
+    if ((r = tr_open(p, ws, n_max, n_lvl, arena, &t)) != IR_OK) return r;
+    IR_CHECK_ARG(dout && g);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* f0 = feats0 ? feats0 : (const float*)(t.ws + t.W.off_feat0);
+    // transposed rulebooks of all nine maps (out_idx for wgrad, slot_in for the dgrad reduce)
+    for (int m = 0; m < 9; ++m) {
+        const int K = m < 5 ? 27 : 8, lout = m < 5 ? m : m - 5 + 1;
+        if ((r = ir_rulebook_transpose(t.in_idx(m), t.slot(m), K, n_max, t.nlvl_dev() + lout, t.n[lout], t.tr_out(m),
+                                       t.tr_slot(m), stream)) != IR_OK) return r;
+    }
+    const float* up = dout;                        // gradient w.r.t. the output of the layer being processed
+    float *S0 = t.grad(0), *S1 = t.grad(1), *S2 = t.grad(2), *S3 = t.grad(3);
+    // one layer: BN backward (-> DY in S1, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`
+    auto layer_bwd = [&](int i, const float* gin, float* dres, float* dx, const float* add) -> int {
+        const LayerInfo li = layer_info(i, p->cin);
+        const float* xin = (i == 0) ? f0 : t.out(i - 1);
+        int rr;
+        if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), nullptr, t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
+                                  t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], stream)) != IR_OK) return rr;
+        if ((rr = ir_spconv_wgrad(xin, li.cin, S1, li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map), t.kcount(li.map), n_max,
+                                  g->dweight[i], stream)) != IR_OK) return rr;
+        if (dx) {
+            const long long tot = (long long)li.K * li.cin * li.cout;
+            k_transpose_w<<<ir_min_i(ir_div_up(tot, 256), IR_NUM_SMS * 4), 256, 0, st>>>(p->weight[i], li.K, li.cin, li.cout, t.wt());
+            IR_CHECK_LAUNCH();
+            // dgrad = forward pipeline on the transposed rulebook with W^T; `add` (the skip gradient) rides in the
+            // reduce epilogue's residual slot.  Exact fp32 SIMT pair-GEMM (gradients span too many orders of
+            // magnitude for the split-fp16 tensor-core operands).
+            if ((rr = ir_spconv_layer(S1, li.cout, li.cin, li.K, t.tr_out(li.map), n_max, t.tr_slot(li.map), t.kcount(li.map),
+                                      t.nlvl_dev() + li.lin, t.n[li.lin], t.wt(), nullptr, 0, nullptr, nullptr, add, 0, t.T(),
+                                      dx, stream)) != IR_OK) return rr;
+        }
+        return IR_OK;
+    };
+    for (int s = 4; s >= 1; --s) {
+        const int a = 1 + 3 * (s - 1), b = a + 1, c = a + 2;
+        if ((r = layer_bwd(c, up, S2, S3, nullptr)) != IR_OK) return r;      // skip gradient -> S2, d out[b] -> S3
+        if ((r = layer_bwd(b, S3, nullptr, S3, S2)) != IR_OK) return r;      // d out[a] = dgrad + skip -> S3 (S3 was consumed by BN bwd)
+        if ((r = layer_bwd(a, S3, nullptr, S0, nullptr)) != IR_OK) return r; // d out[prev] -> S0
+        up = S0;
+    }
+    return layer_bwd(0, up, nullptr, nullptr, nullptr);                       // stem: no input gradient
+}

@@ -45,12 +45,24 @@ extern "C" int ir_rulebook_transpose(const int32_t* in_idx, const int32_t* slot,
 // entries ci = i*16+ty, co = j*16+tx of dW[k] (interleaved so shared-memory reads are conflict-free
 // and the final atomics touch consecutive floats).  Pairs of the CTA's chunk are staged 16 at a time.
 #define WG_PB 16
+template <int V> struct WgVec;
+template <> struct WgVec<4> { typedef float4 T; };
+template <> struct WgVec<2> { typedef float2 T; };
+template <int V> __device__ __forceinline__ void wg_load(const float* p, float* dst) {
+    const typename WgVec<V>::T v = *reinterpret_cast<const typename WgVec<V>::T*>(p);
+    if (V == 4) { const float4 q = *reinterpret_cast<const float4*>(&v); dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w; }
+    else { const float2 q = *reinterpret_cast<const float2*>(&v); dst[0] = q.x; dst[1] = q.y; }
+}
+// Thread (ty,tx) owns ci = (i/VI)*16*VI + ty*VI + i%VI and co = (j/VJ)*16*VJ + tx*VJ + j%VJ: its operands are
+// VI/VJ-wide contiguous groups, so one 16-byte shared-memory load feeds 4 rows/columns of the outer product
+// (the warp's 16 tx lanes read 256 contiguous bytes: conflict-free; the two ty values broadcast).
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __restrict__ in_idx,
         const int* __restrict__ out_idx, const int* __restrict__ count, long long seg_cap,
         float* __restrict__ dW) {
     constexpr int MI = CIN / 16, MJ = COUT / 16;
+    constexpr int VI = MI < 4 ? MI : 4, VJ = MJ < 4 ? MJ : 4;
     __shared__ __align__(16) float xs[WG_PB][CIN];
     __shared__ __align__(16) float ds[WG_PB][COUT];
     const int k = blockIdx.y;
@@ -85,9 +97,9 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
         for (int p = 0; p < WG_PB; ++p) {
             float a[MI], b[MJ];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = xs[p][i * 16 + ty];
+            for (int i = 0; i < MI; i += VI) wg_load<VI>(&xs[p][(i / VI) * 16 * VI + ty * VI], &a[i]);
 #pragma unroll
-            for (int j = 0; j < MJ; ++j) b[j] = ds[p][j * 16 + tx];
+            for (int j = 0; j < MJ; j += VJ) wg_load<VJ>(&ds[p][(j / VJ) * 16 * VJ + tx * VJ], &b[j]);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -99,7 +111,8 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < MJ; ++j) atomicAdd(&Wk[(i * 16 + ty) * COUT + j * 16 + tx], acc[i][j]);
+        for (int j = 0; j < MJ; ++j)
+            atomicAdd(&Wk[((i / VI) * 16 * VI + ty * VI + i % VI) * COUT + (j / VJ) * 16 * VJ + tx * VJ + j % VJ], acc[i][j]);
 }
 
 // small-Cin form (the stem, Cin = 7): one thread per (ci, co), pairs streamed from L2
@@ -116,7 +129,18 @@ k_wgrad_small(const float* __restrict__ X, const float* __restrict__ dY, const i
     const int ci = tid / cout, co = tid - ci * cout;
     const long long base = (long long)k * seg_cap;
     float acc = 0.f;
-    for (int p = p_begin; p < p_end; ++p)
+    int p = p_begin;
+    for (; p + 4 <= p_end; p += 4) {                 // four independent gather chains in flight
+        int i[4], o[4];
+        float xv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { i[u] = in_idx[base + p + u]; o[u] = out_idx[base + p + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xv[u] = __ldg(X + (long long)i[u] * cin + ci); dv[u] = __ldg(dY + (long long)o[u] * cout + co); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], dv[u], acc);
+    }
+    for (; p < p_end; ++p)
         acc = fmaf(__ldg(X + (long long)in_idx[base + p] * cin + ci), __ldg(dY + (long long)out_idx[base + p] * cout + co), acc);
     atomicAdd(&dW[((long long)k * cin + ci) * cout + co], acc);
 }
@@ -133,7 +157,7 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
     else if (cin == 64 && cout == 128) k_wgrad<64, 128><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
     else if (cin == 64 && cout == 64) k_wgrad<64, 64><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
     else if (cin == 32 && cout == 64) k_wgrad<32, 64><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
-    else if (cin * cout <= 256) k_wgrad_small<<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, cin, cout, dW);
+    else if (cin * cout <= 256) k_wgrad_small<<<dim3(ir_div_up(16 * IR_NUM_SMS, K), K), 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, cin, cout, dW);
     else { ir_set_error("spconv_wgrad: unsupported channels %d -> %d", cin, cout); return IR_ERR_UNSUPPORTED; }
     IR_CHECK_LAUNCH();
     return IR_OK;
@@ -141,40 +165,60 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
 
 // ------------------------------------------------------------------ BatchNorm, train mode, (rows, C)
 // Used for spnn.BatchNorm over voxels, nn.BatchNorm1d over samples and nn.BatchNorm2d over NHWC cells
-// (rows = B*H*W).  Statistics are accumulated per CTA in fp32 over <= ~100 rows, then in fp64 atomics.
-// scratch: double[2*C].
+// (rows = B*H*W).  Two-level deterministic reductions: every CTA writes fp32 partial sums of its row
+// stripe to scratch[part][2*C]; a finalize kernel adds the <= BN_MAX_PARTS partials in fp64.
+// scratch: float[BN_MAX_PARTS * 2 * C] (ir_bn_scratch_floats).
+#define BN_MAX_PARTS (IR_NUM_SMS * 4)
+#define BN_ROWS_PER_CTA 32
+static inline int bn_parts(long long n) { return ir_min_i(ir_div_up(n > 0 ? n : 1, BN_ROWS_PER_CTA), BN_MAX_PARTS); }
+extern "C" int64_t ir_bn_scratch_floats(int32_t C) { return (int64_t)BN_MAX_PARTS * 2 * C; }
+
+// mode 0: (sum x, sum x^2);  mode 1 (backward): g = dy*[y>0]; (sum g, sum g*xhat)
+template <int MODE>
 __global__ void __launch_bounds__(256)
-k_bn_stats(const float* __restrict__ x, const int* __restrict__ n_dev, int n_host, int C,
-           double* __restrict__ scratch) {
+k_bn_partials(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+              const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
+              const float* __restrict__ rstd, int relu, float* __restrict__ scratch) {
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const int tid = threadIdx.x;
     const int c = tid % C, g = tid / C, G = blockDim.x / C;
-    float s = 0.f, ss = 0.f;
-    for (long long r = (long long)blockIdx.x * G + g; r < n; r += (long long)gridDim.x * G) {
-        const float v = x[r * C + c];
-        s += v;
-        ss = fmaf(v, v, ss);
+    float mu = 0.f, rs = 1.f;
+    if (MODE == 1) { mu = mean[c]; rs = rstd[c]; }
+    float s0 = 0.f, s1 = 0.f;
+    const long long step = (long long)gridDim.x * G;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * G + g; r < n; r += step) {
+        const float xv = x[r * C + c];
+        if (MODE == 0) { s0 += xv; s1 = fmaf(xv, xv, s1); }
+        else {
+            float gv = dy[r * C + c];
+            if (relu && !(y[r * C + c] > 0.f)) gv = 0.f;
+            s0 += gv;
+            s1 = fmaf(gv, (xv - mu) * rs, s1);
+        }
     }
     __shared__ float sh[2][256];
-    sh[0][tid] = s; sh[1][tid] = ss;
+    sh[0][tid] = s0; sh[1][tid] = s1;
     __syncthreads();
     if (g == 0) {
-        for (int q = 1; q < G; ++q) { s += sh[0][q * C + c]; ss += sh[1][q * C + c]; }
-        atomicAdd(&scratch[c], (double)s);
-        atomicAdd(&scratch[C + c], (double)ss);
+        for (int q = 1; q < G; ++q) { s0 += sh[0][q * C + c]; s1 += sh[1][q * C + c]; }
+        scratch[(long long)blockIdx.x * 2 * C + c] = s0;
+        scratch[(long long)blockIdx.x * 2 * C + C + c] = s1;
     }
 }
 
-__global__ void k_bn_finalize(const double* __restrict__ scratch, const int* __restrict__ n_dev, int n_host,
+__global__ void k_bn_finalize(const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
                               int C, float eps, float momentum, float* __restrict__ running_mean,
                               float* __restrict__ running_var, float* __restrict__ mean_out,
                               float* __restrict__ rstd_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
+    double s = 0.0, ss = 0.0;
+    for (int p = 0; p < parts; ++p) { s += scratch[(long long)p * 2 * C + c]; ss += scratch[(long long)p * 2 * C + C + c]; }
     const double inv = n > 0 ? 1.0 / n : 0.0;
-    const double m = scratch[c] * inv;
-    double var = scratch[C + c] * inv - m * m;
+    const double m = s * inv;
+    double var = ss * inv - m * m;
     if (var < 0) var = 0;
     mean_out[c] = (float)m;
     rstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -187,28 +231,35 @@ k_bn_apply(const float* __restrict__ x, const int* __restrict__ n_dev, int n_hos
            const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
            const float* __restrict__ beta, const float* __restrict__ resid, int relu, float* __restrict__ y) {
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    const long long total = (long long)n * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        float v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-        if (resid) v += resid[i];
-        if (relu) v = fmaxf(v, 0.f);
-        y[i] = v;
+    const long long total4 = (long long)n * C / 4;                 // C is a multiple of 4
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* r4 = reinterpret_cast<const float4*>(resid);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % C);
+        const float4 xv = x4[i];
+        float v[4] = {xv.x, xv.y, xv.z, xv.w};
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (resid) { const float4 q = r4[i]; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float o = (v[u] - mean[c + u]) * rstd[c + u] * gamma[c + u] + beta[c + u] + r[u];
+            v[u] = relu ? fmaxf(o, 0.f) : o;
+        }
+        y4[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
 extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, int32_t C, const float* gamma,
                                const float* beta, const float* resid, int32_t relu, float eps, float momentum,
-                               float* running_mean, float* running_var, double* scratch, float* mean,
+                               float* running_mean, float* running_var, float* scratch, float* mean,
                                float* rstd, float* y, ir_stream_t stream) {
-    IR_CHECK_ARG(x && gamma && beta && scratch && mean && rstd && y && n > 0 && C > 0 && C <= 256 && 256 % C == 0);
+    IR_CHECK_ARG(x && gamma && beta && scratch && mean && rstd && y && n > 0 && C >= 4 && C <= 256 && 256 % C == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    IR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)2 * C * sizeof(double), st));
-    const int G = 256 / C;
-    const int grid = ir_min_i(ir_div_up(n, (long long)G * 64), IR_NUM_SMS * 4);
-    k_bn_stats<<<grid, 256, 0, st>>>(x, n_dev, n, C, scratch);
+    const int parts = bn_parts(n);
+    k_bn_partials<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, n_dev, n, C, nullptr, nullptr, 0, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_finalize<<<ir_div_up(C, 128), 128, 0, st>>>(scratch, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
+    k_bn_finalize<<<ir_div_up(C, 128), 128, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
     IR_CHECK_LAUNCH();
     k_bn_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(x, n_dev, n, C, mean, rstd, gamma, beta, resid, relu, y);
     IR_CHECK_LAUNCH();
@@ -217,69 +268,63 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
 
 // backward: g = dy * [y > 0] (if relu); dbeta = sum g; dgamma = sum g*xhat;
 //           dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n); dresid = g
-__global__ void __launch_bounds__(256)
-k_bn_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
-                const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
-                const float* __restrict__ rstd, int relu, double* __restrict__ scratch) {
-    const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    const int tid = threadIdx.x;
-    const int c = tid % C, g = tid / C, G = blockDim.x / C;
-    const float mu = mean[c], rs = rstd[c];
-    float s = 0.f, sx = 0.f;
-    for (long long r = (long long)blockIdx.x * G + g; r < n; r += (long long)gridDim.x * G) {
-        float gv = dy[r * C + c];
-        if (relu && !(y[r * C + c] > 0.f)) gv = 0.f;
-        s += gv;
-        sx = fmaf(gv, (x[r * C + c] - mu) * rs, sx);
-    }
-    __shared__ float sh[2][256];
-    sh[0][tid] = s; sh[1][tid] = sx;
-    __syncthreads();
-    if (g == 0) {
-        for (int q = 1; q < G; ++q) { s += sh[0][q * C + c]; sx += sh[1][q * C + c]; }
-        atomicAdd(&scratch[c], (double)s);
-        atomicAdd(&scratch[C + c], (double)sx);
-    }
+__global__ void k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, sx = 0.0;
+    for (int p = 0; p < parts; ++p) { s += scratch[(long long)p * 2 * C + c]; sx += scratch[(long long)p * 2 * C + C + c]; }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)sx;
 }
 
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
                const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
                const float* __restrict__ rstd, const float* __restrict__ gamma, int relu,
-               const double* __restrict__ scratch, float* __restrict__ dx, float* __restrict__ dresid,
-               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+               const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx,
+               float* __restrict__ dresid) {
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const float inv = n > 0 ? 1.f / n : 0.f;
-    if (blockIdx.x == 0)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            dbeta[c] = (float)scratch[c];
-            dgamma[c] = (float)scratch[C + c];
+    const long long total4 = (long long)n * C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % C);
+        const float4 d4 = reinterpret_cast<const float4*>(dy)[i];
+        const float4 x4 = reinterpret_cast<const float4*>(x)[i];
+        float g[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        if (relu) {
+            const float4 y4 = reinterpret_cast<const float4*>(y)[i];
+            if (!(y4.x > 0.f)) g[0] = 0.f;
+            if (!(y4.y > 0.f)) g[1] = 0.f;
+            if (!(y4.z > 0.f)) g[2] = 0.f;
+            if (!(y4.w > 0.f)) g[3] = 0.f;
         }
-    const long long total = (long long)n * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        float gv = dy[i];
-        if (relu && !(y[i] > 0.f)) gv = 0.f;
-        const float xh = (x[i] - mean[c]) * rstd[c];
-        dx[i] = gamma[c] * rstd[c] * (gv - (float)scratch[c] * inv - xh * (float)scratch[C + c] * inv);
-        if (dresid) dresid[i] = gv;
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xv[u] - mean[c + u]) * rstd[c + u];
+            o[u] = gamma[c + u] * rstd[c + u] * (g[u] - dbeta[c + u] * inv - xh * dgamma[c + u] * inv);
+        }
+        reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dresid) reinterpret_cast<float4*>(dresid)[i] = make_float4(g[0], g[1], g[2], g[3]);
     }
 }
 
 extern "C" int ir_bn_train_bwd(const float* dy, const float* y, const float* x, const int32_t* n_dev, int32_t n,
                                int32_t C, const float* mean, const float* rstd, const float* gamma, int32_t relu,
-                               double* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
+                               float* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
                                ir_stream_t stream) {
-    IR_CHECK_ARG(dy && x && mean && rstd && gamma && scratch && dx && dgamma && dbeta && n > 0 && C > 0 && C <= 256 && 256 % C == 0);
+    IR_CHECK_ARG(dy && x && mean && rstd && gamma && scratch && dx && dgamma && dbeta && n > 0 && C >= 4 && C <= 256 && 256 % C == 0);
     IR_CHECK_ARG(!relu || y);
     cudaStream_t st = (cudaStream_t)stream;
-    IR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)2 * C * sizeof(double), st));
-    const int G = 256 / C;
-    const int grid = ir_min_i(ir_div_up(n, (long long)G * 64), IR_NUM_SMS * 4);
-    k_bn_bwd_reduce<<<grid, 256, 0, st>>>(dy, y, x, n_dev, n, C, mean, rstd, relu, scratch);
+    const int parts = bn_parts(n);
+    k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch);
+    IR_CHECK_LAUNCH();
+    k_bn_bwd_finalize<<<ir_div_up(C, 128), 128, 0, st>>>(scratch, parts, C, dgamma, dbeta);
     IR_CHECK_LAUNCH();
     k_bn_bwd_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(
-        dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, scratch, dx, dresid, dgamma, dbeta);
+        dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

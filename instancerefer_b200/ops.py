@@ -292,11 +292,14 @@ def spconv_wgrad(x, dy, in_idx, out_idx, count):
     return dW
 
 
+BN_PARTS = 148 * 4          # ir_bn_scratch_floats(C) = BN_PARTS * 2 * C
+
+
 def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, running_var):
     """x (n,C) fp32 -> (y, mean, rstd); running statistics are updated in place."""
     n, Cc = x.shape
     dev = x.device
-    scratch = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+    scratch = torch.empty(BN_PARTS * 2 * Cc, dtype=torch.float32, device=dev)
     mean = torch.empty(Cc, dtype=torch.float32, device=dev)
     rstd = torch.empty(Cc, dtype=torch.float32, device=dev)
     y = torch.empty_like(x)
@@ -309,7 +312,7 @@ def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, runni
 def bn_train_bwd(dy, y, x, mean, rstd, gamma, relu, want_resid):
     n, Cc = x.shape
     dev = x.device
-    scratch = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+    scratch = torch.empty(BN_PARTS * 2 * Cc, dtype=torch.float32, device=dev)
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_resid else None
     dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
@@ -513,11 +516,14 @@ def token_attention_bwd(feats, embed, lengths, fcw, fcb, atten, dpooled):
 def gru_layer_bwd(xproj, whh, bhh, lengths, out, dout, B, L, H=128):
     dev = xproj.device
     dxp = torch.empty_like(xproj)
-    dw = torch.empty(B, 2 * 3 * H * H, dtype=torch.float32, device=dev)
-    db = torch.empty(B, 2 * 3 * H, dtype=torch.float32, device=dev)
+    dhp = torch.empty(B * L, 2 * 3 * H, dtype=torch.float32, device=dev)
+    hprev = torch.empty(B * L, 2 * H, dtype=torch.float32, device=dev)
     call("ir_gru_layer_bwd", _p(xproj, torch.float32), _p(whh, torch.float32), _p(bhh, torch.float32),
-         _p(lengths, torch.int64), _p(out, torch.float32), _p(dout, torch.float32), B, L, H, _p(dxp), _p(dw), _p(db), _stream())
-    return dxp, colsum(dw).view(2, 3 * H, H), colsum(db).view(2, 3 * H)
+         _p(lengths, torch.int64), _p(out, torch.float32), _p(dout, torch.float32), B, L, H, _p(dxp), _p(dhp), _p(hprev), _stream())
+    dw = torch.empty(2, 3 * H, H, dtype=torch.float32, device=dev)
+    for d in (0, 1):            # dW_hh[d] = dhp_d^T @ hprev_d over all (sample, step) rows
+        gemm(dhp[:, d * 3 * H:(d + 1) * 3 * H], hprev[:, d * H:(d + 1) * H], ta=True, out=dw[d])
+    return dxp, dw, colsum(dhp).view(2, 3 * H)
 
 
 def edge_inputs(x, xyz, qidx, nbr, ncls, w=None):

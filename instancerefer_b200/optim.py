@@ -30,11 +30,13 @@ class FlatAdam:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views = []
         for p, o in zip(self.params, ofs):
             n = p.numel()
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view_as(p)              # parameters become views of the flat buffer
-            p.grad = self.flat_grad[o:o + n].view_as(p)         # autograd accumulates straight into it
+            self.grad_views.append(self.flat_grad[o:o + n].view_as(p))
+            p.grad = None
         self.offsets, self.numel = ofs, total
         self.step_count = 0
         self.group = process_group
@@ -43,10 +45,25 @@ class FlatAdam:
             self.world = torch.distributed.get_world_size(process_group)
 
     def zero_grad(self):
-        self.flat_grad.zero_()
-        for p, o in zip(self.params, self.offsets):             # re-attach if something replaced .grad
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
-                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        """.grad = None: backward then hands over each gradient tensor without an accumulation kernel."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """Pack the per-parameter gradients of this backward into the flat buffer (one multi-tensor
+        copy; parameters that received no gradient contribute zeros) and point .grad at the views."""
+        src, dst, zero = [], [], []
+        for v, p in zip(self.grad_views, self.params):
+            if p.grad is None:
+                zero.append(v)
+            elif p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+            p.grad = v
+        if zero:
+            torch._foreach_zero_(zero)
+        if src:
+            torch._foreach_copy_(dst, src)
 
     def allreduce(self):
         """Sum over ranks (the mean is folded into the Adam kernel)."""
@@ -54,6 +71,7 @@ class FlatAdam:
             torch.distributed.all_reduce(self.flat_grad, group=self.group)
 
     def step(self):
+        self.gather_grads()
         self.allreduce()
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],

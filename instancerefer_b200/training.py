@@ -110,16 +110,71 @@ class SegMax(Function):
             None, None, None, None
 
 
+class EncoderTrain(Function):
+    """All 13 layers of an encoder as ONE library call per direction (ir_encoder_train_forward /
+    ir_encoder_train_backward): activations stay in an arena owned by this node of the autograd graph."""
+
+    @staticmethod
+    def forward(ctx, feats0, net, G, *params):
+        import ctypes as C
+        from . import _lib
+        ws, dev = G.ws, G.ws.buf.device
+        layers = net._layers()
+        P = _lib.EncoderTrainParams()
+        P.cin, P.use_tc, P.eps = net.input_dim, 1 if net.use_tc else 0, layers[0][1].eps
+        keep = []
+        for i, (conv, bn) in enumerate(layers):
+            w, g, b = (t.detach().contiguous() for t in params[3 * i:3 * i + 3])
+            keep += [w, g, b]
+            P.weight[i], P.gamma[i], P.beta[i] = w.data_ptr(), g.data_ptr(), b.data_ptr()
+            P.running_mean[i], P.running_var[i] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            P.momentum[i] = bn.momentum if bn.momentum is not None else 0.1
+        n_lvl = (C.c_int32 * 5)(*G.n)
+        lay = _lib.EncoderTrainLayout()
+        _lib.call("ir_encoder_train_layout", ws.n_max, n_lvl, net.input_dim, C.byref(lay))
+        arena = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+        f0 = feats0.contiguous() if feats0 is not None else None
+        _lib.call("ir_encoder_train_forward", C.byref(P), ops._p(f0), ws.ptr, ws.n_max, n_lvl, ops._p(arena), ops._stream())
+        torch._foreach_add_([bn.num_batches_tracked for _, bn in layers], 1)
+        ctx.state = (P, keep, n_lvl, arena, f0, G, [tuple(t.shape) for t in params])
+        o = lay.off_out[12]
+        return arena[o:o + G.n[4] * 128 * 4].view(torch.float32).view(G.n[4], 128)
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        from . import _lib
+        P, keep, n_lvl, arena, f0, G, shapes = ctx.state
+        ws = G.ws
+        sizes = [(int(torch.Size(sh).numel()) + 63) // 64 * 64 for sh in shapes]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=arena.device)
+        grads, o = [], 0
+        for sh, sz in zip(shapes, sizes):
+            grads.append(flat[o:o + torch.Size(sh).numel()].view(sh))
+            o += sz
+        Gr = _lib.EncoderTrainGrads()
+        for i in range(13):
+            Gr.dweight[i], Gr.dgamma[i], Gr.dbeta[i] = (grads[3 * i + q].data_ptr() for q in range(3))
+        _lib.call("ir_encoder_train_backward", C.byref(P), ops._p(f0), ws.ptr, ws.n_max, n_lvl, ops._p(arena),
+                  ops._p(dout.contiguous(), torch.float32), C.byref(Gr), ops._stream())
+        return (None, None, None, *grads)
+
+
 def encoder_forward_train(net, ws, feats0=None, coords0=None):
     """Train-mode pass of a SparseConvEncoder / BEVEncoder over a workspace whose level 0 is
     already voxelised (feats0 None) or given by (feats0, coords0).
-    -> (F4 (n4,128) with autograd history, EncoderGraph)."""
+    -> (F4 (n4,128) with autograd history, EncoderGraph).  IR_TRAIN_ENCODER=layers selects the
+    per-layer autograd path (13 SparseConvBN nodes; what the unit tests dissect)."""
+    import os
     ops.encoder_build_maps(ws, coords0)
     G = EncoderGraph(ws)
+    layers = net._layers()
+    if os.environ.get('IR_TRAIN_ENCODER', 'fused') != 'layers':
+        flat = [t for conv, bn in layers for t in (conv.kernel, bn.weight, bn.bias)]
+        return EncoderTrain.apply(feats0, net, G, *flat), G
     if feats0 is None:
         feats0 = ws.feat0(net.input_dim)[:G.n[0]].clone()
     tc = net.use_tc
-    layers = net._layers()
 
     def cbr(x, idx, kind, level, relu=True, resid=None):
         conv, bn = layers[idx]

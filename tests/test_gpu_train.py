@@ -439,10 +439,13 @@ def test_encoder_train_matches_torch_replica(ops, lib_built, state_dict, args):
         acts.append(out)
         return out
     T.SparseConvBN.apply = spy
+    os.environ['IR_TRAIN_ENCODER'] = 'layers'
     try:
         f4, G = T.encoder_forward_train(net, ws)
     finally:
         T.SparseConvBN.apply = orig
+        del os.environ['IR_TRAIN_ENCODER']
+    assert len(acts) == 13
     wgt = torch.randn(f4.shape, generator=torch.Generator().manual_seed(0))
     (f4 * wgt.cuda()).sum().backward()
     torch.cuda.synchronize()
@@ -473,6 +476,48 @@ def test_encoder_train_matches_torch_replica(ops, lib_built, state_dict, args):
         errs = (rel(a.detach(), c.detach()), rel(a.grad, c.grad), rel(conv.kernel.grad, w.grad),
                 rel(bn.weight.grad, ga.grad), rel(bn.bias.grad, be.grad))
         assert max(errs) < 1e-4, (i, errs)
+
+
+@pytest.mark.parametrize('which', ['attribute', 'scene'])
+def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, which):
+    """ir_encoder_train_forward/backward (one call per direction) == the 13 per-layer autograd nodes."""
+    from instancerefer_b200 import SparseTensor, training as T
+    from instancerefer_b200.candidates import CandidatePack, target_classes
+    from instancerefer_b200.instancerefer import InstanceRefer
+    b = synthetic.make_batch(17, batch_size=2, num_points=9000, n_inst=10, n_cand=[4, 3], n_tokens=[5, 6])
+    res = {}
+    for mode in ('layers', 'fused'):
+        model = InstanceRefer(7, args)
+        model.load_state_dict(state_dict, strict=True)
+        model = model.cuda().train()
+        dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
+        os.environ['IR_TRAIN_ENCODER'] = mode
+        try:
+            if which == 'attribute':
+                pack = CandidatePack(dd, target_classes(dd, args), 'cuda')
+                net = model.attribute.net
+                ws = net.workspace(pack.M * 1024, 'cuda')
+                ops.encoder_reset(ws)
+                ops.voxelize(pack.points, pack.cand_rows, 0.02, ws)
+                f4, G = T.encoder_forward_train(net, ws)
+            else:
+                net = model.scene.net
+                F0, C0 = dd['lidar'].F.float().contiguous(), dd['lidar'].C.int().contiguous()
+                ws = net.workspace(F0.shape[0], 'cuda')
+                f4, G = T.encoder_forward_train(net, ws, F0, C0)
+        finally:
+            del os.environ['IR_TRAIN_ENCODER']
+        wgt = torch.randn(f4.shape, generator=torch.Generator().manual_seed(1)).cuda()
+        (f4 * wgt).sum().backward()
+        torch.cuda.synchronize()
+        res[mode] = (f4.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()},
+                     {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k})
+    assert torch.equal(res['layers'][0], res['fused'][0])
+    for k, g in res['layers'][1].items():
+        e = float((g - res['fused'][1][k]).abs().max())
+        assert e <= 1e-5 * float(g.abs().max()) + 1e-9, (k, e)          # wgrad sums with float atomics
+    for k, v in res['layers'][2].items():
+        assert torch.equal(v, res['fused'][2][k]), k
 
 
 # ----------------------------------------------------------------------------- whole iteration
