@@ -29,7 +29,11 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += GM_BK) {
+    // split-K: slice z of gridDim.z handles a GM_BK-aligned K range and adds into C with atomics
+    const int kper = ((K + gridDim.z - 1) / gridDim.z + GM_BK - 1) / GM_BK * GM_BK;
+    const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+    const bool split = gridDim.z > 1;
+    for (int k0 = kbeg; k0 < kend; k0 += GM_BK) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int idx = tid + q * 256;
@@ -37,13 +41,13 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const 
             if (ta) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
             const int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
-            if (gm < M && gk < K) v = ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
+            if (gm < M && gk < kend) v = ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
             As[k][m] = v;
             int n, kb;
             if (tb) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
             const int gn = n0 + n, gkb = k0 + kb;
             float u = 0.f;
-            if (gn < N && gkb < K) u = tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn];
+            if (gn < N && gkb < kend) u = tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn];
             Bs[kb][n] = u;
         }
         __syncthreads();
@@ -70,7 +74,8 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const 
             const int gn = n0 + tx + 16 * j;
             if (gn >= N) continue;
             float v = acc[i][j];
-            if (bias) v += bias[gn];
+            if (bias && blockIdx.z == 0) v += bias[gn];
+            if (split) { atomicAdd(&C[(long long)gm * ldc + gn], v); continue; }
             if (accumulate) v += C[(long long)gm * ldc + gn];
             if (relu) v = fmaxf(v, 0.f);
             C[(long long)gm * ldc + gn] = v;
@@ -82,7 +87,17 @@ extern "C" int ir_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t 
                        const float* B, int32_t ldb, int32_t trans_b, float* C, int32_t ldc, const float* bias,
                        int32_t relu, int32_t accumulate, ir_stream_t stream) {
     IR_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
-    const dim3 grid(ir_div_up(N, GM_BN), ir_div_up(M, GM_BM));
+    dim3 grid(ir_div_up(N, GM_BN), ir_div_up(M, GM_BM));
+    // few output tiles and a long K (im2col conv GEMMs, weight gradients): split K over gridDim.z so the
+    // launch fills the GPU; partial tiles are added with atomics into a zeroed (or accumulated-into) C
+    const int tiles = grid.x * grid.y;
+    if (!relu && tiles < IR_NUM_SMS && K >= 256 && ldc == N) {
+        int z = ir_min_i(ir_div_up(2 * IR_NUM_SMS, tiles), K / 64);
+        if (z > 1) {
+            grid.z = z;
+            if (!accumulate) IR_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * 4, (cudaStream_t)stream));
+        }
+    }
     k_gemm<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, bias, relu, accumulate);
     IR_CHECK_LAUNCH();
     return IR_OK;

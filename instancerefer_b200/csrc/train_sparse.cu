@@ -207,15 +207,30 @@ k_bn_partials(const float* __restrict__ x, const float* __restrict__ dy, const f
     }
 }
 
-__global__ void k_bn_finalize(const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
-                              int C, float eps, float momentum, float* __restrict__ running_mean,
-                              float* __restrict__ running_var, float* __restrict__ mean_out,
-                              float* __restrict__ rstd_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// grid = C/32 CTAs of 256 threads: lane = channel, the 8 warps split the partials, fp64 accumulation
+__device__ __forceinline__ void bn_sum_parts(const float* __restrict__ scratch, int parts, int C, int c, double& s, double& ss) {
+    __shared__ double sh[2][8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (int p = w; p < parts; p += 8) { a += scratch[(long long)p * 2 * C + c]; b += scratch[(long long)p * 2 * C + C + c]; }
+    sh[0][w][lane] = a; sh[1][w][lane] = b;
+    __syncthreads();
+    s = 0.0; ss = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { s += sh[0][q][lane]; ss += sh[1][q][lane]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
+              int C, float eps, float momentum, float* __restrict__ running_mean,
+              float* __restrict__ running_var, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, ss;
+    bn_sum_parts(scratch, parts, C, c, s, ss);
+    if (c >= C || threadIdx.x >= 32) return;
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    double s = 0.0, ss = 0.0;
-    for (int p = 0; p < parts; ++p) { s += scratch[(long long)p * 2 * C + c]; ss += scratch[(long long)p * 2 * C + C + c]; }
     const double inv = n > 0 ? 1.0 / n : 0.0;
     const double m = s * inv;
     double var = ss * inv - m * m;
@@ -259,7 +274,7 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
     const int parts = bn_parts(n);
     k_bn_partials<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, n_dev, n, C, nullptr, nullptr, 0, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_finalize<<<ir_div_up(C, 128), 128, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
+    k_bn_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
     IR_CHECK_LAUNCH();
     k_bn_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(x, n_dev, n, C, mean, rstd, gamma, beta, resid, relu, y);
     IR_CHECK_LAUNCH();
@@ -268,12 +283,13 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
 
 // backward: g = dy * [y > 0] (if relu); dbeta = sum g; dgamma = sum g*xhat;
 //           dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n); dresid = g
-__global__ void k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
-                                  float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, sx = 0.0;
-    for (int p = 0; p < parts; ++p) { s += scratch[(long long)p * 2 * C + c]; sx += scratch[(long long)p * 2 * C + C + c]; }
+__global__ void __launch_bounds__(256)
+k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
+                  float* __restrict__ dbeta) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, sx;
+    bn_sum_parts(scratch, parts, C, c, s, sx);
+    if (c >= C || threadIdx.x >= 32) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)sx;
 }
@@ -321,7 +337,7 @@ extern "C" int ir_bn_train_bwd(const float* dy, const float* y, const float* x, 
     const int parts = bn_parts(n);
     k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_bwd_finalize<<<ir_div_up(C, 128), 128, 0, st>>>(scratch, parts, C, dgamma, dbeta);
+    k_bn_bwd_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, C, dgamma, dbeta);
     IR_CHECK_LAUNCH();
     k_bn_bwd_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(
         dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid);

@@ -75,3 +75,59 @@ def test_sharded_forward_matches_single_process():
         assert p.exitcode == 0
     assert res.pop('n') == 9
     assert max(res.values()) < 1e-6, res
+
+
+# ----------------------------------------------------------------------------- training step, data parallel
+
+def _grad_worker(rank, world, port, q):
+    """Flat-buffer optimiser plumbing on CPU: parameters become views of one buffer, the gradients of a
+    backward are packed with one multi-tensor copy, ONE all-reduce sums them over ranks (SURVEY §8(e));
+    the Adam kernel itself is CUDA-only and must refuse to run here."""
+    sys.path.insert(0, ROOT)
+    from instancerefer_b200 import _lib
+    from instancerefer_b200.optim import ALIGN, FlatAdam
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+    ref = [p.detach().clone() for p in model.parameters()]
+    opt = FlatAdam(model, lr=1e-3)
+    ok = all(torch.equal(p.detach(), r) for p, r in zip(model.parameters(), ref))
+    ok &= all(p.data_ptr() == opt.flat.data_ptr() + 4 * o and o % ALIGN == 0 for p, o in zip(opt.params, opt.offsets))
+    x = torch.randn(4, 7, generator=torch.Generator().manual_seed(10 + rank))
+    opt.zero_grad()
+    model(x).square().sum().backward()
+    local = [p.grad.clone() for p in model.parameters()]
+    model[2].bias.grad = None                                      # a parameter without gradient packs as zeros
+    opt.gather_grads()
+    opt.allreduce()
+    summed = []
+    for i, g in enumerate(local):
+        t = g.clone() if i != len(local) - 1 else torch.zeros_like(g)
+        dist.all_reduce(t)
+        summed.append(t)
+    ok &= all(torch.allclose(p.grad, s) for p, s in zip(model.parameters(), summed))
+    ok &= opt.world == world
+    try:
+        opt.step()
+        refused = False
+    except _lib.IrError:
+        refused = True                                             # no CPU fallback for the Adam kernel
+    if rank == 0:
+        q.put(dict(ok=bool(ok), refused=refused))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == dict(ok=True, refused=True), res
