@@ -261,7 +261,113 @@ def main_train(a):
             final_loss=losses[-1], first_loss=losses[0], cpu_baseline=cb)))
 
 
+def _forward_setup(local):
+    import __graft_entry__ as g
+    g.build()
+    import weights
+    from instancerefer_b200 import ops
+    from instancerefer_b200.instancerefer import InstanceRefer
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    ops.check_device(local)
+    model = InstanceRefer(7, make_args())
+    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    return model.to(dev).eval(), dev
+
+
+def _resident_dict(b, dev):
+    """Inputs of one batch staged in HBM (loader tensors + the packed instance buffer)."""
+    from instancerefer_b200 import SparseTensor, synthetic
+    from instancerefer_b200.candidates import KEY, CandidatePack
+    d = synthetic.to_data_dict(b, SparseTensor, dev)
+    pack = CandidatePack(d, d['object_cat'], dev)
+    pack.resident = True
+    d[KEY] = pack
+    d['_ir_lang_len_max'] = int(np.max(b['lang_len']))
+    return d
+
+
+def _time_graph(model, d, steps, warmup, flush):
+    """CUDA-graph replay of model(d): per-step CUDA events, L2 flushed between steps -> ms/step."""
+    for _ in range(2):
+        model(dict(d))
+    torch.cuda.synchronize()
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_):
+        model(dict(d))
+    for _ in range(warmup):
+        g_.replay()
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g_.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    return ms / steps
+
+
+def main_sweep(a):
+    """--workload sweep: BASELINE.json configs[4] — forward throughput over 10k-200k points x 8-128 instances
+    (n = c), one scene per step per GPU, inputs resident, CUDA-graph replay; --workload relation:
+    configs[3] — relation module alone (kNN + EdgeConv + match) on 32 scenes x 64 instances."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    from instancerefer_b200 import synthetic
+    model, dev = _forward_setup(local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps, warmup = max(a.steps, 5), max(a.warmup, 3)
+    rows = []
+    if a.workload == 'relation':
+        b = synthetic.make_batch(7000 + rank, batch_size=32, num_points=40000, n_inst=64, n_cand=64, n_tokens=20)
+        d = _resident_dict(b, dev)
+        d['lang_rel_feats'] = torch.randn(32, 256, device=dev)
+        rel = model.relation
+        ms = _time_graph(lambda x: rel(x), d, steps, warmup, flush)
+        rows.append(dict(scenes=32, instances_per_scene=64, edges=32 * 64 * 8, ms_per_step=ms, referrals_per_sec=world * 32 / (ms * 1e-3)))
+        name = 'configs[3]: relation_module kNN + EdgeConv + cosine match, 32 scenes x 64 instances (64 candidates each), k=8, eval'
+    else:
+        pts = [10000, 20000, 40000, 80000, 120000, 200000] if not a.quick else [10000, 200000]
+        inst = [8, 16, 32, 64, 128] if not a.quick else [8, 128]
+        for npts in pts:
+            for n in inst:
+                room = tuple(np.array([8.0, 6.0, 3.0]) * np.array([(npts / 40000) ** 0.5, (npts / 40000) ** 0.5, 1.0]))
+                b = synthetic.make_batch(9000 + rank, batch_size=1, num_points=npts, n_inst=n, n_cand=n, n_tokens=20,
+                                         room=tuple(min(v, m) for v, m in zip(room, (11.9, 19.9, 3.9))))
+                d = _resident_dict(b, dev)
+                ms = _time_graph(model, d, steps, warmup, flush)
+                rows.append(dict(points=npts, scene_voxels=int(b['lidar_coords'].shape[0]), instances=n, ms_per_step=ms,
+                                 referrals_per_sec=world * 1.0 / (ms * 1e-3)))
+                del d
+                torch.cuda.empty_cache()
+        name = 'configs[4]: forward sweep, points x instances (n = c), 1 scene per step per GPU, eval, CUDA-graph replay'
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        t = torch.tensor([r['ms_per_step'] for r in rows], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for r, v in zip(rows, t.tolist()):
+            r['ms_per_step'] = v
+            r['referrals_per_sec'] = world * (32 if a.workload == 'relation' else 1) / (v * 1e-3)
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(dict(metric=METRIC, unit=METRIC, n_gpus=world, steps=steps, warmup=warmup, higher_is_better=True,
+                              scaling='weak', dtype='f32', data='synthetic', config=dict(workload=name), table=rows,
+                              value=rows[0]['referrals_per_sec'], ms_per_step=rows[0]['ms_per_step'])))
+
+
 def main():
+    if '--workload' in sys.argv and sys.argv[sys.argv.index('--workload') + 1] in ('sweep', 'relation'):
+        ap = argparse.ArgumentParser()
+        ap.add_argument('--workload')
+        ap.add_argument('--gpus', type=int, default=1)
+        ap.add_argument('--steps', type=int, default=10)
+        ap.add_argument('--warmup', type=int, default=3)
+        ap.add_argument('--quick', action='store_true')
+        return main_sweep(ap.parse_args())
     if '--workload' in sys.argv and sys.argv[sys.argv.index('--workload') + 1] == 'train':
         ap = argparse.ArgumentParser()
         ap.add_argument('--workload')
@@ -272,7 +378,7 @@ def main():
         ap.add_argument('--no-cpu-baseline', action='store_true')
         return main_train(ap.parse_args())
     ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', default='forward', choices=['forward', 'train'])
+    ap.add_argument('--workload', default='forward', choices=['forward', 'train', 'sweep', 'relation'])
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)

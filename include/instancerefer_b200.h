@@ -273,6 +273,15 @@ int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt
                 const float* s_scene, float margin, float gamma, float iou_thresh, float* label,
                 float* loss_scene, float* dscore, float* iou_max, ir_stream_t stream);
 
+/* get_eval (lib/eval_helper.py:11-114): per scene the candidate with the highest summed score, IoU of
+ * its box with gt_obb[b] (utils/box_util.py:95-133), ref_acc (arg-max == IoU label for >= 2 candidates,
+ * IoU > 0.25 otherwise; a scene without candidates scores a zero box) and the corner boxes of
+ * construct_bbox_corners (utils/util.py:21-32), (B,8,3) fp64.  label = ir_ref_loss's one-hot labels. */
+int ir_ref_eval(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
+                const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
+                const float* s_scene, const float* label, int32_t* pred_idx, float* ref_acc,
+                double* iou, double* pred_corners, double* gt_corners, ir_stream_t stream);
+
 /* torch.optim.Adam (amsgrad off) on one flat fp32 buffer; gradient = grad_scale*g + weight_decay*p
  * (grad_scale = 1/world_size after a sum all-reduce).  `step` counts from 1.                      */
 int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "ir_cross_entropy": (i32, [p, p, i32, i32, p, p, p]),
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
     "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
+    "ir_ref_eval": (i32, [p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p]),
     "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p]),
     "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),
     "ir_encoder_train_forward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p]),

@@ -210,3 +210,72 @@ extern "C" int ir_adam_step(float* params, const float* grads, float* exp_avg, f
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ get_eval (lib/eval_helper.py:11-114)
+// One warp per scene: candidate with the highest summed score (first maximum), its box against the
+// ground-truth box (axis-aligned IoU of the rotated corner boxes, utils/box_util.py:95-133,290-308),
+// ref_acc (= argmax matches the IoU label when the scene has >= 2 candidates, IoU > 0.25 otherwise) and the
+// un-rotated corner boxes of construct_bbox_corners (utils/util.py:21-32) for the visualisation lists.
+__global__ void __launch_bounds__(32)
+k_ref_eval(const double* __restrict__ pred_obb, const int* __restrict__ obb_ofs, const double* __restrict__ gt_obb,
+           const int* __restrict__ score_ofs, const float* __restrict__ sa, const float* __restrict__ sr,
+           const float* __restrict__ ss, const float* __restrict__ label, int* __restrict__ pred_idx,
+           float* __restrict__ ref_acc, double* __restrict__ iou_out, double* __restrict__ pred_corners,
+           double* __restrict__ gt_corners) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int o0 = obb_ofs[b], n = obb_ofs[b + 1] - o0;
+    const int s0 = score_ofs[b];
+    int best_j = 0, target = 0;
+    if (n >= 2 && s0 >= 0) {
+        float best = -INFINITY, bl = -INFINITY;
+        best_j = 0x7fffffff; target = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+            const float v = sa[s0 + j] + sr[s0 + j] + ss[s0 + j];
+            if (v > best) { best = v; best_j = j; }
+            const float l = label[o0 + j];
+            if (l > bl) { bl = l; target = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+            if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+            const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, target, o);
+            if (ol > bl || (ol == bl && ot < target)) { bl = ol; target = ot; }
+        }
+    }
+    if (lane != 0) return;
+    double po[7] = {0, 0, 0, 0, 0, 0, 0};                            // no candidate: a zero box (:55-57)
+    if (n >= 1) for (int q = 0; q < 7; ++q) po[q] = pred_obb[(long long)(o0 + best_j) * 7 + q];
+    const double* go = gt_obb + (long long)b * 7;
+    double mn1[3], mx1[3], mn2[3], mx2[3];
+    box_min_max(po, mn1, mx1);
+    box_min_max(go, mn2, mx2);
+    double inter = 1.0;
+    for (int a = 0; a < 3; ++a) inter *= fmax(fmin(mx1[a], mx2[a]) - fmax(mn1[a], mn2[a]), 0.0);
+    const double v1 = (mx1[0] - mn1[0]) * (mx1[1] - mn1[1]) * (mx1[2] - mn1[2]);
+    const double v2 = (mx2[0] - mn2[0]) * (mx2[1] - mn2[1]) * (mx2[2] - mn2[2]);
+    const double iou = inter / (v1 + v2 - inter + 1e-8);
+    iou_out[b] = iou;
+    pred_idx[b] = n >= 1 ? best_j : -1;
+    ref_acc[b] = (n >= 2) ? (target == best_j ? 1.f : 0.f) : (iou > 0.25 ? 1.f : 0.f);
+    for (int q = 0; q < 8; ++q) {
+        const double sx = ((q & 3) < 2 ? 0.5 : -0.5), sy = ((q & 3) == 0 || (q & 3) == 3 ? 0.5 : -0.5), sz = (q < 4 ? 0.5 : -0.5);
+        double* pc = pred_corners + ((long long)b * 8 + q) * 3;
+        double* gc = gt_corners + ((long long)b * 8 + q) * 3;
+        pc[0] = sx * po[3] + po[0]; pc[1] = sy * po[4] + po[1]; pc[2] = sz * po[5] + po[2];
+        gc[0] = sx * go[3] + go[0]; gc[1] = sy * go[4] + go[1]; gc[2] = sz * go[5] + go[2];
+    }
+}
+
+extern "C" int ir_ref_eval(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
+                           const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
+                           const float* s_scene, const float* label, int32_t* pred_idx, float* ref_acc,
+                           double* iou, double* pred_corners, double* gt_corners, ir_stream_t stream) {
+    IR_CHECK_ARG(pred_obb && obb_ofs && gt_obb && score_ofs && s_attr && s_rel && s_scene && label && pred_idx &&
+                 ref_acc && iou && pred_corners && gt_corners && B > 0);
+    k_ref_eval<<<B, 32, 0, (cudaStream_t)stream>>>(pred_obb, obb_ofs, gt_obb, score_ofs, s_attr, s_rel, s_scene, label,
+                                                   pred_idx, ref_acc, iou, pred_corners, gt_corners);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}

@@ -56,16 +56,12 @@ def _gt_obb(data_dict, config):
                                              t('ref_size_residual_label')), np.float64)
 
 
-def get_loss(data_dict, config):
-    dev = data_dict['lang_scores'].device
-    lang_loss = _CrossEntropy.apply(data_dict['lang_scores'], data_dict['object_cat'].to(dev).long())[0]
-    data_dict['lang_loss'] = lang_loss
-    seg_label = ops.region_label(data_dict['ref_center_label'].to(dev), data_dict['point_min'].to(dev),
-                                 data_dict['point_max'].to(dev))
-    seg_scores = data_dict['seg_scores']
-    seg_loss = _CrossEntropy.apply(seg_scores, seg_label)[0]
-    seg_acc = (seg_scores.detach().argmax(1) == seg_label).sum() / float(seg_label.numel())
+BOXES = '_ir_boxes'       # packed candidate / ground-truth boxes on the device, shared by get_loss and get_eval
 
+
+def pack_boxes(data_dict, config, dev):
+    """pred_obb_batch (host list of (c_b,7) float64) + the GT boxes -> one H2D copy.
+    -> dict(pred (Nc,7) f64, gt (B,7) f64, obb_ofs (B+1) i32, score_ofs (B) i32 [-1: scene not scored], counts)."""
     pred = data_dict['pred_obb_batch']
     B = len(pred)
     counts = [int(np.asarray(p).reshape(-1, 7).shape[0]) if len(p) else 0 for p in pred]
@@ -75,13 +71,27 @@ def get_loss(data_dict, config):
         score_ofs.append(s if c >= 2 else -1)
         s += c if c >= 2 else 0
     allobb = np.concatenate([np.asarray(p, np.float64).reshape(-1, 7) for p in pred if len(p)] or [np.zeros((1, 7))], 0)
-    host = torch.from_numpy(np.concatenate([allobb.reshape(-1), _gt_obb(data_dict, config).reshape(-1)]))
-    devbuf = host.to(dev)
-    pred_d = devbuf[:allobb.size].view(-1, 7)
-    gt_d = devbuf[allobb.size:].view(B, 7)
+    devbuf = torch.from_numpy(np.concatenate([allobb.reshape(-1), _gt_obb(data_dict, config).reshape(-1)])).to(dev)
     ints = torch.from_numpy(np.concatenate([obb_ofs, np.asarray(score_ofs, np.int32)])).to(dev)
+    return dict(pred=devbuf[:allobb.size].view(-1, 7), gt=devbuf[allobb.size:].view(B, 7), obb_ofs=ints[:B + 1],
+                score_ofs=ints[B + 1:], counts=counts, host_ofs=obb_ofs)
+
+
+def get_loss(data_dict, config):
+    dev = data_dict['lang_scores'].device
+    lang_loss = _CrossEntropy.apply(data_dict['lang_scores'], data_dict['object_cat'].to(dev).long())[0]
+    data_dict['lang_loss'] = lang_loss
+    seg_label = ops.region_label(data_dict['ref_center_label'].to(dev), data_dict['point_min'].to(dev),
+                                 data_dict['point_max'].to(dev))
+    seg_scores = data_dict['seg_scores']
+    seg_loss = _CrossEntropy.apply(seg_scores, seg_label)[0]
+    seg_acc = (seg_scores.detach().argmax(1) == seg_label).sum() / float(seg_label.numel())
+    bx = pack_boxes(data_dict, config, dev)
+    data_dict[BOXES] = bx
+    B, obb_ofs = len(bx['counts']), bx['host_ofs']
     ref_loss, label, iou_max = _RefLoss.apply(data_dict['attribute_scores'], data_dict['relation_scores'],
-                                              data_dict['scene_scores'], pred_d, ints[:B + 1], gt_d, ints[B + 1:])
+                                              data_dict['scene_scores'], bx['pred'], bx['obb_ofs'], bx['gt'], bx['score_ofs'])
+    data_dict['_ir_cluster_label_flat'] = label
     data_dict['ref_loss'] = ref_loss
     data_dict['loss'] = 10 * ref_loss + lang_loss + seg_loss                    # (lib/loss_helper.py:263)
     data_dict['seg_loss'] = seg_loss

@@ -550,3 +550,18 @@ def edge_max_bwd(dout, arg, k):
     dmsg = torch.empty(nq * k, Cc, dtype=torch.float32, device=dout.device)
     call("ir_edge_max_bwd", _p(dout, torch.float32), _p(arg, torch.int32), nq, k, Cc, _p(dmsg), _stream())
     return dmsg
+
+
+def ref_eval(pred_obb, obb_ofs, gt_obb, score_ofs, sa, sr, ss, label):
+    """-> (pred_idx (B,) i32, ref_acc (B,) f32, iou (B,) f64, pred_corners (B,8,3) f64, gt_corners (B,8,3) f64)."""
+    B = gt_obb.shape[0]
+    dev = sa.device
+    pred_idx = torch.empty(B, dtype=torch.int32, device=dev)
+    ref_acc = torch.empty(B, dtype=torch.float32, device=dev)
+    iou = torch.empty(B, dtype=torch.float64, device=dev)
+    pc = torch.empty(B, 8, 3, dtype=torch.float64, device=dev)
+    gc = torch.empty(B, 8, 3, dtype=torch.float64, device=dev)
+    call("ir_ref_eval", _p(pred_obb, torch.float64), _p(obb_ofs, torch.int32), _p(gt_obb, torch.float64),
+         _p(score_ofs, torch.int32), B, _p(sa.contiguous(), torch.float32), _p(sr.contiguous(), torch.float32),
+         _p(ss.contiguous(), torch.float32), _p(label, torch.float32), _p(pred_idx), _p(ref_acc), _p(iou), _p(pc), _p(gc), _stream())
+    return pred_idx, ref_acc, iou, pc, gc

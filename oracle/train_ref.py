@@ -177,3 +177,45 @@ def adam_update(params, grads, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, wei
         denom = v.sqrt() / (1 - betas[1] ** step) ** 0.5 + eps
         out[k] = p - lr / (1 - betas[0] ** step) * m / denom
     return out
+
+
+def get_eval(out, data, cluster_label, config=None):
+    """lib/eval_helper.py:11-114 on the forward's outputs and get_loss's cluster labels: language
+    accuracy, per-scene referred box (arg-max of the summed scores), its IoU with the ground truth
+    (utils/box_util.py:95-133: the same axis-aligned min/max IoU as the batch form), ref_acc and the
+    IoU rates.  -> dict with the reference's keys."""
+    config = config or SyntheticConfig()
+    t = lambda k: np.asarray(data[k])
+    lang_pred = out['lang_scores'].argmax(1)
+    res = dict(lang_acc=(lang_pred == torch.as_tensor(t('object_cat'))).float().mean())
+    gt = config.param2obb_batch(t('ref_center_label'), t('ref_heading_class_label'), t('ref_heading_residual_label'),
+                                t('ref_size_class_label'), t('ref_size_residual_label'))
+    ious, ref_acc, pred_boxes, gt_boxes = [], [], [], []
+    start = 0
+    for i, pred in enumerate(out['pred_obb_batch']):
+        pred = np.asarray(pred).reshape(-1, 7)
+        n = pred.shape[0]
+        if n == 0:
+            obb = np.zeros(7)
+        elif n == 1:
+            obb = pred[0]
+        else:
+            score = (out['attribute_scores'][start:start + n] + out['relation_scores'][start:start + n]
+                     + out['scene_scores'][start:start + n])
+            start += n
+            cp = int(torch.argmax(score))
+            ref_acc.append(1. if int(np.argmax(cluster_label[i])) == cp else 0.)
+            obb = pred[cp]
+        iou = float(iou_batch(obb[None], gt[i])[0])
+        ious.append(iou)
+        if n <= 1:
+            ref_acc.append(1. if iou > 0.25 else 0.)
+        corners = lambda o: box_min_max(np.concatenate([o[:6], [0.0]])[None])       # un-rotated (utils/util.py:21-32)
+        pred_boxes.append(np.stack(corners(obb), 0)[:, 0])
+        gt_boxes.append(np.stack(corners(gt[i]), 0)[:, 0])
+    a = np.asarray(ious)
+    res.update(ref_acc=ref_acc, ref_iou=ious, pred_box_min_max=pred_boxes, gt_box_min_max=gt_boxes)
+    res['ref_iou_rate_0.25'] = float((a >= 0.25).sum()) / a.shape[0]
+    res['ref_iou_rate_0.5'] = float((a >= 0.5).sum()) / a.shape[0]
+    res['ref_others_mask'] = [1 if int(c) == 17 else 0 for c in t('object_cat')]
+    return res

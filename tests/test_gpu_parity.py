@@ -455,3 +455,42 @@ def test_encoder_sparse_tensor_api(ops, state_dict):
                                           torch.from_numpy(b['lidar_coords']))
     assert y.s == 16 and np.array_equal(y.C.cpu().numpy(), Cr.numpy())
     assert float((y.F.cpu() - Fr).abs().max()) < TOL
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[3] / [4] shapes
+
+def test_relation_stress_c4(gpu_model, state_dict, args):
+    """configs[3]: 64-instance scenes, batch 32 (S = 2048 instances, 2048 queries, k = 8) through the
+    relation module alone against the oracle (kNN edges bit-exact, scores 1e-4)."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.candidates import KEY
+    b = synthetic.make_batch(700, batch_size=32, num_points=6000, n_inst=64, n_cand=64, n_tokens=5)
+    d = synthetic.to_data_dict(b, SparseTensor, 'cuda')
+    lang = torch.randn(32, 256, generator=torch.Generator().manual_seed(1))
+    d['lang_rel_feats'] = lang.cuda()
+    with torch.no_grad():
+        d = gpu_model.relation(d)
+    torch.cuda.synchronize()
+    data = model_ref.data_from_batch(b)
+    cands, _, _ = model_ref.candidate_lists(data, data['object_cat'])
+    trace = {}
+    sd = {k: v.float() if v.is_floating_point() else v for k, v in state_dict.items()}
+    ref = model_ref.relation_forward(sd, data, {'lang_rel_feats': lang}, cands, args, trace=trace)
+    assert d['relation_scores'].shape == (2048,)
+    assert float((d['relation_scores'].cpu() - ref['relation_scores']).abs().max()) < TOL
+    nbr = d['_ir_knn'].cpu().numpy()
+    assert np.array_equal(nbr.reshape(-1), trace['knn_col'])                 # every query has k = 8 neighbours here
+
+
+def test_forward_large_sweep_point(gpu_model, state_dict, args):
+    """configs[4], one large point of the sweep (120k points, 64 instances = 64 candidates): whole forward
+    against the oracle."""
+    from instancerefer_b200 import SparseTensor
+    b = synthetic.make_batch(900, batch_size=1, num_points=120000, n_inst=64, n_cand=64, n_tokens=20,
+                             room=(11.9, 10.4, 3.0))
+    with torch.no_grad():
+        out = gpu_model(synthetic.to_data_dict(b, SparseTensor, 'cuda'))
+    torch.cuda.synchronize()
+    ref = model_ref.forward(state_dict, model_ref.data_from_batch(b), args)
+    for k in ('lang_scores', 'obj_feats', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores'):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k

@@ -609,3 +609,30 @@ def run_train_step_noreset(model, batch):
     dd = get_loss(model(synthetic.to_data_dict(batch, SparseTensor, 'cuda')), train_ref.SyntheticConfig())
     dd['loss'].backward()
     return dd
+
+
+def test_get_eval_matches_oracle(lib_built, state_dict, args):
+    """Drop-in get_loss + get_eval on the CUDA outputs vs the oracle's (scenes with 0 / 1 / many candidates)."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.eval_helper import get_eval
+    from instancerefer_b200.loss_helper import get_loss
+    b = synthetic.make_batch(91, batch_size=4, num_points=5000, n_inst=9, n_cand=[5, 2, 1, 0], n_tokens=[11, 4, 8, 5])
+    model = make_train_model(state_dict, args).eval()
+    dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
+    dd['unique_multiple'] = torch.tensor([1, 0, 0, 1], device='cuda')
+    with torch.no_grad():
+        dd = get_eval(get_loss(model(dd), train_ref.SyntheticConfig()), train_ref.SyntheticConfig())
+    data = model_ref.data_from_batch(b)
+    out = model_ref.forward(state_dict, data, args)
+    L = train_ref.get_loss(out, data)
+    e = train_ref.get_eval(out, data, L['cluster_label'])
+    for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss'):
+        assert abs(float(dd[k].reshape(-1)[0]) - float(L[k].reshape(-1)[0])) < 1e-4 * max(1.0, abs(float(L[k].reshape(-1)[0]))), k
+    assert dd['ref_acc'] == e['ref_acc'] and np.allclose(dd['ref_iou'], e['ref_iou'], atol=1e-12)
+    assert dd['ref_iou_rate_0.25'] == e['ref_iou_rate_0.25'] and dd['ref_iou_rate_0.5'] == e['ref_iou_rate_0.5']
+    assert float(dd['lang_acc']) == float(e['lang_acc']) and dd['ref_others_mask'] == e['ref_others_mask']
+    assert dd['ref_multiple_mask'] == [1, 0, 0, 1]
+    for key, want in (('pred_bboxes', e['pred_box_min_max']), ('gt_bboxes', e['gt_box_min_max'])):
+        got = np.stack([np.stack([p.min(0), p.max(0)]) for p in dd[key]])
+        assert np.abs(got - np.stack(want)).max() < 1e-12, key
+    assert all(np.array_equal(a.cpu().numpy(), np.asarray(c, np.float32)) for a, c in zip(dd['cluster_label'], L['cluster_label']))
