@@ -96,6 +96,15 @@ int ir_encoder_reset(void* ws, int64_t n_max, ir_stream_t stream);
 int ir_voxelize(const float* pts, const int32_t* cand, int32_t n_cand, int32_t ppi, int32_t fdim,
                 double voxel, void* ws, int64_t n_max, ir_stream_t stream);
 
+/* Loader-side voxelisation (sparse_quantize of whole scenes + sparse_collate batch index,
+ * lib/dataset.py:255-261,456-469): clouds (n, ppi, fdim) fp32, cloud[m] = which cloud feeds batch index
+ * m; first point wins, rows in first-occurrence order.  coords_out (n_cloud*ppi, 4) int32 [x,y,z,b],
+ * feats_out (n_cloud*ppi, fdim), count_out device int32.  scratch: ir_voxelize_points_scratch_bytes. */
+size_t ir_voxelize_points_scratch_bytes(int64_t n_pts);
+int ir_voxelize_points(const float* pts, const int32_t* cloud, int32_t n_cloud, int32_t ppi, int32_t fdim,
+                       double voxel, void* scratch, int32_t* coords_out, float* feats_out,
+                       int32_t* count_out, ir_stream_t stream);
+
 /* Builds levels 1-4 and all 9 kernel maps.  coords0==NULL: level 0 comes from ir_voxelize in
  * `ws`; otherwise coords0 (n0,4) int32 is hashed here (ir_encoder_reset is implied).  n0 is an
  * upper bound on the row count when n0_dev (device int, e.g. inside a CUDA graph) is given. */

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),
     "ir_encoder_reset": (i32, [p, i64, p]),
     "ir_voxelize": (i32, [p, p, i32, i32, i32, f64, p, i64, p]),
+    "ir_voxelize_points_scratch_bytes": (C.c_size_t, [i64]),
+    "ir_voxelize_points": (i32, [p, p, i32, i32, i32, f64, p, p, p, p, p]),
     "ir_encoder_build_maps": (i32, [p, i32, p, p, i64, p]),
     "ir_encoder_features": (i32, [C.POINTER(EncoderParams), p, p, i64, p, p]),
     "ir_encoder_features_pair": (i32, [C.POINTER(EncoderParams), p, p, i64, p, C.POINTER(EncoderParams), p, p, i64, p, p]),

@@ -68,8 +68,12 @@ class CandidatePack:
         cand_ofs = np.concatenate([[0], np.cumsum([len(self.cands[i]) for i in self.active])])
         if _last_h2d.get(tag) is not None:
             _last_h2d[tag].synchronize()               # previous copies out of these staging buffers are done
-        h_points = _pinned_buf('points' + tag, (self.n_inst, ppi, fdim), torch.float32)
-        np.stack(pts, 0, out=h_points.numpy())
+        packed = data_dict.get('_ir_packed')
+        if packed is not None and len(self.active) == len(classes) and packed['points'].shape[0] == self.n_inst:
+            h_points = packed['points']             # loader.collate_packed: every instance already in one pinned buffer
+        else:
+            h_points = _pinned_buf('points' + tag, (self.n_inst, ppi, fdim), torch.float32)
+            np.stack(pts, 0, out=h_points.numpy())
         h_meta = _pinned_buf('meta' + tag, (self.n_inst, 4), torch.float32)
         m = h_meta.numpy()
         m[:, :3] = np.asarray(centres, np.float64)

@@ -297,3 +297,37 @@ int irk_kmap_all(const IrKmapArgs& a, long long rows_max, cudaStream_t st) {
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ standalone voxeliser (loader side)
+// sparse_quantize of whole scenes in the loader (lib/dataset.py:255-261) + sparse_collate batch index:
+// first-point-wins voxelisation of (n_cloud, ppi, fdim) point clouds into caller buffers, with its own
+// small scratch (hash table sized by the POINT count, insert slots, scan state) instead of an encoder
+// workspace.  Same kernels as ir_voxelize, so rows come out in first-occurrence order, bit-exact.
+#include "../../include/instancerefer_b200.h"
+static inline long long vp_cap(long long n_pts) { long long c = 1024; while (c < 2 * n_pts) c <<= 1; return c; }
+extern "C" size_t ir_voxelize_points_scratch_bytes(int64_t n_pts) {
+    const long long cap = vp_cap(n_pts);
+    return (size_t)(cap * 16 + ((n_pts * 4 + 1023) / 1024) * 1024 + (3 + n_pts / SCAN_TILE) * 8 + 1024);
+}
+extern "C" int ir_voxelize_points(const float* pts, const int32_t* cloud, int32_t n_cloud, int32_t ppi, int32_t fdim,
+                                  double voxel, void* scratch, int32_t* coords_out, float* feats_out,
+                                  int32_t* count_out, ir_stream_t stream) {
+    IR_CHECK_ARG(pts && cloud && scratch && coords_out && feats_out && count_out);
+    IR_CHECK_ARG(n_cloud > 0 && n_cloud < IR_MAX_BATCH && ppi > 0 && fdim >= 3 && fdim <= 8 && voxel > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_pts = (long long)n_cloud * ppi;
+    IR_CHECK_ARG(n_pts < (1ll << 30));
+    const long long cap = vp_cap(n_pts);
+    char* base = (char*)scratch;
+    const IrTable t = ir_table_view(base, cap);                          // keys u64[cap] | minrow | row
+    int* vslot = (int*)(base + cap * 16);
+    unsigned long long* state = (unsigned long long*)(base + cap * 16 + ((n_pts * 4 + 1023) / 1024) * 1024);
+    IR_CHECK_CUDA(cudaMemsetAsync(base, 0x7F, (size_t)cap * 16, st));
+    IR_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)(3 + n_pts / SCAN_TILE) * 8, st));
+    k_vox_insert<<<grid_for(n_pts, 256), 256, 0, st>>>(pts, cloud, (int)n_pts, ppi, fdim, voxel, t, vslot);
+    IR_CHECK_LAUNCH();
+    k_vox_compact<<<scan_grid(n_pts), SCAN_THREADS, 0, st>>>(pts, cloud, (int)n_pts, ppi, fdim, voxel, t, vslot,
+                                                            (int4*)coords_out, feats_out, count_out, state);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
