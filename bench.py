@@ -209,7 +209,7 @@ def main_train(a):
         ev[3].record()
         opt.step()
         ev[4].record()
-        loss = float(d['loss'])                                # D2H of the step's result
+        loss = float(d['loss'].detach())                       # D2H of the step's result
         if timed:
             for j, k in enumerate(ph):
                 ph[k] += ev[j].elapsed_time(ev[j + 1])

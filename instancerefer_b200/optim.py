@@ -76,3 +76,37 @@ class FlatAdam:
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
                       self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / self.world)
+
+    # --- checkpoint format of torch.optim.Adam (lib/solver.py:376-381 stores optimizer.state_dict()) ------
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam.state_dict()``: per-parameter step / exp_avg / exp_avg_sq (copies
+        of the flat moments) and one param group, so ``checkpoint.tar`` is interchangeable with the reference's."""
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = dict(step=torch.tensor(float(self.step_count)),
+                                exp_avg=self.exp_avg[o:o + n].view_as(p).clone(),
+                                exp_avg_sq=self.exp_avg_sq[o:o + n].view_as(p).clone())
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     decoupled_weight_decay=False, params=list(range(len(self.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        g = sd['param_groups'][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g['lr'], tuple(g['betas']), g['eps'], g['weight_decay']
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count = 0
+        for i, st in sd['state'].items():
+            o, p = self.offsets[int(i)], self.params[int(i)]
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            self.step_count = max(self.step_count, int(float(st['step'])))
+
+    @property
+    def param_groups(self):
+        """Read-only view for code that prints / schedules ``optimizer.param_groups[0]['lr']``."""
+        return [dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, params=self.params)]
