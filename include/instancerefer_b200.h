@@ -133,6 +133,15 @@ int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, int32_t K,
                     const float* shift, const float* resid, int32_t relu, float* T, float* out,
                     ir_stream_t stream);
 
+/* ir_spconv_layer without BN epilogue whose tcgen05 pair-GEMM scales the gathered rows by the power of
+ * two that brings *in_absmax (device scalar, max |feat_in|) to 2^13 before the fp16 hi/lo split and
+ * scales the result back exactly: inputs of any magnitude (gradients: this is the dgrad of the training
+ * step, run on the transposed rulebook with W^T) keep ~22 significant bits relative to their maximum. */
+int ir_spconv_layer_scaled(const float* feat_in, const float* in_absmax, int32_t cin, int32_t cout, int32_t K,
+                           const int32_t* in_idx, int64_t seg_cap, const int32_t* slot, const int32_t* count,
+                           const int32_t* n_out_dev, int64_t n_max, const float* weight, int32_t use_tc,
+                           const float* resid, float* T, float* out, ir_stream_t stream);
+
 /* Weight buffer the tcgen05 pair-GEMM reads: a 16-byte aligned copy of the reference layout
  * (K,Cin,Cout); W[k] is staged by one TMA bulk copy per CTA and split into fp16 hi / lo parts on its
  * way into TMEM.  out holds ir_spconv_wprep_floats(K,cin,cout) floats. */
@@ -250,11 +259,12 @@ int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, int32_t C, 
                     const float* beta, const float* resid, int32_t relu, float eps, float momentum,
                     float* running_mean, float* running_var, float* scratch, float* mean,
                     float* rstd, float* y, ir_stream_t stream);
-/* g = dy*[y>0] (relu); dbeta = sum g; dgamma = sum g*xhat; dx; dresid = g (optional).             */
+/* g = dy*[y>0] (relu); dbeta = sum g; dgamma = sum g*xhat; dx; dresid = g (optional);
+ * absmax_out (optional device float) = max |dx|, the range hint of ir_spconv_layer_scaled.        */
 int ir_bn_train_bwd(const float* dy, const float* y, const float* x, const int32_t* n_dev, int32_t n,
                     int32_t C, const float* mean, const float* rstd, const float* gamma, int32_t relu,
                     float* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
-                    ir_stream_t stream);
+                    float* absmax_out, ir_stream_t stream);
 
 /* Backward of ir_segmax: the gradient of out[b,c] goes to the first row attaining the maximum.
  * arg_scratch: int32 (n_seg, C). */
@@ -303,7 +313,8 @@ int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
  * transposed rulebooks and gradient scratch live in a caller-owned arena.  n_lvl = HOST row counts of
  * the five levels (read back once from the workspace after ir_encoder_build_maps).               */
 typedef struct {
-    int32_t cin, use_tc;                      /* use_tc: forward pair-GEMM on tcgen05 (weights 16-B aligned) */
+    int32_t cin, use_tc;                      /* bit 0: forward pair-GEMM on tcgen05 (weights 16-B aligned);
+                                                 bit 1: dgrad on tcgen05 (range-scaled, ir_spconv_layer_scaled) */
     const float* weight[IR_ENC_LAYERS];       /* (K,Cin,Cout)                                          */
     const float* gamma[IR_ENC_LAYERS];
     const float* beta[IR_ENC_LAYERS];
@@ -326,7 +337,8 @@ typedef struct {
     int64_t off_bn_scratch;
     int64_t off_tr_out[9], off_tr_slot[9];                     /* transposed rulebooks, int32 [K][n_max]  */
     int64_t off_grad[4];                                       /* fp32 (max rows, 128) gradient buffers   */
-    int64_t off_wt;                                            /* fp32 (27,128,128) transposed weight      */
+    int64_t off_wt;                                            /* fp32 transposed weights (K,Cout,Cin), layers 1..12 */
+    int64_t off_absmax;                                        /* fp32 scalar: max |dY| of the current layer */
 } ir_encoder_train_layout_t;
 
 int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int32_t cin, ir_encoder_train_layout_t* out);

@@ -47,7 +47,8 @@ class EncoderTrainGrads(C.Structure):
 class EncoderTrainLayout(C.Structure):
     _fields_ = [("total_bytes", i64), ("off_y", i64 * ENC_LAYERS), ("off_out", i64 * ENC_LAYERS),
                 ("off_mean", i64 * ENC_LAYERS), ("off_rstd", i64 * ENC_LAYERS), ("off_bn_scratch", i64),
-                ("off_tr_out", i64 * 9), ("off_tr_slot", i64 * 9), ("off_grad", i64 * 4), ("off_wt", i64)]
+                ("off_tr_out", i64 * 9), ("off_tr_slot", i64 * 9), ("off_grad", i64 * 4), ("off_wt", i64),
+                ("off_absmax", i64)]
 
 
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
@@ -88,7 +89,8 @@ SIGNATURES = {
     "ir_spconv_wgrad": (i32, [p, i32, p, i32, i32, p, p, p, i64, p, p]),
     "ir_bn_scratch_floats": (i64, [i32]),
     "ir_bn_train_fwd": (i32, [p, p, i32, i32, p, p, p, i32, f32, f32, p, p, p, p, p, p, p]),
-    "ir_bn_train_bwd": (i32, [p, p, p, p, i32, i32, p, p, p, i32, p, p, p, p, p, p]),
+    "ir_bn_train_bwd": (i32, [p, p, p, p, i32, i32, p, p, p, i32, p, p, p, p, p, p, p]),
+    "ir_spconv_layer_scaled": (i32, [p, p, i32, i32, i32, p, i64, p, p, p, i64, p, i32, p, p, p, p]),
     "ir_segmax_bwd": (i32, [p, p, p, i64, i32, i32, p, p, p, p, p]),
     "ir_cross_entropy": (i32, [p, p, i32, i32, p, p, p]),
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),

@@ -256,6 +256,23 @@ extern "C" int ir_spconv_layer(const float* feat_in, int32_t cin, int32_t cout, 
     return conv_layer(b, cin, cout, K, &wprep, use_tc, (cudaStream_t)stream);
 }
 
+// ir_spconv_layer with the tcgen05 input-range scale (kernels.cuh: IrConvProblem::in_absmax); used by the
+// dgrad of the training step, whose inputs are gradients of arbitrary magnitude.
+extern "C" int ir_spconv_layer_scaled(const float* feat_in, const float* in_absmax, int32_t cin, int32_t cout, int32_t K,
+                                      const int32_t* in_idx, int64_t seg_cap, const int32_t* slot, const int32_t* count,
+                                      const int32_t* n_out_dev, int64_t n_max, const float* weight, int32_t use_tc,
+                                      const float* resid, float* T, float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(feat_in && in_idx && slot && count && n_out_dev && weight && T && out);
+    IrConvBatch b;
+    memset(&b, 0, sizeof(b));
+    b.G = 1;
+    b.p[0] = IrConvProblem{feat_in, in_idx, slot, count, n_out_dev, weight, nullptr, nullptr, resid, T, out,
+                           (long long)seg_cap, (long long)n_max, 0, in_absmax};
+    const bool tc = use_tc && cin >= 32 && cout >= 32 && in_absmax != nullptr && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;
+    const float* wp = tc ? weight : nullptr;
+    return conv_layer(b, cin, cout, K, &wp, tc, (cudaStream_t)stream);
+}
+
 // The 13-layer feature pass for one or two encoders (same topology) with shared launches.
 static int encoder_features_multi(int G, const ir_encoder_params* const* ps, const float* const* feats0,
                                   void* const* wss, const int64_t* n_maxs, float* const* outs, cudaStream_t st) {

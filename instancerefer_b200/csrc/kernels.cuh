@@ -45,6 +45,10 @@ struct IrConvProblem {
     long long seg_cap;
     long long n_max;
     int relu;
+    const float* in_absmax;  // tcgen05 path only: device scalar max|fin| (or NULL).  The gathered rows are scaled by
+                             // the power of two that brings this maximum to 2^13 before the fp16 hi/lo split and the
+                             // result is scaled back exactly: keeps small-magnitude inputs (gradients) out of fp16's
+                             // subnormal range.
 };
 struct IrConvBatch {
     IrConvProblem p[IR_MAX_GROUPS];

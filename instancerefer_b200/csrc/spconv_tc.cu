@@ -276,6 +276,13 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     const long long seg_cap = P.seg_cap;
     const float* __restrict__ weight = P.weight;
     float* __restrict__ T = P.T;
+    const float* __restrict__ in_absmax = P.in_absmax;
+    // input scale (power of two, exact): 2^13 / 2^floor(log2(max|F|)); 1 when no maximum is supplied
+    auto input_scale = [&]() -> float {
+        if (in_absmax == nullptr) return 1.f;
+        const float m = *in_absmax;
+        return (m > 0.f && m < 3.0e38f) ? exp2f(13.f - floorf(log2f(m))) : 1.f;
+    };
 
     // W[k] (Cin,Cout) fp32 is staged in shared memory by one TMA bulk-copy chain (issued by thread 0);
     // 16 warps (4 per TMEM sub-partition) then scale it by 2^8, split it into fp16 hi/lo and park it in
@@ -345,6 +352,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
         if (grp < n_items) load_idx(grp);                       // the rulebook is final long before this launch
         if (t_end > t_begin) weights_to_tmem(1 + pw / 4);       // this warp's share of the weight columns
         ir_pdl_wait();                                          // feature rows come from the previous kernel
+        const float in_s = input_scale();
         if (grp < n_items) {
             load_rows(grp);
             load_idx(grp + NS);
@@ -361,10 +369,10 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
                 const int r = rbase + 16 * i;
                 const int off = r * 128 + ((j ^ (r & 7)) << 4);
                 uint4 h, l;
-                split2(va[i].x, va[i].y, h.x, l.x);
-                split2(va[i].z, va[i].w, h.y, l.y);
-                split2(vb[i].x, vb[i].y, h.z, l.z);
-                split2(vb[i].z, vb[i].w, h.w, l.w);
+                split2(va[i].x * in_s, va[i].y * in_s, h.x, l.x);
+                split2(va[i].z * in_s, va[i].w * in_s, h.y, l.y);
+                split2(vb[i].x * in_s, vb[i].y * in_s, h.z, l.z);
+                split2(vb[i].z * in_s, vb[i].w * in_s, h.w, l.w);
                 *reinterpret_cast<uint4*>(st_hi + off) = h;
                 *reinterpret_cast<uint4*>(st_lo + off) = l;
             }
@@ -425,6 +433,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
             weights_to_tmem(0);
         }
         ir_pdl_wait();                                          // T is still being read by the previous reduce
+        const float out_s = W_UNSCALE / input_scale();
         uint32_t acc_it = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int p0 = tile * TILE_M;
@@ -445,7 +454,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
                     if (!(dbg & 2)) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q)
-                            if (c0 + q < np) tcol[(long long)(c0 + q) * COUT] = __uint_as_float(v[q]) * W_UNSCALE;
+                            if (c0 + q < np) tcol[(long long)(c0 + q) * COUT] = __uint_as_float(v[q]) * out_s;
                     }
                 }
             }
@@ -489,6 +498,8 @@ int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t
     if (cin == 64 && cout == 64) return tc::launch<64, 64>(b, K, st);
     if (cin == 64 && cout == 128) return tc::launch<64, 128>(b, K, st);
     if (cin == 128 && cout == 128) return tc::launch<128, 128>(b, K, st);
+    if (cin == 64 && cout == 32) return tc::launch<64, 32>(b, K, st);        // dgrad of the 32 -> 64 down conv
+    if (cin == 128 && cout == 64) return tc::launch<128, 64>(b, K, st);      // dgrad of the 64 -> 128 down conv
     ir_set_error("pairgemm_tc: unsupported channels %d -> %d", cin, cout);
     return IR_ERR_UNSUPPORTED;
 }

@@ -44,7 +44,12 @@ extern "C" int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int3
         L->off_tr_slot[m] = take((int64_t)K * n_max * 4);
     }
     for (int i = 0; i < 4; ++i) L->off_grad[i] = take(rows_max * 128 * 4);
-    L->off_wt = take((int64_t)27 * 128 * 128 * 4);
+    {   // transposed weights (K,Cout,Cin) of layers 1..12, back to back (256-byte aligned each)
+        int64_t tot = 0;
+        for (int i = 1; i < IR_ENC_LAYERS; ++i) { const LayerInfo li = layer_info(i, cin); tot += al((int64_t)li.K * li.cin * li.cout * 4); }
+        L->off_wt = take(tot);
+    }
+    L->off_absmax = take(256);
     L->total_bytes = off;
     return IR_OK;
 }
@@ -78,7 +83,12 @@ struct Tr {
     int* tr_out(int map) const { return (int*)(ar + A.off_tr_out[map]); }
     int* tr_slot(int map) const { return (int*)(ar + A.off_tr_slot[map]); }
     float* grad(int i) const { return (float*)(ar + A.off_grad[i]); }
-    float* wt() const { return (float*)(ar + A.off_wt); }
+    float* wt(int layer, int cin0) const {
+        int64_t o = A.off_wt;
+        for (int i = 1; i < layer; ++i) { const LayerInfo li = layer_info(i, cin0); o += al((int64_t)li.K * li.cin * li.cout * 4); }
+        return (float*)(ar + o);
+    }
+    float* absmax() const { return (float*)(ar + A.off_absmax); }
 };
 
 static int tr_open(const ir_encoder_train_params* p, void* ws, int64_t n_max, const int32_t* n_lvl, void* arena, Tr* t) {
@@ -100,7 +110,7 @@ extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const 
     for (int i = 0; i < IR_ENC_LAYERS; ++i) {
         const LayerInfo li = layer_info(i, p->cin);
         const float* fin = (i == 0) ? f0 : t.out(i - 1);
-        const int tc = p->use_tc && li.cin >= 32 && ((reinterpret_cast<uintptr_t>(p->weight[i]) & 15) == 0);
+        const int tc = (p->use_tc & 1) && li.cin >= 32 && ((reinterpret_cast<uintptr_t>(p->weight[i]) & 15) == 0);
         if ((r = ir_spconv_layer(fin, li.cin, li.cout, li.K, t.in_idx(li.map), n_max, t.slot(li.map), t.kcount(li.map),
                                  t.nlvl_dev() + li.lout, t.n[li.lout], p->weight[i], tc ? p->weight[i] : nullptr, tc,
                                  nullptr, nullptr, nullptr, 0, t.T(), t.y(i), stream)) != IR_OK) return r;
@@ -127,6 +137,14 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         if ((r = ir_rulebook_transpose(t.in_idx(m), t.slot(m), K, n_max, t.nlvl_dev() + lout, t.n[lout], t.tr_out(m),
                                        t.tr_slot(m), stream)) != IR_OK) return r;
     }
+    // W^T of every layer with an input gradient, up front: the tcgen05 dgrad stages its weights by TMA in its
+    // PDL prologue (before it waits on its stream predecessor), so they must be final long before it launches
+    for (int i = 1; i < IR_ENC_LAYERS; ++i) {
+        const LayerInfo li = layer_info(i, p->cin);
+        const long long tot = (long long)li.K * li.cin * li.cout;
+        k_transpose_w<<<ir_min_i(ir_div_up(tot, 256), IR_NUM_SMS * 4), 256, 0, st>>>(p->weight[i], li.K, li.cin, li.cout, t.wt(i, p->cin));
+        IR_CHECK_LAUNCH();
+    }
     const float* up = dout;                        // gradient w.r.t. the output of the layer being processed
     float *S0 = t.grad(0), *S1 = t.grad(1), *S2 = t.grad(2), *S3 = t.grad(3);
     // one layer: BN backward (-> DY in S1, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`
@@ -135,19 +153,16 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         const float* xin = (i == 0) ? f0 : t.out(i - 1);
         int rr;
         if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), nullptr, t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
-                                  t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], stream)) != IR_OK) return rr;
+                                  t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], t.absmax(), stream)) != IR_OK) return rr;
         if ((rr = ir_spconv_wgrad(xin, li.cin, S1, li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map), t.kcount(li.map), n_max,
                                   g->dweight[i], stream)) != IR_OK) return rr;
         if (dx) {
-            const long long tot = (long long)li.K * li.cin * li.cout;
-            k_transpose_w<<<ir_min_i(ir_div_up(tot, 256), IR_NUM_SMS * 4), 256, 0, st>>>(p->weight[i], li.K, li.cin, li.cout, t.wt());
-            IR_CHECK_LAUNCH();
             // dgrad = forward pipeline on the transposed rulebook with W^T; `add` (the skip gradient) rides in the
-            // reduce epilogue's residual slot.  Exact fp32 SIMT pair-GEMM (gradients span too many orders of
-            // magnitude for the split-fp16 tensor-core operands).
-            if ((rr = ir_spconv_layer(S1, li.cout, li.cin, li.K, t.tr_out(li.map), n_max, t.tr_slot(li.map), t.kcount(li.map),
-                                      t.nlvl_dev() + li.lin, t.n[li.lin], t.wt(), nullptr, 0, nullptr, nullptr, add, 0, t.T(),
-                                      dx, stream)) != IR_OK) return rr;
+            // reduce epilogue's residual slot.  use_tc bit 1: tcgen05 pair-GEMM with the gathered gradient rows
+            // range-scaled by max|dY| (written by the BN backward above); otherwise the exact fp32 SIMT pair-GEMM.
+            if ((rr = ir_spconv_layer_scaled(S1, t.absmax(), li.cout, li.cin, li.K, t.tr_out(li.map), n_max, t.tr_slot(li.map),
+                                             t.kcount(li.map), t.nlvl_dev() + li.lin, t.n[li.lin], t.wt(i, p->cin), (p->use_tc >> 1) & 1,
+                                             add, t.T(), dx, stream)) != IR_OK) return rr;
         }
         return IR_OK;
     };

@@ -56,6 +56,14 @@ template <int V> __device__ __forceinline__ void wg_load(const float* p, float* 
 // Thread (ty,tx) owns ci = (i/VI)*16*VI + ty*VI + i%VI and co = (j/VJ)*16*VJ + tx*VJ + j%VJ: its operands are
 // VI/VJ-wide contiguous groups, so one 16-byte shared-memory load feeds 4 rows/columns of the outer product
 // (the warp's 16 tx lanes read 256 contiguous bytes: conflict-free; the two ty values broadcast).
+// Gathered rows are staged by a 3-deep cp.async pipeline (16 pairs per stage): the L2 round trip of the
+// next two batches overlaps the outer products of the current one.
+#define WG_STAGES 3
+__device__ __forceinline__ void wg_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;                                        // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __restrict__ in_idx,
@@ -63,8 +71,9 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
         float* __restrict__ dW) {
     constexpr int MI = CIN / 16, MJ = COUT / 16;
     constexpr int VI = MI < 4 ? MI : 4, VJ = MJ < 4 ? MJ : 4;
-    __shared__ __align__(16) float xs[WG_PB][CIN];
-    __shared__ __align__(16) float ds[WG_PB][COUT];
+    extern __shared__ __align__(16) float wg_smem[];
+    float (*xs)[WG_PB][CIN] = reinterpret_cast<float (*)[WG_PB][CIN]>(wg_smem);
+    float (*ds)[WG_PB][COUT] = reinterpret_cast<float (*)[WG_PB][COUT]>(wg_smem + WG_STAGES * WG_PB * CIN);
     const int k = blockIdx.y;
     const int cnt = count[k];
     const int chunk = (cnt + gridDim.x - 1) / gridDim.x;
@@ -77,35 +86,44 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
 #pragma unroll
         for (int j = 0; j < MJ; ++j) acc[i][j] = 0.f;
     const long long base = (long long)k * seg_cap;
-    for (int p0 = p_begin; p0 < p_end; p0 += WG_PB) {
-        const int np = min(WG_PB, p_end - p0);
-        // stage gathered rows with 16-byte loads (CIN, COUT are multiples of 16)
-        for (int i = tid; i < WG_PB * (CIN / 4); i += 256) {
-            const int r = i / (CIN / 4), c4 = i - r * (CIN / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < np) v = __ldg(reinterpret_cast<const float4*>(X + (long long)in_idx[base + p0 + r] * CIN) + c4);
-            reinterpret_cast<float4*>(&xs[r][0])[c4] = v;
+    const int nb = (p_end - p_begin + WG_PB - 1) / WG_PB;
+    auto issue = [&](int bi) {
+        if (bi < nb) {
+            const int p0 = p_begin + bi * WG_PB, np = min(WG_PB, p_end - p0), st = bi % WG_STAGES;
+            for (int i = tid; i < WG_PB * (CIN / 4); i += 256) {
+                const int r = i / (CIN / 4), c4 = i - r * (CIN / 4);
+                const bool v = r < np;
+                const float* src = v ? X + (long long)in_idx[base + p0 + r] * CIN + c4 * 4 : X;
+                wg_cp_async16(&xs[st][r][c4 * 4], src, v);
+            }
+            for (int i = tid; i < WG_PB * (COUT / 4); i += 256) {
+                const int r = i / (COUT / 4), c4 = i - r * (COUT / 4);
+                const bool v = r < np;
+                const float* src = v ? dY + (long long)out_idx[base + p0 + r] * COUT + c4 * 4 : dY;
+                wg_cp_async16(&ds[st][r][c4 * 4], src, v);
+            }
         }
-        for (int i = tid; i < WG_PB * (COUT / 4); i += 256) {
-            const int r = i / (COUT / 4), c4 = i - r * (COUT / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < np) v = __ldg(reinterpret_cast<const float4*>(dY + (long long)out_idx[base + p0 + r] * COUT) + c4);
-            reinterpret_cast<float4*>(&ds[r][0])[c4] = v;
-        }
+        asm volatile("cp.async.commit_group;" ::: "memory");               // one group per batch slot, empty or not
+    };
+    for (int bi = 0; bi < WG_STAGES - 1; ++bi) issue(bi);
+    for (int bi = 0; bi < nb; ++bi) {
+        issue(bi + WG_STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(WG_STAGES - 1) : "memory");   // batch bi has landed
         __syncthreads();
+        const int st = bi % WG_STAGES;
 #pragma unroll 4
         for (int p = 0; p < WG_PB; ++p) {
             float a[MI], b[MJ];
 #pragma unroll
-            for (int i = 0; i < MI; i += VI) wg_load<VI>(&xs[p][(i / VI) * 16 * VI + ty * VI], &a[i]);
+            for (int i = 0; i < MI; i += VI) wg_load<VI>(&xs[st][p][(i / VI) * 16 * VI + ty * VI], &a[i]);
 #pragma unroll
-            for (int j = 0; j < MJ; j += VJ) wg_load<VJ>(&ds[p][(j / VJ) * 16 * VJ + tx * VJ], &b[j]);
+            for (int j = 0; j < MJ; j += VJ) wg_load<VJ>(&ds[st][p][(j / VJ) * 16 * VJ + tx * VJ], &b[j]);
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < MJ; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
+        __syncthreads();                                                     // stage st is refilled by the next issue
     }
     float* Wk = dW + (long long)k * CIN * COUT;
 #pragma unroll
@@ -113,6 +131,19 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
 #pragma unroll
         for (int j = 0; j < MJ; ++j)
             atomicAdd(&Wk[((i / VI) * 16 * VI + ty * VI + i % VI) * COUT + (j / VJ) * 16 * VJ + tx * VJ + j % VJ], acc[i][j]);
+}
+
+template <int CIN, int COUT>
+static int wgrad_launch(dim3 grid, cudaStream_t st, const float* x, const float* dy, const int* in_idx, const int* out_idx,
+                        const int* count, long long seg_cap, float* dW) {
+    constexpr int smem = WG_STAGES * WG_PB * (CIN + COUT) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    k_wgrad<CIN, COUT><<<grid, 256, smem, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
+    return IR_OK;
 }
 
 // small-Cin form (the stem, Cin = 7): one thread per (ci, co), pairs streamed from L2
@@ -153,12 +184,14 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
     IR_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * cin * cout * 4, st));
     const int nsplit = ir_div_up(4 * IR_NUM_SMS, K);
     const dim3 grid(nsplit, K);
-    if (cin == 128 && cout == 128) k_wgrad<128, 128><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
-    else if (cin == 64 && cout == 128) k_wgrad<64, 128><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
-    else if (cin == 64 && cout == 64) k_wgrad<64, 64><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
-    else if (cin == 32 && cout == 64) k_wgrad<32, 64><<<grid, 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dW);
+    int r = IR_OK;
+    if (cin == 128 && cout == 128) r = wgrad_launch<128, 128>(grid, st, x, dy, in_idx, out_idx, count, seg_cap, dW);
+    else if (cin == 64 && cout == 128) r = wgrad_launch<64, 128>(grid, st, x, dy, in_idx, out_idx, count, seg_cap, dW);
+    else if (cin == 64 && cout == 64) r = wgrad_launch<64, 64>(grid, st, x, dy, in_idx, out_idx, count, seg_cap, dW);
+    else if (cin == 32 && cout == 64) r = wgrad_launch<32, 64>(grid, st, x, dy, in_idx, out_idx, count, seg_cap, dW);
     else if (cin * cout <= 256) k_wgrad_small<<<dim3(ir_div_up(16 * IR_NUM_SMS, K), K), 256, 0, st>>>(x, dy, in_idx, out_idx, count, seg_cap, cin, cout, dW);
     else { ir_set_error("spconv_wgrad: unsupported channels %d -> %d", cin, cout); return IR_ERR_UNSUPPORTED; }
+    if (r != IR_OK) return r;
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
@@ -212,8 +245,10 @@ __device__ __forceinline__ void bn_sum_parts(const float* __restrict__ scratch, 
     __shared__ double sh[2][8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double a = 0.0, b = 0.0;
-    if (c < C)
+    if (c < C) {
+#pragma unroll 8
         for (int p = w; p < parts; p += 8) { a += scratch[(long long)p * 2 * C + c]; b += scratch[(long long)p * 2 * C + C + c]; }
+    }
     sh[0][w][lane] = a; sh[1][w][lane] = b;
     __syncthreads();
     s = 0.0; ss = 0.0;
@@ -285,7 +320,8 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
 //           dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n); dresid = g
 __global__ void __launch_bounds__(256)
 k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta) {
+                  float* __restrict__ dbeta, float* __restrict__ absmax_out) {
+    if (absmax_out && blockIdx.x == 0 && threadIdx.x == 0) *absmax_out = 0.f;    // k_bn_bwd_apply (next launch) maxes into it
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, sx;
     bn_sum_parts(scratch, parts, C, c, s, sx);
@@ -299,10 +335,11 @@ k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
                const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
                const float* __restrict__ rstd, const float* __restrict__ gamma, int relu,
                const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx,
-               float* __restrict__ dresid) {
+               float* __restrict__ dresid, float* __restrict__ absmax_out) {
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const float inv = n > 0 ? 1.f / n : 0.f;
     const long long total4 = (long long)n * C / 4;
+    float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)((i * 4) % C);
         const float4 d4 = reinterpret_cast<const float4*>(dy)[i];
@@ -321,26 +358,31 @@ k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
         for (int u = 0; u < 4; ++u) {
             const float xh = (xv[u] - mean[c + u]) * rstd[c + u];
             o[u] = gamma[c + u] * rstd[c + u] * (g[u] - dbeta[c + u] * inv - xh * dgamma[c + u] * inv);
+            amax = fmaxf(amax, fabsf(o[u]));
         }
         reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
         if (dresid) reinterpret_cast<float4*>(dresid)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (absmax_out) {                      // max |dx| (non-negative floats order like their bit patterns)
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0 && amax > 0.f && amax < 3.0e38f) atomicMax(reinterpret_cast<unsigned*>(absmax_out), __float_as_uint(amax));
     }
 }
 
 extern "C" int ir_bn_train_bwd(const float* dy, const float* y, const float* x, const int32_t* n_dev, int32_t n,
                                int32_t C, const float* mean, const float* rstd, const float* gamma, int32_t relu,
                                float* scratch, float* dx, float* dresid, float* dgamma, float* dbeta,
-                               ir_stream_t stream) {
+                               float* absmax_out, ir_stream_t stream) {
     IR_CHECK_ARG(dy && x && mean && rstd && gamma && scratch && dx && dgamma && dbeta && n > 0 && C >= 4 && C <= 256 && 256 % C == 0);
     IR_CHECK_ARG(!relu || y);
     cudaStream_t st = (cudaStream_t)stream;
     const int parts = bn_parts(n);
     k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_bwd_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, C, dgamma, dbeta);
+    k_bn_bwd_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, C, dgamma, dbeta, absmax_out);
     IR_CHECK_LAUNCH();
     k_bn_bwd_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(
-        dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid);
+        dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid, absmax_out);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -309,7 +309,7 @@ def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, runni
     return y, mean, rstd
 
 
-def bn_train_bwd(dy, y, x, mean, rstd, gamma, relu, want_resid):
+def bn_train_bwd(dy, y, x, mean, rstd, gamma, relu, want_resid, absmax=None):
     n, Cc = x.shape
     dev = x.device
     scratch = torch.empty(BN_PARTS * 2 * Cc, dtype=torch.float32, device=dev)
@@ -318,7 +318,8 @@ def bn_train_bwd(dy, y, x, mean, rstd, gamma, relu, want_resid):
     dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
     dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
     call("ir_bn_train_bwd", _p(dy, torch.float32), _p(y), _p(x, torch.float32), None, n, Cc, _p(mean), _p(rstd),
-         _p(gamma, torch.float32), 1 if relu else 0, _p(scratch), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _stream())
+         _p(gamma, torch.float32), 1 if relu else 0, _p(scratch), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(absmax),
+         _stream())
     return dx, dres, dgamma, dbeta
 
 
@@ -565,3 +566,13 @@ def ref_eval(pred_obb, obb_ofs, gt_obb, score_ofs, sa, sr, ss, label):
          _p(score_ofs, torch.int32), B, _p(sa.contiguous(), torch.float32), _p(sr.contiguous(), torch.float32),
          _p(ss.contiguous(), torch.float32), _p(label, torch.float32), _p(pred_idx), _p(ref_acc), _p(iou), _p(pc), _p(gc), _stream())
     return pred_idx, ref_acc, iou, pc, gc
+
+
+def spconv_layer_scaled(feat_in, absmax, in_idx, slot, count, n_out_dev, n_rows, weight, resid, T, out, use_tc=True):
+    """ir_spconv_layer_scaled: conv without BN epilogue; tcgen05 pair-GEMM with the input rows range-scaled
+    by ``absmax`` (device scalar max|feat_in|) — the dgrad of the training step."""
+    K, cin, cout = weight.shape
+    call("ir_spconv_layer_scaled", _p(feat_in, torch.float32), _p(absmax, torch.float32), cin, cout, K,
+         _p(in_idx, torch.int32), in_idx.shape[1], _p(slot, torch.int32), _p(count, torch.int32),
+         _p(n_out_dev, torch.int32), int(n_rows), _p(weight, torch.float32), 1 if use_tc else 0, _p(resid),
+         _p(T, torch.float32), _p(out, torch.float32), _stream())

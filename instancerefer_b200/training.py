@@ -117,11 +117,13 @@ class EncoderTrain(Function):
     @staticmethod
     def forward(ctx, feats0, net, G, *params):
         import ctypes as C
+        import os
         from . import _lib
         ws, dev = G.ws, G.ws.buf.device
         layers = net._layers()
         P = _lib.EncoderTrainParams()
-        P.cin, P.use_tc, P.eps = net.input_dim, 1 if net.use_tc else 0, layers[0][1].eps
+        dgrad_tc = os.environ.get('IR_DGRAD', 'tc') != 'simt'
+        P.cin, P.use_tc, P.eps = net.input_dim, (1 | (2 if dgrad_tc else 0)) if net.use_tc else 0, layers[0][1].eps
         keep = []
         for i, (conv, bn) in enumerate(layers):
             w, g, b = (t.detach().contiguous() for t in params[3 * i:3 * i + 3])

@@ -98,6 +98,14 @@ def test_spconv_dgrad_wgrad(ops, graph, kind, level, cin, cout):
         ops.spconv_layer(dy.cuda(), out_idx, slot_in, cnt, n_in_dev, n_in, wt, None, None, None, False,
                          graph.ws.T(), dx)
         assert float((dx.cpu() - x.grad).abs().max()) < 1e-4 * float(x.grad.abs().max()) + 1e-9
+        # the same dgrad on tcgen05 with the range-scaled split-fp16 operands, at gradient-like magnitudes
+        for mag in (1.0, 1e-7):
+            dys = (dy * mag).cuda()
+            amax = dys.abs().max().reshape(1)
+            dx2 = torch.empty(n_in, cin, device='cuda')
+            ops.spconv_layer_scaled(dys, amax, out_idx, slot_in, cnt, n_in_dev, n_in, wt, None, graph.ws.T(), dx2)
+            err = float((dx2.cpu() - x.grad * mag).abs().max())
+            assert err < 1e-4 * float(x.grad.abs().max()) * mag, (mag, err)
 
 
 @pytest.mark.parametrize('n,C,relu,resid', [(5000, 32, True, False), (777, 128, True, True), (3, 256, True, False),
@@ -478,8 +486,8 @@ def test_encoder_train_matches_torch_replica(ops, lib_built, state_dict, args):
         assert max(errs) < 1e-4, (i, errs)
 
 
-@pytest.mark.parametrize('which', ['attribute', 'scene'])
-def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, which):
+@pytest.mark.parametrize('which,dgrad', [('attribute', 'simt'), ('scene', 'simt'), ('attribute', 'tc'), ('scene', 'tc')])
+def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, which, dgrad):
     """ir_encoder_train_forward/backward (one call per direction) == the 13 per-layer autograd nodes."""
     from instancerefer_b200 import SparseTensor, training as T
     from instancerefer_b200.candidates import CandidatePack, target_classes
@@ -492,6 +500,7 @@ def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, 
         model = model.cuda().train()
         dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
         os.environ['IR_TRAIN_ENCODER'] = mode
+        os.environ['IR_DGRAD'] = dgrad
         try:
             if which == 'attribute':
                 pack = CandidatePack(dd, target_classes(dd, args), 'cuda')
@@ -505,17 +514,18 @@ def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, 
                 F0, C0 = dd['lidar'].F.float().contiguous(), dd['lidar'].C.int().contiguous()
                 ws = net.workspace(F0.shape[0], 'cuda')
                 f4, G = T.encoder_forward_train(net, ws, F0, C0)
+            wgt = torch.randn(f4.shape, generator=torch.Generator().manual_seed(1)).cuda()
+            (f4 * wgt).sum().backward()
+            torch.cuda.synchronize()
         finally:
-            del os.environ['IR_TRAIN_ENCODER']
-        wgt = torch.randn(f4.shape, generator=torch.Generator().manual_seed(1)).cuda()
-        (f4 * wgt).sum().backward()
-        torch.cuda.synchronize()
+            del os.environ['IR_TRAIN_ENCODER'], os.environ['IR_DGRAD']
         res[mode] = (f4.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()},
                      {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k})
     assert torch.equal(res['layers'][0], res['fused'][0])
     for k, g in res['layers'][1].items():
         e = float((g - res['fused'][1][k]).abs().max())
-        assert e <= 1e-5 * float(g.abs().max()) + 1e-9, (k, e)          # wgrad sums with float atomics
+        # wgrad sums with float atomics; the tcgen05 dgrad carries ~2^-22 of each layer's largest gradient
+        assert e <= (1e-5 if dgrad == 'simt' else 3e-4) * float(g.abs().max()) + 1e-9, (k, e)
     for k, v in res['layers'][2].items():
         assert torch.equal(v, res['fused'][2][k]), k
 
