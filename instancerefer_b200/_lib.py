@@ -147,10 +147,15 @@ def load():
     return lib
 
 
+_fn = {}
+
+
 def call(name, *args):
     """Invoke an ``int ir_*`` entry point; raise IrError with the library's message on failure."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fn.get(name)
+    if fn is None:
+        fn = _fn[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise IrError(f"{name} failed ({rc}): {lib.ir_last_error().decode(errors='replace')}")
+        raise IrError(f"{name} failed ({rc}): {load().ir_last_error().decode(errors='replace')}")
     return rc

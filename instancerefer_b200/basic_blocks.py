@@ -106,11 +106,15 @@ class SparseConvEncoder(nn.Module, PrepCache):
         self._ws = {}
 
     def _layers(self):
+        cached = self.__dict__.get('_layer_list')
+        if cached is not None:
+            return cached
         out = [(self.stem[0].net[0], self.stem[0].net[1])]
         for st in (self.stage1, self.stage2, self.stage3, self.stage4):
             out.append((st[0].net[0], st[0].net[1]))
             out.append((st[1].net[0], st[1].net[1]))
             out.append((st[1].net[3], st[1].net[4]))
+        self.__dict__['_layer_list'] = out          # module structure is fixed after construction
         return out
 
     def _prepare(self):

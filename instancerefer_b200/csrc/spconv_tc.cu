@@ -165,7 +165,9 @@ struct Cfg {
     static_assert(STAGE_AREA % 1024 == 0, "barriers follow the stage area");
 };
 
-template <int CIN, int COUT>
+// SCALED: the gathered rows are multiplied by a power of two derived from *in_absmax (IrConvProblem) before
+// the fp16 split and the result is scaled back (training dgrad); the inference kernel carries no such code.
+template <int CIN, int COUT, bool SCALED>
 __global__ void __launch_bounds__(N_THREADS, 2)
 k_pairgemm_tc(IrConvBatch batch, int K) {
     using C = Cfg<CIN, COUT>;
@@ -279,7 +281,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     const float* __restrict__ in_absmax = P.in_absmax;
     // input scale (power of two, exact): 2^13 / 2^floor(log2(max|F|)); 1 when no maximum is supplied
     auto input_scale = [&]() -> float {
-        if (in_absmax == nullptr) return 1.f;
+        if (!SCALED || in_absmax == nullptr) return 1.f;
         const float m = *in_absmax;
         return (m > 0.f && m < 3.0e38f) ? exp2f(13.f - floorf(log2f(m))) : 1.f;
     };
@@ -369,10 +371,14 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
                 const int r = rbase + 16 * i;
                 const int off = r * 128 + ((j ^ (r & 7)) << 4);
                 uint4 h, l;
-                split2(va[i].x * in_s, va[i].y * in_s, h.x, l.x);
-                split2(va[i].z * in_s, va[i].w * in_s, h.y, l.y);
-                split2(vb[i].x * in_s, vb[i].y * in_s, h.z, l.z);
-                split2(vb[i].z * in_s, vb[i].w * in_s, h.w, l.w);
+                if (SCALED) {
+                    va[i].x *= in_s; va[i].y *= in_s; va[i].z *= in_s; va[i].w *= in_s;
+                    vb[i].x *= in_s; vb[i].y *= in_s; vb[i].z *= in_s; vb[i].w *= in_s;
+                }
+                split2(va[i].x, va[i].y, h.x, l.x);
+                split2(va[i].z, va[i].w, h.y, l.y);
+                split2(vb[i].x, vb[i].y, h.z, l.z);
+                split2(vb[i].z, vb[i].w, h.w, l.w);
                 *reinterpret_cast<uint4*>(st_hi + off) = h;
                 *reinterpret_cast<uint4*>(st_lo + off) = l;
             }
@@ -433,7 +439,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
             weights_to_tmem(0);
         }
         ir_pdl_wait();                                          // T is still being read by the previous reduce
-        const float out_s = W_UNSCALE / input_scale();
+        const float out_s = SCALED ? W_UNSCALE / input_scale() : W_UNSCALE;
         uint32_t acc_it = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int p0 = tile * TILE_M;
@@ -473,18 +479,18 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     }
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool SCALED = false>
 int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     static bool attr_done = false;
     if (!attr_done) {
-        IR_CHECK_CUDA(cudaFuncSetAttribute(k_pairgemm_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_pairgemm_tc<CIN, COUT, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_done = true;
     }
     long long tiles_max = 0;
     for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
     const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, 2 * IR_NUM_SMS);       // two CTAs per SM
-    IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
+    IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT, SCALED>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
@@ -494,12 +500,18 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
     IR_CHECK_ARG(K <= 27 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
     for (int g = 0; g < b.G; ++g) IR_CHECK_ARG(b.p[g].weight != nullptr && (reinterpret_cast<uintptr_t>(b.p[g].weight) & 15) == 0);
+    if (b.G == 1 && b.p[0].in_absmax != nullptr) {          // range-scaled variant: the dgrad shapes of the training step
+        if (cin == 64 && cout == 32) return tc::launch<64, 32, true>(b, K, st);
+        if (cin == 64 && cout == 64) return tc::launch<64, 64, true>(b, K, st);
+        if (cin == 128 && cout == 64) return tc::launch<128, 64, true>(b, K, st);
+        if (cin == 128 && cout == 128) return tc::launch<128, 128, true>(b, K, st);
+        ir_set_error("pairgemm_tc (scaled): unsupported channels %d -> %d", cin, cout);
+        return IR_ERR_UNSUPPORTED;
+    }
     if (cin == 32 && cout == 64) return tc::launch<32, 64>(b, K, st);
     if (cin == 64 && cout == 64) return tc::launch<64, 64>(b, K, st);
     if (cin == 64 && cout == 128) return tc::launch<64, 128>(b, K, st);
     if (cin == 128 && cout == 128) return tc::launch<128, 128>(b, K, st);
-    if (cin == 64 && cout == 32) return tc::launch<64, 32>(b, K, st);        // dgrad of the 32 -> 64 down conv
-    if (cin == 128 && cout == 64) return tc::launch<128, 64>(b, K, st);      // dgrad of the 64 -> 128 down conv
     ir_set_error("pairgemm_tc: unsupported channels %d -> %d", cin, cout);
     return IR_ERR_UNSUPPORTED;
 }

@@ -87,27 +87,53 @@ k_wgrad(const float* __restrict__ X, const float* __restrict__ dY, const int* __
         for (int j = 0; j < MJ; ++j) acc[i][j] = 0.f;
     const long long base = (long long)k * seg_cap;
     const int nb = (p_end - p_begin + WG_PB - 1) / WG_PB;
-    auto issue = [&](int bi) {
+    // rulebook indices are fetched one batch AHEAD of the cp.async that consumes them, so the issue step never
+    // waits on an L2 round trip: a thread stages (CIN+COUT)/64 row chunks per batch
+    constexpr int NX = WG_PB * (CIN / 4) / 256, ND = WG_PB * (COUT / 4) / 256;     // chunks per thread (1..2 each)
+    constexpr int NXr = NX > 0 ? NX : 1, NDr = ND > 0 ? ND : 1;
+    int ix[NXr], id[NDr];
+    auto load_idx = [&](int bi) {
+        const int p0 = p_begin + bi * WG_PB;
+#pragma unroll
+        for (int q = 0; q < NXr; ++q) {
+            const int i = tid + q * 256, r = i / (CIN / 4);
+            ix[q] = (bi < nb && i < WG_PB * (CIN / 4) && p0 + r < p_end) ? in_idx[base + p0 + r] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < NDr; ++q) {
+            const int i = tid + q * 256, r = i / (COUT / 4);
+            id[q] = (bi < nb && i < WG_PB * (COUT / 4) && p0 + r < p_end) ? out_idx[base + p0 + r] : -1;
+        }
+    };
+    auto issue = [&](int bi) {                       // uses ix/id loaded for batch bi
         if (bi < nb) {
-            const int p0 = p_begin + bi * WG_PB, np = min(WG_PB, p_end - p0), st = bi % WG_STAGES;
-            for (int i = tid; i < WG_PB * (CIN / 4); i += 256) {
-                const int r = i / (CIN / 4), c4 = i - r * (CIN / 4);
-                const bool v = r < np;
-                const float* src = v ? X + (long long)in_idx[base + p0 + r] * CIN + c4 * 4 : X;
-                wg_cp_async16(&xs[st][r][c4 * 4], src, v);
+            const int st = bi % WG_STAGES;
+#pragma unroll
+            for (int q = 0; q < NXr; ++q) {
+                const int i = tid + q * 256;
+                if (i < WG_PB * (CIN / 4)) {
+                    const int r = i / (CIN / 4), c4 = i - r * (CIN / 4);
+                    const bool v = ix[q] >= 0;
+                    wg_cp_async16(&xs[st][r][c4 * 4], v ? X + (long long)ix[q] * CIN + c4 * 4 : X, v);
+                }
             }
-            for (int i = tid; i < WG_PB * (COUT / 4); i += 256) {
-                const int r = i / (COUT / 4), c4 = i - r * (COUT / 4);
-                const bool v = r < np;
-                const float* src = v ? dY + (long long)out_idx[base + p0 + r] * COUT + c4 * 4 : dY;
-                wg_cp_async16(&ds[st][r][c4 * 4], src, v);
+#pragma unroll
+            for (int q = 0; q < NDr; ++q) {
+                const int i = tid + q * 256;
+                if (i < WG_PB * (COUT / 4)) {
+                    const int r = i / (COUT / 4), c4 = i - r * (COUT / 4);
+                    const bool v = id[q] >= 0;
+                    wg_cp_async16(&ds[st][r][c4 * 4], v ? dY + (long long)id[q] * COUT + c4 * 4 : dY, v);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");               // one group per batch slot, empty or not
     };
-    for (int bi = 0; bi < WG_STAGES - 1; ++bi) issue(bi);
+    for (int bi = 0; bi < WG_STAGES - 1; ++bi) { load_idx(bi); issue(bi); }
+    load_idx(WG_STAGES - 1);
     for (int bi = 0; bi < nb; ++bi) {
         issue(bi + WG_STAGES - 1);
+        load_idx(bi + WG_STAGES);                                            // consumed by the NEXT iteration's issue
         asm volatile("cp.async.wait_group %0;" ::"n"(WG_STAGES - 1) : "memory");   // batch bi has landed
         __syncthreads();
         const int st = bi % WG_STAGES;
@@ -201,7 +227,7 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
 // (rows = B*H*W).  Two-level deterministic reductions: every CTA writes fp32 partial sums of its row
 // stripe to scratch[part][2*C]; a finalize kernel adds the <= BN_MAX_PARTS partials in fp64.
 // scratch: float[BN_MAX_PARTS * 2 * C] (ir_bn_scratch_floats).
-#define BN_MAX_PARTS (IR_NUM_SMS * 4)
+#define BN_MAX_PARTS (IR_NUM_SMS * 2)
 #define BN_ROWS_PER_CTA 32
 static inline int bn_parts(long long n) { return ir_min_i(ir_div_up(n > 0 ? n : 1, BN_ROWS_PER_CTA), BN_MAX_PARTS); }
 extern "C" int64_t ir_bn_scratch_floats(int32_t C) { return (int64_t)BN_MAX_PARTS * 2 * C; }
@@ -240,23 +266,31 @@ k_bn_partials(const float* __restrict__ x, const float* __restrict__ dy, const f
     }
 }
 
-// grid = C/32 CTAs of 256 threads: lane = channel, the 8 warps split the partials, fp64 accumulation
+// grid = C/32 CTAs of 1024 threads: lane = channel, the 32 warps split the <= 296 partials (<= 10 independent
+// loads each), fp64 accumulation in a fixed order
+#define BN_FIN_THREADS 1024
+static_assert(BN_MAX_PARTS <= 32 * 10, "bn_sum_parts covers 10 partials per warp");
 __device__ __forceinline__ void bn_sum_parts(const float* __restrict__ scratch, int parts, int C, int c, double& s, double& ss) {
-    __shared__ double sh[2][8][32];
+    __shared__ double sh[2][32][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double a = 0.0, b = 0.0;
-    if (c < C) {
-#pragma unroll 8
-        for (int p = w; p < parts; p += 8) { a += scratch[(long long)p * 2 * C + c]; b += scratch[(long long)p * 2 * C + C + c]; }
+    float fa[10], fb[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const int p = w + 32 * q;
+        const bool ok = c < C && p < parts;
+        fa[q] = ok ? scratch[(long long)p * 2 * C + c] : 0.f;
+        fb[q] = ok ? scratch[(long long)p * 2 * C + C + c] : 0.f;
     }
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) { a += fa[q]; b += fb[q]; }
     sh[0][w][lane] = a; sh[1][w][lane] = b;
     __syncthreads();
     s = 0.0; ss = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { s += sh[0][q][lane]; ss += sh[1][q][lane]; }
+    for (int q = 0; q < 32; ++q) { s += sh[0][q][lane]; ss += sh[1][q][lane]; }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN_FIN_THREADS)
 k_bn_finalize(const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
               int C, float eps, float momentum, float* __restrict__ running_mean,
               float* __restrict__ running_var, float* __restrict__ mean_out,
@@ -309,7 +343,7 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
     const int parts = bn_parts(n);
     k_bn_partials<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, n_dev, n, C, nullptr, nullptr, 0, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
+    k_bn_finalize<<<ir_div_up(C, 32), BN_FIN_THREADS, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
     IR_CHECK_LAUNCH();
     k_bn_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(x, n_dev, n, C, mean, rstd, gamma, beta, resid, relu, y);
     IR_CHECK_LAUNCH();
@@ -318,7 +352,7 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
 
 // backward: g = dy * [y > 0] (if relu); dbeta = sum g; dgamma = sum g*xhat;
 //           dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n); dresid = g
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN_FIN_THREADS)
 k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, float* __restrict__ absmax_out) {
     if (absmax_out && blockIdx.x == 0 && threadIdx.x == 0) *absmax_out = 0.f;    // k_bn_bwd_apply (next launch) maxes into it
@@ -379,7 +413,7 @@ extern "C" int ir_bn_train_bwd(const float* dy, const float* y, const float* x, 
     const int parts = bn_parts(n);
     k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch);
     IR_CHECK_LAUNCH();
-    k_bn_bwd_finalize<<<ir_div_up(C, 32), 256, 0, st>>>(scratch, parts, C, dgamma, dbeta, absmax_out);
+    k_bn_bwd_finalize<<<ir_div_up(C, 32), BN_FIN_THREADS, 0, st>>>(scratch, parts, C, dgamma, dbeta, absmax_out);
     IR_CHECK_LAUNCH();
     k_bn_bwd_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(
         dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid, absmax_out);

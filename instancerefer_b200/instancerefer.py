@@ -49,16 +49,26 @@ class InstanceRefer(nn.Module):
         from . import training as T
         a = self.args
         data_dict.pop(_PACK_KEY, None)
+        full = bool(a.attribute_module and a.relation_module and a.scene_module and a.use_gt_lang)
+        prep_a = prep_s = None
+        if full:
+            # host class filter + packed H2D, then the coordinate phase of both encoders and ONE read-back of
+            # their level sizes, before any feature kernel is queued: the rest of the step is issued without
+            # a host synchronisation
+            dev = data_dict['lang_feat'].device
+            pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+            prep_a, prep_s = T.prepare_encoder_maps(self, data_dict, pack)
         data_dict = T.lang_forward_train(self.lang, data_dict)
-        dev = data_dict['lang_feat'].device
-        pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+        if not full:
+            dev = data_dict['lang_feat'].device
+            pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
         data_dict[_PACK_KEY] = pack
         if a.attribute_module:
-            data_dict = T.attribute_forward_train(self.attribute, data_dict, pack)
+            data_dict = T.attribute_forward_train(self.attribute, data_dict, pack, prep_a)
         if a.relation_module:
             data_dict = T.relation_forward_train(self.relation, data_dict, pack)
         if a.scene_module:
-            data_dict = T.scene_forward_train(self.scene, data_dict, pack)
+            data_dict = T.scene_forward_train(self.scene, data_dict, pack, prep_s)
         return data_dict
 
     def forward(self, data_dict):

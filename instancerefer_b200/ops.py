@@ -8,21 +8,25 @@ from . import _lib
 from ._lib import EncoderLayout, EncoderParams, call
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_dev = torch.cuda.current_device
+
+
 def _stream():
-    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    return _raw_stream(_cur_dev())          # int -> c_void_p by argtypes
 
 
 def _p(t, dtype=None):
     """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise _lib.IrError("expected a CUDA tensor (there is no CPU path)")
-    if not t.is_contiguous():
-        raise _lib.IrError("expected a contiguous tensor")
-    if dtype is not None and t.dtype != dtype:
+    if not (t.is_cuda and t.is_contiguous() and (dtype is None or t.dtype == dtype)):
+        if not t.is_cuda:
+            raise _lib.IrError("expected a CUDA tensor (there is no CPU path)")
+        if not t.is_contiguous():
+            raise _lib.IrError("expected a contiguous tensor")
         raise _lib.IrError(f"expected dtype {dtype}, got {t.dtype}")
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()            # argtypes are c_void_p: a plain int converts without a ctypes object
 
 
 _checked_devices = set()
@@ -292,7 +296,7 @@ def spconv_wgrad(x, dy, in_idx, out_idx, count):
     return dW
 
 
-BN_PARTS = 148 * 4          # ir_bn_scratch_floats(C) = BN_PARTS * 2 * C
+BN_PARTS = 148 * 2          # ir_bn_scratch_floats(C) = BN_PARTS * 2 * C
 
 
 def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, running_var):

@@ -24,10 +24,10 @@ class EncoderGraph:
     """Rulebooks of one encoder pass (inside its workspace) + host row counts, and the transposed
     rulebooks the backward needs (built lazily, once per map per step)."""
 
-    def __init__(self, ws):
+    def __init__(self, ws, n=None):
         self.ws = ws
         self.nlvl_dev = ws.nlvl()
-        self.n = [int(v) for v in self.nlvl_dev.tolist()]          # one small D2H per encoder pass
+        self.n = [int(v) for v in (n if n is not None else self.nlvl_dev.tolist())]   # host row counts (one small D2H)
         self.kcount = ws.kcount()
         self._t = {}
 
@@ -162,14 +162,17 @@ class EncoderTrain(Function):
         return (None, None, None, *grads)
 
 
-def encoder_forward_train(net, ws, feats0=None, coords0=None):
+def encoder_forward_train(net, ws, feats0=None, coords0=None, G=None):
     """Train-mode pass of a SparseConvEncoder / BEVEncoder over a workspace whose level 0 is
-    already voxelised (feats0 None) or given by (feats0, coords0).
+    already voxelised (feats0 None) or given by (feats0, coords0).  ``G``: maps already built and
+    row counts already read back (the model forward builds both encoders' maps first and reads
+    their counts with ONE D2H copy).
     -> (F4 (n4,128) with autograd history, EncoderGraph).  IR_TRAIN_ENCODER=layers selects the
     per-layer autograd path (13 SparseConvBN nodes; what the unit tests dissect)."""
     import os
-    ops.encoder_build_maps(ws, coords0)
-    G = EncoderGraph(ws)
+    if G is None:
+        ops.encoder_build_maps(ws, coords0)
+        G = EncoderGraph(ws)
     layers = net._layers()
     if os.environ.get('IR_TRAIN_ENCODER', 'fused') != 'layers':
         flat = [t for conv, bn in layers for t in (conv.kernel, bn.weight, bn.bias)]
@@ -495,16 +498,39 @@ def lang_forward_train(m, data_dict):
     return data_dict
 
 
-def attribute_forward_train(m, data_dict, pack):
+def prepare_encoder_maps(model, data_dict, pack):
+    """Coordinate phase of BOTH sparse encoders (voxelise the candidates @2 cm, hash the loader's 5 cm
+    voxels, levels + kernel maps), then ONE D2H copy of the ten level row counts — the only host
+    synchronisation of the train-mode forward after the token-length read."""
+    dev = pack.points.device
+    am, sm = model.attribute, model.scene
+    ws_a = am.net.workspace(pack.M * pack.points.shape[1], dev)
+    ops.encoder_reset(ws_a)
+    ops.voxelize(pack.points, pack.cand_rows, float(am.voxel_size[0]), ws_a)
+    ops.encoder_build_maps(ws_a)
+    lidar = data_dict['lidar']
+    F0 = lidar.F.to(dev, torch.float32).contiguous()
+    C0 = lidar.C.to(dev, torch.int32).contiguous()
+    ws_s = sm.net.workspace(F0.shape[0], dev)
+    ops.encoder_build_maps(ws_s, C0)
+    n = torch.cat([ws_a.nlvl(), ws_s.nlvl()]).tolist()
+    return (ws_a, EncoderGraph(ws_a, n[:5])), (ws_s, EncoderGraph(ws_s, n[5:]), F0, C0)
+
+
+def attribute_forward_train(m, data_dict, pack, prepared=None):
     """models/attribute_module.py:83-131 in train mode."""
     dev = pack.points.device
     lang = L2Norm.apply(mlp_head(m.lang_emb_fc, data_dict['lang_attr_feats'], 1, 3))
     data_dict['num_filtered_objs'] = pack.num_filtered
     data_dict['pred_obb_batch'] = pack.pred_obb_batch
-    ws = m.net.workspace(pack.M * pack.points.shape[1], dev)
-    ops.encoder_reset(ws)
-    ops.voxelize(pack.points, pack.cand_rows, float(m.voxel_size[0]), ws)
-    f4, G = encoder_forward_train(m.net, ws)
+    if prepared is None:
+        ws = m.net.workspace(pack.M * pack.points.shape[1], dev)
+        ops.encoder_reset(ws)
+        ops.voxelize(pack.points, pack.cand_rows, float(m.voxel_size[0]), ws)
+        f4, G = encoder_forward_train(m.net, ws)
+    else:
+        ws, G = prepared
+        f4, G = encoder_forward_train(m.net, ws, G=G)
     obj = SegMax.apply(f4, ws.coords(4), G.nlvl_dev[4:5], G.n[4], pack.M)
     data_dict['obj_feats'] = obj
     vis = mlp_head(m.vis_emb_fc, obj, 1, 3)
@@ -536,15 +562,19 @@ def relation_forward_train(m, data_dict, pack):
     return data_dict
 
 
-def scene_forward_train(m, data_dict, pack):
+def scene_forward_train(m, data_dict, pack, prepared=None):
     """models/scene_module.py:60-108 in train mode."""
-    lidar = data_dict['lidar']
     dev = pack.points.device
     B = data_dict['point_min'].shape[0]
-    F0 = lidar.F.to(dev, torch.float32).contiguous()
-    C0 = lidar.C.to(dev, torch.int32).contiguous()
-    ws = m.net.workspace(F0.shape[0], dev)
-    f4, G = encoder_forward_train(m.net, ws, F0, C0)
+    if prepared is None:
+        lidar = data_dict['lidar']
+        F0 = lidar.F.to(dev, torch.float32).contiguous()
+        C0 = lidar.C.to(dev, torch.int32).contiguous()
+        ws = m.net.workspace(F0.shape[0], dev)
+        f4, G = encoder_forward_train(m.net, ws, F0, C0)
+    else:
+        ws, G, F0, C0 = prepared
+        f4, G = encoder_forward_train(m.net, ws, F0, C0, G=G)
     dense = BEV.apply(f4, m.to_bev[1].kernel, ws.coords(4), G.nlvl_dev[4:5], G.n[4], B)     # (B*375,128)
     bn = m.to_bev[2]
     x = BatchNormAct.apply(dense, bn.weight, bn.bias, bn, True).view(B, 15, 25, -1)          # NHWC
