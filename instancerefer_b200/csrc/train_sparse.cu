@@ -165,6 +165,7 @@ static int wgrad_launch(dim3 grid, cudaStream_t st, const float* x, const float*
     constexpr int smem = WG_STAGES * WG_PB * (CIN + COUT) * 4;
     static bool attr_done = false;
     if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CIN, COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         IR_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
@@ -208,7 +209,9 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
     IR_CHECK_ARG(x && dy && in_idx && out_idx && count && dW && K > 0 && K <= 32 && seg_cap > 0);
     cudaStream_t st = (cudaStream_t)stream;
     IR_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * cin * cout * 4, st));
-    const int nsplit = ir_div_up(4 * IR_NUM_SMS, K);
+    // <= 4 CTAs per SM in total and never one more than a whole number of 2-CTA/SM waves (the 128x128 tile is
+    // register-limited to two CTAs per SM: 594 CTAs would leave a 2-CTA third wave)
+    const int nsplit = (4 * IR_NUM_SMS) / K > 0 ? (4 * IR_NUM_SMS) / K : 1;
     const dim3 grid(nsplit, K);
     int r = IR_OK;
     if (cin == 128 && cout == 128) r = wgrad_launch<128, 128>(grid, st, x, dy, in_idx, out_idx, count, seg_cap, dW);
