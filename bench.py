@@ -167,9 +167,7 @@ def main_train(a):
         return
     import __graft_entry__ as g
     g.build()
-    import train_ref
-    import weights
-    from instancerefer_b200 import SparseTensor, _lib, ops
+    from instancerefer_b200 import SparseTensor, _lib, ops, synthetic
     from instancerefer_b200.instancerefer import InstanceRefer
     from instancerefer_b200.loss_helper import get_loss
     from instancerefer_b200.optim import FlatAdam
@@ -181,10 +179,10 @@ def main_train(a):
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     model = InstanceRefer(7, make_args())
-    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)
     model = model.to(dev).train()
     opt = FlatAdam(model, lr=1e-3, weight_decay=1e-5)          # config/InstanceRefer.yaml:48,53
-    cfg = train_ref.SyntheticConfig()                          # dataset-config stand-in (label -> GT box), not on the timed path's arithmetic
+    cfg = synthetic.SyntheticConfig()                          # dataset-config stand-in (labels -> GT box)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     hosts = []
     for b in train_batches(rank):
@@ -264,14 +262,13 @@ def main_train(a):
 def _forward_setup(local):
     import __graft_entry__ as g
     g.build()
-    import weights
-    from instancerefer_b200 import ops
+    from instancerefer_b200 import ops, synthetic
     from instancerefer_b200.instancerefer import InstanceRefer
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
     model = InstanceRefer(7, make_args())
-    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)
     return model.to(dev).eval(), dev
 
 
@@ -405,7 +402,6 @@ def main():
 
     import __graft_entry__ as g
     g.build()
-    import weights
     from instancerefer_b200 import SparseTensor, _lib, ops, synthetic
     from instancerefer_b200.candidates import KEY, CandidatePack
     from instancerefer_b200.instancerefer import InstanceRefer
@@ -419,7 +415,7 @@ def main():
     lib = _lib.load()
     args = make_args()
     model = InstanceRefer(7, args)
-    model.load_state_dict(weights.make_state_dict(123), strict=True)
+    model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)      # random-init weights (no oracle import on this arm)
     model = model.to(dev).eval()
 
     # ---- this rank's stream of scenes (a few distinct scenes, cycled)

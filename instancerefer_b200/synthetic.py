@@ -185,3 +185,61 @@ def to_data_dict(batch, sparse_tensor_cls, device='cpu'):
         instance_obbs=batch['instance_obbs'],
         instance_class=batch['instance_class'],
     )
+
+
+# ----------------------------------------------------------------------------- synthetic weights / dataset config
+
+def make_state_dict(seed=123, spec=None, gain=1.0, model=None):
+    """Deterministic, machine-independent random-init state_dict with the reference's key names and shapes
+    (there is no network for checkpoints).  ``spec`` = [(key, shape, dtype-string)] — e.g.
+    tests/golden/state_dict_spec.json, captured from the reference model — or derived from ``model``.
+    Inits mirror the reference's (torchsparse conv U(+-1/sqrt(Cin*K)), Linear/Conv2d/GRU
+    U(+-1/sqrt(fan_in))); BN statistics are randomised so eval-mode BN is non-trivial.
+    Every tensor has its own generator seeded from (seed, crc32(key)), so the same dict can be rebuilt
+    anywhere (reference run, CPU oracle, CUDA drop-in)."""
+    import math
+    import zlib
+
+    import torch
+    if spec is None:
+        spec = [(k, list(v.shape), str(v.dtype)) for k, v in model.state_dict().items()]
+    sd = {}
+    for key, shape, dtype in spec:
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        if dtype == 'torch.int64':
+            sd[key] = torch.zeros(shape, dtype=torch.int64)
+            continue
+        leaf = key.rsplit('.', 1)[-1]
+        if leaf == 'running_mean':
+            t = torch.randn(shape, generator=g) * 0.1
+        elif leaf == 'running_var':
+            t = torch.rand(shape, generator=g) + 0.5
+        elif leaf == 'kernel':                       # (K,Cin,Cout) sparse conv / (5,128,128) BEV
+            bound = 1.0 / math.sqrt(shape[1] * (shape[0] if shape[0] in (8, 27) else 1))
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound * gain
+        elif len(shape) >= 2:                        # Linear / Conv2d / GRU matrices
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            if '.gru.' in key:
+                fan_in = 128
+            t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in) * gain
+        elif leaf == 'weight':                       # BN / LN scale
+            t = torch.rand(shape, generator=g) * 0.4 + 0.8
+        else:                                        # biases
+            t = torch.randn(shape, generator=g) * 0.05
+        sd[key] = t.float()
+    return sd
+
+
+class SyntheticConfig:
+    """Stand-in for the reference's ScannetDatasetConfig (which needs ScanNet meta files) with the one method
+    ``get_loss`` / ``get_eval`` call (data/scannet/model_util_scannet.py:174-181): ONE size class with zero
+    mean size and ONE heading bin, i.e. box size = size residual, heading = heading residual."""
+
+    def param2obb_batch(self, center, heading_class, heading_residual, size_class, size_residual):
+        obb = np.zeros((heading_class.shape[0], 7))
+        obb[:, 0:3] = center
+        obb[:, 3:6] = size_residual
+        obb[:, 6] = heading_residual * -1
+        return obb

@@ -24,17 +24,13 @@ except ImportError:
     import model_ref
 
 
-class SyntheticConfig:
-    """Stand-in for ScannetDatasetConfig (needs ScanNet meta files): one size class with zero
-    mean size, one heading bin.  Same method name and return layout as
-    data/scannet/model_util_scannet.py:174-181."""
-
-    def param2obb_batch(self, center, heading_class, heading_residual, size_class, size_residual):
-        obb = np.zeros((heading_class.shape[0], 7))
-        obb[:, 0:3] = center
-        obb[:, 3:6] = size_residual
-        obb[:, 6] = heading_residual * -1
-        return obb
+try:                                       # one definition, shared with the product's bench (which may not import oracle/)
+    from instancerefer_b200.synthetic import SyntheticConfig
+except ImportError:                        # oracle/ used standalone
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    from instancerefer_b200.synthetic import SyntheticConfig
 
 
 def box_min_max(obb):
