@@ -249,6 +249,13 @@ int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int32_t cout, 
                     const int32_t* in_idx, const int32_t* out_idx, const int32_t* count,
                     int64_t seg_cap, float* dW, ir_stream_t stream);
 
+/* The same on tcgen05 for Cin, Cout in {64,128}: both gathered operands are MN-major UMMA operands (the
+ * pair index is the contraction), split-fp16 hi/lo with dy range-scaled by *dy_absmax (max |dy|, device
+ * scalar); other shapes, use_tc = 0 or dy_absmax = NULL fall through to ir_spconv_wgrad.            */
+int ir_spconv_wgrad_scaled(const float* x, int32_t cin, const float* dy, const float* dy_absmax, int32_t cout,
+                           int32_t K, const int32_t* in_idx, const int32_t* out_idx, const int32_t* count,
+                           int64_t seg_cap, int32_t use_tc, float* dW, ir_stream_t stream);
+
 /* Train-mode BatchNorm over the rows of a (n, C) matrix (spnn.BatchNorm over voxels, BatchNorm1d,
  * BatchNorm2d on NHWC cells): batch mean / biased variance, y = act((x-mean)*rstd*gamma + beta
  * (+resid)); running statistics updated with `momentum` (unbiased variance) when given.
@@ -314,7 +321,8 @@ int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
  * the five levels (read back once from the workspace after ir_encoder_build_maps).               */
 typedef struct {
     int32_t cin, use_tc;                      /* bit 0: forward pair-GEMM on tcgen05 (weights 16-B aligned);
-                                                 bit 1: dgrad on tcgen05 (range-scaled, ir_spconv_layer_scaled) */
+                                                 bit 1: dgrad on tcgen05 (range-scaled, ir_spconv_layer_scaled);
+                                                 bit 2: wgrad on tcgen05 (ir_spconv_wgrad_scaled)             */
     const float* weight[IR_ENC_LAYERS];       /* (K,Cin,Cout)                                          */
     const float* gamma[IR_ENC_LAYERS];
     const float* beta[IR_ENC_LAYERS];

@@ -87,6 +87,7 @@ SIGNATURES = {
     # training step
     "ir_rulebook_transpose": (i32, [p, p, i32, i64, p, i64, p, p, p]),
     "ir_spconv_wgrad": (i32, [p, i32, p, i32, i32, p, p, p, i64, p, p]),
+    "ir_spconv_wgrad_scaled": (i32, [p, i32, p, p, i32, i32, p, p, p, i64, i32, p, p]),
     "ir_bn_scratch_floats": (i64, [i32]),
     "ir_bn_train_fwd": (i32, [p, p, i32, i32, p, p, p, i32, f32, f32, p, p, p, p, p, p, p]),
     "ir_bn_train_bwd": (i32, [p, p, p, p, i32, i32, p, p, p, i32, p, p, p, p, p, p, p]),

@@ -62,3 +62,5 @@ int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st);   // fused 
 
 // spconv_tc.cu  (tcgen05 / TMEM / TMA pair-GEMM, split-fp16)
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);
+int irk_wgrad_tc(const float* x, int cin, const float* dy, int cout, int K, const int* in_idx, const int* out_idx,
+                 const int* count, long long seg_cap, const float* dy_absmax, float* dW, cudaStream_t st);

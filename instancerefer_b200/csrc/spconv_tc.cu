@@ -495,6 +495,236 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     return IR_OK;
 }
 
+
+// =====================================================================================================
+// wgrad on tcgen05:  dW[k] (Cin x Cout) = sum over the pairs of offset k of  X[in]^T (x) dY[out]
+// (the second GEMM of the sparse-conv backward).  Both operands are GATHERED rows, i.e. matrices whose
+// contraction index (the pair) is the slow one: A = X^T is (M = Cin) x (K = pairs) with M contiguous,
+// B = dY is (K = pairs) x (N = Cout) with N contiguous — MN-major operands for UMMA.  The 128B-swizzled
+// row image the forward producers write (one 128-byte row = 64 fp16 channels of one pair) IS the canonical
+// MN-major SWIZZLE_128B layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) [fp16 elements]: a swizzle atom is
+// 64 channels x 8 pairs, LBO = distance between 64-channel panels, SBO = 1024 B between 8-pair groups.
+//   * grid (splits, K): a CTA owns a contiguous chunk of the pairs of ONE offset and ONE fp32 accumulator
+//     (M = 128 lanes x N = Cout columns) in tensor memory for its whole life;
+//   * 3 producer groups gather 64 pairs per stage: X rows -> fp16 hi/lo panels, dY rows (range-scaled by the
+//     power of two from max|dY|, as in the scaled dgrad) -> fp16 hi/lo panels;
+//   * one thread issues, per 16 pairs, hi*hi + hi*lo + lo*hi (SS-mode tcgen05.mma kind::f16, both MN-major);
+//   * the epilogue drains TMEM once and adds the tile into dW[k] with fp32 atomics (splits share it).
+template <int CIN, int COUT>
+struct WgCfg {
+    static constexpr int PA = 2;                       // A panels: M is always 128 (Cin = 64 -> second panel is zero)
+    static constexpr int PA_REAL = CIN / 64;
+    static constexpr int PB = COUT / 64;
+    static constexpr int PANEL_B = 64 * 128;           // 64 pairs x 128 B
+    static constexpr int OFF_XHI = 0, OFF_XLO = PA * PANEL_B;
+    static constexpr int OFF_DHI = 2 * PA * PANEL_B, OFF_DLO = (2 * PA + PB) * PANEL_B;
+    static constexpr int STAGE_B = 2 * (PA + PB) * PANEL_B;
+    static constexpr int OFF_BAR = NS * STAGE_B;
+    static constexpr int N_BAR = 2 * NS + 1;
+    static constexpr int OFF_MISC = OFF_BAR + N_BAR * 8;
+    static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;
+    static constexpr int TMEM_COLS = 128;
+    static_assert(CIN % 64 == 0 && COUT % 64 == 0 && CIN <= 128 && COUT <= 128, "wgrad_tc shapes");
+};
+
+// MN-major, 128B swizzle: LBO = bytes between 64-element MN atoms, SBO = 1024 B between 8-row K groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(N_THREADS, 1)
+k_wgrad_tc(const float* __restrict__ X, const float* __restrict__ dY, const int* __restrict__ in_idx,
+           const int* __restrict__ out_idx, const int* __restrict__ count, long long seg_cap,
+           const float* __restrict__ dy_absmax, float* __restrict__ dW) {
+    using C = WgCfg<CIN, COUT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t s_bar = base + C::OFF_BAR;
+    auto bar_full = [&](int s) { return s_bar + 8u * s; };
+    auto bar_empty = [&](int s) { return s_bar + 8u * (NS + s); };
+    const uint32_t bar_done = s_bar + 8u * (2 * NS);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + C::OFF_MISC);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int k = blockIdx.y;
+    const int cnt = count[k];
+    int chunk = (cnt + (int)gridDim.x - 1) / (int)gridDim.x;
+    chunk = (chunk + TILE_M - 1) / TILE_M * TILE_M;                     // whole stages per CTA
+    const int p_begin = blockIdx.x * chunk, p_end = min(cnt, p_begin + chunk);
+    const int n_items = p_end > p_begin ? (p_end - p_begin + TILE_M - 1) / TILE_M : 0;
+
+    if (tid == 32) {
+        for (int s = 0; s < NS; ++s) { mbar_init(bar_full(s), WARPS_PER_GROUP); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(s_tmem)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (C::PA_REAL < C::PA) {                                           // Cin = 64: the upper half of M reads zeros
+        for (int s = 0; s < NS; ++s)
+            for (int i = tid; i < C::PANEL_B / 16; i += N_THREADS) {
+                reinterpret_cast<uint4*>(sm + s * C::STAGE_B + C::OFF_XHI + C::PANEL_B)[i] = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(sm + s * C::STAGE_B + C::OFF_XLO + C::PANEL_B)[i] = make_uint4(0, 0, 0, 0);
+            }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const long long kbase = (long long)k * seg_cap;
+    float dy_scale = 1.f;
+    {
+        const float m = dy_absmax ? *dy_absmax : 0.f;
+        if (m > 0.f && m < 3.0e38f) dy_scale = exp2f(13.f - floorf(log2f(m)));
+    }
+
+    if (warp >= 5) {
+        // ===================== gather producers (one group of 128 threads per stage) =====================
+        const int pw = warp - 5;
+        const int grp = pw / WARPS_PER_GROUP;
+        const int gt = (pw % WARPS_PER_GROUP) * 32 + lane;
+        const int j = gt & 7;                 // 16-byte chunk (8 channels) inside a 128-byte panel row
+        const int rbase = gt >> 3;            // rows rbase + 16*i
+        uint32_t round = 0;
+        int nx[TASKS], no[TASKS];                                          // rulebook rows of the group's NEXT item
+        auto load_idx = [&](int it) {
+            const int p0 = p_begin + it * TILE_M;
+#pragma unroll
+            for (int i = 0; i < TASKS; ++i) {
+                const int p = p0 + rbase + 16 * i;
+                const bool ok = it < n_items && p < p_end;
+                nx[i] = ok ? __ldg(in_idx + kbase + p) : -1;
+                no[i] = ok ? __ldg(out_idx + kbase + p) : -1;
+            }
+        };
+        load_idx(grp);
+#pragma unroll 1
+        for (int it = grp; it < n_items; it += NS, ++round) {
+            int ix[TASKS], io[TASKS];
+#pragma unroll
+            for (int i = 0; i < TASKS; ++i) { ix[i] = nx[i]; io[i] = no[i]; }
+            load_idx(it + NS);                                             // in flight while this item is gathered
+            mbar_wait(bar_empty(grp), (round & 1u) ^ 1u);
+            uint8_t* stg = sm + grp * C::STAGE_B;
+#pragma unroll 1
+            for (int pn = 0; pn < C::PA_REAL + C::PB; ++pn) {
+                const bool isx = pn < C::PA_REAL;
+                const int pp = isx ? pn : pn - C::PA_REAL;
+                const float* src = isx ? X : dY;
+                const int width = isx ? CIN : COUT;
+                const float sc = isx ? 1.f : dy_scale;
+                uint8_t* hi = stg + (isx ? C::OFF_XHI : C::OFF_DHI) + pp * C::PANEL_B;
+                uint8_t* lo = stg + (isx ? C::OFF_XLO : C::OFF_DLO) + pp * C::PANEL_B;
+                float4 va[TASKS], vb[TASKS];
+#pragma unroll
+                for (int i = 0; i < TASKS; ++i) {
+                    const int row = isx ? ix[i] : io[i];
+                    va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row >= 0) {
+                        const float4* g = reinterpret_cast<const float4*>(src + (long long)row * width + pp * 64 + j * 8);
+                        va[i] = __ldg(g);
+                        vb[i] = __ldg(g + 1);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < TASKS; ++i) {
+                    const int r = rbase + 16 * i;
+                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                    uint4 h, l;
+                    split2(va[i].x * sc, va[i].y * sc, h.x, l.x);
+                    split2(va[i].z * sc, va[i].w * sc, h.y, l.y);
+                    split2(vb[i].x * sc, vb[i].y * sc, h.z, l.z);
+                    split2(vb[i].z * sc, vb[i].w * sc, h.w, l.w);
+                    *reinterpret_cast<uint4*>(hi + off) = h;
+                    *reinterpret_cast<uint4*>(lo + off) = l;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full(grp));
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && n_items > 0) {
+            // fp32 accumulate, fp16 x fp16, A and B MN-major, N = Cout, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int it = 0; it < n_items; ++it) {
+                const int stage = it % NS;
+                mbar_wait(bar_full(stage), (it / NS) & 1u);
+                tc_fence_after();
+                const uint32_t sb = base + stage * C::STAGE_B;
+#pragma unroll
+                for (int ks = 0; ks < TILE_M / 16; ++ks) {                 // 16 pairs (= 16 rows = 2048 B) per MMA
+                    const uint64_t a_hi = make_desc_mn(sb + C::OFF_XHI + ks * 2048, C::PANEL_B);
+                    const uint64_t a_lo = make_desc_mn(sb + C::OFF_XLO + ks * 2048, C::PANEL_B);
+                    const uint64_t b_hi = make_desc_mn(sb + C::OFF_DHI + ks * 2048, C::PANEL_B);
+                    const uint64_t b_lo = make_desc_mn(sb + C::OFF_DLO + ks * 2048, C::PANEL_B);
+                    mma_f16_ss(tmem_base, a_hi, b_hi, idesc, (it | ks) ? 1u : 0u);
+                    mma_f16_ss(tmem_base, a_hi, b_lo, idesc, 1u);
+                    mma_f16_ss(tmem_base, a_lo, b_hi, idesc, 1u);
+                }
+                tc_commit(bar_empty(stage));
+            }
+            tc_commit(bar_done);
+        }
+    } else if (n_items > 0) {
+        // ===================== epilogue: TMEM lane = ci, column = co =====================
+        mbar_wait(bar_done, 0u);
+        tc_fence_after();
+        const int ci = warp * 32 + lane;
+        if (warp * 32 < CIN) {
+            const float unscale = 1.f / dy_scale;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            float* wrow = dW + ((long long)k * CIN + ci) * COUT;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) atomicAdd(wrow + c0 + q, __uint_as_float(v[q]) * unscale);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+template <int CIN, int COUT>
+int launch_wgrad(const float* x, const float* dy, const int* in_idx, const int* out_idx, const int* count, long long seg_cap,
+                 const float* dy_absmax, float* dW, int K, cudaStream_t st) {
+    using C = WgCfg<CIN, COUT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        IR_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int nsplit = IR_NUM_SMS / K > 0 ? IR_NUM_SMS / K : 1;            // one CTA per SM, one wave
+    k_wgrad_tc<CIN, COUT><<<dim3(nsplit, K), N_THREADS, C::SMEM_BYTES, st>>>(x, dy, in_idx, out_idx, count, seg_cap, dy_absmax, dW);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
 }  // namespace tc
 
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
@@ -528,4 +758,15 @@ extern "C" int ir_spconv_prepare_weights(const float* weight, int32_t K, int32_t
     IR_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     IR_CHECK_CUDA(cudaMemcpyAsync(out, weight, (size_t)K * cin * cout * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return IR_OK;
+}
+
+// wgrad on tcgen05 (see k_wgrad_tc); dW must be zeroed by the caller.  Shapes: Cin, Cout in {64, 128}.
+int irk_wgrad_tc(const float* x, int cin, const float* dy, int cout, int K, const int* in_idx, const int* out_idx,
+                 const int* count, long long seg_cap, const float* dy_absmax, float* dW, cudaStream_t st) {
+    IR_CHECK_ARG(K > 0 && K <= 27);
+    if (cin == 64 && cout == 64) return tc::launch_wgrad<64, 64>(x, dy, in_idx, out_idx, count, seg_cap, dy_absmax, dW, K, st);
+    if (cin == 64 && cout == 128) return tc::launch_wgrad<64, 128>(x, dy, in_idx, out_idx, count, seg_cap, dy_absmax, dW, K, st);
+    if (cin == 128 && cout == 128) return tc::launch_wgrad<128, 128>(x, dy, in_idx, out_idx, count, seg_cap, dy_absmax, dW, K, st);
+    ir_set_error("wgrad_tc: unsupported channels %d -> %d", cin, cout);
+    return IR_ERR_UNSUPPORTED;
 }

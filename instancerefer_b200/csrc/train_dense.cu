@@ -16,7 +16,8 @@
 // 64-byte coalesced stores).
 #define GM_BM 64
 #define GM_BN 64
-#define GM_BK 16
+#define GM_BK 32
+#define GM_LD (GM_BK * GM_BM / 256)     // operand elements per thread and tile (8)
 __global__ void __launch_bounds__(256)
 k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const float* __restrict__ B, int ldb,
        int tb, float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu, int accumulate) {
@@ -33,24 +34,33 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const 
     const int kper = ((K + gridDim.z - 1) / gridDim.z + GM_BK - 1) / GM_BK * GM_BK;
     const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
     const bool split = gridDim.z > 1;
-    for (int k0 = kbeg; k0 < kend; k0 += GM_BK) {
+    // These GEMMs are small and latency-bound: the next tile's global loads are issued into registers before
+    // the current tile is multiplied (software pipeline), 8 + 8 independent loads per thread in flight.
+    float ra[GM_LD], rb[GM_LD];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < GM_LD; ++q) {
             const int idx = tid + q * 256;
             int m, k;
-            if (ta) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            if (ta) { m = idx & 63; k = idx >> 6; } else { k = idx & 31; m = idx >> 5; }
             const int gm = m0 + m, gk = k0 + k;
-            float v = 0.f;
-            if (gm < M && gk < kend) v = ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
-            As[k][m] = v;
+            ra[q] = (gm < M && gk < kend) ? (ta ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk]) : 0.f;
             int n, kb;
-            if (tb) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
+            if (tb) { kb = idx & 31; n = idx >> 5; } else { n = idx & 63; kb = idx >> 6; }
             const int gn = n0 + n, gkb = k0 + kb;
-            float u = 0.f;
-            if (gn < N && gkb < kend) u = tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn];
-            Bs[kb][n] = u;
+            rb[q] = (gn < N && gkb < kend) ? (tb ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn]) : 0.f;
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += GM_BK) {
+#pragma unroll
+        for (int q = 0; q < GM_LD; ++q) {
+            const int idx = tid + q * 256;
+            if (ta) As[idx >> 6][idx & 63] = ra[q]; else As[idx & 31][idx >> 5] = ra[q];
+            if (tb) Bs[idx & 31][idx >> 5] = rb[q]; else Bs[idx >> 6][idx & 63] = rb[q];
         }
         __syncthreads();
+        if (k0 + GM_BK < kend) fetch(k0 + GM_BK);
 #pragma unroll
         for (int kk = 0; kk < GM_BK; ++kk) {
             float a[4], b[4];
@@ -91,7 +101,7 @@ extern "C" int ir_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t 
     // few output tiles and a long K (im2col conv GEMMs, weight gradients): split K over gridDim.z so the
     // launch fills the GPU; partial tiles are added with atomics into a zeroed (or accumulated-into) C
     const int tiles = grid.x * grid.y;
-    if (!relu && tiles < IR_NUM_SMS && K >= 256 && ldc == N) {
+    if (!relu && tiles < IR_NUM_SMS && K >= 128 && ldc == N) {
         int z = ir_min_i(ir_div_up(2 * IR_NUM_SMS, tiles), K / 64);
         if (z > 1) {
             grid.z = z;

@@ -154,8 +154,8 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         int rr;
         if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), nullptr, t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
                                   t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], t.absmax(), stream)) != IR_OK) return rr;
-        if ((rr = ir_spconv_wgrad(xin, li.cin, S1, li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map), t.kcount(li.map), n_max,
-                                  g->dweight[i], stream)) != IR_OK) return rr;
+        if ((rr = ir_spconv_wgrad_scaled(xin, li.cin, S1, t.absmax(), li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map),
+                                         t.kcount(li.map), n_max, (p->use_tc >> 2) & 1, g->dweight[i], stream)) != IR_OK) return rr;
         if (dx) {
             // dgrad = forward pipeline on the transposed rulebook with W^T; `add` (the skip gradient) rides in the
             // reduce epilogue's residual slot.  use_tc bit 1: tcgen05 pair-GEMM with the gathered gradient rows

@@ -9,6 +9,7 @@
 //   BN    : batch statistics over the live rows, normalise (+ residual, ReLU) and the matching backward.
 #include "../../include/instancerefer_b200.h"
 #include "common.cuh"
+#include "kernels.cuh"
 
 // ------------------------------------------------------------------ rulebook transpose
 // forward rulebook of a map: in_idx[k][pos] = input row of pair pos, slot[k][o] = pair of output row o.
@@ -223,6 +224,19 @@ extern "C" int ir_spconv_wgrad(const float* x, int32_t cin, const float* dy, int
     if (r != IR_OK) return r;
     IR_CHECK_LAUNCH();
     return IR_OK;
+}
+
+// wgrad with the tcgen05 kernel where the shape allows (Cin, Cout in {64,128}) and a range hint for dY is
+// available; otherwise the SIMT kernel above.
+extern "C" int ir_spconv_wgrad_scaled(const float* x, int32_t cin, const float* dy, const float* dy_absmax, int32_t cout,
+                                      int32_t K, const int32_t* in_idx, const int32_t* out_idx, const int32_t* count,
+                                      int64_t seg_cap, int32_t use_tc, float* dW, ir_stream_t stream) {
+    const bool tc = use_tc && dy_absmax && (cin == 64 || cin == 128) && (cout == 64 || cout == 128) && !(cin == 128 && cout == 64);
+    if (!tc) return ir_spconv_wgrad(x, cin, dy, cout, K, in_idx, out_idx, count, seg_cap, dW, stream);
+    IR_CHECK_ARG(x && dy && in_idx && out_idx && count && dW && K > 0 && K <= 27 && seg_cap > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    IR_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * cin * cout * 4, st));
+    return irk_wgrad_tc(x, cin, dy, cout, K, in_idx, out_idx, count, seg_cap, dy_absmax, dW, st);
 }
 
 // ------------------------------------------------------------------ BatchNorm, train mode, (rows, C)

@@ -287,10 +287,14 @@ def rulebook_transpose(in_idx, slot, n_out_dev, n_rows_out):
     return out_idx, slot_in
 
 
-def spconv_wgrad(x, dy, in_idx, out_idx, count):
+def spconv_wgrad(x, dy, in_idx, out_idx, count, dy_absmax=None, use_tc=False):
     K, seg_cap = in_idx.shape
     cin, cout = x.shape[1], dy.shape[1]
     dW = torch.empty(K, cin, cout, dtype=torch.float32, device=x.device)
+    if dy_absmax is not None:
+        call("ir_spconv_wgrad_scaled", _p(x, torch.float32), cin, _p(dy, torch.float32), _p(dy_absmax, torch.float32), cout, K,
+             _p(in_idx, torch.int32), _p(out_idx, torch.int32), _p(count, torch.int32), seg_cap, 1 if use_tc else 0, _p(dW), _stream())
+        return dW
     call("ir_spconv_wgrad", _p(x, torch.float32), cin, _p(dy, torch.float32), cout, K, _p(in_idx, torch.int32),
          _p(out_idx, torch.int32), _p(count, torch.int32), seg_cap, _p(dW), _stream())
     return dW

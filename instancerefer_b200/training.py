@@ -123,7 +123,9 @@ class EncoderTrain(Function):
         layers = net._layers()
         P = _lib.EncoderTrainParams()
         dgrad_tc = os.environ.get('IR_DGRAD', 'tc') != 'simt'
-        P.cin, P.use_tc, P.eps = net.input_dim, (1 | (2 if dgrad_tc else 0)) if net.use_tc else 0, layers[0][1].eps
+        wgrad_tc = os.environ.get('IR_WGRAD', 'tc') != 'simt'
+        P.cin, P.eps = net.input_dim, layers[0][1].eps
+        P.use_tc = (1 | (2 if dgrad_tc else 0) | (4 if wgrad_tc else 0)) if net.use_tc else 0
         keep = []
         for i, (conv, bn) in enumerate(layers):
             w, g, b = (t.detach().contiguous() for t in params[3 * i:3 * i + 3])

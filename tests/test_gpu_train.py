@@ -92,6 +92,12 @@ def test_spconv_dgrad_wgrad(ops, graph, kind, level, cin, cout):
     out_idx, slot_in = graph.transposed(kind, level)
     dW = ops.spconv_wgrad(x.detach().cuda(), dy.cuda(), ii, out_idx, cnt)
     assert float((dW.cpu() - w.grad).abs().max()) < 1e-4 * float(w.grad.abs().max()) + 1e-9
+    if cin >= 64:                                   # the same wgrad on tcgen05 (MN-major gathered operands, range-scaled dy)
+        for mag in (1.0, 1e-6):
+            dys = (dy * mag).cuda()
+            dW2 = ops.spconv_wgrad(x.detach().cuda(), dys, ii, out_idx, cnt, dy_absmax=dys.abs().max().reshape(1), use_tc=True)
+            err = float((dW2.cpu() - w.grad * mag).abs().max())
+            assert err < 1e-4 * float(w.grad.abs().max()) * mag, (mag, err)
     if cin >= 32:
         dx = torch.empty(n_in, cin, device='cuda')
         wt = w.detach().transpose(1, 2).contiguous().cuda()
@@ -500,7 +506,7 @@ def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, 
         model = model.cuda().train()
         dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
         os.environ['IR_TRAIN_ENCODER'] = mode
-        os.environ['IR_DGRAD'] = dgrad
+        os.environ['IR_DGRAD'] = os.environ['IR_WGRAD'] = dgrad
         try:
             if which == 'attribute':
                 pack = CandidatePack(dd, target_classes(dd, args), 'cuda')
@@ -518,7 +524,7 @@ def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, 
             (f4 * wgt).sum().backward()
             torch.cuda.synchronize()
         finally:
-            del os.environ['IR_TRAIN_ENCODER'], os.environ['IR_DGRAD']
+            del os.environ['IR_TRAIN_ENCODER'], os.environ['IR_DGRAD'], os.environ['IR_WGRAD']
         res[mode] = (f4.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()},
                      {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k})
     assert torch.equal(res['layers'][0], res['fused'][0])
