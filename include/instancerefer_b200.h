@@ -429,6 +429,23 @@ int ir_edge_max_fwd(const float* msg, const int32_t* nbr, int32_t nq, int32_t k,
 int ir_edge_max_bwd(const float* dout, const int32_t* arg, int32_t nq, int32_t k, int32_t C, float* dmsg,
                     ir_stream_t stream);
 
+/* Fused two-layer head of the matching modules in train mode: Linear(K->N1) -> {norm 1: BatchNorm1d with batch
+ * statistics | norm 2: LayerNorm} -> ReLU [-> Dropout(drop_p, seed)] -> Linear(N1->N2), ONE call per direction
+ * (models/attribute_module.py:22-32, relation_module.py:13-25, scene_module.py:40-58).  Weights in nn.Linear
+ * layout: w1 (N1,K), w2 (N2,N1).  The arena keeps the intermediates for the backward. */
+typedef struct {
+    int32_t M, K, N1, N2, norm;
+    float eps, momentum, drop_p;
+    uint64_t seed;
+    const float *w1, *b1, *gamma, *beta, *w2, *b2;
+    float *running_mean, *running_var;          /* BatchNorm only (updated in place) */
+} ir_mlp_head_t;
+int64_t ir_mlp_head_arena_bytes(int32_t M, int32_t N1);
+int ir_mlp_head_train_fwd(const ir_mlp_head_t* h, const float* x, void* arena, float* y, ir_stream_t stream);
+int ir_mlp_head_train_bwd(const ir_mlp_head_t* h, const float* x, void* arena, const float* dy, float* dx,
+                          float* dw1, float* db1, float* dgamma, float* dbeta, float* dw2, float* db2,
+                          ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

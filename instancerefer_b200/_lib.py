@@ -51,6 +51,13 @@ class EncoderTrainLayout(C.Structure):
                 ("off_absmax", i64)]
 
 
+class MlpHead(C.Structure):
+    _fields_ = [("M", i32), ("K", i32), ("N1", i32), ("N2", i32), ("norm", i32),
+                ("eps", f32), ("momentum", f32), ("drop_p", f32), ("seed", C.c_uint64),
+                ("w1", p), ("b1", p), ("gamma", p), ("beta", p), ("w2", p), ("b2", p),
+                ("running_mean", p), ("running_var", p)]
+
+
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
 SIGNATURES = {
     "ir_version": (i32, []),
@@ -121,6 +128,9 @@ SIGNATURES = {
     "ir_edge_inputs": (i32, [p, p, p, p, i32, i32, i32, i32, p, p, p, p]),
     "ir_edge_max_fwd": (i32, [p, p, i32, i32, i32, p, p, p]),
     "ir_edge_max_bwd": (i32, [p, p, i32, i32, i32, p, p]),
+    "ir_mlp_head_arena_bytes": (i64, [i32, i32]),
+    "ir_mlp_head_train_fwd": (i32, [C.POINTER(MlpHead), p, p, p, p]),
+    "ir_mlp_head_train_bwd": (i32, [C.POINTER(MlpHead), p, p, p, p, p, p, p, p, p, p, p]),
 }
 
 _lib = None

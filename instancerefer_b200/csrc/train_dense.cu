@@ -820,3 +820,81 @@ extern "C" int ir_edge_max_bwd(const float* dout, const int32_t* arg, int32_t nq
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ fused two-layer head (one call per direction)
+// Linear -> {BatchNorm1d (batch statistics) | LayerNorm} -> ReLU [-> Dropout] -> Linear: the nn.Sequential heads of
+// models/{attribute,relation,scene}_module.py as ONE library call forward and ONE backward (the host issues 2 calls
+// per head and step instead of ~14).  Arena (caller-owned, ir_mlp_head_arena_bytes):
+//   h1 (M,N1) pre-norm | h2 (M,N1) normalised + ReLU | h3 (M,N1) after dropout | stats 2*max(M,N1) | mask (M,N1) u8 |
+//   BN partial-sum scratch | backward temporaries 2 x (M,N1).
+extern "C" int ir_bn_train_fwd(const float*, const int32_t*, int32_t, int32_t, const float*, const float*, const float*, int32_t,
+                               float, float, float*, float*, float*, float*, float*, float*, ir_stream_t);
+extern "C" int ir_bn_train_bwd(const float*, const float*, const float*, const int32_t*, int32_t, int32_t, const float*,
+                               const float*, const float*, int32_t, float*, float*, float*, float*, float*, float*, ir_stream_t);
+extern "C" int64_t ir_bn_scratch_floats(int32_t);
+
+struct HeadArena {
+    float *h1, *h2, *h3, *stat_a, *stat_b, *bn_scratch, *t1, *t2;
+    uint8_t* mask;
+    int64_t bytes;
+};
+static HeadArena head_arena(void* base, int64_t M, int64_t N1) {
+    HeadArena a;
+    char* p = (char*)base;
+    auto take = [&](int64_t bytes) { char* o = p; p += (bytes + 255) / 256 * 256; return o; };
+    const int64_t mn = M * N1 * 4, st = (M > N1 ? M : N1) * 4;
+    a.h1 = (float*)take(mn); a.h2 = (float*)take(mn); a.h3 = (float*)take(mn);
+    a.stat_a = (float*)take(st); a.stat_b = (float*)take(st);
+    a.mask = (uint8_t*)take(M * N1);
+    a.bn_scratch = (float*)take(ir_bn_scratch_floats(256) * 4);
+    a.t1 = (float*)take(mn); a.t2 = (float*)take(mn);
+    a.bytes = p - (char*)base;
+    return a;
+}
+extern "C" int64_t ir_mlp_head_arena_bytes(int32_t M, int32_t N1) { return head_arena(nullptr, M, N1).bytes; }
+
+extern "C" int ir_mlp_head_train_fwd(const ir_mlp_head_t* h, const float* x, void* arena, float* y, ir_stream_t stream) {
+    IR_CHECK_ARG(h && x && arena && y && h->M > 0 && h->K > 0 && h->N1 > 0 && h->N2 > 0 && (h->norm == 1 || h->norm == 2));
+    const HeadArena a = head_arena(arena, h->M, h->N1);
+    int r;
+    if ((r = ir_gemm(h->M, h->N1, h->K, x, h->K, 0, h->w1, h->K, 1, a.h1, h->N1, h->b1, 0, 0, stream)) != IR_OK) return r;
+    if (h->norm == 1) r = ir_bn_train_fwd(a.h1, nullptr, h->M, h->N1, h->gamma, h->beta, nullptr, 1, h->eps, h->momentum,
+                                          h->running_mean, h->running_var, a.bn_scratch, a.stat_a, a.stat_b, a.h2, stream);
+    else r = ir_layernorm_fwd(a.h1, h->M, h->N1, h->gamma, h->beta, h->eps, 1, a.h2, a.stat_a, a.stat_b, stream);
+    if (r != IR_OK) return r;
+    const float* h3 = a.h2;
+    if (h->drop_p > 0.f) {
+        if ((r = ir_dropout_fwd(a.h2, (int64_t)h->M * h->N1, h->drop_p, h->seed, a.h3, a.mask, stream)) != IR_OK) return r;
+        h3 = a.h3;
+    }
+    return ir_gemm(h->M, h->N2, h->N1, h3, h->N1, 0, h->w2, h->N1, 1, y, h->N2, h->b2, 0, 0, stream);
+}
+
+extern "C" int ir_mlp_head_train_bwd(const ir_mlp_head_t* h, const float* x, void* arena, const float* dy, float* dx,
+                                     float* dw1, float* db1, float* dgamma, float* dbeta, float* dw2, float* db2,
+                                     ir_stream_t stream) {
+    IR_CHECK_ARG(h && x && arena && dy && dw1 && db1 && dgamma && dbeta && dw2 && db2);
+    const HeadArena a = head_arena(arena, h->M, h->N1);
+    const float* h3 = h->drop_p > 0.f ? a.h3 : a.h2;
+    int r;
+    // second Linear: dW2 = dy^T h3, db2 = colsum(dy), dh3 = dy W2
+    if ((r = ir_gemm(h->N2, h->N1, h->M, dy, h->N2, 1, h3, h->N1, 0, dw2, h->N1, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(dy, h->M, h->N2, db2, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(h->M, h->N1, h->N2, dy, h->N2, 0, h->w2, h->N1, 0, a.t1, h->N1, nullptr, 0, 0, stream)) != IR_OK) return r;
+    const float* dh2 = a.t1;
+    if (h->drop_p > 0.f) {
+        if ((r = ir_dropout_bwd(a.t1, a.mask, (int64_t)h->M * h->N1, h->drop_p, a.t2, stream)) != IR_OK) return r;
+        dh2 = a.t2;
+    }
+    // norm + ReLU backward -> dh1 (into the buffer dh2 does not occupy)
+    float* dh1 = (dh2 == a.t1) ? a.t2 : a.t1;
+    if (h->norm == 1) r = ir_bn_train_bwd(dh2, a.h2, a.h1, nullptr, h->M, h->N1, a.stat_a, a.stat_b, h->gamma, 1, a.bn_scratch,
+                                          dh1, nullptr, dgamma, dbeta, nullptr, stream);
+    else r = ir_layernorm_bwd(dh2, a.h2, a.h1, h->M, h->N1, h->gamma, a.stat_a, a.stat_b, 1, dh1, dgamma, dbeta, stream);
+    if (r != IR_OK) return r;
+    // first Linear
+    if ((r = ir_gemm(h->N1, h->K, h->M, dh1, h->N1, 1, x, h->K, 0, dw1, h->K, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(dh1, h->M, h->N1, db1, stream)) != IR_OK) return r;
+    if (dx) return ir_gemm(h->M, h->K, h->N1, dh1, h->N1, 0, h->w1, h->K, 0, dx, h->K, nullptr, 0, 0, stream);
+    return IR_OK;
+}

@@ -450,11 +450,68 @@ class EdgeMax(Function):
         return ops.edge_max_bwd(dout.contiguous(), arg, ctx.k), None
 
 
+class MLPHead(Function):
+    """Linear -> {BatchNorm1d | LayerNorm} -> ReLU [-> Dropout] -> Linear of the reference's nn.Sequential heads
+    as ONE library call per direction (ir_mlp_head_train_fwd / _bwd); intermediates stay in an arena owned by this
+    node of the autograd graph."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, g, beta, w2, b2, nm, drop_p):
+        import ctypes as C
+        from . import _lib
+        x = x.contiguous()
+        M, K = x.shape
+        N1, N2 = w1.shape[0], w2.shape[0]
+        H = _lib.MlpHead()
+        H.M, H.K, H.N1, H.N2 = M, K, N1, N2
+        H.norm = 2 if isinstance(nm, torch.nn.LayerNorm) else 1
+        H.eps, H.drop_p = nm.eps, float(drop_p)
+        keep = [t.detach().contiguous() for t in (w1, b1, g, beta, w2, b2)]
+        H.w1, H.b1, H.gamma, H.beta, H.w2, H.b2 = (t.data_ptr() for t in keep)
+        if H.norm == 1:
+            H.momentum = nm.momentum if nm.momentum is not None else 0.1
+            H.running_mean, H.running_var = nm.running_mean.data_ptr(), nm.running_var.data_ptr()
+        if drop_p > 0:
+            _dropout_calls[0] += 1
+            H.seed = (torch.initial_seed() * 0x9E3779B1 + _dropout_calls[0] * 0x85EBCA6B) & (2 ** 63 - 1)
+        arena = torch.empty(_lib.load().ir_mlp_head_arena_bytes(M, N1), dtype=torch.uint8, device=x.device)
+        y = torch.empty(M, N2, dtype=torch.float32, device=x.device)
+        _lib.call("ir_mlp_head_train_fwd", C.byref(H), ops._p(x), ops._p(arena), ops._p(y), ops._stream())
+        if H.norm == 1:
+            nm.num_batches_tracked += 1
+        ctx.state = (H, keep, arena, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes as C
+        from . import _lib
+        H, keep, arena, x = ctx.state
+        dev = x.device
+        M, K, N1, N2 = H.M, H.K, H.N1, H.N2
+        sizes = [N1 * K, N1, N1, N1, N2 * N1, N2]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 63) // 64 * 64
+        flat = torch.empty(o, dtype=torch.float32, device=dev)
+        dw1, db1, dg, dbeta, dw2, db2 = (flat[a:a + n] for a, n in zip(offs, sizes))
+        dx = torch.empty(M, K, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        _lib.call("ir_mlp_head_train_bwd", C.byref(H), ops._p(x), ops._p(arena), ops._p(dy.contiguous(), torch.float32), ops._p(dx),
+                  ops._p(dw1), ops._p(db1), ops._p(dg), ops._p(dbeta), ops._p(dw2), ops._p(db2), ops._stream())
+        return dx, dw1.view(N1, K), db1, dg, dbeta, dw2.view(N2, N1), db2, None, None
+
+
 def mlp_head(seq, x, norm_idx, last_idx, drop_idx=None):
     """Linear -> {BatchNorm1d | LayerNorm} -> ReLU [-> Dropout] -> Linear of the reference's
-    nn.Sequential heads (e.g. models/relation_module.py:13-25), every stage a CUDA-library kernel."""
-    h = Linear.apply(x, seq[0].weight, seq[0].bias, False)
+    nn.Sequential heads (e.g. models/relation_module.py:13-25).  IR_TRAIN_HEADS=ops runs it as separate
+    autograd nodes (Linear / norm / Dropout / Linear: what the per-op tests cover)."""
+    import os
     nm = seq[norm_idx]
+    if os.environ.get('IR_TRAIN_HEADS', 'fused') != 'ops':
+        p = float(seq[drop_idx].p) if drop_idx is not None else 0.0
+        return MLPHead.apply(x, seq[0].weight, seq[0].bias, nm.weight, nm.bias, seq[last_idx].weight, seq[last_idx].bias, nm, p)
+    h = Linear.apply(x, seq[0].weight, seq[0].bias, False)
     if isinstance(nm, torch.nn.LayerNorm):
         h = LayerNormAct.apply(h, nm.weight, nm.bias, nm.eps, True)
     else:

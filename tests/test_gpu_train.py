@@ -308,6 +308,33 @@ def test_batchnorm_fn(ops):
     assert float((bn_g.running_var.cpu() - bn_r.running_var).abs().max()) < 1e-5 and int(bn_g.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize('norm,M,K,N1,N2', [('bn', 5, 256, 256, 256), ('ln', 37, 128, 128, 128), ('bn', 2, 128, 128, 9), ('ln', 700, 128, 256, 256)])
+def test_fused_mlp_head(ops, norm, M, K, N1, N2):
+    """ir_mlp_head_train_fwd/_bwd (one call per direction) against torch's Linear-norm-ReLU-Linear."""
+    from instancerefer_b200.training import MLPHead
+    Fn = torch.nn.functional
+    nm_g = (torch.nn.BatchNorm1d(N1) if norm == 'bn' else torch.nn.LayerNorm(N1)).cuda().train()
+    rm, rv = torch.zeros(N1), torch.ones(N1)
+
+    def ref(x, w1, b1, g, be, w2, b2):
+        h = Fn.linear(x, w1, b1)
+        h = Fn.batch_norm(h, rm, rv, g, be, True, 0.1, 1e-5) if norm == 'bn' else Fn.layer_norm(h, (N1,), g, be, 1e-5)
+        return Fn.linear(torch.relu(h), w2, b2)
+    _check(lambda x, w1, b1, g, be, w2, b2: MLPHead.apply(x, w1, b1, g, be, w2, b2, nm_g, 0.0), ref,
+           [R(M, K), R(N1, K, scale=K ** -0.5), R(N1, scale=0.1), R(N1) * 0.2 + 1, R(N1, seed=3) * 0.1,
+            R(N2, N1, scale=N1 ** -0.5), R(N2, scale=0.1)], tol=2e-4, nondiff=(2,) if norm == 'bn' else ())
+    if norm == 'bn':
+        assert float((nm_g.running_var.cpu() - rv).abs().max()) < 1e-5 and int(nm_g.num_batches_tracked) == 1
+    # dropout inside the fused head: the kept fraction and the mask reuse in backward
+    x = torch.randn(64, K, device='cuda', requires_grad=True)
+    w1, w2 = torch.randn(N1, K, device='cuda') * K ** -0.5, torch.eye(N1, device='cuda')[:min(N1, N2)]
+    if N2 == N1:
+        y = MLPHead.apply(x, w1, torch.zeros(N1, device='cuda'), torch.ones(N1, device='cuda'), torch.ones(N1, device='cuda'),
+                          w2, torch.zeros(N1, device='cuda'), nm_g, 0.15)
+        frac = float((y == 0).float().mean())            # beta = 1 keeps most activations positive: zeros are drops
+        assert 0.10 < frac < 0.30, frac
+
+
 def test_dropout_fn(ops):
     from instancerefer_b200.training import Dropout
     x = torch.randn(200, 128, device='cuda', requires_grad=True)
