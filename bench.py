@@ -370,7 +370,7 @@ def main():
         ap.add_argument('--workload')
         ap.add_argument('--gpus', type=int, default=1)
         ap.add_argument('--steps', type=int, default=20)
-        ap.add_argument('--warmup', type=int, default=3)
+        ap.add_argument('--warmup', type=int, default=10)      # each of the 4 cycled batches once eagerly, once capturing its CUDA graphs
         ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
         ap.add_argument('--no-cpu-baseline', action='store_true')
         return main_train(ap.parse_args())
@@ -574,8 +574,7 @@ def main():
             torch.cuda.synchronize()
             _lib.call('ir_profile_read', gm, rm, meta, cap, ctypes.byref(nout))
             # pair counts of this step's rulebooks (attribute encoder first, scene encoder second)
-            kc = [model.attribute.net._ws[next(iter(model.attribute.net._ws))].kcount().cpu().numpy(),
-                  model.scene.net._ws[next(iter(model.scene.net._ws))].kcount().cpu().numpy()]
+            kc = [model.attribute.net._last_ws.kcount().cpu().numpy(), model.scene.net._last_ws.kcount().cpu().numpy()]
             maps = [0, 5, 1, 1, 6, 2, 2, 7, 3, 3, 8, 4, 4]                  # layer -> kernel map id
             for j in range(nout.value):
                 enc, layer = divmod(j, 13)

@@ -318,7 +318,9 @@ int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
  * All 13 [conv -> train-mode BN (-> + skip) -> ReLU] layers forward, and their backward, as one chain
  * of launches each.  Activations (pre-BN y, post-activation out, batch mean / rstd per layer), the
  * transposed rulebooks and gradient scratch live in a caller-owned arena.  n_lvl = HOST row counts of
- * the five levels (read back once from the workspace after ir_encoder_build_maps).               */
+ * the five levels (read back once from the workspace after ir_encoder_build_maps), or NULL: every buffer
+ * is laid out for the capacity n_max and every kernel reads its row count on the device, so the launch
+ * sequence does not depend on the input and can be captured ONCE per capacity into a CUDA graph.   */
 typedef struct {
     int32_t cin, use_tc;                      /* bit 0: forward pair-GEMM on tcgen05 (weights 16-B aligned);
                                                  bit 1: dgrad on tcgen05 (range-scaled, ir_spconv_layer_scaled);

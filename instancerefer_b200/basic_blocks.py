@@ -130,11 +130,17 @@ class SparseConvEncoder(nn.Module, PrepCache):
         return dict(params=params, keep=keep)
 
     def workspace(self, n_rows, device):
+        """Smallest cached workspace whose capacity covers ``n_rows`` (grown, never shrunk or freed: captured CUDA
+        graphs — inference replay, training passes — hold pointers into it, and a stable capacity keeps them valid
+        from batch to batch)."""
         n_max = ops.round_rows(n_rows)
-        key = (n_max, str(device))
-        if key not in self._ws:
-            self._ws = {key: ops.EncoderWorkspace(n_max, device)}      # keep only the latest bucket
-        return self._ws[key]
+        dev = str(device)
+        fit = [k for k in self._ws if k[1] == dev and k[0] >= n_max]
+        if not fit:
+            self._ws[(n_max, dev)] = ops.EncoderWorkspace(n_max, device)
+            fit = [(n_max, dev)]
+        self.__dict__['_last_ws'] = self._ws[min(fit)]
+        return self._last_ws
 
     def encode(self, ws, feats0=None, coords0=None, n0_dev=None):
         """Run maps + 13 layers.  Level 0 either comes from ``ops.voxelize`` (already in ``ws``) or

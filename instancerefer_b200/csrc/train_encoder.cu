@@ -23,9 +23,12 @@ static LayerInfo layer_info(int idx, int cin0) {
 
 static inline int64_t al(int64_t x) { return (x + 255) / 256 * 256; }
 
-extern "C" int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int32_t cin, ir_encoder_train_layout_t* L) {
-    IR_CHECK_ARG(n_max > 0 && n_lvl && L && cin >= 1 && cin <= 128);
+extern "C" int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl_in, int32_t cin, ir_encoder_train_layout_t* L) {
+    IR_CHECK_ARG(n_max > 0 && L && cin >= 1 && cin <= 128);
     memset(L, 0, sizeof(*L));
+    int32_t bound[5];
+    for (int l = 0; l < 5; ++l) bound[l] = n_lvl_in ? n_lvl_in[l] : (int32_t)n_max;     // NULL: shape-independent (capacity) layout
+    const int32_t* n_lvl = bound;
     int64_t off = 0, rows_max = 1;
     auto take = [&](int64_t bytes) { int64_t o = off; off = al(off + bytes); return o; };
     for (int l = 0; l < 5; ++l) { IR_CHECK_ARG(n_lvl[l] >= 0 && n_lvl[l] <= n_max); if (n_lvl[l] > rows_max) rows_max = n_lvl[l]; }
@@ -69,8 +72,10 @@ struct Tr {
     ir_encoder_train_layout_t A;    // arena
     char *ws, *ar;
     int64_t n_max;
-    const int32_t* n;
+    int32_t n[5];                   // host row counts, or the capacity n_max when the caller gave none
+    bool bounded;                   // true: row counts are read on the device (launch sequence independent of the input)
     const int* nlvl_dev() const { return (const int*)(ws + W.off_nlvl); }
+    const int* ndev(int l) const { return bounded ? nlvl_dev() + l : nullptr; }
     const int* kcount(int map) const { return (const int*)(ws + W.off_kcount) + map * 32; }
     const int* in_idx(int map) const { return (const int*)(ws + (map < 5 ? W.off_k3_in[map] : W.off_k2_in[map - 5])); }
     const int* slot(int map) const { return (const int*)(ws + (map < 5 ? W.off_k3_slot[map] : W.off_k2_slot[map - 5])); }
@@ -92,12 +97,15 @@ struct Tr {
 };
 
 static int tr_open(const ir_encoder_train_params* p, void* ws, int64_t n_max, const int32_t* n_lvl, void* arena, Tr* t) {
-    IR_CHECK_ARG(p && ws && arena && n_lvl);
+    IR_CHECK_ARG(p && ws && arena);
     int r;
     if ((r = ir_encoder_layout(n_max, &t->W)) != IR_OK) return r;
     if ((r = ir_encoder_train_layout(n_max, n_lvl, p->cin, &t->A)) != IR_OK) return r;
-    t->ws = (char*)ws; t->ar = (char*)arena; t->n_max = n_max; t->n = n_lvl;
-    for (int l = 0; l < 5; ++l) IR_CHECK_ARG(n_lvl[l] > 0);
+    t->ws = (char*)ws; t->ar = (char*)arena; t->n_max = n_max; t->bounded = (n_lvl == nullptr);
+    for (int l = 0; l < 5; ++l) {
+        t->n[l] = n_lvl ? n_lvl[l] : (int32_t)n_max;
+        IR_CHECK_ARG(t->n[l] > 0);
+    }
     return IR_OK;
 }
 
@@ -114,7 +122,7 @@ extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const 
         if ((r = ir_spconv_layer(fin, li.cin, li.cout, li.K, t.in_idx(li.map), n_max, t.slot(li.map), t.kcount(li.map),
                                  t.nlvl_dev() + li.lout, t.n[li.lout], p->weight[i], tc ? p->weight[i] : nullptr, tc,
                                  nullptr, nullptr, nullptr, 0, t.T(), t.y(i), stream)) != IR_OK) return r;
-        if ((r = ir_bn_train_fwd(t.y(i), nullptr, t.n[li.lout], li.cout, p->gamma[i], p->beta[i],
+        if ((r = ir_bn_train_fwd(t.y(i), t.ndev(li.lout), t.n[li.lout], li.cout, p->gamma[i], p->beta[i],
                                  li.resid_from >= 0 ? t.out(li.resid_from) : nullptr, 1, p->eps, p->momentum[i],
                                  p->running_mean[i], p->running_var[i], t.bn_scratch(), t.mean(i), t.rstd(i), t.out(i),
                                  stream)) != IR_OK) return r;
@@ -152,7 +160,7 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         const LayerInfo li = layer_info(i, p->cin);
         const float* xin = (i == 0) ? f0 : t.out(i - 1);
         int rr;
-        if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), nullptr, t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
+        if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), t.ndev(li.lout), t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
                                   t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], t.absmax(), stream)) != IR_OK) return rr;
         if ((rr = ir_spconv_wgrad_scaled(xin, li.cin, S1, t.absmax(), li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map),
                                          t.kcount(li.map), n_max, (p->use_tc >> 2) & 1, g->dweight[i], stream)) != IR_OK) return rr;

@@ -164,20 +164,142 @@ class EncoderTrain(Function):
         return (None, None, None, *grads)
 
 
+class _EncoderGraphState:
+    """Static buffers + captured CUDA graphs of one encoder at one workspace capacity (n_max bucket)."""
+
+
+class EncoderTrainGraphed(Function):
+    """EncoderTrain with the ~65 forward / ~150 backward launches of an encoder replayed from two CUDA graphs.
+    The library calls run in capacity mode (n_lvl = NULL: buffers laid out for n_max rows, row counts read on
+    the device), so the launch sequence depends only on the workspace capacity and the graphs are captured once
+    per (encoder, n_max bucket) and reused for every batch that fits the bucket.  Inputs that live at changing
+    addresses (scene features, the upstream gradient) are copied into static buffers first; parameter gradients
+    are returned as views of a static buffer that the next backward of this encoder overwrites."""
+
+    @staticmethod
+    def _state(net, G, params, f0_cols):
+        import ctypes as C
+        import os
+        from . import _lib
+        ws = G.ws
+        layers = net._layers()
+        moms = tuple(float(bn.momentum if bn.momentum is not None else 0.1) for _, bn in layers)
+        dgrad_tc = os.environ.get('IR_DGRAD', 'tc') != 'simt'
+        wgrad_tc = os.environ.get('IR_WGRAD', 'tc') != 'simt'
+        use_tc = (1 | (2 if dgrad_tc else 0) | (4 if wgrad_tc else 0)) if net.use_tc else 0
+        key = (ws.n_max, ws.buf.data_ptr(), f0_cols, moms, use_tc, tuple(t.data_ptr() for t in params))
+        cache = net.__dict__.setdefault('_train_graphs', {})
+        st = cache.get(key)
+        if st is not None:
+            return st
+        if len(cache) >= 4:
+            cache.clear()
+        dev = ws.buf.device
+        st = _EncoderGraphState()
+        P = _lib.EncoderTrainParams()
+        P.cin, P.use_tc, P.eps = net.input_dim, use_tc, layers[0][1].eps
+        for i, (conv, bn) in enumerate(layers):
+            w, g, b = params[3 * i:3 * i + 3]
+            assert w.is_contiguous() and g.is_contiguous() and b.is_contiguous()
+            P.weight[i], P.gamma[i], P.beta[i] = w.data_ptr(), g.data_ptr(), b.data_ptr()
+            P.running_mean[i], P.running_var[i] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            P.momentum[i] = moms[i]
+        lay = _lib.EncoderTrainLayout()
+        _lib.call("ir_encoder_train_layout", ws.n_max, None, net.input_dim, C.byref(lay))
+        st.P, st.lay = P, lay
+        st.arena = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+        st.f0 = torch.zeros(ws.n_max, f0_cols, dtype=torch.float32, device=dev) if f0_cols else None
+        st.dout = torch.zeros(ws.n_max, 128, dtype=torch.float32, device=dev)
+        shapes = [tuple(t.shape) for t in params]
+        sizes = [(int(torch.Size(sh).numel()) + 63) // 64 * 64 for sh in shapes]
+        st.gflat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        st.gslices, o = [], 0
+        for sh, sz in zip(shapes, sizes):
+            st.gslices.append((o, int(torch.Size(sh).numel()), sh))
+            o += sz
+        Gr = _lib.EncoderTrainGrads()
+        base = st.gflat.data_ptr()
+        for i in range(13):
+            Gr.dweight[i], Gr.dgamma[i], Gr.dbeta[i] = (base + 4 * st.gslices[3 * i + q][0] for q in range(3))
+        st.Gr = Gr
+        st.fwd_graph = st.bwd_graph = None
+        st.fwd_runs = st.bwd_runs = 0
+        o4 = lay.off_out[12]
+        st.f4 = st.arena[o4:o4 + ws.n_max * 128 * 4].view(torch.float32).view(ws.n_max, 128)
+        cache[key] = st
+        return st
+
+    @staticmethod
+    def _run(st, which, ws):
+        """First call eager (also initialises one-time kernel attributes), second call captures, then replay."""
+        import ctypes as C
+        from . import _lib
+
+        def launch():
+            f0 = ops._p(st.f0)
+            if which == 'fwd':
+                _lib.call("ir_encoder_train_forward", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena), ops._stream())
+            else:
+                _lib.call("ir_encoder_train_backward", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena),
+                          ops._p(st.dout), C.byref(st.Gr), ops._stream())
+        runs = st.fwd_runs if which == 'fwd' else st.bwd_runs
+        graph = st.fwd_graph if which == 'fwd' else st.bwd_graph
+        if graph is not None:
+            graph.replay()
+        elif runs == 0:
+            launch()
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                launch()
+            g.replay()
+            if which == 'fwd':
+                st.fwd_graph = g
+            else:
+                st.bwd_graph = g
+        if which == 'fwd':
+            st.fwd_runs += 1
+        else:
+            st.bwd_runs += 1
+
+    @staticmethod
+    def forward(ctx, feats0, net, G, *params):
+        ws = G.ws
+        st = EncoderTrainGraphed._state(net, G, params, feats0.shape[1] if feats0 is not None else 0)
+        if feats0 is not None:
+            st.f0[:feats0.shape[0]].copy_(feats0)
+        EncoderTrainGraphed._run(st, 'fwd', ws)
+        torch._foreach_add_([bn.num_batches_tracked for _, bn in net._layers()], 1)
+        ctx.st, ctx.ws, ctx.n4 = st, ws, G.n[4]
+        return st.f4[:G.n[4]]
+
+    @staticmethod
+    def backward(ctx, dout):
+        st = ctx.st
+        st.dout[:ctx.n4].copy_(dout)
+        EncoderTrainGraphed._run(st, 'bwd', ctx.ws)
+        # fresh view objects of the static gradient buffer: autograd adopts them as .grad without a copy kernel
+        return (None, None, None, *(st.gflat[o:o + n].view(sh) for o, n, sh in st.gslices))
+
+
 def encoder_forward_train(net, ws, feats0=None, coords0=None, G=None):
     """Train-mode pass of a SparseConvEncoder / BEVEncoder over a workspace whose level 0 is
     already voxelised (feats0 None) or given by (feats0, coords0).  ``G``: maps already built and
     row counts already read back (the model forward builds both encoders' maps first and reads
     their counts with ONE D2H copy).
-    -> (F4 (n4,128) with autograd history, EncoderGraph).  IR_TRAIN_ENCODER=layers selects the
-    per-layer autograd path (13 SparseConvBN nodes; what the unit tests dissect)."""
+    -> (F4 (n4,128) with autograd history, EncoderGraph).  IR_TRAIN_ENCODER = graph (default: one-call passes
+    replayed from CUDA graphs) | fused (one-call passes, launched eagerly) | layers (13 SparseConvBN autograd
+    nodes; what the unit tests dissect)."""
     import os
     if G is None:
         ops.encoder_build_maps(ws, coords0)
         G = EncoderGraph(ws)
     layers = net._layers()
-    if os.environ.get('IR_TRAIN_ENCODER', 'fused') != 'layers':
+    mode = os.environ.get('IR_TRAIN_ENCODER', 'graph')
+    if mode != 'layers':
         flat = [t for conv, bn in layers for t in (conv.kernel, bn.weight, bn.bias)]
+        if mode == 'graph' and all(t.is_contiguous() for t in flat):
+            return EncoderTrainGraphed.apply(feats0, net, G, *flat), G
         return EncoderTrain.apply(feats0, net, G, *flat), G
     if feats0 is None:
         feats0 = ws.feat0(net.input_dim)[:G.n[0]].clone()

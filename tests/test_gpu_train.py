@@ -519,18 +519,25 @@ def test_encoder_train_matches_torch_replica(ops, lib_built, state_dict, args):
         assert max(errs) < 1e-4, (i, errs)
 
 
-@pytest.mark.parametrize('which,dgrad', [('attribute', 'simt'), ('scene', 'simt'), ('attribute', 'tc'), ('scene', 'tc')])
-def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, which, dgrad):
-    """ir_encoder_train_forward/backward (one call per direction) == the 13 per-layer autograd nodes."""
+@pytest.mark.parametrize('which,dgrad,fmode', [('attribute', 'simt', 'fused'), ('scene', 'simt', 'fused'), ('attribute', 'tc', 'fused'),
+                                               ('scene', 'tc', 'fused'), ('attribute', 'tc', 'graph'), ('scene', 'tc', 'graph')])
+def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, which, dgrad, fmode):
+    """ir_encoder_train_forward/backward (one call per direction; launched eagerly or replayed from CUDA graphs
+    in capacity mode) == the 13 per-layer autograd nodes.  The graph mode runs three iterations (eager, capture,
+    replay) on different inputs and compares the last."""
     from instancerefer_b200 import SparseTensor, training as T
     from instancerefer_b200.candidates import CandidatePack, target_classes
     from instancerefer_b200.instancerefer import InstanceRefer
-    b = synthetic.make_batch(17, batch_size=2, num_points=9000, n_inst=10, n_cand=[4, 3], n_tokens=[5, 6])
     res = {}
-    for mode in ('layers', 'fused'):
-        model = InstanceRefer(7, args)
-        model.load_state_dict(state_dict, strict=True)
-        model = model.cuda().train()
+    for mode, seed in (('layers', 17), (fmode, 15), (fmode, 16), (fmode, 17)) if fmode == 'graph' else (('layers', 17), (fmode, 17)):
+        b = synthetic.make_batch(seed, batch_size=2, num_points=9000, n_inst=10, n_cand=[4, 3], n_tokens=[5, 6])
+        if mode == 'layers' or seed != 16 and seed != 17 or fmode != 'graph':
+            model = InstanceRefer(7, args)
+            model.load_state_dict(state_dict, strict=True)
+            model = model.cuda().train()
+        else:                                   # graph mode, later iterations: same model object (cached graphs), fresh weights / stats
+            model.load_state_dict(state_dict, strict=True)
+            model.zero_grad()
         dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
         os.environ['IR_TRAIN_ENCODER'] = mode
         os.environ['IR_DGRAD'] = os.environ['IR_WGRAD'] = dgrad
@@ -554,13 +561,14 @@ def test_fused_encoder_matches_per_layer_path(ops, lib_built, state_dict, args, 
             del os.environ['IR_TRAIN_ENCODER'], os.environ['IR_DGRAD'], os.environ['IR_WGRAD']
         res[mode] = (f4.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()},
                      {k: v.clone() for k, v in net.state_dict().items() if 'running' in k or 'tracked' in k})
-    assert torch.equal(res['layers'][0], res['fused'][0])
+    # capacity mode partitions the BatchNorm reductions differently: same sums, different fp32 order
+    assert torch.equal(res['layers'][0], res[fmode][0]) if fmode != 'graph' else float((res['layers'][0] - res[fmode][0]).abs().max()) < 1e-4
     for k, g in res['layers'][1].items():
-        e = float((g - res['fused'][1][k]).abs().max())
+        e = float((g - res[fmode][1][k]).abs().max())
         # wgrad sums with float atomics; the tcgen05 dgrad carries ~2^-22 of each layer's largest gradient
         assert e <= (1e-5 if dgrad == 'simt' else 3e-4) * float(g.abs().max()) + 1e-9, (k, e)
     for k, v in res['layers'][2].items():
-        assert torch.equal(v, res['fused'][2][k]), k
+        assert torch.equal(v, res[fmode][2][k]) if fmode != 'graph' else float((v.float() - res[fmode][2][k].float()).abs().max()) < 1e-5, k
 
 
 # ----------------------------------------------------------------------------- whole iteration
