@@ -559,6 +559,7 @@ k_wgrad_tc(const float* __restrict__ X, const float* __restrict__ dY, const int*
     const int k = blockIdx.y;
     const int cnt = count[k];
     int chunk = (cnt + (int)gridDim.x - 1) / (int)gridDim.x;
+    chunk = max(chunk, 8 * TILE_M);                                     // small offsets: fewer CTAs, fewer redundant tile adds
     chunk = (chunk + TILE_M - 1) / TILE_M * TILE_M;                     // whole stages per CTA
     const int p_begin = blockIdx.x * chunk, p_end = min(cnt, p_begin + chunk);
     const int n_items = p_end > p_begin ? (p_end - p_begin + TILE_M - 1) / TILE_M : 0;
