@@ -102,5 +102,9 @@ class AttributeModule(nn.Module, PrepCache):
 
     def forward(self, data_dict):
         ops.check_device()
+        if self.training:
+            from . import training
+            pack = get_pack(data_dict, self.args, data_dict['lang_attr_feats'].device, rebuild=True)
+            return training.attribute_forward_train(self, data_dict, pack)
         data_dict = self.encode_candidates(data_dict, data_dict['lang_attr_feats'].device)
         return self.match(data_dict)

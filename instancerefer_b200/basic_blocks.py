@@ -4,7 +4,8 @@
 The ``nn.Module`` tree only *holds parameters* in the reference's layout (so checkpoints load
 strict); the arithmetic is done by ``SparseConvEncoder.encode`` / ``DynamicEdgeConv.forward`` /
 ``ToDenseBEVConvolution`` via instancerefer_b200.ops (hash build -> kernel maps -> pair-GEMM ->
-reduce with fused BN/ReLU/residual).  Eval-mode only in this round (BatchNorm folded)."""
+reduce with fused BN/ReLU/residual).  These classes hold the eval-mode entry points (BatchNorm folded);
+in train mode the modules' ``forward`` dispatch to instancerefer_b200.training (batch statistics, autograd)."""
 import math
 import os
 
@@ -47,9 +48,9 @@ def fold_bn(bn):
 
 def require_eval(module):
     if module.training:
-        raise NotImplementedError(
-            "instancerefer_b200: the training step (autograd / train-mode BatchNorm) is not built yet; "
-            "call .eval() — forward kernels fold BatchNorm running statistics")
+        raise RuntimeError(
+            "instancerefer_b200: this helper folds BatchNorm running statistics (eval mode); in train mode go "
+            "through the module's forward(), which dispatches to instancerefer_b200.training")
 
 
 class Conv3d(nn.Module):

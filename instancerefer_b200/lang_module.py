@@ -82,6 +82,9 @@ class LangModule(nn.Module, PrepCache):
 
     def forward(self, data_dict):
         ops.check_device()
+        if self.training:                                   # batch-statistics / Dropout / autograd path
+            from . import training
+            return training.lang_forward_train(self, data_dict)
         data_dict = self.rnn_encoding(data_dict['lang_feat'], data_dict['lang_len'], data_dict)
         if self.use_lang_classifier:
             p = self.prepared()

@@ -79,5 +79,9 @@ class RelationModule(nn.Module, PrepCache):
 
     def forward(self, data_dict):
         ops.check_device()
+        if self.training:
+            from . import training
+            pack = get_pack(data_dict, self.args, data_dict['lang_rel_feats'].device)
+            return training.relation_forward_train(self, data_dict, pack)
         data_dict = self.encode_graph(data_dict, data_dict['lang_rel_feats'].device)
         return self.match(data_dict)

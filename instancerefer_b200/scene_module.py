@@ -123,5 +123,9 @@ class SceneModule(nn.Module, PrepCache):
 
     def forward(self, data_dict):
         ops.check_device()
+        if self.training:
+            from . import training
+            pack = get_pack(data_dict, self.args, data_dict['lang_scene_feats'].device)
+            return training.scene_forward_train(self, data_dict, pack)
         data_dict = self.encode_scene(data_dict, data_dict['lang_scene_feats'].device)
         return self.match(data_dict)

@@ -77,9 +77,24 @@ def test_no_cpu_fallback(lib_built, args, state_dict):
         m(synthetic.to_data_dict(b, SparseTensor, 'cpu'))
 
 
-def test_train_mode_is_rejected_loudly(args):
+def test_eval_only_helpers_refuse_train_mode(args):
+    """The eval-mode helpers fold BatchNorm running statistics; in train mode they must fail loudly instead of
+    silently using stale statistics (the modules' forward() dispatches to the training path)."""
     from instancerefer_b200.basic_blocks import SparseConvEncoder, require_eval
     enc = SparseConvEncoder(7)
     enc.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         require_eval(enc)
+
+
+def test_training_path_has_no_cpu_fallback(args):
+    """Train-mode forward on a CUDA-less host raises (no torch/CPU fallback for the training step either)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from instancerefer_b200 import SparseTensor, _lib, synthetic
+    from instancerefer_b200.instancerefer import InstanceRefer
+    m = InstanceRefer(7, args).train()
+    b = synthetic.make_batch(3, batch_size=1, num_points=2000, n_inst=4, n_cand=3, n_tokens=4)
+    with pytest.raises(_lib.IrError):
+        m(synthetic.to_data_dict(b, SparseTensor, 'cpu'))

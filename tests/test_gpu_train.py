@@ -723,3 +723,50 @@ def test_full_size_directional_derivative(lib_built, state_dict, args):
             params[k].add_(d, alpha=eps)
     numeric = (lp - lm) / (2 * eps)
     assert abs(numeric - analytic) < 0.1 * max(abs(analytic), abs(numeric)) + 1e-3, (numeric, analytic)
+
+
+def test_module_forwards_dispatch_in_train_mode(lib_built, state_dict, args):
+    """The drop-in route that keeps the reference's own InstanceRefer shell calls the four modules one by one
+    (models/instancerefer.py:56-70): in train mode each module's forward must take the training path and the
+    chain must give the same scores and gradients as the package's own shell."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.loss_helper import get_loss
+    b = synthetic.make_batch(5, batch_size=2, num_points=6000, n_inst=8, n_cand=[4, 3], n_tokens=[6, 9])
+    res = []
+    for chain in (False, True):
+        model = make_train_model(state_dict, args)
+        dd = synthetic.to_data_dict(b, SparseTensor, 'cuda')
+        if chain:
+            for m in (model.lang, model.attribute, model.relation, model.scene):
+                dd = m(dd)
+        else:
+            dd = model(dd)
+        dd = get_loss(dd, train_ref.SyntheticConfig())
+        dd['loss'].backward()
+        torch.cuda.synchronize()
+        res.append((dd, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    # (split-K partial sums are added with float atomics, and the region classifier's BatchNorm over 2 samples
+    #  amplifies the last-bit differences: the forward tolerance of the task, not bitwise equality)
+    for k in ('attribute_scores', 'relation_scores', 'scene_scores', 'lang_scores', 'seg_scores', 'loss'):
+        assert float((res[0][0][k].detach() - res[1][0][k].detach()).abs().max()) < 1e-4, k
+    scale = max(float(g.abs().max()) for g in res[0][1].values())
+    for k, g in res[0][1].items():
+        assert float((g - res[1][1][k]).abs().max()) < 2e-3 * max(float(g.abs().max()), 1e-3 * scale), k
+
+
+def test_train_step_with_predicted_language_class(lib_built, state_dict):
+    """use_gt_lang: False — the candidate filter uses argmax(lang_scores) (models/attribute_module.py:93-97)."""
+    from conftest import make_args
+    a = make_args(use_gt_lang=False)
+    b = synthetic.make_batch(41, batch_size=3, num_points=9000, n_inst=36, n_cand=[2, 2, 2], n_tokens=[9, 14, 3])
+    # whatever class the language head predicts must have candidates: every scene holds each of the 18 classes twice
+    for sc in b['instance_class']:
+        sc[:] = [i % 18 for i in range(len(sc))]
+    model = make_train_model(state_dict, a)
+    dd, grads = run_train_step(model, b)
+    r = train_ref.train_step(state_dict, model_ref.data_from_batch(b), a)
+    assert dd['num_filtered_objs'] == r['outputs']['num_filtered_objs']
+    for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss'):
+        assert abs(float(dd[k].detach().reshape(-1)[0]) - float(r[k].reshape(-1)[0])) < 1e-4 * max(1.0, abs(float(r[k].reshape(-1)[0]))), k
+    scale = max(float(g.abs().max()) for g in r['grads'].values())
+    assert_grads_agree({k: (grads[k], g) for k, g in r['grads'].items()}, scale)
