@@ -43,6 +43,10 @@ int64_t ir_launch_count(void);
 int ir_profile_enable(int on);
 int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out);
 
+/* Tuning knobs: CTAs per pair-GEMM launch (default 2 per SM = 296) and per reduce / stem launch (default
+ * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
+int ir_tune_set(int pairgemm_ctas, int reduce_ctas);
+
 /* Tuning aid for the tcgen05 pair-GEMM (tools/bench_spconv.py): bit0 skip gather loads, bit1 skip T
  * stores, bit2 skip MMA issue.  0 = normal operation. */
 int ir_debug_set(int flags);

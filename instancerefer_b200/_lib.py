@@ -67,6 +67,7 @@ SIGNATURES = {
     "ir_profile_enable": (i32, [i32]),
     "ir_profile_read": (i32, [p, p, p, i32, p]),
     "ir_debug_set": (i32, [i32]),
+    "ir_tune_set": (i32, [i32, i32]),
     "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),
     "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),
     "ir_encoder_reset": (i32, [p, i64, p]),

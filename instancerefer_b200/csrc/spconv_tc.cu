@@ -29,6 +29,14 @@ extern "C" int ir_debug_set(int flags) {
     return cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? IR_OK : IR_ERR_CUDA;
 }
 
+int g_tune_pairgemm_ctas = 2 * IR_NUM_SMS;      // tuning knobs (ir_tune_set): CTAs of a pair-GEMM launch ...
+int g_tune_reduce_ctas = 8 * IR_NUM_SMS;        // ... and of a reduce / stem launch
+extern "C" int ir_tune_set(int pairgemm_ctas, int reduce_ctas) {
+    if (pairgemm_ctas > 0) g_tune_pairgemm_ctas = pairgemm_ctas;
+    if (reduce_ctas > 0) g_tune_reduce_ctas = reduce_ctas;
+    return IR_OK;
+}
+
 namespace tc {
 
 constexpr int TILE_M = 64;           // pairs per tile (UMMA N); 64 keeps a CTA at half an SM's TMEM / registers
@@ -489,7 +497,7 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
     }
     long long tiles_max = 0;
     for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
-    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, 2 * IR_NUM_SMS);       // two CTAs per SM
+    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, g_tune_pairgemm_ctas);   // default: two CTAs per SM
     IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT, SCALED>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
     IR_CHECK_LAUNCH();
     return IR_OK;
