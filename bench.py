@@ -169,7 +169,7 @@ def main_train(a):
     g.build()
     from instancerefer_b200 import SparseTensor, _lib, ops, synthetic
     from instancerefer_b200.instancerefer import InstanceRefer
-    from instancerefer_b200.loss_helper import get_loss
+    from instancerefer_b200.loss_helper import get_loss, stash_host_labels
     from instancerefer_b200.optim import FlatAdam
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -196,7 +196,8 @@ def main_train(a):
         h = hosts[i % len(hosts)]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in h.items()}
+        d = stash_host_labels(dict(h))                          # like the solver: host label copies survive the move
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in d.items()}
         d['lidar'] = SparseTensor(d.pop('lidar_feats'), d.pop('lidar_coords'))
         opt.zero_grad()
         d = model(d)

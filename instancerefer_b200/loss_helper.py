@@ -47,10 +47,24 @@ class _RefLoss(Function):
         return d, d, d, None, None, None, None
 
 
+HOST_LABELS = '_ir_host_labels'
+LABEL_KEYS = ('ref_center_label', 'ref_heading_class_label', 'ref_heading_residual_label', 'ref_size_class_label',
+              'ref_size_residual_label')
+
+
+def stash_host_labels(data_dict):
+    """Call BEFORE moving a batch to the GPU: keeps the host copies of the five box-label tensors, so that
+    get_loss / get_eval can build the ground-truth boxes (a host numpy function of the dataset config) without
+    reading them back — each read-back would stall the host until the whole forward has executed."""
+    data_dict[HOST_LABELS] = {k: data_dict[k] for k in LABEL_KEYS if k in data_dict and not data_dict[k].is_cuda}
+    return data_dict
+
+
 def _gt_obb(data_dict, config):
     """config.param2obb_batch on the label tensors (lib/loss_helper.py:212-219), host numpy like the
-    reference (five tiny D2H copies of (B,) / (B,3) labels)."""
-    t = lambda k: data_dict[k].detach().cpu().numpy()
+    reference; labels that only exist on the device are read back (D2H, synchronising)."""
+    host = data_dict.get(HOST_LABELS, {})
+    t = lambda k: (host[k] if k in host else data_dict[k].detach().cpu()).numpy()
     return np.asarray(config.param2obb_batch(t('ref_center_label'), t('ref_heading_class_label'),
                                              t('ref_heading_residual_label'), t('ref_size_class_label'),
                                              t('ref_size_residual_label')), np.float64)

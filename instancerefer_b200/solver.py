@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .eval_helper import get_eval
-from .loss_helper import get_loss
+from .loss_helper import get_loss, stash_host_labels
 
 DEVICE_KEYS = ('lang_feat', 'lang_len', 'object_cat', 'lidar', 'point_min', 'point_max', 'ref_center_label',
                'ref_size_residual_label')                     # lib/solver.py:242-245
@@ -80,6 +80,7 @@ class Solver:
             print(msg, flush=True)
 
     def _to_device(self, data_dict):
+        stash_host_labels(data_dict)
         for k in DEVICE_KEYS:
             if k in data_dict and hasattr(data_dict[k], 'cuda'):
                 data_dict[k] = data_dict[k].cuda()

@@ -411,6 +411,35 @@ def test_streams_and_graph_replay_bitwise(gpu_model):
     gpu_model.concurrent = True
 
 
+def test_graph_replay_survives_workspace_growth(lib_built, state_dict, args):
+    """Encoder workspaces only grow and are never freed: a graph captured for a small scene must still replay
+    correctly after a larger scene forced a bigger workspace (and vice versa)."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.graphed import GraphedInstanceRefer
+    from instancerefer_b200.instancerefer import InstanceRefer
+    m = InstanceRefer(7, args)
+    m.load_state_dict(state_dict, strict=True)
+    m = m.cuda().eval()
+    runner = GraphedInstanceRefer(m)
+    small = [synthetic.make_batch(s_, batch_size=1, num_points=5000, n_inst=6, n_cand=4, n_tokens=7) for s_ in (401, 402)]
+    big = synthetic.make_batch(403, batch_size=1, num_points=30000, n_inst=24, n_cand=20, n_tokens=7)
+    keys = ('attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'lang_scores')
+    order = [small[0], big, small[1], big, small[0]]
+    got = []
+    for b in order:
+        r = runner(synthetic.to_data_dict(b, SparseTensor, 'cpu'))
+        got.append({k: r['host_scores'][k].clone() for k in keys})
+    assert len(runner.cache) == 2 and len(m.scene.net._ws) == 2
+    ref = InstanceRefer(7, args)
+    ref.load_state_dict(state_dict, strict=True)
+    ref = ref.cuda().eval()
+    ref.concurrent = False
+    for b, g in zip(order, got):
+        want = _run(ref, b)
+        for k in keys:
+            assert torch.equal(g[k], want[k].cpu()), k
+
+
 def test_forward_predicted_language_class(lib_built, state_dict):
     """use_gt_lang: False — candidates filtered by argmax(lang_scores) (models/attribute_module.py:93-97)."""
     from conftest import make_args
