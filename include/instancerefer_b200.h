@@ -452,6 +452,35 @@ int ir_mlp_head_train_bwd(const ir_mlp_head_t* h, const float* x, void* arena, c
                           float* dw1, float* db1, float* dgamma, float* dbeta, float* dw2, float* db2,
                           ir_stream_t stream);
 
+/* Language encoder in train mode (models/lang_module.py:51-108) as ONE call per direction: word MLP
+ * (Linear-ReLU-Dropout-Linear-ReLU on the B*L live tokens) -> 2-layer packed biGRU (H = 128, D = 2H = 256) -> four
+ * masked attention pools over the projected embeddings -> classifier on pooled[1].  All weights in the reference's
+ * nn layouts; [layer][direction] for the GRU tensors.  Outputs: pooled (4,B,D) [attr, cls, rel, scene], scores
+ * (B,n_cls); the GRU output (lang_feat) and the attention maps stay in the arena (ir_lang_train_view).  */
+typedef struct {
+    int32_t B, L, E_in, D, H, n_cls;
+    float drop_p;
+    uint64_t seed;
+    const float *w0, *b0, *w3, *b3;
+    const float *wih[2][2], *bih[2][2], *whh[2][2], *bhh[2][2];
+    const float *fcw[4], *fcb[4];
+    const float *wc, *bc;
+} ir_lang_t;
+typedef struct {
+    float *dw0, *db0, *dw3, *db3;
+    float *dwih[2][2], *dwhh[2][2];
+    float *dbih[2], *dbhh[2];                 /* (2,3H) contiguous per layer: [direction][gate row] */
+    float *dfcw, *dfcb;                       /* (4,D), (4) contiguous: fc_a, fc_cls, fc_rel, fc_scene */
+    float *dwc, *dbc;
+} ir_lang_grads_t;
+int64_t ir_lang_train_arena_bytes(const ir_lang_t* p);
+int ir_lang_train_fwd(const ir_lang_t* p, const float* x, const int64_t* lengths, void* arena, float* pooled,
+                      float* scores, ir_stream_t stream);
+int ir_lang_train_bwd(const ir_lang_t* p, const float* x, const int64_t* lengths, void* arena, const float* pooled,
+                      const float* dpooled, const float* dscores, const ir_lang_grads_t* g, ir_stream_t stream);
+/* Byte offsets inside the arena of the GRU output (B,L,2H) and the attention maps (4,B,L). */
+int ir_lang_train_view(const ir_lang_t* p, int64_t* off_feats, int64_t* off_atten);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,20 @@ class MlpHead(C.Structure):
                 ("running_mean", p), ("running_var", p)]
 
 
+class LangParams(C.Structure):
+    _fields_ = [("B", i32), ("L", i32), ("E_in", i32), ("D", i32), ("H", i32), ("n_cls", i32),
+                ("drop_p", f32), ("seed", C.c_uint64),
+                ("w0", p), ("b0", p), ("w3", p), ("b3", p),
+                ("wih", (p * 2) * 2), ("bih", (p * 2) * 2), ("whh", (p * 2) * 2), ("bhh", (p * 2) * 2),
+                ("fcw", p * 4), ("fcb", p * 4), ("wc", p), ("bc", p)]
+
+
+class LangGrads(C.Structure):
+    _fields_ = [("dw0", p), ("db0", p), ("dw3", p), ("db3", p),
+                ("dwih", (p * 2) * 2), ("dwhh", (p * 2) * 2), ("dbih", p * 2), ("dbhh", p * 2),
+                ("dfcw", p), ("dfcb", p), ("dwc", p), ("dbc", p)]
+
+
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
 SIGNATURES = {
     "ir_version": (i32, []),
@@ -129,6 +143,10 @@ SIGNATURES = {
     "ir_edge_inputs": (i32, [p, p, p, p, i32, i32, i32, i32, p, p, p, p]),
     "ir_edge_max_fwd": (i32, [p, p, i32, i32, i32, p, p, p]),
     "ir_edge_max_bwd": (i32, [p, p, i32, i32, i32, p, p]),
+    "ir_lang_train_arena_bytes": (i64, [C.POINTER(LangParams)]),
+    "ir_lang_train_fwd": (i32, [C.POINTER(LangParams), p, p, p, p, p, p]),
+    "ir_lang_train_bwd": (i32, [C.POINTER(LangParams), p, p, p, p, p, p, C.POINTER(LangGrads), p]),
+    "ir_lang_train_view": (i32, [C.POINTER(LangParams), C.POINTER(i64), C.POINTER(i64)]),
     "ir_mlp_head_arena_bytes": (i64, [i32, i32]),
     "ir_mlp_head_train_fwd": (i32, [C.POINTER(MlpHead), p, p, p, p]),
     "ir_mlp_head_train_bwd": (i32, [C.POINTER(MlpHead), p, p, p, p, p, p, p, p, p, p, p]),

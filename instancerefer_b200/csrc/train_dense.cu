@@ -898,3 +898,130 @@ extern "C" int ir_mlp_head_train_bwd(const ir_mlp_head_t* h, const float* x, voi
     if (dx) return ir_gemm(h->M, h->K, h->N1, dh1, h->N1, 0, h->w1, h->K, 0, dx, h->K, nullptr, 0, 0, stream);
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ language encoder, train mode, one call per direction
+// models/lang_module.py:51-108: word MLP (Linear-ReLU-Dropout-Linear-ReLU) -> 2-layer packed biGRU -> four masked
+// attention pools over the projected embeddings -> classifier.  The chain of primitives above behind ONE library call
+// forward and ONE backward; intermediates in a caller-owned arena (ir_lang_train_arena_bytes).
+struct LangArena {
+    float *h1, *h1d, *e, *xp[2], *out[2], *whh[2], *bhh[2], *fcw, *fcb, *atten;
+    float *dpooled, *dfeats, *dembed, *dxp, *dhp, *hprev, *dout0, *t1, *t2, *dfcw_part, *dfcb_part;
+    uint8_t* mask;
+    int64_t bytes;
+};
+static LangArena lang_arena(void* base, const ir_lang_t* p) {
+    LangArena a;
+    char* q = (char*)base;
+    auto take = [&](int64_t bytes) { char* o = q; q += (bytes + 255) / 256 * 256; return o; };
+    const int64_t BL = (int64_t)p->B * p->L, D = p->D, H = p->H;
+    a.h1 = (float*)take(BL * D * 4); a.h1d = (float*)take(BL * D * 4); a.e = (float*)take(BL * D * 4);
+    for (int l = 0; l < 2; ++l) {
+        a.xp[l] = (float*)take(BL * 6 * H * 4); a.out[l] = (float*)take(BL * 2 * H * 4);
+        a.whh[l] = (float*)take(2 * 3 * H * H * 4); a.bhh[l] = (float*)take(2 * 3 * H * 4);
+    }
+    a.fcw = (float*)take(4 * 2 * H * 4); a.fcb = (float*)take(256);
+    a.atten = (float*)take(4 * (int64_t)p->B * p->L * 4);
+    a.mask = (uint8_t*)take(BL * D);
+    a.dpooled = (float*)take(4 * (int64_t)p->B * D * 4);
+    a.dfeats = (float*)take(BL * 2 * H * 4); a.dembed = (float*)take(BL * D * 4);
+    a.dxp = (float*)take(BL * 6 * H * 4); a.dhp = (float*)take(BL * 6 * H * 4); a.hprev = (float*)take(BL * 2 * H * 4);
+    a.dout0 = (float*)take(BL * 2 * H * 4); a.t1 = (float*)take(BL * D * 4); a.t2 = (float*)take(BL * D * 4);
+    a.dfcw_part = (float*)take((int64_t)p->B * 4 * 2 * H * 4); a.dfcb_part = (float*)take((int64_t)p->B * 4 * 4);
+    a.bytes = q - (char*)base;
+    return a;
+}
+extern "C" int64_t ir_lang_train_arena_bytes(const ir_lang_t* p) { return p ? lang_arena(nullptr, p).bytes : 0; }
+
+#define LANG_CHECK(p) IR_CHECK_ARG((p) && (p)->B > 0 && (p)->L > 0 && (p)->H == 128 && (p)->D == 2 * (p)->H && (p)->E_in > 0 && (p)->n_cls > 0)
+
+extern "C" int ir_lang_train_fwd(const ir_lang_t* p, const float* x, const int64_t* lengths, void* arena, float* pooled,
+                                 float* scores, ir_stream_t stream) {
+    LANG_CHECK(p);
+    IR_CHECK_ARG(x && lengths && arena && pooled);
+    const LangArena a = lang_arena(arena, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BL = p->B * p->L, D = p->D, H = p->H, G3 = 3 * p->H;
+    int r;
+    if ((r = ir_gemm(BL, D, p->E_in, x, p->E_in, 0, p->w0, p->E_in, 1, a.h1, D, p->b0, 1, 0, stream)) != IR_OK) return r;
+    const float* h1d = a.h1;
+    if (p->drop_p > 0.f) {
+        if ((r = ir_dropout_fwd(a.h1, (int64_t)BL * D, p->drop_p, p->seed, a.h1d, a.mask, stream)) != IR_OK) return r;
+        h1d = a.h1d;
+    }
+    if ((r = ir_gemm(BL, D, D, h1d, D, 0, p->w3, D, 1, a.e, D, p->b3, 1, 0, stream)) != IR_OK) return r;
+    for (int l = 0; l < 2; ++l) {
+        const float* in = l == 0 ? a.e : a.out[0];
+        for (int d = 0; d < 2; ++d) {
+            if ((r = ir_gemm(BL, G3, D, in, D, 0, p->wih[l][d], D, 1, a.xp[l] + d * G3, 2 * G3, p->bih[l][d], 0, 0, stream)) != IR_OK) return r;
+            IR_CHECK_CUDA(cudaMemcpyAsync(a.whh[l] + (size_t)d * G3 * H, p->whh[l][d], (size_t)G3 * H * 4, cudaMemcpyDeviceToDevice, st));
+            IR_CHECK_CUDA(cudaMemcpyAsync(a.bhh[l] + d * G3, p->bhh[l][d], (size_t)G3 * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if ((r = ir_gru_layer(a.xp[l], a.whh[l], a.bhh[l], lengths, p->B, p->L, H, a.out[l], stream)) != IR_OK) return r;
+    }
+    for (int h = 0; h < 4; ++h) {
+        IR_CHECK_CUDA(cudaMemcpyAsync(a.fcw + h * D, p->fcw[h], (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+        IR_CHECK_CUDA(cudaMemcpyAsync(a.fcb + h, p->fcb[h], 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((r = ir_token_attention(a.out[1], a.e, (int64_t)p->L * D, lengths, a.fcw, a.fcb, p->B, p->L, D, D, a.atten, pooled, stream)) != IR_OK) return r;
+    if (scores && p->wc)
+        return ir_gemm(p->B, p->n_cls, D, pooled + (size_t)p->B * D, D, 0, p->wc, D, 1, scores, p->n_cls, p->bc, 0, 0, stream);
+    return IR_OK;
+}
+
+extern "C" int ir_lang_train_bwd(const ir_lang_t* p, const float* x, const int64_t* lengths, void* arena, const float* pooled,
+                                 const float* dpooled, const float* dscores, const ir_lang_grads_t* g, ir_stream_t stream) {
+    LANG_CHECK(p);
+    IR_CHECK_ARG(x && lengths && arena && pooled && dpooled && g);
+    const LangArena a = lang_arena(arena, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = p->B, BL = p->B * p->L, D = p->D, H = p->H, G3 = 3 * p->H;
+    int r;
+    IR_CHECK_CUDA(cudaMemcpyAsync(a.dpooled, dpooled, (size_t)4 * B * D * 4, cudaMemcpyDeviceToDevice, st));
+    if (dscores && p->wc) {                                    // classifier on pooled[1]
+        if ((r = ir_gemm(p->n_cls, D, B, dscores, p->n_cls, 1, pooled + (size_t)B * D, D, 0, g->dwc, D, nullptr, 0, 0, stream)) != IR_OK) return r;
+        if ((r = ir_colsum(dscores, B, p->n_cls, g->dbc, stream)) != IR_OK) return r;
+        if ((r = ir_gemm(B, D, p->n_cls, dscores, p->n_cls, 0, p->wc, D, 0, a.dpooled + (size_t)B * D, D, nullptr, 0, 1, stream)) != IR_OK) return r;
+    }
+    if ((r = ir_token_attention_bwd(a.out[1], a.e, (int64_t)p->L * D, lengths, a.fcw, a.fcb, a.atten, a.dpooled, B, p->L, D, D,
+                                    a.dfeats, a.dembed, a.dfcw_part, a.dfcb_part, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.dfcw_part, B, 4 * D, g->dfcw, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.dfcb_part, B, 4, g->dfcb, stream)) != IR_OK) return r;
+    const float* dout = a.dfeats;
+    for (int l = 1; l >= 0; --l) {
+        const float* in = l == 0 ? a.e : a.out[0];
+        if ((r = ir_gru_layer_bwd(a.xp[l], a.whh[l], a.bhh[l], lengths, a.out[l], dout, B, p->L, H, a.dxp, a.dhp, a.hprev, stream)) != IR_OK) return r;
+        if ((r = ir_colsum(a.dhp, BL, 2 * G3, g->dbhh[l], stream)) != IR_OK) return r;          // (2,3H) contiguous
+        if ((r = ir_colsum(a.dxp, BL, 2 * G3, g->dbih[l], stream)) != IR_OK) return r;
+        float* din = l == 0 ? a.dembed : a.dout0;              // layer 0 adds into the pools' gradient of e
+        for (int d = 0; d < 2; ++d) {
+            if ((r = ir_gemm(G3, H, BL, a.dhp + d * G3, 2 * G3, 1, a.hprev + d * H, 2 * H, 0, g->dwhh[l][d], H, nullptr, 0, 0, stream)) != IR_OK) return r;
+            if ((r = ir_gemm(G3, D, BL, a.dxp + d * G3, 2 * G3, 1, in, D, 0, g->dwih[l][d], D, nullptr, 0, 0, stream)) != IR_OK) return r;
+            if ((r = ir_gemm(BL, D, G3, a.dxp + d * G3, 2 * G3, 0, p->wih[l][d], D, 0, din, D, nullptr, 0, (l == 0 || d > 0) ? 1 : 0, stream)) != IR_OK) return r;
+        }
+        dout = a.dout0;
+    }
+    // word MLP: e = relu(h1d W3^T + b3), h1 = relu(x W0^T + b0)
+    const float* h1d = p->drop_p > 0.f ? a.h1d : a.h1;
+    if ((r = ir_relu_bwd(a.dembed, a.e, (int64_t)BL * D, a.t1, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(D, D, BL, a.t1, D, 1, h1d, D, 0, g->dw3, D, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.t1, BL, D, g->db3, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(BL, D, D, a.t1, D, 0, p->w3, D, 0, a.t2, D, nullptr, 0, 0, stream)) != IR_OK) return r;
+    const float* dh1 = a.t2;
+    if (p->drop_p > 0.f) {
+        if ((r = ir_dropout_bwd(a.t2, a.mask, (int64_t)BL * D, p->drop_p, a.t1, stream)) != IR_OK) return r;
+        dh1 = a.t1;
+    }
+    float* gbuf = (dh1 == a.t1) ? a.t2 : a.t1;
+    if ((r = ir_relu_bwd(dh1, a.h1, (int64_t)BL * D, gbuf, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(D, p->E_in, BL, gbuf, D, 1, x, p->E_in, 0, g->dw0, p->E_in, nullptr, 0, 0, stream)) != IR_OK) return r;
+    return ir_colsum(gbuf, BL, D, g->db0, stream);
+}
+
+extern "C" int ir_lang_train_view(const ir_lang_t* p, int64_t* off_feats, int64_t* off_atten) {
+    LANG_CHECK(p);
+    IR_CHECK_ARG(off_feats && off_atten);
+    const LangArena a = lang_arena(nullptr, p);
+    *off_feats = (char*)a.out[1] - (char*)nullptr;
+    *off_atten = (char*)a.atten - (char*)nullptr;
+    return IR_OK;
+}

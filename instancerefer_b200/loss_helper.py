@@ -56,7 +56,7 @@ def stash_host_labels(data_dict):
     """Call BEFORE moving a batch to the GPU: keeps the host copies of the five box-label tensors, so that
     get_loss / get_eval can build the ground-truth boxes (a host numpy function of the dataset config) without
     reading them back — each read-back would stall the host until the whole forward has executed."""
-    data_dict[HOST_LABELS] = {k: data_dict[k] for k in LABEL_KEYS if k in data_dict and not data_dict[k].is_cuda}
+    data_dict[HOST_LABELS] = {k: data_dict[k] for k in LABEL_KEYS + ('lang_len',) if k in data_dict and not data_dict[k].is_cuda}
     return data_dict
 
 

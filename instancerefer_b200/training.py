@@ -645,15 +645,129 @@ def mlp_head(seq, x, norm_idx, last_idx, drop_idx=None):
 
 # ----------------------------------------------------------------------------- module forwards
 
+class LangTrain(Function):
+    """The whole language encoder in train mode as ONE library call per direction (ir_lang_train_fwd / _bwd).
+    Parameter order: word_projection.{0,3}.{weight,bias}; for layer 0,1 / direction fwd,rev: weight_ih, weight_hh,
+    bias_ih, bias_hh; fc_a, fc_cls, fc_rel, fc_scene {weight,bias}; lang_cls.0.{weight,bias}."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, B, L, drop_p, *params):
+        import ctypes as C
+        from . import _lib
+        x = x.contiguous()
+        dev = x.device
+        keep = [t.detach().contiguous() for t in params]
+        P = _lib.LangParams()
+        P.B, P.L, P.E_in, P.D, P.H, P.n_cls = B, L, x.shape[1], 256, 128, keep[28].shape[0]
+        P.drop_p = float(drop_p)
+        if drop_p > 0:
+            _dropout_calls[0] += 1
+            P.seed = (torch.initial_seed() * 0x9E3779B1 + _dropout_calls[0] * 0x85EBCA6B) & (2 ** 63 - 1)
+        P.w0, P.b0, P.w3, P.b3 = (t.data_ptr() for t in keep[0:4])
+        for l in range(2):
+            for d in range(2):
+                wih, whh, bih, bhh = keep[4 + 8 * l + 4 * d: 8 + 8 * l + 4 * d]
+                P.wih[l][d], P.whh[l][d], P.bih[l][d], P.bhh[l][d] = wih.data_ptr(), whh.data_ptr(), bih.data_ptr(), bhh.data_ptr()
+        for h in range(4):
+            P.fcw[h], P.fcb[h] = keep[20 + 2 * h].data_ptr(), keep[21 + 2 * h].data_ptr()
+        P.wc, P.bc = keep[28].data_ptr(), keep[29].data_ptr()
+        lib = _lib.load()
+        arena = torch.empty(lib.ir_lang_train_arena_bytes(C.byref(P)), dtype=torch.uint8, device=dev)
+        pooled = torch.empty(4, B, 256, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, P.n_cls, dtype=torch.float32, device=dev)
+        _lib.call("ir_lang_train_fwd", C.byref(P), ops._p(x), ops._p(lengths, torch.int64), ops._p(arena), ops._p(pooled),
+                  ops._p(scores), ops._stream())
+        of, oa = C.c_int64(0), C.c_int64(0)
+        _lib.call("ir_lang_train_view", C.byref(P), C.byref(of), C.byref(oa))
+        feats = arena[of.value:of.value + B * L * 256 * 4].view(torch.float32).view(B, L, 256)
+        atten = arena[oa.value:oa.value + 4 * B * L * 4].view(torch.float32).view(4, B, L)
+        ctx.state = (P, keep, arena, x, lengths, pooled, [tuple(t.shape) for t in params])
+        ctx.mark_non_differentiable(feats, atten)
+        return pooled, scores, feats, atten
+
+    @staticmethod
+    def backward(ctx, dpooled, dscores, _df, _da):
+        import ctypes as C
+        from . import _lib
+        P, keep, arena, x, lengths, pooled, shapes = ctx.state
+        dev = x.device
+        H3 = 3 * 128
+        # flat gradient buffer; the per-direction bias gradients of a layer and the four fc_* gradients are
+        # contiguous blocks that the library fills with one column sum each
+        numel = [int(torch.Size(sh).numel()) for sh in shapes]
+        order = list(range(30))
+        offs, o = {}, 0
+
+        def seg(i):
+            nonlocal o
+            offs[i] = o
+            o += (numel[i] + 63) // 64 * 64
+        for i in (0, 1, 2, 3):
+            seg(i)
+        for l in range(2):
+            base = 4 + 8 * l
+            seg(base + 0); seg(base + 1); seg(base + 4); seg(base + 5)               # wih, whh (fwd / rev)
+            offs[base + 2] = o; offs[base + 6] = o + H3; o += 2 * H3 + 0               # bih fwd | rev contiguous
+            o = (o + 63) // 64 * 64
+            offs[base + 3] = o; offs[base + 7] = o + H3; o += 2 * H3
+            o = (o + 63) // 64 * 64
+        for h in range(4):                                                           # fc weights (4,D) contiguous
+            offs[20 + 2 * h] = o + 256 * h
+        o += 4 * 256
+        for h in range(4):                                                           # fc biases (4) contiguous
+            offs[21 + 2 * h] = o + h
+        o += 64
+        seg(28); seg(29)
+        flat = torch.empty(o, dtype=torch.float32, device=dev)
+        ptr = lambda i: flat.data_ptr() + 4 * offs[i]
+        G = _lib.LangGrads()
+        G.dw0, G.db0, G.dw3, G.db3 = ptr(0), ptr(1), ptr(2), ptr(3)
+        for l in range(2):
+            base = 4 + 8 * l
+            G.dwih[l][0], G.dwhh[l][0], G.dwih[l][1], G.dwhh[l][1] = ptr(base), ptr(base + 1), ptr(base + 4), ptr(base + 5)
+            G.dbih[l], G.dbhh[l] = ptr(base + 2), ptr(base + 3)
+        G.dfcw, G.dfcb, G.dwc, G.dbc = ptr(20), ptr(21), ptr(28), ptr(29)
+        ds = dscores.contiguous() if dscores is not None else None
+        _lib.call("ir_lang_train_bwd", C.byref(P), ops._p(x), ops._p(lengths, torch.int64), ops._p(arena), ops._p(pooled),
+                  ops._p(dpooled.contiguous(), torch.float32), ops._p(ds), C.byref(G), ops._stream())
+        grads = [flat[offs[i]:offs[i] + numel[i]].view(shapes[i]) for i in order]
+        return (None, None, None, None, None, *grads)
+
+
+def lang_params(m):
+    g = m.gru
+    ps = [m.word_projection[0].weight, m.word_projection[0].bias, m.word_projection[3].weight, m.word_projection[3].bias]
+    for l in (0, 1):
+        for sfx in ('', '_reverse'):
+            ps += [getattr(g, f'weight_ih_l{l}{sfx}'), getattr(g, f'weight_hh_l{l}{sfx}'),
+                   getattr(g, f'bias_ih_l{l}{sfx}'), getattr(g, f'bias_hh_l{l}{sfx}')]
+    for fc in (m.fc_a, m.fc_cls, m.fc_rel, m.fc_scene):
+        ps += [fc.weight, fc.bias]
+    ps += [m.lang_cls[0].weight, m.lang_cls[0].bias]
+    return ps
+
+
 def lang_forward_train(m, data_dict):
     """models/lang_module.py:51-108 in train mode: word MLP (+Dropout), 2-layer packed biGRU, four
-    masked attention pools over the PROJECTED embeddings, classifier."""
+    masked attention pools over the PROJECTED embeddings, classifier.  One library call per direction
+    (LangTrain); IR_TRAIN_LANG=ops runs the chain as separate autograd nodes (what the per-op tests cover)."""
+    import os
     x, length = data_dict['lang_feat'], data_dict['lang_len']
     dev = x.device
-    L = int(length.detach().to('cpu').max())
+    host = data_dict.get('_ir_host_labels', {}).get('lang_len')
+    L = int((host if host is not None else length.detach().to('cpu')).max())
     B = x.shape[0]
     len_dev = length.to(dev, torch.int64).contiguous()
     wp = m.word_projection
+    if os.environ.get('IR_TRAIN_LANG', 'fused') != 'ops' and m.use_lang_classifier and m.use_bidir and m.hidden_size == 128:
+        pooled, scores, feats, atten = LangTrain.apply(x[:, :L].float().reshape(B * L, -1), len_dev, B, L, float(wp[2].p),
+                                                       *lang_params(m))
+        data_dict['lang_feat'] = feats
+        data_dict['atten_attr'], data_dict['atten_rel'], data_dict['atten_scene'] = atten[0], atten[2], atten[3]
+        data_dict['lang_attr_feats'], data_dict['lang_cls_feats'] = pooled[0], pooled[1]
+        data_dict['lang_rel_feats'], data_dict['lang_scene_feats'] = pooled[2], pooled[3]
+        data_dict['lang_scores'] = scores
+        return data_dict
     h = Linear.apply(x[:, :L].float().reshape(B * L, -1), wp[0].weight, wp[0].bias, True)
     h = dropout(h, wp[2])
     e = Linear.apply(h, wp[3].weight, wp[3].bias, True)                                     # (B*L, 256)
