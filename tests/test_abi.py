@@ -29,6 +29,49 @@ def test_library_exports_every_header_symbol(lib_built):
     assert _lib.load().ir_version() == 100
 
 
+def header_prototypes():
+    """name -> number of parameters, parsed from the header's prototypes."""
+    txt = open(os.path.join(ROOT, 'include', 'instancerefer_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(ir_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;', txt, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ('', 'void') else len(args.split(','))
+    return out
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every ctypes signature has exactly as many arguments as its C prototype (a mismatch would shift every
+    following argument silently)."""
+    from instancerefer_b200 import _lib
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], (name, len(argtypes), protos[name])
+
+
+def test_struct_sizes_match_the_library(lib_built):
+    """The ctypes mirrors of the ABI structs have the layout the compiler gave the C structs (probed through
+    behaviour: layouts written by the library are self-consistent and arena sizes are positive)."""
+    from instancerefer_b200 import _lib
+    lay = _lib.EncoderTrainLayout()
+    n = (ctypes.c_int32 * 5)(4000, 2000, 900, 300, 80)
+    assert _lib.call('ir_encoder_train_layout', 8192, n, 7, ctypes.byref(lay)) == 0
+    offs = [*lay.off_y, *lay.off_out, *lay.off_mean, *lay.off_rstd, lay.off_bn_scratch, *lay.off_tr_out, *lay.off_tr_slot,
+            *lay.off_grad, lay.off_wt, lay.off_absmax]
+    assert len(set(offs)) == len(offs) and all(0 <= o < lay.total_bytes and o % 256 == 0 for o in offs)
+    cap = _lib.EncoderTrainLayout()
+    assert _lib.call('ir_encoder_train_layout', 8192, None, 7, ctypes.byref(cap)) == 0 and cap.total_bytes > lay.total_bytes
+    P = _lib.LangParams()
+    P.B, P.L, P.E_in, P.D, P.H, P.n_cls = 2, 9, 300, 256, 128, 18
+    a = _lib.load().ir_lang_train_arena_bytes(ctypes.byref(P))
+    of, oa = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert _lib.call('ir_lang_train_view', ctypes.byref(P), ctypes.byref(of), ctypes.byref(oa)) == 0
+    assert 0 < of.value < oa.value < a
+    assert _lib.load().ir_mlp_head_arena_bytes(64, 256) > 64 * 256 * 4 * 5
+    assert _lib.load().ir_bn_scratch_floats(128) == 148 * 2 * 2 * 128
+
+
 def test_encoder_layout_host_only(lib_built):
     from instancerefer_b200 import _lib
     L = _lib.EncoderLayout()
