@@ -239,6 +239,15 @@ def main_train(a):
         dev_ms, wall = float(t[0]), float(t[1])
     launches = lib.ir_launch_count() - c0
     clocks = sampler.stop() if sampler else None
+    # data-parallel sanity: every rank applied the same averaged gradients, so the parameter buffers must be
+    # bitwise identical across ranks (BatchNorm running statistics are per rank and live outside the flat buffer)
+    in_sync = True
+    if world > 1:
+        chk = opt.flat.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool((hi - lo).abs().item() == 0.0)
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_train_leg(2, 1, per_gpu)
@@ -257,7 +266,7 @@ def main_train(a):
             e2e=dict(value=world * per_gpu * a.steps / wall, unit=METRIC, ms_per_step=wall / a.steps * 1e3,
                      h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
             phases_ms={k: v / a.steps for k, v in ph.items()}, gpu_launches=int(launches), clocks=clocks,
-            final_loss=losses[-1], first_loss=losses[0], cpu_baseline=cb)))
+            final_loss=losses[-1], first_loss=losses[0], ranks_in_sync=in_sync, cpu_baseline=cb)))
 
 
 def _forward_setup(local):
