@@ -481,6 +481,21 @@ int ir_lang_train_bwd(const ir_lang_t* p, const float* x, const int64_t* lengths
 /* Byte offsets inside the arena of the GRU output (B,L,2H) and the attention maps (4,B,L). */
 int ir_lang_train_view(const ir_lang_t* p, int64_t* off_feats, int64_t* off_atten);
 
+/* DynamicEdgeConv in train mode given the kNN lists (models/basic_blocks.py:98-133), ONE call per direction:
+ * w = W2w relu(W1w [p_j-p_i, onehot_i, onehot_j]); msg = W2m relu(W1m [x_i, w, x_j]); out_i = max over the valid
+ * edges.  Weights in nn.Linear layout: ww1 (H1, 3+2*ncls), ww2 (F, H1), wm1 (Fout, 3F), wm2 (Fout, Fout).  x / xyz
+ * carry no gradient; the backward produces the eight parameter gradients. */
+typedef struct {
+    int32_t nq, k, F, ncls, H1, Fout;
+    const float *ww1, *bw1, *ww2, *bw2, *wm1, *bm1, *wm2, *bm2;
+} ir_edgeconv_t;
+typedef struct { float *dww1, *dbw1, *dww2, *dbw2, *dwm1, *dbm1, *dwm2, *dbm2; } ir_edgeconv_grads_t;
+int64_t ir_edgeconv_train_arena_bytes(const ir_edgeconv_t* p);
+int ir_edgeconv_train_fwd(const ir_edgeconv_t* p, const float* x, const float* xyz, const int32_t* qidx,
+                          const int32_t* nbr, void* arena, float* out, ir_stream_t stream);
+int ir_edgeconv_train_bwd(const ir_edgeconv_t* p, void* arena, const float* dout, const ir_edgeconv_grads_t* g,
+                          ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

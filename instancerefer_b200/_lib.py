@@ -72,6 +72,15 @@ class LangGrads(C.Structure):
                 ("dfcw", p), ("dfcb", p), ("dwc", p), ("dbc", p)]
 
 
+class EdgeConvParams(C.Structure):
+    _fields_ = [("nq", i32), ("k", i32), ("F", i32), ("ncls", i32), ("H1", i32), ("Fout", i32),
+                ("ww1", p), ("bw1", p), ("ww2", p), ("bw2", p), ("wm1", p), ("bm1", p), ("wm2", p), ("bm2", p)]
+
+
+class EdgeConvGrads(C.Structure):
+    _fields_ = [(n, p) for n in ("dww1", "dbw1", "dww2", "dbw2", "dwm1", "dbm1", "dwm2", "dbm2")]
+
+
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
 SIGNATURES = {
     "ir_version": (i32, []),
@@ -147,6 +156,9 @@ SIGNATURES = {
     "ir_lang_train_fwd": (i32, [C.POINTER(LangParams), p, p, p, p, p, p]),
     "ir_lang_train_bwd": (i32, [C.POINTER(LangParams), p, p, p, p, p, p, C.POINTER(LangGrads), p]),
     "ir_lang_train_view": (i32, [C.POINTER(LangParams), C.POINTER(i64), C.POINTER(i64)]),
+    "ir_edgeconv_train_arena_bytes": (i64, [C.POINTER(EdgeConvParams)]),
+    "ir_edgeconv_train_fwd": (i32, [C.POINTER(EdgeConvParams), p, p, p, p, p, p, p]),
+    "ir_edgeconv_train_bwd": (i32, [C.POINTER(EdgeConvParams), p, p, C.POINTER(EdgeConvGrads), p]),
     "ir_mlp_head_arena_bytes": (i64, [i32, i32]),
     "ir_mlp_head_train_fwd": (i32, [C.POINTER(MlpHead), p, p, p, p]),
     "ir_mlp_head_train_bwd": (i32, [C.POINTER(MlpHead), p, p, p, p, p, p, p, p, p, p, p]),

@@ -1025,3 +1025,68 @@ extern "C" int ir_lang_train_view(const ir_lang_t* p, int64_t* off_feats, int64_
     *off_atten = (char*)a.atten - (char*)nullptr;
     return IR_OK;
 }
+
+// ------------------------------------------------------------------ DynamicEdgeConv, train mode, one call per direction
+// models/basic_blocks.py:98-133 given the kNN lists: per edge w = W2w relu(W1w [p_j-p_i, oh_i, oh_j]),
+// msg = W2m relu(W1m [x_i, w, x_j]); out_i = max_j msg.  x carries no gradient (instance statistics), so the backward
+// ends at the two edge MLPs' parameters.  Arena: ir_edgeconv_train_arena_bytes.
+struct EdgeArena {
+    float *w_in, *a1, *w, *e_in, *m1, *msg, *t1, *t2, *t3, *t4;
+    int* arg;
+    int64_t bytes;
+};
+static EdgeArena edge_arena(void* base, const ir_edgeconv_t* p) {
+    EdgeArena a;
+    char* q = (char*)base;
+    auto take = [&](int64_t bytes) { char* o = q; q += (bytes + 255) / 256 * 256; return o; };
+    const int64_t E = (int64_t)p->nq * p->k;
+    a.w_in = (float*)take(E * (3 + 2 * p->ncls) * 4); a.a1 = (float*)take(E * p->H1 * 4); a.w = (float*)take(E * p->F * 4);
+    a.e_in = (float*)take(E * 3 * p->F * 4); a.m1 = (float*)take(E * p->Fout * 4); a.msg = (float*)take(E * p->Fout * 4);
+    a.arg = (int*)take((int64_t)p->nq * p->Fout * 4);
+    a.t1 = (float*)take(E * p->Fout * 4); a.t2 = (float*)take(E * p->Fout * 4);
+    a.t3 = (float*)take(E * p->H1 * 4); a.t4 = (float*)take(E * p->H1 * 4);
+    a.bytes = q - (char*)base;
+    return a;
+}
+extern "C" int64_t ir_edgeconv_train_arena_bytes(const ir_edgeconv_t* p) { return p ? edge_arena(nullptr, p).bytes : 0; }
+#define EDGE_CHECK(p) IR_CHECK_ARG((p) && (p)->nq > 0 && (p)->k > 0 && (p)->F > (p)->ncls && (p)->ncls > 0 && (p)->H1 > 0 && (p)->Fout > 0 && (p)->F <= (p)->H1)
+
+extern "C" int ir_edgeconv_train_fwd(const ir_edgeconv_t* p, const float* x, const float* xyz, const int32_t* qidx,
+                                     const int32_t* nbr, void* arena, float* out, ir_stream_t stream) {
+    EDGE_CHECK(p);
+    IR_CHECK_ARG(x && xyz && qidx && nbr && arena && out);
+    const EdgeArena a = edge_arena(arena, p);
+    const int E = p->nq * p->k, Dw = 3 + 2 * p->ncls, De = 3 * p->F;
+    int r;
+    if ((r = ir_edge_inputs(x, xyz, qidx, nbr, p->nq, p->k, p->F, p->ncls, nullptr, a.w_in, nullptr, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, p->H1, Dw, a.w_in, Dw, 0, p->ww1, Dw, 1, a.a1, p->H1, p->bw1, 1, 0, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, p->F, p->H1, a.a1, p->H1, 0, p->ww2, p->H1, 1, a.w, p->F, p->bw2, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_edge_inputs(x, xyz, qidx, nbr, p->nq, p->k, p->F, p->ncls, a.w, nullptr, a.e_in, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, p->Fout, De, a.e_in, De, 0, p->wm1, De, 1, a.m1, p->Fout, p->bm1, 1, 0, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, p->Fout, p->Fout, a.m1, p->Fout, 0, p->wm2, p->Fout, 1, a.msg, p->Fout, p->bm2, 0, 0, stream)) != IR_OK) return r;
+    return ir_edge_max_fwd(a.msg, nbr, p->nq, p->k, p->Fout, out, a.arg, stream);
+}
+
+extern "C" int ir_edgeconv_train_bwd(const ir_edgeconv_t* p, void* arena, const float* dout, const ir_edgeconv_grads_t* g,
+                                     ir_stream_t stream) {
+    EDGE_CHECK(p);
+    IR_CHECK_ARG(arena && dout && g);
+    const EdgeArena a = edge_arena(arena, p);
+    const int E = p->nq * p->k, Dw = 3 + 2 * p->ncls, De = 3 * p->F, Fo = p->Fout;
+    int r;
+    if ((r = ir_edge_max_bwd(dout, a.arg, p->nq, p->k, Fo, a.t1, stream)) != IR_OK) return r;                 // dmsg (0 on unused edges)
+    if ((r = ir_gemm(Fo, Fo, E, a.t1, Fo, 1, a.m1, Fo, 0, g->dwm2, Fo, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.t1, E, Fo, g->dbm2, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, Fo, Fo, a.t1, Fo, 0, p->wm2, Fo, 0, a.t2, Fo, nullptr, 0, 0, stream)) != IR_OK) return r;   // dm1
+    if ((r = ir_relu_bwd(a.t2, a.m1, (int64_t)E * Fo, a.t1, stream)) != IR_OK) return r;                       // g1
+    if ((r = ir_gemm(Fo, De, E, a.t1, Fo, 1, a.e_in, De, 0, g->dwm1, De, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.t1, E, Fo, g->dbm1, stream)) != IR_OK) return r;
+    // dw = g1 @ W1m[:, F:2F]  (only the w slice of [x_i, w, x_j] carries a gradient)
+    if ((r = ir_gemm(E, p->F, Fo, a.t1, Fo, 0, p->wm1 + p->F, De, 0, a.t3, p->F, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(p->F, p->H1, E, a.t3, p->F, 1, a.a1, p->H1, 0, g->dww2, p->H1, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_colsum(a.t3, E, p->F, g->dbw2, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(E, p->H1, p->F, a.t3, p->F, 0, p->ww2, p->H1, 0, a.t4, p->H1, nullptr, 0, 0, stream)) != IR_OK) return r;   // da1
+    if ((r = ir_relu_bwd(a.t4, a.a1, (int64_t)E * p->H1, a.t2, stream)) != IR_OK) return r;                    // g2 (t2 is large enough)
+    if ((r = ir_gemm(p->H1, Dw, E, a.t2, p->H1, 1, a.w_in, Dw, 0, g->dww1, Dw, nullptr, 0, 0, stream)) != IR_OK) return r;
+    return ir_colsum(a.t2, E, p->H1, g->dbw1, stream);
+}

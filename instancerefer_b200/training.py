@@ -624,6 +624,44 @@ class MLPHead(Function):
         return dx, dw1.view(N1, K), db1, dg, dbeta, dw2.view(N2, N1), db2, None, None
 
 
+class EdgeConvTrain(Function):
+    """DynamicEdgeConv (edge-weight MLP, message MLP, max aggregation) as ONE library call per direction.
+    Parameter order: weight.0.{weight,bias}, weight.2.{weight,bias}, mlp.0.{weight,bias}, mlp.2.{weight,bias}."""
+
+    @staticmethod
+    def forward(ctx, feats, xyz, qidx, nbr, ncls, *params):
+        import ctypes as C
+        from . import _lib
+        keep = [t.detach().contiguous() for t in params]
+        P = _lib.EdgeConvParams()
+        P.nq, P.k, P.F, P.ncls = nbr.shape[0], nbr.shape[1], feats.shape[1], ncls
+        P.H1, P.Fout = keep[0].shape[0], keep[6].shape[0]
+        P.ww1, P.bw1, P.ww2, P.bw2, P.wm1, P.bm1, P.wm2, P.bm2 = (t.data_ptr() for t in keep)
+        dev = feats.device
+        arena = torch.empty(_lib.load().ir_edgeconv_train_arena_bytes(C.byref(P)), dtype=torch.uint8, device=dev)
+        out = torch.empty(P.nq, P.Fout, dtype=torch.float32, device=dev)
+        _lib.call("ir_edgeconv_train_fwd", C.byref(P), ops._p(feats, torch.float32), ops._p(xyz, torch.float32),
+                  ops._p(qidx, torch.int32), ops._p(nbr, torch.int32), ops._p(arena), ops._p(out), ops._stream())
+        ctx.state = (P, keep, arena, [tuple(t.shape) for t in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        from . import _lib
+        P, keep, arena, shapes = ctx.state
+        numel = [int(torch.Size(sh).numel()) for sh in shapes]
+        offs, o = [], 0
+        for n in numel:
+            offs.append(o)
+            o += (n + 63) // 64 * 64
+        flat = torch.empty(o, dtype=torch.float32, device=arena.device)
+        G = _lib.EdgeConvGrads()
+        G.dww1, G.dbw1, G.dww2, G.dbw2, G.dwm1, G.dbm1, G.dwm2, G.dbm2 = (flat.data_ptr() + 4 * a for a in offs)
+        _lib.call("ir_edgeconv_train_bwd", C.byref(P), ops._p(arena), ops._p(dout.contiguous(), torch.float32), C.byref(G), ops._stream())
+        return (None, None, None, None, None, *(flat[a:a + n].view(sh) for a, n, sh in zip(offs, numel, shapes)))
+
+
 def mlp_head(seq, x, norm_idx, last_idx, drop_idx=None):
     """Linear -> {BatchNorm1d | LayerNorm} -> ReLU [-> Dropout] -> Linear of the reference's
     nn.Sequential heads (e.g. models/relation_module.py:13-25).  IR_TRAIN_HEADS=ops runs it as separate
@@ -845,6 +883,14 @@ def relation_forward_train(m, data_dict, pack):
     feats = torch.cat([xyz, mean[:, 3:], onehot], 1).contiguous()
     gcn = m.gcn
     nbr = ops.knn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, gcn.k)                  # (M,k), -1 padded
+    import os
+    if os.environ.get('IR_TRAIN_EDGECONV', 'fused') != 'ops':
+        g = EdgeConvTrain.apply(feats, xyz, pack.cand_rows, nbr, ncls, gcn.weight[0].weight, gcn.weight[0].bias,
+                                gcn.weight[2].weight, gcn.weight[2].bias, gcn.mlp[0].weight, gcn.mlp[0].bias,
+                                gcn.mlp[2].weight, gcn.mlp[2].bias)
+        vis = mlp_head(m.vis_emb_fc, g, 1, 4, 3)
+        data_dict['relation_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 1)
+        return data_dict
     w_in = ops.edge_inputs(feats, xyz, pack.cand_rows, nbr, ncls)
     w = Linear.apply(Linear.apply(w_in, gcn.weight[0].weight, gcn.weight[0].bias, True),
                      gcn.weight[2].weight, gcn.weight[2].bias, False)
