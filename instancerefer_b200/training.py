@@ -278,8 +278,11 @@ class EncoderTrainGraphed(Function):
         st = ctx.st
         st.dout[:ctx.n4].copy_(dout)
         EncoderTrainGraphed._run(st, 'bwd', ctx.ws)
-        # fresh view objects of the static gradient buffer: autograd adopts them as .grad without a copy kernel
-        return (None, None, None, *(st.gflat[o:o + n].view(sh) for o, n, sh in st.gslices))
+        # one copy of the static gradient buffer per backward (a single D2D kernel), returned as views: autograd
+        # adopts them as .grad without per-parameter kernels, and nothing the caller holds aliases the buffer the
+        # next replay overwrites (gradient accumulation over several backwards stays correct)
+        flat = st.gflat.clone()
+        return (None, None, None, *(flat[o:o + n].view(sh) for o, n, sh in st.gslices))
 
 
 def encoder_forward_train(net, ws, feats0=None, coords0=None, G=None):

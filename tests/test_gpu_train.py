@@ -770,3 +770,35 @@ def test_train_step_with_predicted_language_class(lib_built, state_dict):
         assert abs(float(dd[k].detach().reshape(-1)[0]) - float(r[k].reshape(-1)[0])) < 1e-4 * max(1.0, abs(float(r[k].reshape(-1)[0]))), k
     scale = max(float(g.abs().max()) for g in r['grads'].values())
     assert_grads_agree({k: (grads[k], g) for k, g in r['grads'].items()}, scale)
+
+
+def test_gradient_accumulation_over_two_backwards(lib_built, state_dict, args):
+    """Two forward/backward passes without zeroing (gradient accumulation) must give the sum of the two gradients
+    — guards the static buffers of the graph-replayed encoder passes against aliasing with .grad."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.loss_helper import get_loss
+    bs = [synthetic.make_batch(s_, batch_size=2, num_points=6000, n_inst=8, n_cand=[4, 3], n_tokens=[6, 9]) for s_ in (5, 6)]
+    cfg = train_ref.SyntheticConfig()
+
+    def grads_of(model, batches, zero_between):
+        out = []
+        model.zero_grad()
+        for b in batches:
+            if zero_between:
+                model.zero_grad()
+            get_loss(model(synthetic.to_data_dict(b, SparseTensor, 'cuda')), cfg)['loss'].backward()
+            if zero_between:
+                out.append({k: p.grad.clone() for k, p in model.named_parameters()})
+        torch.cuda.synchronize()
+        return out if zero_between else {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    model = make_train_model(state_dict, args)
+    for bn in [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]:
+        bn.momentum = 0.0                                   # keep the running statistics fixed across the passes
+    grads_of(model, bs, True)                                # warm-up: eager pass, then graph capture
+    single = grads_of(model, bs, True)
+    acc = grads_of(model, bs, False)
+    scale = max(float(g.abs().max()) for g in acc.values())
+    for k, g in acc.items():
+        want = single[0][k] + single[1][k]
+        assert float((g - want).abs().max()) < 2e-3 * max(float(want.abs().max()), 1e-3 * scale), k
