@@ -496,6 +496,26 @@ int ir_edgeconv_train_fwd(const ir_edgeconv_t* p, const float* x, const float* x
 int ir_edgeconv_train_bwd(const ir_edgeconv_t* p, void* arena, const float* dout, const ir_edgeconv_grads_t* g,
                           ir_stream_t stream);
 
+/* Scene tail in train mode (models/scene_module.py:25-38,70-71), ONE call per direction: SparseCrop +
+ * ToDenseBEVConvolution -> BatchNorm2d (batch statistics) -> ReLU -> Conv2d 3x3 -> BatchNorm2d -> ReLU -> Dropout ->
+ * Conv2d 3x3.  f4 (n_rows,128) / coords / n_dev = the stride-16 output of the scene encoder; out (B,11,21,128) NHWC.
+ * Conv weights in the reference layout (Cout,Cin,3,3); kernel (5,128,128). */
+typedef struct {
+    int32_t B;
+    int64_t n_rows;
+    float eps, mom0, mom1, drop_p;
+    uint64_t seed;
+    const float *kernel, *g0, *be0, *w1, *b1, *g1, *be1, *w2, *b2;
+    float *rm0, *rv0, *rm1, *rv1;
+} ir_scene_tail_t;
+typedef struct { float *dkernel, *dg0, *dbe0, *dw1, *db1, *dg1, *dbe1, *dw2, *db2; } ir_scene_tail_grads_t;
+int64_t ir_scene_tail_arena_bytes(int64_t n_rows, int32_t B);
+int ir_scene_tail_train_fwd(const ir_scene_tail_t* p, const float* f4, const int32_t* coords, const int32_t* n_dev,
+                            void* arena, float* out, ir_stream_t stream);
+int ir_scene_tail_train_bwd(const ir_scene_tail_t* p, const float* f4, const int32_t* coords, const int32_t* n_dev,
+                            void* arena, const float* dout, float* df4, const ir_scene_tail_grads_t* g,
+                            ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

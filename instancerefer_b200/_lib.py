@@ -81,6 +81,16 @@ class EdgeConvGrads(C.Structure):
     _fields_ = [(n, p) for n in ("dww1", "dbw1", "dww2", "dbw2", "dwm1", "dbm1", "dwm2", "dbm2")]
 
 
+class SceneTail(C.Structure):
+    _fields_ = [("B", i32), ("n_rows", i64), ("eps", f32), ("mom0", f32), ("mom1", f32), ("drop_p", f32), ("seed", C.c_uint64),
+                ("kernel", p), ("g0", p), ("be0", p), ("w1", p), ("b1", p), ("g1", p), ("be1", p), ("w2", p), ("b2", p),
+                ("rm0", p), ("rv0", p), ("rm1", p), ("rv1", p)]
+
+
+class SceneTailGrads(C.Structure):
+    _fields_ = [(n, p) for n in ("dkernel", "dg0", "dbe0", "dw1", "db1", "dg1", "dbe1", "dw2", "db2")]
+
+
 # name -> (restype, argtypes); mirrors include/instancerefer_b200.h one to one
 SIGNATURES = {
     "ir_version": (i32, []),
@@ -159,6 +169,9 @@ SIGNATURES = {
     "ir_edgeconv_train_arena_bytes": (i64, [C.POINTER(EdgeConvParams)]),
     "ir_edgeconv_train_fwd": (i32, [C.POINTER(EdgeConvParams), p, p, p, p, p, p, p]),
     "ir_edgeconv_train_bwd": (i32, [C.POINTER(EdgeConvParams), p, p, C.POINTER(EdgeConvGrads), p]),
+    "ir_scene_tail_arena_bytes": (i64, [i64, i32]),
+    "ir_scene_tail_train_fwd": (i32, [C.POINTER(SceneTail), p, p, p, p, p, p]),
+    "ir_scene_tail_train_bwd": (i32, [C.POINTER(SceneTail), p, p, p, p, p, p, C.POINTER(SceneTailGrads), p]),
     "ir_mlp_head_arena_bytes": (i64, [i32, i32]),
     "ir_mlp_head_train_fwd": (i32, [C.POINTER(MlpHead), p, p, p, p]),
     "ir_mlp_head_train_bwd": (i32, [C.POINTER(MlpHead), p, p, p, p, p, p, p, p, p, p, p]),

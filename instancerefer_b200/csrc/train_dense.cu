@@ -1090,3 +1090,110 @@ extern "C" int ir_edgeconv_train_bwd(const ir_edgeconv_t* p, void* arena, const 
     if ((r = ir_gemm(p->H1, Dw, E, a.t2, p->H1, 1, a.w_in, Dw, 0, g->dww1, Dw, nullptr, 0, 0, stream)) != IR_OK) return r;
     return ir_colsum(a.t2, E, p->H1, g->dbw1, stream);
 }
+
+// ------------------------------------------------------------------ scene tail, train mode, one call per direction
+// models/scene_module.py:25-38,70-71: SparseCrop + ToDenseBEVConvolution -> BatchNorm2d (batch statistics) -> ReLU ->
+// Conv2d 3x3 -> BatchNorm2d -> ReLU -> Dropout -> Conv2d 3x3, NHWC, as a chain of the primitives above behind one
+// library call per direction.  Arena: ir_scene_tail_arena_bytes.
+__global__ void k_pack_conv_w(const float* __restrict__ w, int cout, int cin, float* __restrict__ wp, int unpack) {
+    // pack: wp[(tap*cin + ci)*cout + co] = w[((co*cin + ci)*9) + tap];  unpack: the inverse (w <- wp)
+    const int total = cout * cin * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % cout, t = i / cout, ci = t % cin, tap = t / cin;
+        const int j = (co * cin + ci) * 9 + tap;
+        if (unpack) const_cast<float*>(w)[j] = wp[i]; else wp[i] = w[j];
+    }
+}
+extern "C" int ir_bev(const float*, const int32_t*, const int32_t*, int64_t, int32_t, const float*, const float*, const float*,
+                      int32_t, float*, int32_t*, float*, ir_stream_t);
+
+struct SceneArena {
+    float *tmp, *dense, *a0, *st0a, *st0b, *wp1, *col1, *y1, *a1, *st1a, *st1b, *a1d, *wp2, *col2, *bn_scratch;
+    float *dcol, *t1, *t2, *dwp;
+    int* cell;
+    uint8_t* mask;
+    int64_t bytes;
+};
+static SceneArena scene_arena(void* base, int64_t n_rows, int64_t B) {
+    SceneArena a;
+    char* q = (char*)base;
+    auto take = [&](int64_t bytes) { char* o = q; q += (bytes + 255) / 256 * 256; return o; };
+    const int64_t C = 128, r0 = B * 375, r1 = B * 299, r2 = B * 231;
+    a.tmp = (float*)take((n_rows > 0 ? n_rows : 1) * C * 4); a.cell = (int*)take((n_rows > 0 ? n_rows : 1) * 4);
+    a.dense = (float*)take(r0 * C * 4); a.a0 = (float*)take(r0 * C * 4); a.st0a = (float*)take(C * 4); a.st0b = (float*)take(C * 4);
+    a.wp1 = (float*)take(9 * C * C * 4); a.col1 = (float*)take(r1 * 9 * C * 4); a.y1 = (float*)take(r1 * C * 4); a.a1 = (float*)take(r1 * C * 4);
+    a.st1a = (float*)take(C * 4); a.st1b = (float*)take(C * 4); a.a1d = (float*)take(r1 * C * 4); a.mask = (uint8_t*)take(r1 * C);
+    a.wp2 = (float*)take(9 * C * C * 4); a.col2 = (float*)take(r2 * 9 * C * 4);
+    a.bn_scratch = (float*)take(ir_bn_scratch_floats(256) * 4);
+    a.dcol = (float*)take(r1 * 9 * C * 4); a.t1 = (float*)take(r0 * C * 4); a.t2 = (float*)take(r0 * C * 4); a.dwp = (float*)take(9 * C * C * 4);
+    a.bytes = q - (char*)base;
+    return a;
+}
+extern "C" int64_t ir_scene_tail_arena_bytes(int64_t n_rows, int32_t B) { return scene_arena(nullptr, n_rows, B).bytes; }
+#define SCENE_CHECK(p) IR_CHECK_ARG((p) && (p)->B > 0 && (p)->n_rows > 0 && (p)->kernel && (p)->w1 && (p)->w2)
+
+extern "C" int ir_scene_tail_train_fwd(const ir_scene_tail_t* p, const float* f4, const int32_t* coords, const int32_t* n_dev,
+                                       void* arena, float* out, ir_stream_t stream) {
+    SCENE_CHECK(p);
+    IR_CHECK_ARG(f4 && coords && n_dev && arena && out);
+    const SceneArena a = scene_arena(arena, p->n_rows, p->B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = p->B, C = 128, r0 = B * 375, r1 = B * 299, r2 = B * 231;
+    int r;
+    if ((r = ir_bev(f4, coords, n_dev, p->n_rows, 16, p->kernel, nullptr, nullptr, B, a.tmp, a.cell, a.dense, stream)) != IR_OK) return r;
+    if ((r = ir_bn_train_fwd(a.dense, nullptr, r0, C, p->g0, p->be0, nullptr, 1, p->eps, p->mom0, p->rm0, p->rv0, a.bn_scratch,
+                             a.st0a, a.st0b, a.a0, stream)) != IR_OK) return r;
+    k_pack_conv_w<<<IR_NUM_SMS * 2, 256, 0, st>>>(p->w1, C, C, a.wp1, 0);
+    IR_CHECK_LAUNCH();
+    if ((r = ir_im2col_3x3(a.a0, B, 15, 25, C, a.col1, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(r1, C, 9 * C, a.col1, 9 * C, 0, a.wp1, C, 0, a.y1, C, p->b1, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_bn_train_fwd(a.y1, nullptr, r1, C, p->g1, p->be1, nullptr, 1, p->eps, p->mom1, p->rm1, p->rv1, a.bn_scratch,
+                             a.st1a, a.st1b, a.a1, stream)) != IR_OK) return r;
+    const float* a1d = a.a1;
+    if (p->drop_p > 0.f) {
+        if ((r = ir_dropout_fwd(a.a1, (int64_t)r1 * C, p->drop_p, p->seed, a.a1d, a.mask, stream)) != IR_OK) return r;
+        a1d = a.a1d;
+    }
+    k_pack_conv_w<<<IR_NUM_SMS * 2, 256, 0, st>>>(p->w2, C, C, a.wp2, 0);
+    IR_CHECK_LAUNCH();
+    if ((r = ir_im2col_3x3(a1d, B, 13, 23, C, a.col2, stream)) != IR_OK) return r;
+    return ir_gemm(r2, C, 9 * C, a.col2, 9 * C, 0, a.wp2, C, 0, out, C, p->b2, 0, 0, stream);
+}
+
+extern "C" int ir_scene_tail_train_bwd(const ir_scene_tail_t* p, const float* f4, const int32_t* coords, const int32_t* n_dev,
+                                       void* arena, const float* dout, float* df4, const ir_scene_tail_grads_t* g,
+                                       ir_stream_t stream) {
+    SCENE_CHECK(p);
+    IR_CHECK_ARG(f4 && coords && n_dev && arena && dout && df4 && g);
+    const SceneArena a = scene_arena(arena, p->n_rows, p->B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = p->B, C = 128, r0 = B * 375, r1 = B * 299, r2 = B * 231;
+    int r;
+    // conv 2
+    if ((r = ir_gemm(9 * C, C, r2, a.col2, 9 * C, 1, dout, C, 0, a.dwp, C, nullptr, 0, 0, stream)) != IR_OK) return r;
+    k_pack_conv_w<<<IR_NUM_SMS * 2, 256, 0, st>>>(g->dw2, C, C, a.dwp, 1);
+    IR_CHECK_LAUNCH();
+    if ((r = ir_colsum(dout, r2, C, g->db2, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(r2, 9 * C, C, dout, C, 0, a.wp2, C, 1, a.dcol, 9 * C, nullptr, 0, 0, stream)) != IR_OK) return r;
+    if ((r = ir_col2im_3x3(a.dcol, B, 13, 23, C, a.t1, stream)) != IR_OK) return r;                        // d a1d
+    const float* da1 = a.t1;
+    if (p->drop_p > 0.f) {
+        if ((r = ir_dropout_bwd(a.t1, a.mask, (int64_t)r1 * C, p->drop_p, a.t2, stream)) != IR_OK) return r;
+        da1 = a.t2;
+    }
+    float* dy1 = (da1 == a.t1) ? a.t2 : a.t1;
+    if ((r = ir_bn_train_bwd(da1, a.a1, a.y1, nullptr, r1, C, a.st1a, a.st1b, p->g1, 1, a.bn_scratch, dy1, nullptr, g->dg1, g->dbe1,
+                             nullptr, stream)) != IR_OK) return r;
+    // conv 1
+    if ((r = ir_gemm(9 * C, C, r1, a.col1, 9 * C, 1, dy1, C, 0, a.dwp, C, nullptr, 0, 0, stream)) != IR_OK) return r;
+    k_pack_conv_w<<<IR_NUM_SMS * 2, 256, 0, st>>>(g->dw1, C, C, a.dwp, 1);
+    IR_CHECK_LAUNCH();
+    if ((r = ir_colsum(dy1, r1, C, g->db1, stream)) != IR_OK) return r;
+    if ((r = ir_gemm(r1, 9 * C, C, dy1, C, 0, a.wp1, C, 1, a.dcol, 9 * C, nullptr, 0, 0, stream)) != IR_OK) return r;
+    float* da0 = (dy1 == a.t1) ? a.t2 : a.t1;
+    if ((r = ir_col2im_3x3(a.dcol, B, 15, 25, C, da0, stream)) != IR_OK) return r;
+    float* dd = (da0 == a.t1) ? a.t2 : a.t1;
+    if ((r = ir_bn_train_bwd(da0, a.a0, a.dense, nullptr, r0, C, a.st0a, a.st0b, p->g0, 1, a.bn_scratch, dd, nullptr, g->dg0, g->dbe0,
+                             nullptr, stream)) != IR_OK) return r;
+    return ir_bev_bwd(dd, f4, coords, a.cell, n_dev, p->n_rows, 16, p->kernel, 5, df4, g->dkernel, stream);
+}

@@ -11,6 +11,7 @@ ReLU); backward = BN backward, dgrad (the same pair-GEMM/reduce on the transpose
 W^T) and wgrad (per-offset gathered outer products).
 """
 import math
+import os
 
 import torch
 from torch.autograd import Function
@@ -665,6 +666,56 @@ class EdgeConvTrain(Function):
         return (None, None, None, None, None, *(flat[a:a + n].view(sh) for a, n, sh in zip(offs, numel, shapes)))
 
 
+class SceneTailTrain(Function):
+    """models/scene_module.py:25-38,70-71 in train mode as ONE library call per direction (ir_scene_tail_train_fwd /
+    _bwd): BEV -> BN -> ReLU -> Conv3x3 -> BN -> ReLU -> Dropout -> Conv3x3.  Parameter order: to_bev.1.kernel,
+    to_bev.2.{weight,bias}, vis_emb_fc.0.{weight,bias}, vis_emb_fc.1.{weight,bias}, vis_emb_fc.4.{weight,bias}."""
+
+    @staticmethod
+    def forward(ctx, f4, coords, n_dev, n_rows, B, bn0, bn1, drop_p, *params):
+        import ctypes as C
+        from . import _lib
+        f4 = f4.contiguous()
+        dev = f4.device
+        keep = [t.detach().contiguous() for t in params]
+        P = _lib.SceneTail()
+        P.B, P.n_rows, P.eps, P.drop_p = B, int(n_rows), bn0.eps, float(drop_p)
+        P.mom0 = bn0.momentum if bn0.momentum is not None else 0.1
+        P.mom1 = bn1.momentum if bn1.momentum is not None else 0.1
+        P.kernel, P.g0, P.be0, P.w1, P.b1, P.g1, P.be1, P.w2, P.b2 = (t.data_ptr() for t in keep)
+        P.rm0, P.rv0 = bn0.running_mean.data_ptr(), bn0.running_var.data_ptr()
+        P.rm1, P.rv1 = bn1.running_mean.data_ptr(), bn1.running_var.data_ptr()
+        if drop_p > 0:
+            _dropout_calls[0] += 1
+            P.seed = (torch.initial_seed() * 0x9E3779B1 + _dropout_calls[0] * 0x85EBCA6B) & (2 ** 63 - 1)
+        arena = torch.empty(_lib.load().ir_scene_tail_arena_bytes(int(n_rows), B), dtype=torch.uint8, device=dev)
+        out = torch.empty(B, 11, 21, 128, dtype=torch.float32, device=dev)
+        _lib.call("ir_scene_tail_train_fwd", C.byref(P), ops._p(f4, torch.float32), ops._p(coords, torch.int32),
+                  ops._p(n_dev, torch.int32), ops._p(arena), ops._p(out), ops._stream())
+        bn0.num_batches_tracked += 1
+        bn1.num_batches_tracked += 1
+        ctx.state = (P, keep, arena, f4, coords, n_dev, [tuple(t.shape) for t in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        from . import _lib
+        P, keep, arena, f4, coords, n_dev, shapes = ctx.state
+        numel = [int(torch.Size(sh).numel()) for sh in shapes]
+        offs, o = [], 0
+        for n in numel:
+            offs.append(o)
+            o += (n + 63) // 64 * 64
+        flat = torch.empty(o, dtype=torch.float32, device=f4.device)
+        G = _lib.SceneTailGrads()
+        G.dkernel, G.dg0, G.dbe0, G.dw1, G.db1, G.dg1, G.dbe1, G.dw2, G.db2 = (flat.data_ptr() + 4 * a for a in offs)
+        df4 = torch.empty_like(f4)
+        _lib.call("ir_scene_tail_train_bwd", C.byref(P), ops._p(f4), ops._p(coords), ops._p(n_dev), ops._p(arena),
+                  ops._p(dout.contiguous(), torch.float32), ops._p(df4), C.byref(G), ops._stream())
+        return (df4, None, None, None, None, None, None, None, *(flat[a:a + n].view(sh) for a, n, sh in zip(offs, numel, shapes)))
+
+
 def mlp_head(seq, x, norm_idx, last_idx, drop_idx=None):
     """Linear -> {BatchNorm1d | LayerNorm} -> ReLU [-> Dropout] -> Linear of the reference's
     nn.Sequential heads (e.g. models/relation_module.py:13-25).  IR_TRAIN_HEADS=ops runs it as separate
@@ -919,14 +970,19 @@ def scene_forward_train(m, data_dict, pack, prepared=None):
     else:
         ws, G, F0, C0 = prepared
         f4, G = encoder_forward_train(m.net, ws, F0, C0, G=G)
-    dense = BEV.apply(f4, m.to_bev[1].kernel, ws.coords(4), G.nlvl_dev[4:5], G.n[4], B)     # (B*375,128)
     bn = m.to_bev[2]
-    x = BatchNormAct.apply(dense, bn.weight, bn.bias, bn, True).view(B, 15, 25, -1)          # NHWC
     ve = m.vis_emb_fc
-    x = Conv3x3.apply(x, ve[0].weight, ve[0].bias)
-    x = BatchNormAct.apply(x.reshape(-1, x.shape[-1]), ve[1].weight, ve[1].bias, ve[1], True).view(x.shape)
-    x = dropout(x, ve[3])
-    x = Conv3x3.apply(x, ve[4].weight, ve[4].bias)                                           # (B,11,21,128)
+    if os.environ.get('IR_TRAIN_SCENE', 'fused') != 'ops' and G.n[4] > 0:
+        x = SceneTailTrain.apply(f4, ws.coords(4), G.nlvl_dev[4:5], G.n[4], B, bn, ve[1], float(ve[3].p),
+                                 m.to_bev[1].kernel, bn.weight, bn.bias, ve[0].weight, ve[0].bias,
+                                 ve[1].weight, ve[1].bias, ve[4].weight, ve[4].bias)       # (B,11,21,128)
+    else:                                                # separate autograd nodes (what the per-op tests cover)
+        dense = BEV.apply(f4, m.to_bev[1].kernel, ws.coords(4), G.nlvl_dev[4:5], G.n[4], B)     # (B*375,128)
+        x = BatchNormAct.apply(dense, bn.weight, bn.bias, bn, True).view(B, 15, 25, -1)          # NHWC
+        x = Conv3x3.apply(x, ve[0].weight, ve[0].bias)
+        x = BatchNormAct.apply(x.reshape(-1, x.shape[-1]), ve[1].weight, ve[1].bias, ve[1], True).view(x.shape)
+        x = dropout(x, ve[3])
+        x = Conv3x3.apply(x, ve[4].weight, ve[4].bias)                                           # (B,11,21,128)
     h, w = x.shape[1], x.shape[2]
     q = mlp_head(m.lang_emb_fc, data_dict['lang_scene_feats'], 1, 4, 3)
     scene_feats, atten = SceneAttention.apply(x.view(B, h * w, -1), q)

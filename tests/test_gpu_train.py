@@ -627,6 +627,37 @@ def test_train_step_matches_oracle(lib_built, state_dict, args):
         assert float((sd[k].cpu().float() - v.float()).abs().max()) < 1e-4, k
 
 
+@pytest.mark.parametrize('drop', [0.0, 0.3])
+def test_fused_scene_tail_matches_per_op_path(lib_built, state_dict, args, drop):
+    """ir_scene_tail_train_fwd/_bwd (one call per direction) against the same chain as separate autograd nodes
+    (IR_TRAIN_SCENE=ops), whole iteration: outputs, every gradient and the running statistics.  Same kernels in the
+    same order, so only the split-K atomics of the small GEMMs may differ; with Dropout on, both paths draw the
+    same counter-based mask."""
+    import instancerefer_b200.training as T
+    b = synthetic.make_batch(43, batch_size=3, num_points=8000, n_inst=10, n_cand=[4, 1, 6], n_tokens=[7, 12, 2])
+    res = {}
+    for mode in ('ops', 'fused'):
+        os.environ['IR_TRAIN_SCENE'] = mode
+        os.environ['IR_TRAIN_ENCODER'] = 'fused'          # eager encoder: bit-identical f4 for both runs
+        try:
+            torch.manual_seed(5)
+            T._dropout_calls[0] = 0
+            model = make_train_model(state_dict, args)
+            model.scene.vis_emb_fc[3].p = drop
+            dd, grads = run_train_step(model, b)
+            res[mode] = (dd['scene_scores'].detach().cpu(), dd['seg_scores'].detach().cpu(), float(dd['loss']), grads,
+                         {k: v.cpu() for k, v in model.state_dict().items() if 'running' in k or 'tracked' in k})
+        finally:
+            del os.environ['IR_TRAIN_SCENE'], os.environ['IR_TRAIN_ENCODER']
+    a, f = res['ops'], res['fused']
+    assert torch.allclose(a[0], f[0], atol=1e-5) and torch.allclose(a[1], f[1], atol=1e-5) and abs(a[2] - f[2]) < 1e-5
+    scale = max(float(g.abs().max()) for g in a[3].values())
+    for k in a[3]:
+        assert float((a[3][k] - f[3][k]).abs().max()) < 2e-4 * scale + 1e-7, k   # split-K atomics + a rare ReLU flip
+    for k in a[4]:
+        assert torch.allclose(a[4][k].float(), f[4][k].float(), atol=1e-6), k
+
+
 def test_flat_adam_matches_oracle_update(lib_built, state_dict, args):
     """Two iterations with the flat-buffer Adam against oracle forward/backward + adam_update."""
     from instancerefer_b200.optim import FlatAdam
