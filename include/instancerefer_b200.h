@@ -516,6 +516,39 @@ int ir_scene_tail_train_bwd(const ir_scene_tail_t* p, const float* f4, const int
                             void* arena, const float* dout, float* df4, const ir_scene_tail_grads_t* g,
                             ir_stream_t stream);
 
+/* ------------------------------------------------------------------ scan preprocessing
+ * The array work of data/scannet/prepare_data.py:30-216; the host side (PLY/JSON/TSV parsing, .npy output) is
+ * instancerefer_b200/prepare_data.py.  Vertex rows are (n,9) fp32: xyz, rgb (0-255), normal.  All pointers are
+ * device pointers unless named *_host.  scratch: ir_prepare_scratch_bytes(n_verts, n_faces, n_objects) bytes. */
+int64_t ir_prepare_scratch_bytes(int64_t n_verts, int64_t n_faces, int32_t n_objects);
+/* scannet_utils.py:18-44,111-115 (compute_normal, incl. its last-write-wins accumulation): fills columns 6..8. */
+int ir_mesh_normals(float* verts9, int64_t n_verts, const int32_t* faces, int64_t n_faces, void* scratch,
+                    ir_stream_t stream);
+/* prepare_data.py:60-66: xyz <- fp32([x y z 1] . M^T) computed in fp64; the other six columns are copied. */
+int ir_align_vertices(const float* verts9, int64_t n_verts, const double* matrix16_host, float* aligned9,
+                      ir_stream_t stream);
+/* prepare_data.py:73-90: label_ids[v] = seg_label[seg[v]], instance_ids[v] = seg_object[seg[v]] (0 = unannotated);
+ * the dense per-segment tables are built on the host from the aggregation JSON (later groups overwrite). */
+int ir_vertex_labels(const int32_t* seg_of_vert, int64_t n_verts, const int32_t* seg_label,
+                     const int32_t* seg_object, int32_t n_seg_table, uint32_t* label_ids, uint32_t* instance_ids,
+                     ir_stream_t stream);
+/* prepare_data.py:92-131: boxes (n_objects,8) fp64 = (cx,cy,cz,dx,dy,dz,label,obj_id-1) of the vertices with
+ * instance id o+1, fp32 arithmetic as numpy's; an object without vertices keeps a zero row. */
+int ir_instance_boxes(const float* verts9, const uint32_t* instance_ids, int64_t n_verts, int32_t n_objects,
+                      const int32_t* obj_label, void* scratch, double* boxes, ir_stream_t stream);
+/* prepare_data.py:141-148: masks (n_inst, n_verts) u8 of the PointGroup proposals in list order, cls (n_inst);
+ * the last proposal covering a vertex wins; ids are 1-based, 0 = none. */
+int ir_pointgroup_labels(const uint8_t* masks, const int32_t* cls, int32_t n_inst, int64_t n_verts,
+                         uint32_t* label_ids_pg, uint32_t* instance_ids_pg, ir_stream_t stream);
+/* prepare_data.py:185 (np.logical_not(np.in1d(labels, DONOTCARE_CLASS_IDS))): ascending indices of the kept
+ * vertices -> idx, their number -> *count_dev. */
+int ir_keep_index(const uint32_t* sem_labels, int64_t n_verts, const int32_t* donotcare, int32_t n_donotcare,
+                  void* scratch, int64_t* idx, int64_t* count_dev, ir_stream_t stream);
+/* prepare_data.py:186-189,206-212 (boolean / fancy row indexing): dst[i] = src[idx[i]] for i < min(*count_dev,
+ * m_max) (count_dev may be NULL); row_bytes a multiple of 4. */
+int ir_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, const int64_t* count_dev, int64_t m_max,
+                   void* dst, ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,6 +169,14 @@ SIGNATURES = {
     "ir_edgeconv_train_arena_bytes": (i64, [C.POINTER(EdgeConvParams)]),
     "ir_edgeconv_train_fwd": (i32, [C.POINTER(EdgeConvParams), p, p, p, p, p, p, p]),
     "ir_edgeconv_train_bwd": (i32, [C.POINTER(EdgeConvParams), p, p, C.POINTER(EdgeConvGrads), p]),
+    "ir_prepare_scratch_bytes": (i64, [i64, i64, i32]),
+    "ir_mesh_normals": (i32, [p, i64, p, i64, p, p]),
+    "ir_align_vertices": (i32, [p, i64, p, p, p]),
+    "ir_vertex_labels": (i32, [p, i64, p, p, i32, p, p, p]),
+    "ir_instance_boxes": (i32, [p, p, i64, i32, p, p, p, p]),
+    "ir_pointgroup_labels": (i32, [p, p, i32, i64, p, p, p]),
+    "ir_keep_index": (i32, [p, i64, p, i32, p, p, p, p]),
+    "ir_gather_rows": (i32, [p, i64, p, p, i64, p, p]),
     "ir_scene_tail_arena_bytes": (i64, [i64, i32]),
     "ir_scene_tail_train_fwd": (i32, [C.POINTER(SceneTail), p, p, p, p, p, p]),
     "ir_scene_tail_train_bwd": (i32, [C.POINTER(SceneTail), p, p, p, p, p, p, C.POINTER(SceneTailGrads), p]),

@@ -107,7 +107,44 @@ def main_train():
         print(name, float(out['loss']), len(names))
 
 
+PREPARE_CASES = {                       # name -> (synth_scan kwargs, split the reference is told, directory written)
+    'prepare_a': (dict(seed=11, n_verts=3000, n_faces=5600, n_objects=9, n_props=7), 'train', 'val'),
+    'prepare_b': (dict(seed=12, n_verts=700, n_faces=900, n_objects=4, n_props=3), 'val', 'test'),
+    'prepare_nolabels': (dict(seed=13, n_verts=500, n_faces=800, n_objects=3, n_props=2), 'test', 'test'),
+}
+
+
+def main_prepare():
+    """Golden fixtures of the scan preprocessing: the reference's data/scannet/prepare_data.py export_one_scan run
+    verbatim on synthetic scan files (scratch under oracle/_ref/, git-ignored); inputs + the eight saved arrays."""
+    import shutil
+    from oracle import prepare_ref as PR
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'prepare_tmp')
+    shutil.rmtree(root, ignore_errors=True)
+    os.makedirs(root)
+    tsv = os.path.join(root, 'labels.tsv')
+    PR.write_label_map(tsv)
+    for name, (kw, split, folder) in PREPARE_CASES.items():
+        s = PR.synth_scan(**kw)
+        labelled = 'nolabels' not in name
+        dirs = PR.write_scan(root, 'scene0000_00', s, split=folder, with_labels=labelled)
+        out = H.run_reference_prepare(dirs, 'scene0000_00', split, tsv, os.path.join(root, name))
+        arrs = {'out/' + k: v for k, v in out.items()}
+        for k in ('xyz', 'rgb', 'faces', 'seg_indices', 'matrix', 'masks', 'cls'):
+            arrs['in/' + k] = s[k]
+        arrs['in/seg_groups_json'] = np.frombuffer(json.dumps(s['seg_groups']).encode(), dtype=np.uint8)
+        arrs['config_json'] = np.frombuffer(json.dumps({'synth': kw, 'split': split, 'folder': folder, 'labelled': labelled}).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(GOLD, f'golden_{name}.npz'), **arrs)
+        print(name, {k: (v.shape, str(v.dtype)) for k, v in out.items()})
+        shutil.rmtree(os.path.join(root, 'scans'))
+        shutil.rmtree(os.path.join(root, 'PointGroupInst'))
+    shutil.rmtree(root, ignore_errors=True)
+
+
 if __name__ == '__main__':
+    if '--prepare' in sys.argv:
+        main_prepare()
+        sys.exit(0)
     if '--train' in sys.argv:
         main_train()
         sys.exit(0)

@@ -149,3 +149,64 @@ def run_reference_train_step(model, data_dict, config):
             torch.ones, torch.zeros = orig_ones, orig_zeros
     out['loss'].backward()
     return out
+
+
+# ----------------------------------------------------------------------------- scan preprocessing (§8(f)-4)
+
+def _plyfile_stub():
+    """The reference's scannet_utils.py imports ``plyfile`` (absent here) and exits without it.  This stand-in serves
+    ``PlyData.read`` for the binary little-endian files ``oracle.prepare_ref.write_scan`` writes: ``['vertex']`` with
+    ``.count`` / ``.data`` (structured array) and ``['face'].data`` (records whose first field is the index list) — the
+    only members data/scannet/scannet_utils.py:97-116 touches."""
+    import numpy as np
+
+    class _El:
+        def __init__(self, data):
+            self.data, self.count = data, len(data)
+
+    class PlyData(dict):
+        @staticmethod
+        def read(f):
+            raw = f.read()
+            end = raw.index(b'end_header\n') + len(b'end_header\n')
+            head = raw[:end].decode('ascii').split('\n')
+            nv = int([l for l in head if l.startswith('element vertex')][0].split()[-1])
+            nf = int([l for l in head if l.startswith('element face')][0].split()[-1])
+            vt = np.dtype([('x', '<f4'), ('y', '<f4'), ('z', '<f4'), ('red', 'u1'), ('green', 'u1'), ('blue', 'u1'), ('alpha', 'u1')])
+            ft = np.dtype([('n', 'u1'), ('v', '<i4', (3,))])
+            v = np.frombuffer(raw, vt, nv, end)
+            fc = np.frombuffer(raw, ft, nf, end + nv * vt.itemsize)
+            out = PlyData()
+            out['vertex'] = _El(v)
+            out['face'] = _El([(np.array(r['v']),) for r in fc])
+            return out
+
+    m = types.ModuleType('plyfile')
+    m.PlyData, m.PlyElement = PlyData, object
+    return m
+
+
+def run_reference_prepare(dirs, scan, split, label_map_file, out_prefix, donotcare=()):
+    """data/scannet/prepare_data.py ``export_one_scan`` VERBATIM on the scan files under ``dirs`` (written by
+    ``oracle.prepare_ref.write_scan``); the module-level names its ``__main__`` block would set are set here.
+    Returns the eight saved arrays."""
+    import numpy as np
+    d = os.path.join(REF, 'data', 'scannet')
+    sys.modules['plyfile'] = _plyfile_stub()
+    sys.path.insert(0, d)
+    try:
+        for name in ('scannet_utils', 'load_scannet_data', 'prepare_data'):
+            sys.modules.pop(name, None)
+        mod = importlib.import_module('prepare_data')
+        PR = importlib.import_module('oracle.prepare_ref')
+        mod.split, mod.SCANNET_DIR, mod.POINTGROUP_DIR = split, dirs['scannet'], dirs['pointgroup']
+        mod.LABEL_MAP_FILE, mod.DONOTCARE_CLASS_IDS = label_map_file, np.array(list(donotcare))
+        mod.OBJ_CLASS_IDS, mod.MAX_NUM_POINT = PR.OBJ_CLASS_IDS, PR.MAX_NUM_POINT
+        with contextlib.redirect_stdout(open(os.devnull, 'w')):
+            mod.export_one_scan(scan, out_prefix)
+    finally:
+        sys.path.remove(d)
+        for name in ('scannet_utils', 'load_scannet_data', 'prepare_data', 'plyfile'):
+            sys.modules.pop(name, None)
+    keys = ('vert', 'aligned_vert', 'sem_label', 'ins_label', 'sem_label_pg', 'ins_label_pg', 'bbox', 'aligned_bbox')
+    return {k: np.load(f'{out_prefix}_{k}.npy') for k in keys}

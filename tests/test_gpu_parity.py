@@ -328,7 +328,7 @@ def _run(gpu_model, b):
     return out
 
 
-@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, 'golden_*.npz')) if 'golden_train_' not in p))
+@pytest.mark.parametrize('path', sorted(p for p in glob.glob(os.path.join(GOLD, 'golden_*.npz')) if 'golden_train_' not in p and 'golden_prepare_' not in p))
 def test_forward_vs_golden(gpu_model, path):
     """Committed outputs of the reference's models/*.py executed verbatim (oracle/make_golden.py)."""
     z = np.load(path)
