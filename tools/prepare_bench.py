@@ -90,7 +90,7 @@ def main():
     cpu_ms = (time.perf_counter() - t0) * 1e3
     print(json.dumps({'metric': 'scan_preprocess', 'config': {'verts': n, 'faces': nf, 'objects': no, 'proposals': ni},
                       'device_ms': dev_ms, 'device_gbps_algorithmic': bytes_ / dev_ms / 1e6, 'e2e_ms_host_to_host': e2e_ms,
-                      'cpu_oracle_ms': cpu_ms, 'cpu_kind': 'port (numpy, 1 process)', 'launches_per_scan': 20}))
+                      'cpu_oracle_ms': cpu_ms, 'cpu_kind': 'port (numpy, 1 process)', 'launches_per_scan': 17}))
 
 
 if __name__ == '__main__':
