@@ -136,6 +136,18 @@ def read_axis_alignment(meta_file):
     return None if m is None else np.array(m, np.float64).reshape(4, 4)
 
 
+def read_mask(path):
+    """One PointGroup proposal mask (a text column of 0/1, `np.loadtxt` in prepare_data.py:146) as a bool array.
+    Files of single digits, one per line, are decoded from the raw bytes; anything else goes through np.loadtxt."""
+    with open(path, 'rb') as f:
+        raw = np.frombuffer(f.read(), np.uint8)
+    if raw.size and raw.size % 2 == 0 and np.all(raw[1::2] == 10):
+        d = raw[0::2]
+        if np.all((d >= 48) & (d <= 57)):
+            return d != 48
+    return np.atleast_1d(np.loadtxt(path)) != 0
+
+
 def read_pointgroup(pointgroup_file, scene, split):
     """prepare_data.py:38-47,144-148: (masks (n_inst, n_verts) uint8, cls (n_inst,) int32) of the scan's proposals.
     ``train`` scans are looked up under train/ then val/, all others under test/ — as the reference does."""
@@ -151,7 +163,7 @@ def read_pointgroup(pointgroup_file, scene, split):
             if not line:
                 continue
             txt_path, c, _ = line.split(' ')
-            masks.append(np.loadtxt(os.path.join(temp_dir, txt_path)) != 0)
+            masks.append(read_mask(os.path.join(temp_dir, txt_path)))
             cls.append(int(c))
     if not masks:
         return np.zeros((0, 0), np.uint8), np.zeros(0, np.int32)
@@ -364,12 +376,17 @@ def export_one_scan(scan_name, output_filename_prefix, scannet_dir, pointgroup_d
     return out
 
 
-def batch_export(scan_names, output_folder, **kw):
-    """prepare_data.py:219-234."""
+def shard_scans(scan_names, rank, world):
+    """Scans are independent: rank r of `world` processes takes every world-th scan (no collective)."""
+    return list(scan_names)[rank::world]
+
+
+def batch_export(scan_names, output_folder, rank=0, world=1, **kw):
+    """prepare_data.py:219-234; under torchrun (RANK / WORLD_SIZE) each process converts its own share of the scans."""
     if not os.path.exists(output_folder):
         print('Creating new data folder: {}'.format(output_folder))
-        os.mkdir(output_folder)
-    for scan_name in scan_names:
+        os.makedirs(output_folder, exist_ok=True)
+    for scan_name in shard_scans(scan_names, rank, world):
         print(scan_name)
         print('-' * 20 + 'begin')
         print(datetime.datetime.now())
@@ -390,7 +407,10 @@ def parse_args(argv=None):
 def main(argv=None):
     args = parse_args(argv)
     names = sorted(line.rstrip() for line in open(os.path.join(args.meta_path, 'scannetv2_%s.txt' % args.split)))
-    batch_export(names, args.output_path, scannet_dir=args.scannet_path, pointgroup_dir=args.pointgroupinst_path,
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)) % torch.cuda.device_count())
+    batch_export(names, args.output_path, rank=rank, world=world, scannet_dir=args.scannet_path, pointgroup_dir=args.pointgroupinst_path,
                  label_map_file=os.path.join(args.meta_path, 'scannetv2-labels.combined.tsv'), split=args.split)
 
 

@@ -51,6 +51,20 @@ def test_host_parsers_read_what_write_scan_wrote(tmp_path):
         P.read_pointgroup(dirs['pointgroup'], 'scene0002_00', 'test')
 
 
+def test_mask_reader_and_scan_sharding(tmp_path):
+    from instancerefer_b200 import prepare_data as P
+    m = (np.random.RandomState(0).rand(500) < 0.3).astype(np.int64)
+    np.savetxt(tmp_path / 'a.txt', m, fmt='%d')
+    np.savetxt(tmp_path / 'b.txt', m.astype(np.float64))                  # '0.000000e+00' lines: the loadtxt route
+    np.savetxt(tmp_path / 'c.txt', m * 12, fmt='%d')                      # two-digit entries: the loadtxt route
+    for name in ('a.txt', 'b.txt', 'c.txt'):
+        assert np.array_equal(P.read_mask(str(tmp_path / name)), m != 0), name
+    names = [f'scene{i:04d}_00' for i in range(11)]
+    parts = [P.shard_scans(names, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == names and max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert P.shard_scans(names, 0, 1) == names
+
+
 def test_ascii_ply(tmp_path):
     from instancerefer_b200 import prepare_data as P
     p = tmp_path / 'a.ply'
