@@ -7,12 +7,9 @@ Pinned: ``oracle/make_golden.py --prepare`` runs the reference's own ``export`` 
 synthetic scan written to disk (its ``plyfile`` import is served by a reader stub, see ``ref_harness``) and stores
 inputs and outputs as ``tests/golden/golden_prepare_*.npz``; ``tests/test_oracle.py`` checks this file against them.
 
-Everything is written on arrays (the parsed contents of the scan's files); ``write_scan`` is the synthetic scan
-generator that produces those files in ScanNet's formats.
+Everything is written on arrays (the parsed contents of the scan's files); ``instancerefer_b200.synthetic.write_scan``
+is the synthetic scan generator that produces those files in ScanNet's formats.
 """
-import json
-import os
-
 import numpy as np
 
 OBJ_CLASS_IDS = np.array([3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 23, 24, 25, 26, 27, 28,
@@ -142,88 +139,5 @@ def export_one_scan(exported, donotcare=(), choices=None):
             'ins_label_pg': ins_pg, 'bbox': bb, 'aligned_bbox': bb_al}
 
 
-# ----------------------------------------------------------------------------- synthetic scan on disk
-
-RAW_LABELS = ['chair', 'table', 'wall', 'floor', 'cabinet', 'sofa', 'door', 'window']
-
-
-def synth_scan(seed, n_verts=3000, n_faces=5600, n_objects=9, n_props=7, n_segments=None):
-    """Seeded scan contents in ScanNet's shapes: vertices with colour, a face list with repeated vertices, an
-    over-segmentation, labelled objects (one segment listed by two objects), an axis alignment
-    and PointGroup proposals that overlap."""
-    rng = np.random.default_rng(seed)
-    n_segments = n_segments or max(n_objects * 4, n_verts // 40)
-    xyz = (rng.random((n_verts, 3)) * [8.0, 6.0, 3.0] - [4.0, 3.0, 0.2]).astype(np.float32)
-    rgb = rng.integers(0, 256, (n_verts, 3)).astype(np.uint8)
-    faces = rng.integers(0, n_verts, (n_faces, 3)).astype(np.int32)
-    if n_faces:
-        faces[: min(5, n_faces)] = faces[0]                      # degenerate / repeated faces
-        faces[min(7, n_faces - 1)] = [3, 3, 3]                   # zero-area face
-    seg_indices = rng.integers(0, n_segments, n_verts).astype(np.int64) * 3 + 1     # sparse segment ids
-    seg_ids = np.unique(seg_indices)
-    rng.shuffle(seg_ids)
-    per = np.array_split(seg_ids[: max(1, int(len(seg_ids) * 0.8))], n_objects)
-    groups = []
-    for o in range(n_objects):
-        segs = [int(s) for s in per[o]]
-        if o == n_objects - 2 and o > 0 and groups[0]['segments']:
-            segs.append(groups[0]['segments'][0])               # a segment claimed by two objects: the later one wins
-        groups.append({'objectId': o, 'label': RAW_LABELS[int(rng.integers(0, len(RAW_LABELS)))], 'segments': segs})
-    th = float(rng.random() * 6.28)
-    matrix = np.array([[np.cos(th), -np.sin(th), 0, rng.normal()], [np.sin(th), np.cos(th), 0, rng.normal()],
-                       [0, 0, 1, rng.normal() * 0.1], [0, 0, 0, 1]], np.float64)
-    masks = (rng.random((n_props, n_verts)) < 0.15).astype(np.uint8)
-    cls = rng.integers(3, 40, n_props).astype(np.int64)
-    return {'xyz': xyz, 'rgb': rgb, 'faces': faces, 'seg_indices': seg_indices, 'seg_groups': groups, 'matrix': matrix,
-            'masks': masks, 'cls': cls}
-
-
-def write_label_map(path):
-    """A cut-down scannetv2-labels.combined.tsv with the two columns the preprocessing reads."""
-    nyu = {'chair': 5, 'table': 7, 'wall': 1, 'floor': 2, 'cabinet': 3, 'sofa': 6, 'door': 8, 'window': 9}
-    with open(path, 'w') as f:
-        f.write('id\traw_category\tcategory\tnyu40id\n')
-        for i, (k, v) in enumerate(nyu.items()):
-            f.write(f'{i + 1}\t{k}\t{k}\t{v}\n')
-    return nyu
-
-
-def write_scan(root, scan, s, split='val', with_labels=True):
-    """Write the files the reference reads for one scan (prepare_data.py:167-176, :38-47):
-    <root>/scans/<scan>/<scan>_vh_clean_2.ply, .aggregation.json, _vh_clean_2.0.010000.segs.json, <scan>.txt and
-    <root>/PointGroupInst/<train|val|test>/<scan>.txt + one mask file per proposal.  Returns the directory dict."""
-    d = os.path.join(root, 'scans', scan)
-    os.makedirs(d, exist_ok=True)
-    n, nf = s['xyz'].shape[0], s['faces'].shape[0]
-    head = ('ply\nformat binary_little_endian 1.0\ncomment synthetic\n'
-            f'element vertex {n}\nproperty float x\nproperty float y\nproperty float z\n'
-            'property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n'
-            f'element face {nf}\nproperty list uchar int vertex_indices\nend_header\n')
-    vt = np.zeros(n, dtype=[('x', '<f4'), ('y', '<f4'), ('z', '<f4'), ('red', 'u1'), ('green', 'u1'), ('blue', 'u1'), ('alpha', 'u1')])
-    vt['x'], vt['y'], vt['z'] = s['xyz'].T
-    vt['red'], vt['green'], vt['blue'] = s['rgb'].T
-    vt['alpha'] = 255
-    ft = np.zeros(nf, dtype=[('n', 'u1'), ('v', '<i4', (3,))])
-    ft['n'] = 3
-    ft['v'] = s['faces']
-    with open(os.path.join(d, scan + '_vh_clean_2.ply'), 'wb') as f:
-        f.write(head.encode('ascii'))
-        f.write(vt.tobytes())
-        f.write(ft.tobytes())
-    if with_labels:
-        with open(os.path.join(d, scan + '.aggregation.json'), 'w') as f:
-            json.dump({'sceneId': scan, 'segGroups': [dict(g, id=g['objectId']) for g in s['seg_groups']]}, f)
-    with open(os.path.join(d, scan + '_vh_clean_2.0.010000.segs.json'), 'w') as f:
-        json.dump({'sceneId': scan, 'segIndices': [int(x) for x in s['seg_indices']]}, f)
-    with open(os.path.join(d, scan + '.txt'), 'w') as f:
-        if s.get('matrix') is not None:
-            f.write('axisAlignment = ' + ' '.join(repr(float(x)) for x in s['matrix'].reshape(-1)) + '\n')
-        f.write('colorHeight = 968\nnumDepthFrames = 100\n')
-    pg = os.path.join(root, 'PointGroupInst', split)
-    os.makedirs(os.path.join(pg, 'predicted_masks'), exist_ok=True)
-    with open(os.path.join(pg, scan + '.txt'), 'w') as f:
-        for i, c in enumerate(s['cls']):
-            rel = f'predicted_masks/{scan}_{i:03d}.txt'
-            f.write(f'{rel} {int(c)} {0.5 + 0.01 * i:.4f}\n')
-            np.savetxt(os.path.join(pg, rel), s['masks'][i], fmt='%d')
-    return {'scannet': os.path.join(root, 'scans'), 'pointgroup': os.path.join(root, 'PointGroupInst')}
+# synthetic scan generator (shared with the tests and tools): lives in the package, re-exported here
+from instancerefer_b200.synthetic import RAW_LABELS, synth_scan, write_label_map, write_scan   # noqa: E402,F401

@@ -28,7 +28,8 @@ def main():
     ap.add_argument('--props', type=int, default=80)
     ap.add_argument('--reps', type=int, default=20)
     a = ap.parse_args()
-    s = PR.synth_scan(seed=41, n_verts=a.verts, n_faces=a.faces, n_objects=a.objects, n_props=a.props)
+    from instancerefer_b200 import synthetic
+    s = synthetic.synth_scan(seed=41, n_verts=a.verts, n_faces=a.faces, n_objects=a.objects, n_props=a.props)
     vertex = np.concatenate([s['xyz'], s['rgb'].astype(np.float32)], 1)
     n, nf, no, ni = a.verts, a.faces, a.objects, a.props
     ch = np.random.RandomState(0).choice(n, min(n, P.MAX_NUM_POINT), replace=False)
