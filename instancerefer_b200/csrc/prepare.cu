@@ -173,15 +173,51 @@ __global__ void k_box_finish(const uint32_t* __restrict__ mm, const int32_t* __r
     b[7] = (double)o;
 }
 
-// ---- PointGroup proposals -> per-vertex labels: prepare_data.py:141-148 (later proposals overwrite earlier ones)
+// ---- PointGroup proposals -> per-vertex labels: prepare_data.py:141-148 (later proposals overwrite earlier ones).
+// A stream over the (n_inst, n) byte masks from the last proposal down: every thread owns 4 consecutive vertices (one
+// 32-bit load per proposal row when n % 4 == 0), issues PG_DEPTH row loads before looking at them, and stops as soon
+// as its four vertices are decided.
+constexpr int PG_DEPTH = 8;
+template <bool VEC>
 __global__ void k_pointgroup(const uint8_t* __restrict__ masks, const int32_t* __restrict__ cls, int32_t n_inst, int64_t n,
                              uint32_t* __restrict__ label, uint32_t* __restrict__ inst) {
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t id = 0u, lb = 0u;
-        for (int i = n_inst - 1; i >= 0; --i)
-            if (masks[(int64_t)i * n + v]) { id = (uint32_t)(i + 1); lb = (uint32_t)cls[i]; break; }
-        inst[v] = id;
-        label[v] = lb;
+    const int64_t groups = (n + 3) / 4;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v0 = 4 * g;
+        const int lanes = (int)(n - v0 < 4 ? n - v0 : 4);
+        uint32_t id[4] = {0u, 0u, 0u, 0u};
+        uint32_t open_mask = lanes == 4 ? 0xffffffffu : ((1u << (8 * lanes)) - 1u);   // byte j nonzero = vertex j undecided
+        for (int hi = n_inst - 1; hi >= 0 && open_mask; hi -= PG_DEPTH) {
+            uint32_t w[PG_DEPTH];
+#pragma unroll
+            for (int d = 0; d < PG_DEPTH; ++d) {
+                const int i = hi - d;
+                uint32_t x = 0u;
+                if (i >= 0) {
+                    const uint8_t* row = masks + (int64_t)i * n + v0;
+                    if (VEC) x = *reinterpret_cast<const uint32_t*>(row);
+                    else
+                        for (int j = 0; j < lanes; ++j) x |= (uint32_t)row[j] << (8 * j);
+                }
+                w[d] = x;
+            }
+#pragma unroll
+            for (int d = 0; d < PG_DEPTH; ++d) {
+                const int i = hi - d;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t byte = 0xffu << (8 * j);
+                    if ((w[d] & byte) && (open_mask & byte)) {
+                        id[j] = (uint32_t)(i + 1);
+                        open_mask &= ~byte;
+                    }
+                }
+            }
+        }
+        for (int j = 0; j < lanes; ++j) {
+            inst[v0 + j] = id[j];
+            label[v0 + j] = id[j] ? (uint32_t)cls[id[j] - 1] : 0u;
+        }
     }
 }
 
@@ -339,8 +375,11 @@ extern "C" int ir_pointgroup_labels(const uint8_t* masks, const int32_t* cls, in
     IR_CHECK_ARG(n_verts >= 0 && n_inst >= 0);
     if (n_verts == 0) return IR_OK;
     IR_CHECK_ARG(label_ids_pg && instance_ids_pg && (n_inst == 0 || (masks && cls)));
-    k_pointgroup<<<grid_for(n_verts), TPB, 0, (cudaStream_t)stream>>>(masks, cls, n_inst, n_verts, label_ids_pg,
-                                                                       instance_ids_pg);
+    const int grid = grid_for((n_verts + 3) / 4);
+    if (n_verts % 4 == 0 && (reinterpret_cast<uintptr_t>(masks) & 3) == 0)
+        k_pointgroup<true><<<grid, TPB, 0, (cudaStream_t)stream>>>(masks, cls, n_inst, n_verts, label_ids_pg, instance_ids_pg);
+    else
+        k_pointgroup<false><<<grid, TPB, 0, (cudaStream_t)stream>>>(masks, cls, n_inst, n_verts, label_ids_pg, instance_ids_pg);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
