@@ -3,7 +3,6 @@ candidates are voxelised at 2 cm ON THE GPU (first-point-wins), encoded by the s
 max-pooled per candidate and matched against the language feature.
 Reference lines: models/attribute_module.py:12-40 (ctor), :42-81 (filter_candidates), :83-131."""
 import numpy as np
-import torch
 import torch.nn as nn
 
 from . import ops

@@ -7,7 +7,6 @@ reference's solver does (lib/solver.py:207-216).
 The reference loops over the scenes on the host with a D2H sync per scene (``torch.argmax`` → numpy
 indexing) ; here one kernel (``ir_ref_eval``) scores every scene and the results come back in ONE
 copy."""
-import numpy as np
 import torch
 
 from . import ops

@@ -10,7 +10,6 @@ conv = pair-GEMM + reduce (the eval kernels, identity epilogue) -> train-mode BN
 ReLU); backward = BN backward, dgrad (the same pair-GEMM/reduce on the transposed rulebook with
 W^T) and wgrad (per-offset gathered outer products).
 """
-import math
 import os
 
 import torch
