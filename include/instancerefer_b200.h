@@ -47,6 +47,15 @@ int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap
  * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
 int ir_tune_set(int pairgemm_ctas, int reduce_ctas);
 
+/* Feature-pass mode of ir_encoder_features[_pair]: 1 (default) = all 13 layers in ONE persistent launch (ticketed
+ * pair-GEMM / reduce items, device-side tile counts, range-scaled split-fp16); 0 = one pair-GEMM + one reduce launch
+ * per layer (also taken while ir_profile_enable is on, and for the SIMT path). */
+int ir_encoder_mode_set(int mode);
+
+/* Timeline aid: a one-thread kernel writes the GPU nanosecond timer into buf[idx] on `stream` (works inside stream
+ * capture, so a replayed CUDA graph leaves a branch-level timeline behind; tools/timeline.py). */
+int ir_debug_stamp(uint64_t* buf, int32_t idx, ir_stream_t stream);
+
 /* Tuning aid for the tcgen05 pair-GEMM (tools/bench_spconv.py): bit0 skip gather loads, bit1 skip T
  * stores, bit2 skip MMA issue.  0 = normal operation. */
 int ir_debug_set(int flags);
@@ -75,6 +84,8 @@ typedef struct {
     int64_t off_kcount;                    /* int32[9][32]: pairs per offset; maps 0-4 = k3 at
                                               level l, maps 5-8 = k2s2 from level l to l+1        */
     int64_t off_scan, scan_stride;         /* u64[5][scan_stride] compaction state                */
+    int64_t off_sync;                      /* 512 B: ticket / phase counters / range maxima / time stamps of
+                                              the persistent encoder kernel (inside the zeroed prefix)       */
     int64_t zero_bytes;                    /* bytes cleared from off_nlvl on reset                 */
     int64_t off_keys, off_vals;            /* 5 tables: keys u64[cap]; vals {minrow,row} i32[cap]  */
     int64_t off_coords[IR_ENC_LEVELS];     /* int32 (n_max,4) [x,y,z,b] per level                 */
@@ -313,10 +324,12 @@ int ir_ref_eval(const double* pred_obb, const int32_t* obb_ofs, const double* gt
                 double* iou, double* pred_corners, double* gt_corners, ir_stream_t stream);
 
 /* torch.optim.Adam (amsgrad off) on one flat fp32 buffer; gradient = grad_scale*g + weight_decay*p
- * (grad_scale = 1/world_size after a sum all-reduce).  `step` counts from 1.                      */
+ * (grad_scale = 1/world_size after a sum all-reduce).  `step` counts from 1.  block_skip (or NULL): one byte per
+ * 64 floats, 1 = the block belongs to a parameter that received no gradient this step and is left untouched
+ * (parameter and both moments), as torch.optim.Adam does for grad None.                                    */
 int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                 float grad_scale, ir_stream_t stream);
+                 float grad_scale, const uint8_t* block_skip, ir_stream_t stream);
 
 /* ------------------------------------------------------------------ one-call encoder training passes
  * All 13 [conv -> train-mode BN (-> + skip) -> ReLU] layers forward, and their backward, as one chain

@@ -25,7 +25,7 @@ class EncoderParams(C.Structure):
 
 class EncoderLayout(C.Structure):
     _fields_ = [("n_max", i64), ("cap", i64), ("total_bytes", i64),
-                ("off_nlvl", i64), ("off_kcount", i64), ("off_scan", i64), ("scan_stride", i64),
+                ("off_nlvl", i64), ("off_kcount", i64), ("off_scan", i64), ("scan_stride", i64), ("off_sync", i64),
                 ("zero_bytes", i64), ("off_keys", i64), ("off_vals", i64),
                 ("off_coords", i64 * ENC_LEVELS), ("off_pslot", i64),
                 ("off_k3_in", i64 * ENC_LEVELS), ("off_k3_slot", i64 * ENC_LEVELS),
@@ -100,6 +100,8 @@ SIGNATURES = {
     "ir_profile_enable": (i32, [i32]),
     "ir_profile_read": (i32, [p, p, p, i32, p]),
     "ir_debug_set": (i32, [i32]),
+    "ir_debug_stamp": (i32, [p, i32, p]),
+    "ir_encoder_mode_set": (i32, [i32]),
     "ir_tune_set": (i32, [i32, i32]),
     "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),
     "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),
@@ -138,7 +140,7 @@ SIGNATURES = {
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
     "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
     "ir_ref_eval": (i32, [p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p]),
-    "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p]),
+    "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p, p]),
     "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),
     "ir_encoder_train_forward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p]),
     "ir_encoder_train_backward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p, C.POINTER(EncoderTrainGrads), p]),

@@ -55,10 +55,14 @@ class AttributeModule(nn.Module, PrepCache):
         data_dict['num_filtered_objs'] = pack.num_filtered
         ppi = pack.points.shape[1]
         ws = self.net.workspace(pack.M * ppi, device)
+        ops.stamp('attr:start')
         ops.encoder_reset(ws)
         ops.voxelize(pack.points, pack.cand_rows, float(self.voxel_size[0]), ws)
+        ops.stamp('attr:voxelized')
         f4, c4, n4 = self.net.encode(ws)
+        ops.stamp('attr:features')
         data_dict['obj_feats'] = ops.segmax(f4, c4, n4, ws.n_max, pack.M)
+        ops.stamp('attr:pooled')
         data_dict['pred_obb_batch'] = pack.pred_obb_batch
         return data_dict
 
@@ -97,6 +101,7 @@ class AttributeModule(nn.Module, PrepCache):
         _, scores = ops.mlp_head(data_dict['obj_feats'], p['vw1'], p['vb1'], ops.NORM_LAYER, p['vg'], p['vbeta'],
                                  p['vw2'], p['vb2'], ops.MODE_DOT, partner=lang_emb, seg=pack.cand_scene)
         data_dict['attribute_scores'] = scores
+        ops.stamp('attr:matched')
         return data_dict
 
     def forward(self, data_dict):

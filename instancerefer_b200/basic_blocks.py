@@ -16,9 +16,24 @@ from . import ops
 from .sparse_tensor import SparseTensor
 
 
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    """Called by whoever writes parameters behind torch's back (``FlatAdam.step`` updates the flat parameter buffer
+    through a raw-pointer kernel, which does not move any tensor ``_version``): every prepared copy and every captured
+    graph that baked one in becomes stale."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def weights_epoch():
+    return _WEIGHTS_EPOCH[0]
+
+
 class PrepCache:
     """Kernel-friendly copies of the parameters (folded BN, repacked weights), rebuilt only when a
-    parameter/buffer changed (tensor ``_version``) or moved."""
+    parameter/buffer changed (tensor ``_version``), moved, or the global weights epoch advanced (raw-pointer
+    optimiser updates, see ``bump_weights_epoch``)."""
 
     def _prep_tensors(self):
         return list(self.parameters()) + list(self.buffers())
@@ -28,7 +43,7 @@ class PrepCache:
         if ts is None:                      # module structure is fixed after construction
             ts = self._prep_tensors()
             self.__dict__['_prep_ts'] = ts
-        return [(t.data_ptr(), t._version) for t in ts]
+        return [_WEIGHTS_EPOCH[0]] + [(t.data_ptr(), t._version) for t in ts]
 
     def prepared(self):
         key = self._prep_key()
@@ -149,6 +164,7 @@ class SparseConvEncoder(nn.Module, PrepCache):
         require_eval(self)
         prep = self.prepared()
         ops.encoder_build_maps(ws, coords0, n0_dev)
+        ops.stamp('enc:maps')
         out = torch.empty(ws.n_max, 128, dtype=torch.float32, device=ws.buf.device)
         ops.encoder_features(prep['params'], ws, feats0, out)
         return out, ws.coords(4), ws.nlvl()[4:5]

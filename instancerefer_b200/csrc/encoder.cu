@@ -74,6 +74,28 @@ static cudaEvent_t prof_event(int i, int j) {
     return g_prof_ev[i][j];
 }
 
+// 1 (default): the 13 layers of ir_encoder_features[_pair] run as ONE persistent launch (encoder_persist.cu);
+// 0: one pair-GEMM + one reduce launch per layer (k_pairgemm_tc / k_reduce_epilogue).
+static int g_encoder_mode = 1;
+extern "C" int ir_encoder_mode_set(int mode) {
+    IR_CHECK_ARG(mode == 0 || mode == 1);
+    g_encoder_mode = mode;
+    return IR_OK;
+}
+
+// timeline aid (tools/timeline.py): one thread writes %globaltimer into buf[idx]; usable inside stream capture
+__global__ void k_stamp(unsigned long long* buf, int idx) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    buf[idx] = t;
+}
+extern "C" int ir_debug_stamp(uint64_t* buf, int32_t idx, ir_stream_t stream) {
+    IR_CHECK_ARG(buf != nullptr && idx >= 0);
+    k_stamp<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)buf, idx);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
 // ------------------------------------------------------------------ layout
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -90,6 +112,7 @@ extern "C" int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* L) {
     L->off_kcount = take(9 * 32 * 4);
     L->scan_stride = 1 + (n_max + 2047) / 2048 + 1;
     L->off_scan = take(5 * L->scan_stride * 8);
+    L->off_sync = take(512);               // ticket / phase counters of the persistent encoder kernel
     L->zero_bytes = off - L->off_nlvl;
     L->off_keys = take(5 * cap * 8);
     L->off_vals = take(5 * cap * 8);
@@ -121,6 +144,7 @@ struct Ws {
     char* base;
     int* nlvl() const { return (int*)(base + L.off_nlvl); }
     int* kcount(int map) const { return (int*)(base + L.off_kcount) + map * 32; }
+    void* sync() const { return (void*)(base + L.off_sync); }
     unsigned long long* scan(int i) const { return (unsigned long long*)(base + L.off_scan) + i * L.scan_stride; }
     IrTable table(int l) const {
         return ir_table_view2(base + L.off_keys + (int64_t)l * L.cap * 8,
@@ -284,14 +308,15 @@ static int encoder_features_multi(int G, const ir_encoder_params* const* ps, con
         IR_CHECK_ARG(ps[g]->cin == ps[0]->cin && ps[g]->use_tc == ps[0]->use_tc);
     }
     static const int ch[5] = {32, 64, 128, 128, 128};
-    // per problem: fin, map (in/slot/count), output level, residual, destination, for layer `idx`
-    auto run = [&](int idx, int cin, int cout, int K, auto&& fill) -> int {
-        IrConvBatch b;
-        memset(&b, 0, sizeof(b));
-        b.G = G;
-        const float* wp[IR_MAX_GROUPS] = {nullptr, nullptr};
+    // the 13 layers as (shape, per-problem buffers); executed either by ONE persistent launch (encoder_persist.cu)
+    // or layer by layer (pair-GEMM + reduce launches; the profiling hooks and the SIMT path live there)
+    IrConvProblem layers[IR_ENC_LAYERS][IR_MAX_GROUPS];
+    int cins[IR_ENC_LAYERS], couts[IR_ENC_LAYERS], Ks[IR_ENC_LAYERS];
+    memset(layers, 0, sizeof(layers));
+    auto add = [&](int idx, int cin, int cout, int K, auto&& fill) {
+        cins[idx] = cin; couts[idx] = cout; Ks[idx] = K;
         for (int g = 0; g < G; ++g) {
-            IrConvProblem& P = b.p[g];
+            IrConvProblem& P = layers[idx][g];
             fill(g, P);
             P.weight = ps[g]->weight[idx];
             P.scale = ps[g]->bn_scale[idx];
@@ -300,36 +325,52 @@ static int encoder_features_multi(int G, const ir_encoder_params* const* ps, con
             P.seg_cap = n_maxs[g];
             P.n_max = n_maxs[g];
             P.relu = 1;
-            wp[g] = ps[g]->wprep[idx];
         }
-        return conv_layer(b, cin, cout, K, wp, ps[0]->use_tc, st);
     };
     // stem: k3 at level 0
-    if ((r = run(0, ps[0]->cin, ch[0], 27, [&](int g, IrConvProblem& P) {
-             P.fin = feats0[g] ? feats0[g] : w[g].feat0();
-             P.in_idx = w[g].k3_in(0); P.slot = w[g].k3_slot(0); P.count = w[g].kcount(0);
-             P.n_out_dev = w[g].nlvl() + 0; P.resid = nullptr; P.out = w[g].feat(0);
-         })) != IR_OK) return r;
+    add(0, ps[0]->cin, ch[0], 27, [&](int g, IrConvProblem& P) {
+        P.fin = feats0[g] ? feats0[g] : w[g].feat0();
+        P.in_idx = w[g].k3_in(0); P.slot = w[g].k3_slot(0); P.count = w[g].kcount(0);
+        P.n_out_dev = w[g].nlvl() + 0; P.resid = nullptr; P.out = w[g].feat(0);
+    });
     for (int s = 1; s <= 4; ++s) {
         const int l = s - 1, li = 1 + 3 * (s - 1);
         // down: k2 s2, level l -> l+1
-        if ((r = run(li + 0, ch[l], ch[s], 8, [&](int g, IrConvProblem& P) {
-                 P.fin = w[g].feat(0);
-                 P.in_idx = w[g].k2_in(l); P.slot = w[g].k2_slot(l); P.count = w[g].kcount(5 + l);
-                 P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(1);
-             })) != IR_OK) return r;
+        add(li + 0, ch[l], ch[s], 8, [&](int g, IrConvProblem& P) {
+            P.fin = w[g].feat(0);
+            P.in_idx = w[g].k2_in(l); P.slot = w[g].k2_slot(l); P.count = w[g].kcount(5 + l);
+            P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(1);
+        });
         // residual block at level s: relu(bn(conv(relu(bn(conv(X))))) + X)
-        if ((r = run(li + 1, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
-                 P.fin = w[g].feat(1);
-                 P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
-                 P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(2);
-             })) != IR_OK) return r;
-        if ((r = run(li + 2, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
-                 P.fin = w[g].feat(2);
-                 P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
-                 P.n_out_dev = w[g].nlvl() + s; P.resid = w[g].feat(1);
-                 P.out = (s == 4) ? outs[g] : w[g].feat(0);
-             })) != IR_OK) return r;
+        add(li + 1, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
+            P.fin = w[g].feat(1);
+            P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
+            P.n_out_dev = w[g].nlvl() + s; P.resid = nullptr; P.out = w[g].feat(2);
+        });
+        add(li + 2, ch[s], ch[s], 27, [&](int g, IrConvProblem& P) {
+            P.fin = w[g].feat(2);
+            P.in_idx = w[g].k3_in(s); P.slot = w[g].k3_slot(s); P.count = w[g].kcount(s);
+            P.n_out_dev = w[g].nlvl() + s; P.resid = w[g].feat(1);
+            P.out = (s == 4) ? outs[g] : w[g].feat(0);
+        });
+    }
+    bool persist = g_encoder_mode == 1 && ps[0]->use_tc && !g_prof_on && ps[0]->cin <= 8;
+    for (int g = 0; g < G && persist; ++g)
+        for (int i = 1; i < IR_ENC_LAYERS; ++i) persist = persist && ps[g]->wprep[i] != nullptr;
+    if (persist) {
+        IrConvProblem lt[IR_ENC_LAYERS][IR_MAX_GROUPS];
+        memcpy(lt, layers, sizeof(lt));
+        for (int i = 1; i < IR_ENC_LAYERS; ++i)
+            for (int g = 0; g < G; ++g) lt[i][g].weight = ps[g]->wprep[i];     // 16-byte aligned copies (TMA bulk source)
+        return irk_encoder_persist(G, lt, cins, couts, Ks, IR_ENC_LAYERS, w[0].sync(), st);
+    }
+    for (int i = 0; i < IR_ENC_LAYERS; ++i) {
+        IrConvBatch b;
+        memset(&b, 0, sizeof(b));
+        b.G = G;
+        const float* wp[IR_MAX_GROUPS] = {nullptr, nullptr};
+        for (int g = 0; g < G; ++g) { b.p[g] = layers[i][g]; wp[g] = ps[g]->wprep[i]; }
+        if ((r = conv_layer(b, cins[i], couts[i], Ks[i], wp, ps[0]->use_tc, st)) != IR_OK) return r;
     }
     return IR_OK;
 }

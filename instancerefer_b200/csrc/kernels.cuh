@@ -64,3 +64,7 @@ int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st);   // fused 
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);
 int irk_wgrad_tc(const float* x, int cin, const float* dy, int cout, int K, const int* in_idx, const int* out_idx,
                  const int* count, long long seg_cap, const float* dy_absmax, float* dW, cudaStream_t st);
+
+// encoder_persist.cu  (all conv layers of one or two encoders in one persistent launch; `sync` = 512 zeroed bytes)
+int irk_encoder_persist(int G, const IrConvProblem (*layers)[IR_MAX_GROUPS], const int* cin, const int* cout, const int* K,
+                        int n_layers, void* sync, cudaStream_t st);

@@ -185,9 +185,11 @@ extern "C" int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const
 // p <- p - (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)          (torch.optim.Adam, amsgrad off)
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-       long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+       long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+       const unsigned char* __restrict__ block_skip) {
     const float step = lr / bc1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (block_skip && block_skip[i >> 6]) continue;      // parameter without a gradient this step: torch.optim.Adam skips it
         const float pv = p[i];
         const float gv = fmaf(wd, pv, grad_scale * g[i]);
         const float mv = b1 * m[i] + (1.f - b1) * gv;
@@ -200,13 +202,13 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 
 extern "C" int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                             float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                            float grad_scale, ir_stream_t stream) {
+                            float grad_scale, const uint8_t* block_skip, ir_stream_t stream) {
     IR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1);
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
     k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                   weight_decay, bc1, sqrtf(bc2), grad_scale);
+                                                   weight_decay, bc1, sqrtf(bc2), grad_scale, block_skip);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -65,6 +65,8 @@ class GraphedInstanceRefer:
         self.max_graphs = max_graphs
         self.depth = depth
         self.cache = {}
+        self._wts = None                  # tensors whose change invalidates every captured graph
+        self._wkey = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._copy_stream = None
@@ -141,9 +143,26 @@ class GraphedInstanceRefer:
         s.host_flat = torch.empty(s.flat.shape, dtype=torch.float32).pin_memory()
         self.d2h_bytes = s.flat.numel() * 4
 
+    def _weights_key(self):
+        """Captured graphs bake in pointers to the modules' prepared copies (folded BN, repacked weights): a weight
+        update (load_state_dict, in-place edits, FlatAdam.step) must drop them.  Cheap per-step check: global weights
+        epoch + sum of tensor versions + the first parameter's address (a module move re-creates every tensor)."""
+        from .basic_blocks import weights_epoch
+        if self._wts is None:
+            self._wts = list(self.model.parameters()) + list(self.model.buffers())
+        return (weights_epoch(), sum(t._version for t in self._wts), self._wts[0].data_ptr(), len(self._wts))
+
     # --- public API ---------------------------------------------------------------------------
     def submit(self, data_dict):
         m = self.model
+        wkey = self._weights_key()
+        if wkey != self._wkey:
+            if self._wkey is not None:
+                torch.cuda.synchronize()              # replays in flight still read the old prepared copies
+                self.cache.clear()
+                self._wts = None
+                wkey = self._weights_key()
+            self._wkey = wkey
         if not m.args.use_gt_lang:
             raise NotImplementedError("graph replay needs use_gt_lang: True (the class filter runs on the host "
                                       "before the language branch)")

@@ -130,12 +130,17 @@ class InstanceRefer(nn.Module):
                     with torch.cuda.stream(ss):
                         self.scene.encode_scene(data_dict, dev)
                 with torch.cuda.stream(sr):
+                    ops.stamp('rel:start')
                     self.relation.encode_graph(data_dict, dev)
+                    ops.stamp('rel:graph')
+                ops.stamp('lang:start')
                 data_dict = self.lang(data_dict)
+                ops.stamp('lang:encoded')
                 # language-side embeddings need nothing from the encoders
                 data_dict['_ir_attr_lang'] = self.attribute.embed_language(data_dict)
                 data_dict['_ir_rel_lang'] = self.relation.embed_language(data_dict)
                 data_dict['_ir_scene_lang'] = self.scene.embed_language(data_dict)
+                ops.stamp('lang:embedded')
                 ev_lang = torch.cuda.Event()
                 ev_lang.record(main)
                 # each branch finishes with its own matching head on its own stream
@@ -145,6 +150,7 @@ class InstanceRefer(nn.Module):
                 with torch.cuda.stream(sr):
                     sr.wait_event(ev_lang)
                     self.relation.match(data_dict)
+                    ops.stamp('rel:matched')
                 with torch.cuda.stream(ss):
                     ss.wait_event(ev_lang)
                     ss.wait_event(ev_obj)
@@ -159,4 +165,5 @@ class InstanceRefer(nn.Module):
                 prob, arg = ops.candidate_softmax(data_dict['attribute_scores'], data_dict['relation_scores'],
                                                   data_dict['scene_scores'], pack.cand_ofs)
                 data_dict['ref_probs'], data_dict['ref_pred'] = prob, arg
+                ops.stamp('end')
         return data_dict

@@ -89,6 +89,35 @@ class EncoderWorkspace:
         return self._view(self.layout.off_T, 27 * self.n_max * 128 * 4, torch.float32)
 
 
+TIMELINE = None          # tools/timeline.py sets this to a Timeline; None = no stamps (zero overhead)
+
+
+class Timeline:
+    """Branch-level GPU timeline: ``stamp(label)`` queues a one-thread kernel that writes the GPU timer on the current
+    stream (also under stream capture); ``read()`` -> [(label, us since the first stamp)]."""
+
+    def __init__(self, device, cap=256):
+        self.buf = torch.zeros(cap, dtype=torch.int64, device=device)
+        self.labels = []
+        self.frozen = False
+
+    def stamp(self, label):
+        if self.frozen:                       # replay / repeated call: indices are already assigned
+            return
+        call("ir_debug_stamp", C.c_void_p(self.buf.data_ptr()), len(self.labels), _stream())
+        self.labels.append(label)
+
+    def read(self):
+        v = self.buf[:len(self.labels)].cpu().numpy()
+        t0 = int(v.min())
+        return [(l, (int(x) - t0) / 1e3) for l, x in zip(self.labels, v)]
+
+
+def stamp(label):
+    if TIMELINE is not None:
+        TIMELINE.stamp(label)
+
+
 def encoder_reset(ws):
     call("ir_encoder_reset", ws.ptr, ws.n_max, _stream())
 
@@ -372,10 +401,12 @@ def ref_loss(pred_obb, obb_ofs, gt_obb, score_ofs, sa, sr, ss, margin=0.2, gamma
     return label, loss_scene, dscore, iou_max
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+              block_skip=None):
+    """block_skip: uint8 per 64-float block, 1 = leave parameter and moments untouched (no gradient this step)."""
     call("ir_adam_step", _p(params, torch.float32), _p(grads, torch.float32), _p(exp_avg, torch.float32),
          _p(exp_avg_sq, torch.float32), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
-         float(weight_decay), int(step), float(grad_scale), _stream())
+         float(weight_decay), int(step), float(grad_scale), _p(block_skip, torch.uint8), _stream())
 
 
 # ----------------------------------------------------------------------------- dense training-step operators

@@ -14,12 +14,28 @@ from . import ops
 ALIGN = 64          # floats (256 B): keeps every parameter 16-byte aligned for TMA bulk copies
 
 
-class FlatAdam:
-    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (amsgrad off) on a flat buffer."""
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (amsgrad off) on a flat buffer.
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.params = [p for p in model.parameters() if p.requires_grad]
+    A real ``torch.optim.Optimizer``: ONE mutable param group whose ``lr`` / ``betas`` / ``eps`` /
+    ``weight_decay`` the Adam kernel reads at every step, so the reference's own solver works unchanged on it
+    (lib/solver.py:119-125 builds ``MultiStepLR(optimizer, ...)``, scripts/train.py:112-119 loads its
+    ``state_dict``).  ``FlatAdam(model, ...)`` and ``FlatAdam(model.parameters(), ...)`` are both accepted.
+    Like torch's Adam, parameters that received no gradient in a step are left untouched (no weight decay, no
+    moment decay) and own no optimizer state."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        if isinstance(params, torch.nn.Module):
+            params = params.parameters()
+        params = list(params)
+        if params and isinstance(params[0], dict):
+            raise ValueError("FlatAdam keeps one flat buffer: pass a module or a flat iterable of parameters "
+                             "(one param group, as scripts/train.py:93 does)")
+        params = [p for p in params if p.requires_grad]
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
+        super().__init__(params, defaults)
+        self.params = self.param_groups[0]['params']
         assert all(p.dtype == torch.float32 for p in self.params)
         dev = self.params[0].device
         ofs, total = [], 0
@@ -39,23 +55,34 @@ class FlatAdam:
             p.grad = None
         self.offsets, self.numel = ofs, total
         self.step_count = 0
+        self.has_state = [False] * len(self.params)             # parameter saw a gradient at least once
+        self._skip_key, self._skip_mask = None, None            # per-64-float block: 1 = no gradient this step
         self.group = process_group
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
 
-    def zero_grad(self):
+    # hyper-parameters live in the param group (what a scheduler mutates); attribute access for convenience
+    lr = property(lambda self: self.param_groups[0]['lr'], lambda self, v: self.param_groups[0].__setitem__('lr', v))
+    betas = property(lambda self: self.param_groups[0]['betas'], lambda self, v: self.param_groups[0].__setitem__('betas', tuple(v)))
+    eps = property(lambda self: self.param_groups[0]['eps'], lambda self, v: self.param_groups[0].__setitem__('eps', v))
+    weight_decay = property(lambda self: self.param_groups[0]['weight_decay'],
+                            lambda self, v: self.param_groups[0].__setitem__('weight_decay', v))
+
+    def zero_grad(self, set_to_none=True):
         """.grad = None: backward then hands over each gradient tensor without an accumulation kernel."""
         for p in self.params:
             p.grad = None
 
     def gather_grads(self):
         """Pack the per-parameter gradients of this backward into the flat buffer (one multi-tensor
-        copy; parameters that received no gradient contribute zeros) and point .grad at the views."""
-        src, dst, zero = [], [], []
-        for v, p in zip(self.grad_views, self.params):
+        copy; parameters that received no gradient contribute zeros and are masked out of the update)
+        and point .grad at the views.  -> indices of the parameters without a gradient."""
+        src, dst, zero, missing = [], [], [], []
+        for i, (v, p) in enumerate(zip(self.grad_views, self.params)):
             if p.grad is None:
                 zero.append(v)
+                missing.append(i)
             elif p.grad.data_ptr() != v.data_ptr():
                 dst.append(v)
                 src.append(p.grad)
@@ -64,49 +91,76 @@ class FlatAdam:
             torch._foreach_zero_(zero)
         if src:
             torch._foreach_copy_(dst, src)
+        return missing
 
     def allreduce(self):
         """Sum over ranks (the mean is folded into the Adam kernel)."""
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.group)
 
-    def step(self):
-        self.gather_grads()
+    def _block_skip(self, missing):
+        """uint8 per 64-float block (every parameter is block-aligned): 1 where the update is skipped."""
+        if not missing:
+            return None
+        key = tuple(missing)
+        if key != self._skip_key:
+            m = torch.zeros(self.numel // ALIGN, dtype=torch.uint8)
+            for i in missing:
+                o, n = self.offsets[i], self.params[i].numel()
+                m[o // ALIGN:(o + n + ALIGN - 1) // ALIGN] = 1
+            self._skip_key, self._skip_mask = key, m.to(self.flat.device)
+        return self._skip_mask
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        missing = self.gather_grads()
         self.allreduce()
         self.step_count += 1
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
-                      self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / self.world)
+        if not all(self.has_state):
+            gone = set(missing)
+            self.has_state = [h or (i not in gone) for i, h in enumerate(self.has_state)]
+        g = self.param_groups[0]
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g['lr'], g['betas'][0],
+                      g['betas'][1], g['eps'], g['weight_decay'], self.step_count, 1.0 / self.world,
+                      self._block_skip(missing))
+        from .basic_blocks import bump_weights_epoch
+        bump_weights_epoch()           # the kernel wrote the parameters through raw pointers: tensor versions did not move
+        return loss
 
     # --- checkpoint format of torch.optim.Adam (lib/solver.py:376-381 stores optimizer.state_dict()) ------
     def state_dict(self):
         """Same layout as ``torch.optim.Adam.state_dict()``: per-parameter step / exp_avg / exp_avg_sq (copies
         of the flat moments) and one param group, so ``checkpoint.tar`` is interchangeable with the reference's."""
         state = {}
-        if self.step_count > 0:
-            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
-                n = p.numel()
-                state[i] = dict(step=torch.tensor(float(self.step_count)),
-                                exp_avg=self.exp_avg[o:o + n].view_as(p).clone(),
-                                exp_avg_sq=self.exp_avg_sq[o:o + n].view_as(p).clone())
-        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
-                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
-                     decoupled_weight_decay=False, params=list(range(len(self.params))))
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            if not self.has_state[i]:
+                continue
+            n = p.numel()
+            state[i] = dict(step=torch.tensor(float(self.step_count)),
+                            exp_avg=self.exp_avg[o:o + n].view_as(p).clone(),
+                            exp_avg_sq=self.exp_avg_sq[o:o + n].view_as(p).clone())
+        group = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
+        group['params'] = list(range(len(self.params)))
         return dict(state=state, param_groups=[group])
 
     def load_state_dict(self, sd):
         g = sd['param_groups'][0]
-        self.lr, self.betas, self.eps, self.weight_decay = g['lr'], tuple(g['betas']), g['eps'], g['weight_decay']
+        for k in ('lr', 'eps', 'weight_decay', 'initial_lr'):
+            if k in g:
+                self.param_groups[0][k] = g[k]
+        self.param_groups[0]['betas'] = tuple(g['betas'])
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.step_count = 0
+        self.has_state = [False] * len(self.params)
         for i, st in sd['state'].items():
             o, p = self.offsets[int(i)], self.params[int(i)]
             n = p.numel()
             self.exp_avg[o:o + n].copy_(st['exp_avg'].reshape(-1))
             self.exp_avg_sq[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
             self.step_count = max(self.step_count, int(float(st['step'])))
-
-    @property
-    def param_groups(self):
-        """Read-only view for code that prints / schedules ``optimizer.param_groups[0]['lr']``."""
-        return [dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, params=self.params)]
+            self.has_state[int(i)] = True

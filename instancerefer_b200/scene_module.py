@@ -69,10 +69,14 @@ class SceneModule(nn.Module, PrepCache):
         F0 = lidar.F.to(device, torch.float32).contiguous()
         C0 = lidar.C.to(device, torch.int32).contiguous()
         ws = self.net.workspace(F0.shape[0], device)
+        ops.stamp('scene:start')
         f4, c4, n4 = self.net.encode(ws, F0, C0, data_dict.get('_ir_lidar_rows'))
+        ops.stamp('scene:features')
         bev = ops.bev(f4, c4, n4, ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
+        ops.stamp('scene:bev')
         x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
         data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        ops.stamp('scene:conv2d')
         return data_dict
 
     def prepare_maps(self, data_dict, device):
@@ -119,6 +123,7 @@ class SceneModule(nn.Module, PrepCache):
                                  p['obeta'], p['ow2'], p['ob2'], ops.MODE_COS, partner=scene_feats,
                                  seg=pack.cand_scene)
         data_dict['scene_scores'] = scores
+        ops.stamp('scene:matched')
         return data_dict
 
     def forward(self, data_dict):

@@ -116,3 +116,118 @@ def test_solver_trains_and_resumes(tmp_path, lib_built, state_dict, args):
     assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.flat, opt.flat)
     s2(4, verbose=0)
     assert len(s2.history['train']) == 1 and np.isfinite(s2.history['train'][0]['loss'])
+
+
+def test_flat_adam_is_a_torch_optimizer_under_the_reference_scheduler():
+    """lib/solver.py:119-123 builds MultiStepLR(optimizer, [15, 20], 0.1) on whatever scripts/train.py:93 made;
+    FlatAdam must be accepted there and the lr the scheduler writes into the param group is the lr ``step`` reads."""
+    from instancerefer_b200.optim import FlatAdam
+    m = small_model()
+    opt = FlatAdam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [15, 20], 0.1)
+    ref = torch.optim.lr_scheduler.MultiStepLR(torch.optim.Adam(small_model().parameters(), lr=1e-3), [15, 20], 0.1)
+    for e in range(25):
+        assert abs(opt.param_groups[0]['lr'] - ref.get_last_lr()[0]) < 1e-15 and opt.lr == opt.param_groups[0]['lr']
+        opt._opt_called = True                      # no CUDA here: the schedulers only need the step order flag
+        ref.optimizer.step()
+        sched.step()
+        ref.step()
+    assert abs(opt.lr - 1e-5) < 1e-15
+    opt.lr = 3e-4                                   # attribute form used by instancerefer_b200.solver
+    assert opt.param_groups[0]['lr'] == 3e-4
+    # a parameter that never received a gradient owns no state (torch.optim.Adam semantics)
+    sd = opt.state_dict()
+    assert sd['state'] == {} and sd['param_groups'][0]['params'] == list(range(len(opt.params)))
+    with pytest.raises(ValueError):
+        FlatAdam([dict(params=list(small_model().parameters()))])
+
+
+@pytest.mark.gpu
+def test_reference_shaped_solver_loop_matches_torch_adam(lib_built):
+    """zero_grad / backward / step / scheduler.step exactly as lib/solver.py:200-205 + :119-125 drive an optimizer,
+    FlatAdam against torch.optim.Adam on the same model (one parameter never receives a gradient)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from instancerefer_b200.optim import FlatAdam
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(3)
+            self.a, self.b = torch.nn.Linear(6, 8), torch.nn.Linear(8, 3)
+            self.unused = torch.nn.Linear(4, 4)     # in parameters(), never in the graph: grad stays None
+
+        def forward(self, x):
+            return self.b(torch.relu(self.a(x)))
+
+    m1, m2 = Net().cuda(), Net().cuda()
+    o1 = FlatAdam(m1.parameters(), lr=1e-2, weight_decay=1e-3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-2, weight_decay=1e-3)
+    s1 = torch.optim.lr_scheduler.MultiStepLR(o1, [2, 4], 0.1)
+    s2 = torch.optim.lr_scheduler.MultiStepLR(o2, [2, 4], 0.1)
+    unused0 = m1.unused.weight.detach().clone()
+    g = torch.Generator().manual_seed(0)
+    for epoch in range(6):
+        for _ in range(3):
+            x = torch.randn(16, 6, generator=g).cuda()
+            for m, o in ((m1, o1), (m2, o2)):
+                o.zero_grad()
+                m(x).square().mean().backward()
+                o.step()
+        s1.step()
+        s2.step()
+        assert abs(o1.param_groups[0]['lr'] - o2.param_groups[0]['lr']) < 1e-15
+    for (n, p), q in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), n
+    assert torch.equal(m1.unused.weight, unused0)               # no weight decay / moment update without a gradient
+    sd1, sd2 = o1.state_dict(), o2.state_dict()
+    assert set(sd1['state']) == set(sd2['state']) == {0, 1, 2, 3}
+    for i in sd2['state']:
+        assert torch.allclose(sd1['state'][i]['exp_avg_sq'].cpu(), sd2['state'][i]['exp_avg_sq'].cpu(), rtol=1e-4, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_eval_after_flat_adam_steps_uses_the_updated_weights(lib_built, state_dict, args):
+    """FlatAdam.step writes the parameters through a raw-pointer kernel (no tensor version bump): the eval-mode
+    prepared copies (folded BN, repacked / transposed weights) and captured graphs must not survive it.  Train two
+    steps, evaluate, and compare with a freshly built model loaded from the trained state_dict."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import train_ref
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.graphed import GraphedInstanceRefer
+    from instancerefer_b200.instancerefer import InstanceRefer
+    from instancerefer_b200.loss_helper import get_loss
+
+    def batch(seed, dev='cuda'):
+        b = synthetic.make_batch(seed, batch_size=2, num_points=6000, n_inst=8, n_cand=[4, 3], n_tokens=[6, 9])
+        return synthetic.to_data_dict(b, SparseTensor, dev)
+
+    keys = ('lang_scores', 'attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores')
+    model = InstanceRefer(7, args)
+    model.load_state_dict(state_dict, strict=True)
+    model = model.cuda().eval()
+    before = {k: model(batch(11))[k].clone() for k in keys}     # fills every eval-mode cache with the initial weights
+    runner = GraphedInstanceRefer(model)
+    g0 = {k: v.clone() for k, v in runner(batch(11, 'cpu'))['host_scores'].items()}
+    from instancerefer_b200.optim import FlatAdam
+    opt = FlatAdam(model, lr=1e-2)
+    model.train()
+    for seed in (5, 6):
+        opt.zero_grad()
+        get_loss(model(batch(seed)), train_ref.SyntheticConfig())['loss'].backward()
+        opt.step()
+    model.eval()
+    after = {k: model(batch(11))[k].clone() for k in keys}
+    fresh = InstanceRefer(7, args)
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, strict=True)
+    fresh = fresh.cuda().eval()
+    want = {k: fresh(batch(11))[k] for k in keys}
+    for k in keys:
+        assert float((after[k] - want[k]).abs().max()) < 1e-5, k
+    assert any(float((after[k] - before[k]).abs().max()) > 1e-3 for k in keys)      # the weights did move
+    g1 = runner(batch(11, 'cpu'))['host_scores']                                    # graphs re-captured, not replayed stale
+    for k in ('attribute_scores', 'relation_scores', 'scene_scores'):
+        assert float((g1[k] - want[k].cpu()).abs().max()) < 1e-5, k
+        assert float((g1[k] - g0[k]).abs().max()) > 1e-4, k

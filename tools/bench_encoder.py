@@ -1,0 +1,77 @@
+"""Persistent encoder kernel vs per-layer launches on the bench workload's two encoders: output agreement, graph-replay
+timing of the feature pass, and the per-phase time stamps the persistent kernel leaves in its sync area.
+usage: python tools/bench_encoder.py [reps]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import bench
+from instancerefer_b200 import ops, synthetic, _lib
+from instancerefer_b200.instancerefer import InstanceRefer
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+dev = 'cuda'
+lib = _lib.load()
+model = InstanceRefer(7, bench.make_args())
+model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)
+model = model.to(dev).eval()
+b = synthetic.make_batch(1000, batch_size=1, **bench.WORKLOAD)
+pts = torch.from_numpy(np.stack(b['instance_points'][0], 0)).to(dev)
+cand = torch.arange(32, dtype=torch.int32, device=dev)
+ws_i = ops.EncoderWorkspace(ops.round_rows(32 * 1024), dev)
+ops.encoder_reset(ws_i); ops.voxelize(pts, cand, 0.02, ws_i); ops.encoder_build_maps(ws_i)
+lc = torch.from_numpy(b['lidar_coords']).to(dev); lf = torch.from_numpy(b['lidar_feats']).to(dev)
+ws_s = ops.EncoderWorkspace(ops.round_rows(lc.shape[0]), dev)
+ops.encoder_build_maps(ws_s, lc)
+torch.cuda.synchronize()
+pa, ps = model.attribute.net.prepared()['params'], model.scene.net.prepared()['params']
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def run(mode, which):
+    lib.ir_encoder_mode_set(mode)
+    oa = torch.zeros(ws_i.n_max, 128, device=dev); os_ = torch.zeros(ws_s.n_max, 128, device=dev)
+    def go():
+        if which == 'pair':
+            ops.encoder_features_pair(pa, ws_i, None, oa, ps, ws_s, lf, os_)
+        elif which == 'inst':
+            ops.encoder_features(pa, ws_i, None, oa)
+        else:
+            ops.encoder_features(ps, ws_s, lf, os_)
+    go(); go(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        go()
+    ts = []
+    for cold in (False, True):
+        ms = 0.0
+        for _ in range(reps):
+            if cold: flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        ts.append(ms / reps * 1e3)
+    n_i, n_s = int(ws_i.nlvl()[4]), int(ws_s.nlvl()[4])
+    return ts, oa[:n_i].clone(), os_[:n_s].clone()
+
+def stamps(ws):
+    L = ws.layout
+    raw = ws.buf[L.off_sync:L.off_sync + 512].view(torch.int64).cpu().numpy()
+    st = raw[32:64]
+    t0 = st[31]
+    return [(int(st[p]) - int(t0)) / 1e3 for p in range(25)]
+
+res = {}
+for which in ('inst', 'scene', 'pair'):
+    for mode in (0, 1):
+        ts, oa, os_ = run(mode, which)
+        res[(which, mode)] = (ts, oa, os_)
+        print(f'{which:5s} mode={"persist" if mode else "layers "}  warm {ts[0]:7.1f} us  cold {ts[1]:7.1f} us', flush=True)
+        if mode == 1:
+            ws = ws_s if which == 'scene' else ws_i
+            s = stamps(ws)
+            print('   phase end times (us since first ticket):', ' '.join(f'{x:.1f}' for x in s), flush=True)
+    a, bb = res[(which, 0)], res[(which, 1)]
+    if which in ('inst', 'pair'):
+        print(f'   inst  out max|persist-layers| = {float((a[1] - bb[1]).abs().max()):.3e}  (max|out| {float(a[1].abs().max()):.3f})')
+    if which in ('scene', 'pair'):
+        print(f'   scene out max|persist-layers| = {float((a[2] - bb[2]).abs().max()):.3e}  (max|out| {float(a[2].abs().max()):.3f})')
