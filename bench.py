@@ -40,6 +40,14 @@ WORKLOAD_NAME = ('configs[1]: full InstanceRefer.forward, 1 synthetic scene (40k
 METRIC = 'referrals/sec'
 
 
+def forward_config():
+    """`config` of the forward line — identical on both arms (--impl b200 / reference): it names the workload and the
+    cache state of the timed region; how each arm executes it is in `impl_detail`."""
+    return dict(workload=WORKLOAD_NAME, referrals_per_step_per_gpu=1,
+                l2='cold between steps: a 256 MiB write flushes the 126 MB L2 outside the timed spans (GPU arm); the CPU arm '
+                   'cycles the same 4 scenes')
+
+
 def make_args():
     return types.SimpleNamespace(language_module='lang_module', attribute_module='attribute_module',
                                  relation_module='relation_module', scene_module='scene_module',
@@ -55,17 +63,17 @@ def cpu_reference_leg(steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
     sd = weights.make_state_dict(123)
     args = make_args()
-    b = synthetic.make_batch(1000, batch_size=1, **WORKLOAD)
-    data = model_ref.data_from_batch(b)
-    for _ in range(warmup):
-        model_ref.forward(sd, data, args)
+    data = [model_ref.data_from_batch(synthetic.make_batch(1000 + 7 * i, batch_size=1, **WORKLOAD)) for i in range(4)]
+    for i in range(warmup):
+        model_ref.forward(sd, data[i % 4], args)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        model_ref.forward(sd, data, args)
+    for i in range(steps):
+        model_ref.forward(sd, data[i % 4], args)
     dt = (time.perf_counter() - t0) / steps
     return dict(value=1.0 / dt, unit=METRIC, cores=torch.get_num_threads(), kind='port',
-                sample=f'{steps} referrals of the bench workload after {warmup} warm-up, oracle/model_ref.py '
-                       f'(torch CPU fp32, {torch.get_num_threads()} threads), {dt * 1e3:.0f} ms each'), dt
+                sample=f'{steps} referrals of the bench workload after {warmup} warm-up; oracle/model_ref.py = the CPU port of the '
+                       f'reference forward (torch CPU fp32, {torch.get_num_threads()} threads; GRU token loop and kNN query loop in '
+                       f'Python — NOT the reference files verbatim over the shim, which cannot travel to the GPU box), {dt * 1e3:.0f} ms each'), dt
 
 
 class ClockSampler:
@@ -78,7 +86,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '10'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -146,37 +154,29 @@ def cpu_train_leg(steps, warmup, per_gpu=2):
                        f'(torch CPU fp32 autograd, {torch.get_num_threads()} threads, no optimiser step), {dt * 1e3:.0f} ms each'), dt
 
 
-def main_train(a):
-    """--workload train: BASELINE.json configs[2].  One step = train-mode forward + get_loss + backward +
-    ONE flat NCCL all-reduce of the 8.02 M gradients + fused Adam, inputs from HOST buffers every step
-    (so `value` is already end to end); phases are CUDA-event timed."""
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    warmup = max(a.warmup, 3)
-    per_gpu = 2
-    if a.impl == 'reference':
-        if rank != 0:
-            return
-        steps = max(1, min(a.steps, 4))
-        cb, dt = cpu_train_leg(steps, 1, per_gpu)
-        print(json.dumps(dict(metric=METRIC, value=cb['value'], unit=METRIC, impl='reference', n_gpus=a.gpus, steps=steps,
-                              warmup=1, ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
-                              dtype='f32', data='synthetic', config=dict(workload=TRAIN_WORKLOAD_NAME), cpu_baseline=cb,
-                              e2e=dict(value=cb['value'], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
-        return
+def _init_dist(world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=dev)
+
+
+def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
+    """BASELINE.json configs[2]: one step = train-mode forward + get_loss + backward + gradient all-reduce + fused Adam,
+    inputs from HOST buffers every step (so `value` is already end to end); phases are CUDA-event timed.  -> dict."""
     import __graft_entry__ as g
     g.build()
     from instancerefer_b200 import SparseTensor, _lib, ops, synthetic
     from instancerefer_b200.instancerefer import InstanceRefer
     from instancerefer_b200.loss_helper import get_loss, stash_host_labels
     from instancerefer_b200.optim import FlatAdam
+    per_gpu = 2
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
+    _init_dist(world, dev)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     model = InstanceRefer(7, make_args())
     model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)
@@ -204,7 +204,7 @@ def main_train(a):
         ev[1].record()
         d = get_loss(d, cfg)
         ev[2].record()
-        d['loss'].backward()
+        d['loss'].backward()                                    # bucket all-reduces start from the parameter hooks
         ev[3].record()
         opt.step()
         ev[4].record()
@@ -228,7 +228,7 @@ def main_train(a):
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    losses = [step(i, True) for i in range(a.steps)]
+    losses = [step(i, True) for i in range(steps)]
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -249,24 +249,47 @@ def main_train(a):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool((hi - lo).abs().item() == 0.0)
     cb = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and cpu_baseline:
         cb, _ = cpu_train_leg(2, 1, per_gpu)
+    value = world * per_gpu * steps / (dev_ms * 1e-3)
+    return dict(
+        metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=steps, warmup=warmup,
+        ms_per_step=dev_ms / steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype='f32 (rule GEMM, dgrad and wgrad on tcgen05 as split-fp16 hi/lo with fp32 accumulation)', data='synthetic',
+        config=dict(workload=TRAIN_WORKLOAD_NAME, scenes_per_gpu=per_gpu, global_batch=world * per_gpu,
+                    l2='inputs (2.6 MB) and activations change every step; working set > L2 over a step',
+                    parallelism=f'dp{world}: scenes sharded, gradient all-reduce in {opt.n_buckets} buckets launched on a side '
+                                f'stream as each branch\'s backward finishes, Adam replicated'),
+        e2e=dict(value=world * per_gpu * steps / wall, unit=METRIC, ms_per_step=wall / steps * 1e3,
+                 h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
+        phases_ms={k: v / steps for k, v in ph.items()}, allreduce_exposed_ms=ph['allreduce+adam'] / steps,
+        gpu_launches=int(launches), clocks=clocks,
+        final_loss=losses[-1], first_loss=losses[0], ranks_in_sync=in_sync, cpu_baseline=cb)
+
+
+def main_train(a):
+    """--workload train: BASELINE.json configs[2] as its own line."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(a.warmup, 3)
+    per_gpu = 2
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        cb, dt = cpu_train_leg(a.steps, warmup, per_gpu)
+        print(json.dumps(dict(metric=METRIC, value=cb['value'], unit=METRIC, impl='reference', n_gpus=a.gpus, steps=a.steps,
+                              warmup=warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                              dtype='f32', data='synthetic', config=dict(workload=TRAIN_WORKLOAD_NAME), cpu_baseline=cb,
+                              e2e=dict(value=cb['value'], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    line = train_measure(a.steps, warmup, rank, world, local, not a.no_cpu_baseline)
     if world > 1:
+        import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        value = world * per_gpu * a.steps / (dev_ms * 1e-3)
-        print(json.dumps(dict(
-            metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=a.steps, warmup=warmup,
-            ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-            dtype='f32 (forward rule GEMM on tcgen05 split-fp16; dgrad/wgrad fp32 SIMT)', data='synthetic',
-            config=dict(workload=TRAIN_WORKLOAD_NAME, scenes_per_gpu=per_gpu, global_batch=world * per_gpu,
-                        l2='inputs (2.6 MB) and activations change every step; working set > L2 over a step',
-                        parallelism=f'dp{world}: scenes sharded, one flat all-reduce of 8.02 M fp32 grads, Adam replicated'),
-            e2e=dict(value=world * per_gpu * a.steps / wall, unit=METRIC, ms_per_step=wall / a.steps * 1e3,
-                     h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
-            phases_ms={k: v / a.steps for k, v in ph.items()}, gpu_launches=int(launches), clocks=clocks,
-            final_loss=losses[-1], first_loss=losses[0], ranks_in_sync=in_sync, cpu_baseline=cb)))
+        print(json.dumps(line))
 
 
 def _forward_setup(local):
@@ -392,6 +415,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager', action='store_true', help='no CUDA-graph replay (launch every kernel from Python)')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step block of the line')
+    ap.add_argument('--train-steps', type=int, default=20)
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -401,12 +426,13 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return
-        steps = max(1, min(a.steps, 8))
-        cb, dt = cpu_reference_leg(steps, min(warmup, 2))
+        # same --steps / --warmup as the GPU arm; one step = one referral of the same workload on the host cores
+        # (~0.4 s each, so the default 50 + 5 steps end within half a minute)
+        cb, dt = cpu_reference_leg(a.steps, warmup)
         print(json.dumps(dict(metric=METRIC, value=cb['value'], unit=METRIC, impl='reference', n_gpus=a.gpus,
-                              steps=steps, warmup=min(warmup, 2), ms_per_step=dt * 1e3, higher_is_better=True,
+                              steps=a.steps, warmup=warmup, ms_per_step=dt * 1e3, higher_is_better=True,
                               scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                              config=dict(workload=WORKLOAD_NAME), cpu_baseline=cb,
+                              config=forward_config(), impl_detail=cb['sample'], cpu_baseline=cb,
                               e2e=dict(value=cb['value'], unit=METRIC, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
 
@@ -419,9 +445,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
+    _init_dist(world, dev)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     args = make_args()
     model = InstanceRefer(7, args)
@@ -535,10 +561,10 @@ def main():
         return float(t.item())
 
     # ---- value: resident inputs, per-step CUDA events, L2 flush between steps
+    sampler = ClockSampler(local) if rank == 0 else None        # 10 ms samples from before the warm-up to the end of e2e
     for i in range(warmup):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.ir_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     for i in range(a.steps):
@@ -554,7 +580,6 @@ def main():
         launches = (lib.ir_launch_count() - c0) * a.steps
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     dev_ms = max_over_ranks(dev_ms)
-    clocks = sampler.stop() if sampler else None
     value = world * a.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers in, scores out
@@ -567,6 +592,7 @@ def main():
     e2e = dict(value=world * a.steps / e2e_s, unit=METRIC, ms_per_step=e2e_s / a.steps * 1e3,
                h2d_bytes_per_step=int(runner.h2d_bytes if use_graph else h2d_tensor_bytes + resident[0][KEY].h2d_bytes),
                d2h_bytes_per_step=int(d2h_bytes[0]))
+    clocks = sampler.stop() if sampler else None
 
     # ---- roofline pass: event-timed pair-GEMM / reduce launches of the same resident steps
     roofline, detail = None, None
@@ -623,6 +649,15 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_reference_leg(5, 1)
 
+    # ---- the training step (BASELINE configs[2]) at the same N: the path's one collective, under the driver's eyes
+    train = None
+    if not a.no_train:
+        del res_graphs, runner, resident
+        torch.cuda.empty_cache()
+        t = train_measure(a.train_steps, 10, rank, world, local, cpu_baseline=False)
+        train = {k: t[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'warmup', 'phases_ms', 'allreduce_exposed_ms',
+                                   'ranks_in_sync', 'e2e', 'gpu_launches', 'config', 'first_loss', 'final_loss')}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -630,12 +665,11 @@ def main():
         line = dict(metric=METRIC, value=value, unit=METRIC, n_gpus=world, steps=a.steps, warmup=warmup,
                     ms_per_step=dev_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32 (rule GEMM on tcgen05 as split-fp16 hi/lo, fp32 accumulate)', data='synthetic',
-                    config=dict(workload=WORKLOAD_NAME, referrals_per_step_per_gpu=1,
-                                l2='flushed between steps (256 MiB write outside the timed spans)',
-                                parallelism=f'scenes sharded over {world} GPU(s), no data-path collective',
-                                launch='eager' if not use_graph else 'CUDA-graph replay, 4 streams; e2e double-buffered (host of step i+1 overlaps GPU of step i)'),
+                    config=forward_config(),
+                    impl_detail=dict(parallelism=f'scenes sharded over {world} GPU(s), no data-path collective',
+                                     launch='eager' if not use_graph else 'CUDA-graph replay, 4 streams; e2e double-buffered (host of step i+1 overlaps GPU of step i)'),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
-                    cpu_baseline=cb, spconv_detail=detail)
+                    cpu_baseline=cb, spconv_detail=detail, train=train)
         print(json.dumps(line))
 
 

@@ -52,6 +52,11 @@ int ir_tune_set(int pairgemm_ctas, int reduce_ctas);
  * per layer (also taken while ir_profile_enable is on, and for the SIMT path). */
 int ir_encoder_mode_set(int mode);
 
+/* Profiling aid of the persistent encoder kernel: when buf != NULL every item (ticket t) of the following launches
+ * writes GPU-timer stamps into buf[8*t ..]: 0 decoded, 1 weights staged, 2 dependency satisfied, 3 work done (thread 0),
+ * 4 whole CTA done, 5 completion published, 7 = phase << 32 | CTA.  buf must hold 8 * 8192 u64.  NULL switches it off. */
+int ir_encoder_persist_debug(uint64_t* buf);
+
 /* Timeline aid: a one-thread kernel writes the GPU nanosecond timer into buf[idx] on `stream` (works inside stream
  * capture, so a replayed CUDA graph leaves a branch-level timeline behind; tools/timeline.py). */
 int ir_debug_stamp(uint64_t* buf, int32_t idx, ir_stream_t stream);

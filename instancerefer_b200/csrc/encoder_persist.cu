@@ -52,6 +52,7 @@ struct Program {
     int cin[MAX_LAYERS], cout[MAX_LAYERS], K[MAX_LAYERS];
     int n_layers, G, nominal, relu_last;
     unsigned* sync;
+    unsigned long long* dbg;       // optional per-item time stamps [ticket][8] (tools/bench_encoder.py), or NULL
 };
 
 struct Sched {                                 // shared memory, built once per CTA
@@ -95,6 +96,7 @@ struct Ctx {
     uint32_t base;          // shared-space address of sm
     uint32_t tmem_base;
     int tid, lane, warp;
+    unsigned long long* dbg;     // this item's stamp row or NULL
 };
 
 // ------------------------------------------------------------------------------------------ GEMM item
@@ -335,7 +337,9 @@ __device__ __forceinline__ void gemm_item(const Ctx& cx, const GemmArgs* A, cons
         }
         gemm_weights<CIN, COUT>(A, cx.sm, warp < 4 ? 0 : 1 + (warp - 5) / 4, warp, lane);
     }
+    if (cx.dbg && tid == 0) cx.dbg[1] = globaltimer();
     phase_wait(done, need, tid);                                // previous phase complete (CTA barrier inside)
+    if (cx.dbg && tid == 0) cx.dbg[2] = globaltimer();
     if (warp >= 5) gemm_producer<CIN, COUT>(A, cx.sm, warp - 5, lane);
     else if (warp == 4) { if (lane == 0) gemm_mma<CIN, COUT>(A); }
     else gemm_epilogue<CIN, COUT>(A, warp, lane);
@@ -541,8 +545,11 @@ k_encoder_persist(const __grid_constant__ Program P) {
     __syncthreads();
     tc_fence_after();
     cx.tmem_base = *s_tmem;
+    // Every phase hands out exactly `nominal` (= grid size) tickets; the ones beyond its real item count are null
+    // items.  With one ticket taken per CTA per item this keeps ticket rounds and phases aligned: each CTA gets exactly
+    // one (possibly null) item per phase, nobody runs two items of a phase while others idle at its barrier.
     if (warp == 0) {
-        const int v = (lane < n_phases) ? S.items[lane] : 0;
+        const int v = (lane < n_phases) ? P.nominal : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -564,11 +571,12 @@ k_encoder_persist(const __grid_constant__ Program P) {
         const int l = phase_layer(phase);
         const bool is_gemm = phase_is_gemm(phase);
         const int idx = ticket - S.base[phase];
+        const bool null_item = idx >= S.items[phase];
         if (warp == 4 && lane == 0) {                                     // bookkeeping thread (the MMA warp's lane 0)
             next_ticket = (int)atomicAdd(sync + SY_TICKET, 1u);          // consumed at the end of this item
             if (ticket == 0) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + 31] = globaltimer();
         }
-        if (warp == 0) {
+        if (warp == 0 && !null_item) {
             if (is_gemm) {
                 const int K = P.K[l];
 #pragma unroll
@@ -604,15 +612,19 @@ k_encoder_persist(const __grid_constant__ Program P) {
             }
         }
         __syncthreads();
-        const int g = s_item[3];
+        cx.dbg = P.dbg ? P.dbg + (long long)ticket * 8 : nullptr;
+        if (cx.dbg && tid == 0) { cx.dbg[0] = globaltimer(); cx.dbg[7] = ((unsigned long long)phase << 32) | blockIdx.x; }
+        const int g = null_item ? 0 : s_item[3];
         const LayerIO& io = P.io[l][g];
         const long long seg_cap = P.seg_cap[g];
         // dependency of this item: every ticket of the previous phase (skipped when this CTA already saw it complete)
         const unsigned* dep = sync + SY_DONE + (phase > 0 ? phase - 1 : 0);
-        const int need = (phase > 0 && known_done < phase - 1) ? S.items[phase - 1] : -1;
-        if (phase > 0) known_done = phase - 1;
+        const int need = (phase > 0 && known_done < phase - 1) ? P.nominal : -1;
+        if (phase > 0 && !null_item) known_done = phase - 1;
         unsigned* amax_out = sync + SY_ABSMAX + 2 * l + g;
-        if (is_gemm) {
+        if (null_item) {
+            // nothing to do: the item only keeps the ticket rounds aligned with the phases
+        } else if (is_gemm) {
             const int cin = P.cin[l], cout = P.cout[l];
             if (cin == 128)                   gemm_item<128, 128>(cx, s_gemm, dep, need);
             else if (cin == 64 && cout == 64) gemm_item<64, 64>(cx, s_gemm, dep, need);
@@ -631,6 +643,7 @@ k_encoder_persist(const __grid_constant__ Program P) {
             if (lane == 0 && m > 0.f) atomicMax(amax_out, __float_as_uint(m));
         } else {
             phase_wait(dep, need, tid);
+            if (cx.dbg && tid == 0) cx.dbg[2] = globaltimer();
             const int K = P.K[l], cout = P.cout[l];
             const int* s_kofs = &S.kofs[l][g * K];
             const int relu = (l == P.n_layers - 1) ? P.relu_last : 1;
@@ -641,15 +654,18 @@ k_encoder_persist(const __grid_constant__ Program P) {
             if (lane == 0 && m > 0.f) atomicMax(amax_out, __float_as_uint(m));
         }
         tc_fence_before();
+        if (cx.dbg && tid == 0) cx.dbg[3] = globaltimer();
         if (warp == 4 && lane == 0) *s_ticket = next_ticket;
         __syncthreads();                         // every global write of this item has been issued; next ticket published
         tc_fence_after();
         if (warp == 4 && lane == 0) {
+            if (cx.dbg) cx.dbg[4] = globaltimer();
             // completion: release the item's writes, count it.  Only this thread waits for the fence / atomic round
             // trips; the other warps are already decoding the next item (the decode barrier orders the re-init below)
             __threadfence();
             const unsigned old = atomicAdd(sync + SY_DONE + phase, 1u);
-            if ((int)old + 1 == S.items[phase]) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + phase] = globaltimer();
+            if ((int)old + 1 == P.nominal) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + phase] = globaltimer();
+            if (cx.dbg) cx.dbg[5] = globaltimer();
         }
         if (is_gemm && tid == 32) {              // fresh parities for the next GEMM item
             for (int b = 0; b < Smem::N_BAR; ++b)
@@ -679,6 +695,9 @@ k_encoder_persist(const __grid_constant__ Program P) {
 }  // namespace ep
 
 extern int g_tune_pairgemm_ctas;
+static unsigned long long* g_persist_dbg = nullptr;
+// profiling aid: per-item time stamps of the next persistent launches into buf (u64 [n_tickets][8]) or NULL = off
+extern "C" int ir_encoder_persist_debug(uint64_t* buf) { g_persist_dbg = (unsigned long long*)buf; return IR_OK; }
 
 // Builds the 13-layer program of encoder_features_multi (encoder.cu) and launches the persistent kernel.
 int irk_encoder_persist(int G, const IrConvProblem (*layers)[IR_MAX_GROUPS], const int* cin, const int* cout, const int* K,
@@ -706,6 +725,7 @@ int irk_encoder_persist(int G, const IrConvProblem (*layers)[IR_MAX_GROUPS], con
     P.G = G;
     P.relu_last = 1;
     P.sync = (unsigned*)sync;
+    P.dbg = g_persist_dbg;
     static bool attr_done = false;
     if (!attr_done) {
         IR_CHECK_CUDA(cudaFuncSetAttribute(ep::k_encoder_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, ep::Smem::BYTES));

@@ -6,12 +6,20 @@ per GPU: all parameters live in ONE flat fp32 buffer (each tensor a 256-byte-ali
   * ``step``           is one fused Adam kernel (``ir_adam_step``) with the 1/world_size average
                        folded into its gradient read.
 
+Data parallel (world > 1): the flat gradient buffer is cut into a few contiguous buckets; a post-accumulate hook on
+every parameter counts the gradients of its bucket and, when the bucket is complete, packs it and launches its
+all-reduce asynchronously (NCCL's own stream) while the rest of the backward is still running — only the bucket that
+finishes last is exposed (lib/solver.py:200-205 is the step this serves).
+
 ``torch.distributed`` is plumbing only (process group + all-reduce call)."""
+import contextlib
+
 import torch
 
 from . import ops
 
 ALIGN = 64          # floats (256 B): keeps every parameter 16-byte aligned for TMA bulk copies
+BUCKET_FLOATS = 1 << 21   # >= 8 MB of gradients per all-reduce bucket (8.02 M floats -> 4 buckets)
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -61,6 +69,24 @@ class FlatAdam(torch.optim.Optimizer):
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        # --- gradient buckets (contiguous parameter ranges of >= BUCKET_FLOATS) for the overlapped all-reduce
+        self.buckets, lo = [], 0
+        for i in range(len(self.params)):
+            end = ofs[i + 1] if i + 1 < len(ofs) else total
+            if end - ofs[lo] >= BUCKET_FLOATS or i + 1 == len(self.params):
+                self.buckets.append((lo, i + 1, ofs[lo], end))          # params [lo, i+1), floats [ofs[lo], end)
+                lo = i + 1
+        self.n_buckets = len(self.buckets)
+        self._bucket_of = [b for b, (l, h, _, _) in enumerate(self.buckets) for _ in range(h - l)]
+        self._fired = [0] * self.n_buckets          # gradients seen in this backward, per bucket
+        self._expect = [0] * self.n_buckets         # ... in the previous step (0 = unknown: no early launch)
+        self._work = [None] * self.n_buckets        # in-flight all-reduce of the bucket (launched from the hook)
+        self._packed = [False] * self.n_buckets
+        self.overlap = self.world > 1               # launch bucket all-reduces from the backward hooks
+        self._sync = True
+        if self.overlap:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
 
     # hyper-parameters live in the param group (what a scheduler mutates); attribute access for convenience
     lr = property(lambda self: self.param_groups[0]['lr'], lambda self, v: self.param_groups[0].__setitem__('lr', v))
@@ -73,13 +99,34 @@ class FlatAdam(torch.optim.Optimizer):
         """.grad = None: backward then hands over each gradient tensor without an accumulation kernel."""
         for p in self.params:
             p.grad = None
+        self._fired = [0] * self.n_buckets
+        self._packed = [False] * self.n_buckets
 
-    def gather_grads(self):
-        """Pack the per-parameter gradients of this backward into the flat buffer (one multi-tensor
-        copy; parameters that received no gradient contribute zeros and are masked out of the update)
-        and point .grad at the views.  -> indices of the parameters without a gradient."""
+    # --- overlapped bucket all-reduce -------------------------------------------------------------------
+    def _make_hook(self, b):
+        def hook(_p):
+            self._fired[b] += 1
+            if self._sync and self._fired[b] == self._expect[b] and self._work[b] is None and not self._packed[b]:
+                self._launch(b)
+        return hook
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Backward passes inside this context only accumulate (gradient accumulation over several backwards):
+        no bucket is reduced before ``step``."""
+        old, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = old
+
+    def _pack(self, b):
+        """Copy bucket b's gradients of this backward into the flat buffer (missing ones as zeros), point .grad at
+        the views.  -> indices of its parameters without a gradient."""
+        lo, hi, _, _ = self.buckets[b]
         src, dst, zero, missing = [], [], [], []
-        for i, (v, p) in enumerate(zip(self.grad_views, self.params)):
+        for i in range(lo, hi):
+            v, p = self.grad_views[i], self.params[i]
             if p.grad is None:
                 zero.append(v)
                 missing.append(i)
@@ -91,12 +138,46 @@ class FlatAdam(torch.optim.Optimizer):
             torch._foreach_zero_(zero)
         if src:
             torch._foreach_copy_(dst, src)
+        self._packed[b] = True
+        return missing
+
+    def _launch(self, b):
+        """Bucket complete (called from the last hook of the bucket, inside backward): pack it and start its
+        all-reduce; NCCL orders it after the copies on the current stream and runs it beside the backward."""
+        self._pack(b)
+        _, _, a, e = self.buckets[b]
+        self._work[b] = torch.distributed.all_reduce(self.flat_grad[a:e], group=self.group, async_op=True)
+
+    def gather_grads(self):
+        """Pack the per-parameter gradients of this backward into the flat buffer (one multi-tensor
+        copy; parameters that received no gradient contribute zeros and are masked out of the update)
+        and point .grad at the views.  -> indices of the parameters without a gradient."""
+        missing = []
+        for b in range(self.n_buckets):
+            if self._work[b] is None:                 # buckets already in flight were packed by their hook
+                missing += self._pack(b)
+            else:
+                lo, hi, _, _ = self.buckets[b]
+                missing += [i for i in range(lo, hi) if self.params[i].grad is None]
         return missing
 
     def allreduce(self):
-        """Sum over ranks (the mean is folded into the Adam kernel)."""
+        """Sum over ranks (the mean is folded into the Adam kernel): buckets whose all-reduce was launched from the
+        backward hooks are only waited for (stream-side), the others are reduced here."""
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            late = [b for b in range(self.n_buckets) if self._work[b] is None]
+            if len(late) == self.n_buckets:
+                torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            else:
+                for b in late:
+                    _, _, a, e = self.buckets[b]
+                    self._work[b] = torch.distributed.all_reduce(self.flat_grad[a:e], group=self.group, async_op=True)
+            for b in range(self.n_buckets):
+                if self._work[b] is not None:
+                    self._work[b].wait()              # the current stream waits; the host does not
+                    self._work[b] = None
+        self._expect = list(self._fired)              # what a complete bucket looks like, for the next backward
+        self._fired = [0] * self.n_buckets
 
     def _block_skip(self, missing):
         """uint8 per 64-float block (every parameter is block-aligned): 1 where the update is skipped."""

@@ -85,9 +85,11 @@ def _grad_worker(rank, world, port, q):
     the Adam kernel itself is CUDA-only and must refuse to run here."""
     sys.path.insert(0, ROOT)
     from instancerefer_b200 import _lib
+    from instancerefer_b200 import optim
     from instancerefer_b200.optim import ALIGN, FlatAdam
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
+    optim.BUCKET_FLOATS = 64                                        # several buckets even for this toy model
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
     ref = [p.detach().clone() for p in model.parameters()]
@@ -107,7 +109,28 @@ def _grad_worker(rank, world, port, q):
         dist.all_reduce(t)
         summed.append(t)
     ok &= all(torch.allclose(p.grad, s) for p, s in zip(model.parameters(), summed))
-    ok &= opt.world == world
+    ok &= opt.world == world and opt.n_buckets >= 2 and all(w is None for w in opt._work)
+    # second backward: every bucket now knows how many gradients complete it, so its all-reduce is launched from the
+    # parameter hooks DURING backward; step-time packing / reduction only waits for them
+    x2 = torch.randn(4, 7, generator=torch.Generator().manual_seed(20 + rank))
+    opt.zero_grad()
+    model(x2).square().sum().backward()
+    early = sum(w is not None for w in opt._work)
+    local2 = []
+    for r in range(world):                                         # every rank's local gradients, recomputed
+        m2 = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+        m2.load_state_dict(model.state_dict())
+        m2(torch.randn(4, 7, generator=torch.Generator().manual_seed(20 + r))).square().sum().backward()
+        local2.append([p.grad for p in m2.parameters()])
+    miss = opt.gather_grads()
+    opt.allreduce()
+    want = [sum(local2[r][i] for r in range(world)) for i in range(len(local2[0]))]
+    ok &= early == opt.n_buckets and miss == [] and all(w is None for w in opt._work)
+    ok &= all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6) for p, w in zip(model.parameters(), want))
+    with opt.no_sync():                                            # accumulation: nothing is reduced before step
+        opt.zero_grad()
+        model(x2).square().sum().backward()
+        ok &= all(w is None for w in opt._work)
     try:
         opt.step()
         refused = False

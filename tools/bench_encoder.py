@@ -75,3 +75,27 @@ for which in ('inst', 'scene', 'pair'):
         print(f'   inst  out max|persist-layers| = {float((a[1] - bb[1]).abs().max()):.3e}  (max|out| {float(a[1].abs().max()):.3f})')
     if which in ('scene', 'pair'):
         print(f'   scene out max|persist-layers| = {float((a[2] - bb[2]).abs().max()):.3e}  (max|out| {float(a[2].abs().max()):.3f})')
+
+# ---- per-item stamps of one persistent launch (instance encoder)
+if os.environ.get('IR_ITEMS', '1') != '0':
+    import ctypes
+    dbg = torch.zeros(8 * 8192, dtype=torch.int64, device=dev)
+    lib.ir_encoder_mode_set(1)
+    oa = torch.zeros(ws_i.n_max, 128, device=dev)
+    lib.ir_encoder_persist_debug(ctypes.c_void_p(dbg.data_ptr()))
+    ops.encoder_features(pa, ws_i, None, oa)
+    torch.cuda.synchronize()
+    lib.ir_encoder_persist_debug(None)
+    d = dbg.cpu().numpy().reshape(-1, 8)
+    d = d[d[:, 0] > 0]
+    t0 = d[:, 0].min()
+    ph = (d[:, 7] >> 32).astype(int)
+    print('per-phase item stats (us): n, first decode, [median: weights, wait-exit, work-end, cta-done, published] last published')
+    for p in range(25):
+        m = d[ph == p]
+        if not len(m): continue
+        rel = lambda c: (np.median(m[:, c][m[:, c] > 0]) - t0) / 1e3 if (m[:, c] > 0).any() else float('nan')
+        dur = lambda a, b: np.median((m[:, b] - m[:, a])[(m[:, a] > 0) & (m[:, b] > 0)]) / 1e3 if ((m[:, a] > 0) & (m[:, b] > 0)).any() else float('nan')
+        print(f'  ph {p:2d} n={len(m):4d} first {(m[:, 0].min() - t0) / 1e3:7.1f} | dec->wts {dur(0, 1):5.1f} wts->dep {dur(1, 2):5.1f} dec->dep {dur(0, 2):5.1f} '
+              f'dep->work {dur(2, 3):5.1f} work->cta {dur(3, 4):5.1f} cta->pub {dur(4, 5):5.1f} | dep-exit med {rel(2):7.1f} max {(m[:, 2].max() - t0) / 1e3:7.1f} '
+              f'work-end med {rel(3):7.1f} max {(m[:, 3].max() - t0) / 1e3:7.1f} pub max {(m[:, 5].max() - t0) / 1e3:7.1f}')
