@@ -56,6 +56,8 @@ int ir_encoder_mode_set(int mode);
  * writes GPU-timer stamps into buf[8*t ..]: 0 decoded, 1 weights staged, 2 dependency satisfied, 3 work done (thread 0),
  * 4 whole CTA done, 5 completion published, 7 = phase << 32 | CTA.  buf must hold 8 * 8192 u64.  NULL switches it off. */
 int ir_encoder_persist_debug(uint64_t* buf);
+/* Resident CTAs per SM of the persistent encoder kernel as computed by the CUDA runtime (2 expected), -1 on error. */
+int ir_encoder_persist_occupancy(void);
 
 /* Timeline aid: a one-thread kernel writes the GPU nanosecond timer into buf[idx] on `stream` (works inside stream
  * capture, so a replayed CUDA graph leaves a branch-level timeline behind; tools/timeline.py). */

@@ -102,6 +102,7 @@ SIGNATURES = {
     "ir_debug_set": (i32, [i32]),
     "ir_debug_stamp": (i32, [p, i32, p]),
     "ir_encoder_persist_debug": (i32, [p]),
+    "ir_encoder_persist_occupancy": (i32, []),
     "ir_encoder_mode_set": (i32, [i32]),
     "ir_tune_set": (i32, [i32, i32]),
     "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),

@@ -23,6 +23,7 @@
 //     split-fp16 contraction is safe for any activation magnitude (range guard of the inference path);
 //   * in-kernel data (activations, T) is read with ld.global.cg: other CTAs wrote it during this launch.
 // The arithmetic of an item is the one of k_pairgemm_tc / k_reduce_epilogue / k_stem_direct (spconv_tc.cu, spconv.cu).
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/instancerefer_b200.h"
@@ -61,7 +62,7 @@ struct Sched {                                 // shared memory, built once per 
     int cnt[MAX_LAYERS][VSLOTS];
     int kofs[MAX_LAYERS][VSLOTS];              // first T row of the offset inside its problem
     int rows[MAX_LAYERS][2], rpi[MAX_LAYERS][2], ri0[MAX_LAYERS];   // reduce: rows, rows per item, items of problem 0
-    int items[32], base[32];
+    int items[32], base[32], tick[32];       // real items, first ticket, tickets (>= items) per phase
 };
 
 struct Smem {
@@ -121,7 +122,7 @@ __device__ __forceinline__ void phase_wait(const unsigned* done, int need, int t
             if (clock64() - t0 > 4000000000ll) __trap();        // a protocol bug traps instead of hanging the GPU
         }
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(N_THREADS) : "memory");     // named barrier: every role joins where it can
 }
 
 // One pair-GEMM item = offset kk of one problem, tiles [t_begin, t_end) of TILE_M pairs.  Its arguments live in shared
@@ -178,14 +179,14 @@ __device__ __noinline__ void gemm_weights(const GemmArgs* __restrict__ A, const 
 // range scale, fp32 -> fp16 hi/lo split, two 16-byte swizzled stores; the loads of the group's next item are issued
 // right after the current one was handed to the tensor core.
 template <int CIN, int COUT>
-__device__ __noinline__ void gemm_producer(const GemmArgs* __restrict__ A, uint8_t* sm, int pw, int lane) {
+__device__ __noinline__ void gemm_producer(const GemmArgs* __restrict__ A, uint8_t* sm, int pw, int lane,
+                                           const unsigned* done, int need) {
     using C = Cfg<CIN, COUT>;
     const Bars B{A->base + Smem::OFF_BAR};
     const float* F = A->fin;
     const int* __restrict__ idx_k = A->idx_k;
     const int t_begin = A->t_begin, kcount = A->kcount;
     const int n_items = (A->t_end - t_begin) * C::KP;
-    const float in_s = scale_from_absmax(__uint_as_float(__ldcg(A->in_absmax)));
     const int grp = pw / WARPS_PER_GROUP;
     const int gt = (pw % WARPS_PER_GROUP) * 32 + lane;
     const int j = gt & 7;
@@ -213,10 +214,13 @@ __device__ __noinline__ void gemm_producer(const GemmArgs* __restrict__ A, uint8
             }
         }
     };
+    load_idx(grp);                                          // the rulebook is final long before this launch
+    phase_wait(done, need, 1);                              // previous phase complete (tid 0 polls; this is the barrier)
     if (grp >= n_items) return;
-    load_idx(grp);
+    const unsigned amax_bits = __ldcg(A->in_absmax);        // in flight with the row loads; used at the first split
     load_rows(grp);
     load_idx(grp + NS);
+    const float in_s = scale_from_absmax(__uint_as_float(amax_bits));
     uint8_t* st_hi = sm + Smem::OFF_STAGE + grp * STAGE_BYTES;
     uint8_t* st_lo = st_hi + PANEL_BYTES;
     uint32_t round = 0;
@@ -338,11 +342,14 @@ __device__ __forceinline__ void gemm_item(const Ctx& cx, const GemmArgs* A, cons
         gemm_weights<CIN, COUT>(A, cx.sm, warp < 4 ? 0 : 1 + (warp - 5) / 4, warp, lane);
     }
     if (cx.dbg && tid == 0) cx.dbg[1] = globaltimer();
-    phase_wait(done, need, tid);                                // previous phase complete (CTA barrier inside)
-    if (cx.dbg && tid == 0) cx.dbg[2] = globaltimer();
-    if (warp >= 5) gemm_producer<CIN, COUT>(A, cx.sm, warp - 5, lane);
-    else if (warp == 4) { if (lane == 0) gemm_mma<CIN, COUT>(A); }
-    else gemm_epilogue<CIN, COUT>(A, warp, lane);
+    if (warp >= 5) {
+        gemm_producer<CIN, COUT>(A, cx.sm, warp - 5, lane, done, need);     // joins the phase barrier after its index loads
+    } else {
+        phase_wait(done, need, tid);                            // previous phase complete (CTA barrier inside)
+        if (cx.dbg && tid == 0) cx.dbg[2] = globaltimer();
+        if (warp == 4) { if (lane == 0) gemm_mma<CIN, COUT>(A); }
+        else gemm_epilogue<CIN, COUT>(A, warp, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ reduce item
@@ -364,17 +371,21 @@ __device__ __noinline__ float reduce_rows(const LayerIO& io, long long seg_cap, 
         const int my = my_next;
         my_next = (lane < K && o + nwarps < r1) ? __ldg(slot + o + nwarps) : -1;      // next row's pair positions
         const int my_row = my_kofs + (my >= 0 ? my : 0);
+        // present offsets of this row, ascending k: only those T rows are loaded, U at a time (missing pairs cost nothing;
+        // the order of the additions is fixed, so the result is bitwise deterministic)
+        const unsigned present = __ballot_sync(0xffffffffu, my >= 0);
+        const int cnt = __popc(present);
+        // lane L takes over the T row of the L-th present offset: the present rows sit compacted in lanes 0..cnt-1
+        const int crow = __shfl_sync(0xffffffffu, my_row, (lane < cnt) ? (int)__fns(present, 0, lane + 1) : 0);
         float acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.f;
-        for (int k0 = 0; k0 < K; k0 += U) {
+        for (int j0 = 0; j0 < cnt; j0 += U) {
             float t[U][V];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int k = k0 + u;
-                const int pos = __shfl_sync(0xffffffffu, my, k & 31);
-                const int trow = __shfl_sync(0xffffffffu, my_row, k & 31);
-                const bool ok = (k < K) && (pos >= 0);
+                const bool ok = j0 + u < cnt;
+                const int trow = __shfl_sync(0xffffffffu, crow, (j0 + u) & 31);
                 const float* row = T + (long long)trow * COUT + lane * V;
                 if constexpr (V == 4) {
                     const float4 q = ok ? __ldcg(reinterpret_cast<const float4*>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -531,10 +542,12 @@ k_encoder_persist(const __grid_constant__ Program P) {
             }
             if (lane == 0) S.items[2 * l - 1] = total_items;
         }
+        // row items: one size for both problems, chosen so that their item counts together fit one ticket round
         int n = 0, rpi = RMIN, it = 0;
+        if (lane < P.G) n = __ldg(P.io[l][lane].n_out_dev);
+        const int n_all = n + __shfl_xor_sync(0xffffffffu, n, 1);              // lanes 0/1 hold the two row counts
         if (lane < P.G) {
-            n = __ldg(P.io[l][lane].n_out_dev);
-            rpi = max(RMIN, (n + P.nominal - 1) / P.nominal);
+            rpi = max(RMIN, (n_all + P.nominal - 3) / max(P.nominal - 2, 1));
             it = (n + rpi - 1) / rpi;
         }
         const int it0 = __shfl_sync(0xffffffffu, it, 0), it1 = __shfl_sync(0xffffffffu, it, 1);
@@ -549,7 +562,8 @@ k_encoder_persist(const __grid_constant__ Program P) {
     // items.  With one ticket taken per CTA per item this keeps ticket rounds and phases aligned: each CTA gets exactly
     // one (possibly null) item per phase, nobody runs two items of a phase while others idle at its barrier.
     if (warp == 0) {
-        const int v = (lane < n_phases) ? P.nominal : 0;
+        const int v = (lane < n_phases) ? max(P.nominal, S.items[lane]) : 0;
+        S.tick[lane] = v;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -563,7 +577,6 @@ k_encoder_persist(const __grid_constant__ Program P) {
     const int total = S.base[n_phases];
 
     int phase = 0, known_done = -1, stem_loaded = 0;
-    int next_ticket = 0;
     while (true) {
         const int ticket = *s_ticket;
         if (ticket >= total) break;
@@ -572,10 +585,7 @@ k_encoder_persist(const __grid_constant__ Program P) {
         const bool is_gemm = phase_is_gemm(phase);
         const int idx = ticket - S.base[phase];
         const bool null_item = idx >= S.items[phase];
-        if (warp == 4 && lane == 0) {                                     // bookkeeping thread (the MMA warp's lane 0)
-            next_ticket = (int)atomicAdd(sync + SY_TICKET, 1u);          // consumed at the end of this item
-            if (ticket == 0) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + 31] = globaltimer();
-        }
+        if (ticket == 0 && tid == 0) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + 31] = globaltimer();
         if (warp == 0 && !null_item) {
             if (is_gemm) {
                 const int K = P.K[l];
@@ -619,7 +629,7 @@ k_encoder_persist(const __grid_constant__ Program P) {
         const long long seg_cap = P.seg_cap[g];
         // dependency of this item: every ticket of the previous phase (skipped when this CTA already saw it complete)
         const unsigned* dep = sync + SY_DONE + (phase > 0 ? phase - 1 : 0);
-        const int need = (phase > 0 && known_done < phase - 1) ? P.nominal : -1;
+        const int need = (phase > 0 && known_done < phase - 1) ? S.tick[phase - 1] : -1;
         if (phase > 0 && !null_item) known_done = phase - 1;
         unsigned* amax_out = sync + SY_ABSMAX + 2 * l + g;
         if (null_item) {
@@ -655,7 +665,10 @@ k_encoder_persist(const __grid_constant__ Program P) {
         }
         tc_fence_before();
         if (cx.dbg && tid == 0) cx.dbg[3] = globaltimer();
-        if (warp == 4 && lane == 0) *s_ticket = next_ticket;
+        // The next ticket is taken when this CTA is (almost) done with the current one — by the bookkeeping thread (the
+        // MMA warp's lane 0, which finishes a GEMM item before the epilogue drains) — never earlier: tickets claimed
+        // ahead of time by busy CTAs would leave late or slow CTAs without their share of a phase.
+        if (warp == 4 && lane == 0) *s_ticket = (int)atomicAdd(sync + SY_TICKET, 1u);
         __syncthreads();                         // every global write of this item has been issued; next ticket published
         tc_fence_after();
         if (warp == 4 && lane == 0) {
@@ -664,7 +677,7 @@ k_encoder_persist(const __grid_constant__ Program P) {
             // trips; the other warps are already decoding the next item (the decode barrier orders the re-init below)
             __threadfence();
             const unsigned old = atomicAdd(sync + SY_DONE + phase, 1u);
-            if ((int)old + 1 == P.nominal) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + phase] = globaltimer();
+            if ((int)old + 1 == S.tick[phase]) reinterpret_cast<unsigned long long*>(sync)[SY_STAMP64 + phase] = globaltimer();
             if (cx.dbg) cx.dbg[5] = globaltimer();
         }
         if (is_gemm && tid == 32) {              // fresh parities for the next GEMM item
@@ -697,6 +710,30 @@ k_encoder_persist(const __grid_constant__ Program P) {
 extern int g_tune_pairgemm_ctas;
 static unsigned long long* g_persist_dbg = nullptr;
 // profiling aid: per-item time stamps of the next persistent launches into buf (u64 [n_tickets][8]) or NULL = off
+// resident CTAs per SM of the persistent kernel as the runtime computes it (expected: 2)
+extern "C" int ir_encoder_persist_occupancy(void) {
+    int n = 0;
+    cudaFuncSetAttribute(ep::k_encoder_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, ep::Smem::BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ep::k_encoder_persist, tc::N_THREADS, (size_t)ep::Smem::BYTES) != cudaSuccess) return -1;
+    if (getenv("IR_VERBOSE")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, ep::k_encoder_persist);
+        fprintf(stderr, "k_encoder_persist: regs %d static smem %zu max dyn smem %d local %zu maxThreads %d carveout %d -> %d CTAs/SM\n",
+                fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock,
+                fa.preferredShmemCarveout, n);
+        for (int smem = 60000; smem <= 110000; smem += 10000) {
+            int m = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, ep::k_encoder_persist, tc::N_THREADS, (size_t)smem);
+            fprintf(stderr, "  dyn smem %d -> %d\n", smem, m);
+        }
+        for (int thr = 416; thr <= 544; thr += 32) {
+            int m = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, ep::k_encoder_persist, thr, (size_t)60000);
+            fprintf(stderr, "  threads %d (smem 60000) -> %d\n", thr, m);
+        }
+    }
+    return n;
+}
 extern "C" int ir_encoder_persist_debug(uint64_t* buf) { g_persist_dbg = (unsigned long long*)buf; return IR_OK; }
 
 // Builds the 13-layer program of encoder_features_multi (encoder.cu) and launches the persistent kernel.

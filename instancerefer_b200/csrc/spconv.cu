@@ -142,20 +142,24 @@ k_reduce_epilogue(IrConvBatch b, int K) {
     const int wpb = blockDim.x >> 5;
     for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
         const int my = (lane < K) ? slot[(long long)lane * seg_cap + o] : -1;
+        // present offsets of this row, ascending k, compacted into lanes 0..cnt-1 (lane L holds the T row of the L-th
+        // present offset): only those rows are loaded, U at a time; missing pairs cost nothing and the order of the
+        // additions stays fixed (bitwise deterministic)
+        const unsigned present = __ballot_sync(0xffffffffu, my >= 0);
+        const int cnt = __popc(present);
+        const int my_row = ((lane < K) ? s_kofs[lane] : 0) + (my >= 0 ? my : 0);
+        const int crow = __shfl_sync(0xffffffffu, my_row, (lane < cnt) ? (int)__fns(present, 0, lane + 1) : 0);
         float acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.f;
-        // batches of up to 9 independent row loads (missing pairs contribute +0), then a fixed-order
-        // accumulation over k ascending: deterministic and latency-tolerant
         constexpr int U = 9;
-        for (int k0 = 0; k0 < K; k0 += U) {
+        for (int j0 = 0; j0 < cnt; j0 += U) {
             float t[U][V];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int k = k0 + u;
-                const int pos = __shfl_sync(0xffffffffu, my, k & 31);
-                const bool ok = (k < K) && (pos >= 0);
-                const float* row = T + (long long)(s_kofs[k & 31] + (ok ? pos : 0)) * COUT + lane * V;
+                const bool ok = j0 + u < cnt;
+                const int trow = __shfl_sync(0xffffffffu, crow, (j0 + u) & 31);
+                const float* row = T + (long long)trow * COUT + lane * V;
                 if (V == 4) {
                     const float4 q = ok ? *reinterpret_cast<const float4*>(row) : make_float4(0.f, 0.f, 0.f, 0.f);
                     t[u][0] = q.x; t[u][1 % V] = q.y; t[u][2 % V] = q.z; t[u][3 % V] = q.w;

@@ -87,9 +87,13 @@ if os.environ.get('IR_ITEMS', '1') != '0':
     torch.cuda.synchronize()
     lib.ir_encoder_persist_debug(None)
     d = dbg.cpu().numpy().reshape(-1, 8)
+    np.save(os.path.join(ROOT, 'gpurun_out', 'persist_items.npy'), d[d[:, 0] > 0])
     d = d[d[:, 0] > 0]
     t0 = d[:, 0].min()
     ph = (d[:, 7] >> 32).astype(int)
+    cta = (d[:, 7] & 0xffffffff).astype(int)
+    print('occupancy (runtime):', lib.ir_encoder_persist_occupancy(), ' distinct CTAs with items:', len(set(cta.tolist())),
+          ' max items of one CTA in a phase:', max(np.bincount(cta[ph == p]).max() for p in range(25) if (ph == p).any()))
     print('per-phase item stats (us): n, first decode, [median: weights, wait-exit, work-end, cta-done, published] last published')
     for p in range(25):
         m = d[ph == p]
