@@ -47,9 +47,9 @@ int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap
  * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
 int ir_tune_set(int pairgemm_ctas, int reduce_ctas);
 
-/* Feature-pass mode of ir_encoder_features[_pair]: 1 (default) = all 13 layers in ONE persistent launch (ticketed
- * pair-GEMM / reduce items, device-side tile counts, range-scaled split-fp16); 0 = one pair-GEMM + one reduce launch
- * per layer (also taken while ir_profile_enable is on, and for the SIMT path). */
+/* Feature-pass mode of ir_encoder_features[_pair]: 0 (default) = one pair-GEMM + one reduce launch per layer, chained
+ * by programmatic dependent launch; 1 = all 13 layers in ONE persistent launch (ticketed pair-GEMM / reduce items,
+ * device-side tile counts, range-scaled split-fp16; not taken while ir_profile_enable is on or for the SIMT path). */
 int ir_encoder_mode_set(int mode);
 
 /* Profiling aid of the persistent encoder kernel: when buf != NULL every item (ticket t) of the following launches

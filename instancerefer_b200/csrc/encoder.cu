@@ -74,9 +74,10 @@ static cudaEvent_t prof_event(int i, int j) {
     return g_prof_ev[i][j];
 }
 
-// 1 (default): the 13 layers of ir_encoder_features[_pair] run as ONE persistent launch (encoder_persist.cu);
-// 0: one pair-GEMM + one reduce launch per layer (k_pairgemm_tc / k_reduce_epilogue).
-static int g_encoder_mode = 1;
+// 0 (default): one pair-GEMM + one reduce launch per layer (k_pairgemm_tc / k_reduce_epilogue), PDL-chained;
+// 1: the 13 layers of ir_encoder_features[_pair] run as ONE persistent launch (encoder_persist.cu) — measured slower at
+//    the bench size, faster for small scenes where per-launch floors dominate.
+static int g_encoder_mode = 0;
 extern "C" int ir_encoder_mode_set(int mode) {
     IR_CHECK_ARG(mode == 0 || mode == 1);
     g_encoder_mode = mode;
@@ -364,12 +365,29 @@ static int encoder_features_multi(int G, const ir_encoder_params* const* ps, con
             for (int g = 0; g < G; ++g) lt[i][g].weight = ps[g]->wprep[i];     // 16-byte aligned copies (TMA bulk source)
         return irk_encoder_persist(G, lt, cins, couts, Ks, IR_ENC_LAYERS, w[0].sync(), st);
     }
+    // range guard of the split-fp16 GEMM: every reduce / stem epilogue records max|out| of its layer (one float per layer
+    // and problem in the workspace's sync area, cleared here); the next layer's pair-GEMM scales its gathered rows by the
+    // power of two that brings this maximum to 2^13 and un-scales in its epilogue (exact).
+    float* amax[IR_MAX_GROUPS] = {nullptr, nullptr};
+    if (ps[0]->use_tc) {
+        for (int g = 0; g < G; ++g) {
+            amax[g] = (float*)((char*)w[g].sync() + 4 * 34);
+            IR_CHECK_CUDA(cudaMemsetAsync(amax[g], 0, 4 * 2 * IR_ENC_LAYERS, st));
+        }
+    }
     for (int i = 0; i < IR_ENC_LAYERS; ++i) {
         IrConvBatch b;
         memset(&b, 0, sizeof(b));
         b.G = G;
         const float* wp[IR_MAX_GROUPS] = {nullptr, nullptr};
-        for (int g = 0; g < G; ++g) { b.p[g] = layers[i][g]; wp[g] = ps[g]->wprep[i]; }
+        for (int g = 0; g < G; ++g) {
+            b.p[g] = layers[i][g];
+            wp[g] = ps[g]->wprep[i];
+            if (amax[g]) {
+                b.p[g].out_absmax = amax[g] + 2 * i;
+                b.p[g].in_absmax = (i >= 1) ? amax[g] + 2 * (i - 1) : nullptr;
+            }
+        }
         if ((r = conv_layer(b, cins[i], couts[i], Ks[i], wp, ps[0]->use_tc, st)) != IR_OK) return r;
     }
     return IR_OK;

@@ -49,6 +49,8 @@ struct IrConvProblem {
                              // the power of two that brings this maximum to 2^13 before the fp16 hi/lo split and the
                              // result is scaled back exactly: keeps small-magnitude inputs (gradients) out of fp16's
                              // subnormal range.
+    float* out_absmax;       // reduce / stem epilogue: device scalar receiving max|out| of this launch (atomicMax on the
+                             // bit pattern; the caller zeroes it), or NULL.  Feeds the next layer's in_absmax.
 };
 struct IrConvBatch {
     IrConvProblem p[IR_MAX_GROUPS];

@@ -140,6 +140,7 @@ k_reduce_epilogue(IrConvBatch b, int K) {
         sh[v] = shift ? shift[lane * V + v] : 0.f;
     }
     const int wpb = blockDim.x >> 5;
+    float amax = 0.f;
     for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
         const int my = (lane < K) ? slot[(long long)lane * seg_cap + o] : -1;
         // present offsets of this row, ascending k, compacted into lanes 0..cnt-1 (lane L holds the T row of the L-th
@@ -183,10 +184,15 @@ k_reduce_epilogue(IrConvBatch b, int K) {
             if (rrow) y += rrow[v];
             if (relu) y = fmaxf(y, 0.f);
             acc[v] = y;
+            amax = fmaxf(amax, fabsf(y));
         }
         if (V == 4) *reinterpret_cast<float4*>(orow) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
         else if (V == 2) *reinterpret_cast<float2*>(orow) = make_float2(acc[0], acc[1 % V]);
         else orow[0] = acc[0];
+    }
+    if (P.out_absmax) {                   // range guard of the next layer's split-fp16 gather (non-negative floats order as uints)
+        amax = warp_max(amax);
+        if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned*>(P.out_absmax), __float_as_uint(amax));
     }
 }
 
@@ -224,6 +230,7 @@ k_stem_direct(IrConvBatch b, int cin) {
     const int n = *P.n_out_dev;
     const float sc = P.scale ? P.scale[lane] : 1.f, sh = P.shift ? P.shift[lane] : 0.f;
     const int wpb = blockDim.x >> 5;
+    float amax = 0.f;
     for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
         int my_j = -1;
         if (lane < 27) {
@@ -246,6 +253,11 @@ k_stem_direct(IrConvBatch b, int cin) {
         if (P.resid) y += P.resid[o * STEM_COUT + lane];
         if (P.relu) y = fmaxf(y, 0.f);
         P.out[o * STEM_COUT + lane] = y;
+        amax = fmaxf(amax, fabsf(y));
+    }
+    if (P.out_absmax) {
+        amax = warp_max(amax);
+        if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned*>(P.out_absmax), __float_as_uint(amax));
     }
 }
 

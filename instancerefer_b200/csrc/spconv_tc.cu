@@ -627,7 +627,11 @@ int launch_wgrad(const float* x, const float* dy, const int* in_idx, const int* 
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
     IR_CHECK_ARG(K <= 27 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
     for (int g = 0; g < b.G; ++g) IR_CHECK_ARG(b.p[g].weight != nullptr && (reinterpret_cast<uintptr_t>(b.p[g].weight) & 15) == 0);
-    if (b.G == 1 && b.p[0].in_absmax != nullptr) {          // range-scaled variant: the dgrad shapes of the training step
+    bool scaled = true;
+    for (int g = 0; g < b.G; ++g) scaled = scaled && b.p[g].in_absmax != nullptr;
+    if (scaled) {          // range-scaled variant: the guarded inference path and the dgrad shapes of the training step
+        if (cin == 32 && cout == 64) return tc::launch<32, 64, true>(b, K, st);
+        if (cin == 64 && cout == 128) return tc::launch<64, 128, true>(b, K, st);
         if (cin == 64 && cout == 32) return tc::launch<64, 32, true>(b, K, st);
         if (cin == 64 && cout == 64) return tc::launch<64, 64, true>(b, K, st);
         if (cin == 128 && cout == 64) return tc::launch<128, 64, true>(b, K, st);

@@ -32,6 +32,9 @@ def _p(t, dtype=None):
 _checked_devices = set()
 
 
+_MODE_APPLIED = [False]
+
+
 def check_device(device_index=None):
     """Raise unless the current device is a B200-class (sm_100) GPU.  Checked once per device."""
     if not _checked_devices and not torch.cuda.is_available():
@@ -40,6 +43,11 @@ def check_device(device_index=None):
     if idx not in _checked_devices:
         call("ir_check_device", idx)
         _checked_devices.add(idx)
+    if not _MODE_APPLIED[0]:
+        _MODE_APPLIED[0] = True
+        import os
+        if os.environ.get('IR_ENCODER') in ('layers', 'persist'):
+            set_encoder_mode(os.environ['IR_ENCODER'])
 
 
 # ----------------------------------------------------------------------------- encoder workspace
@@ -87,6 +95,12 @@ class EncoderWorkspace:
 
     def T(self):
         return self._view(self.layout.off_T, 27 * self.n_max * 128 * 4, torch.float32)
+
+
+def set_encoder_mode(mode):
+    """'layers' (default): one pair-GEMM + one reduce launch per conv layer; 'persist': all 13 layers of an encoder (or of
+    both, ``encoder_features_pair``) in one persistent launch.  Environment: IR_ENCODER=layers|persist."""
+    call("ir_encoder_mode_set", {'layers': 0, 'persist': 1}[mode])
 
 
 TIMELINE = None          # tools/timeline.py sets this to a Timeline; None = no stamps (zero overhead)

@@ -174,6 +174,73 @@ def test_encoder_features(ops, state_dict, use_tc):
     assert float((f4[:n].cpu() - Fr).abs().max()) < TOL
 
 
+@pytest.mark.parametrize('mode', ['layers', 'persist'])
+@pytest.mark.parametrize('gain', [1e5, 1e-6])
+def test_encoder_range_guard(ops, state_dict, gain, mode):
+    """Split-fp16 rule GEMM with activations far outside fp16's comfortable range (|x| ~ 1e5 would overflow the hi part,
+    |x| ~ 1e-6 would lose the lo part to subnormals): every layer's epilogue records max|out| and the next layer's gather
+    is scaled by a power of two (exact), so the tcgen05 path must still agree with the exact fp32 SIMT kernel."""
+    from instancerefer_b200.basic_blocks import SparseConvEncoder
+    b = synthetic.make_batch(19, batch_size=1, num_points=6000, n_inst=6, n_cand=3, n_tokens=4)
+    C0, F0 = torch.from_numpy(b['lidar_coords']).cuda(), torch.from_numpy(b['lidar_feats']).cuda()
+    outs = {}
+    try:
+        for use_tc in (True, False):
+            enc = SparseConvEncoder(7)
+            enc.use_tc = use_tc
+            enc.load_state_dict({k[len('scene.net.'):]: v for k, v in state_dict.items() if k.startswith('scene.net.')})
+            with torch.no_grad():
+                bn = enc.stem[0].net[1]                     # stem BN gain: everything downstream scales with it
+                bn.weight.mul_(gain)
+                bn.bias.mul_(gain)
+            enc = enc.cuda().eval()
+            ops.set_encoder_mode(mode if use_tc else 'layers')
+            ws = enc.workspace(C0.shape[0], 'cuda')
+            f4, _, n4 = enc.encode(ws, F0, C0)
+            outs[use_tc] = f4[:int(n4)].clone()
+    finally:
+        ops.set_encoder_mode('layers')
+    ref = outs[False]
+    assert torch.isfinite(outs[True]).all() and float(ref.abs().max()) > 0
+    assert float((outs[True] - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('which', ['single', 'pair'])
+def test_persistent_encoder_matches_per_layer_launches(ops, state_dict, which):
+    """ir_encoder_mode_set(1): all 13 layers of one / both encoders in one persistent launch (ticketed pair-GEMM and
+    reduce items) against the per-layer launch chain, same rulebooks; two launches in a row (the kernel resets its own
+    ticket / phase counters)."""
+    from instancerefer_b200.basic_blocks import SparseConvEncoder
+    encs, wss, f0s = [], [], []
+    for seed, key in ((21, 'scene.net.'), (22, 'attribute.net.')):
+        b = synthetic.make_batch(seed, batch_size=2, num_points=7000, n_inst=6, n_cand=3, n_tokens=4)
+        C0, F0 = torch.from_numpy(b['lidar_coords']).cuda(), torch.from_numpy(b['lidar_feats']).cuda()
+        enc = SparseConvEncoder(7)
+        enc.load_state_dict({k[len(key):]: v for k, v in state_dict.items() if k.startswith(key)})
+        enc = enc.cuda().eval()
+        ws = ops.EncoderWorkspace(ops.round_rows(C0.shape[0]), 'cuda')
+        ops.encoder_build_maps(ws, C0)
+        encs.append(enc); wss.append(ws); f0s.append(F0)
+
+    def run(mode):
+        ops.set_encoder_mode(mode)
+        outs = [torch.zeros(w.n_max, 128, device='cuda') for w in wss]
+        for _ in range(2):
+            if which == 'pair':
+                ops.encoder_features_pair(encs[0].prepared()['params'], wss[0], f0s[0], outs[0],
+                                          encs[1].prepared()['params'], wss[1], f0s[1], outs[1])
+            else:
+                ops.encoder_features(encs[0].prepared()['params'], wss[0], f0s[0], outs[0])
+        torch.cuda.synchronize()
+        return [o[:int(w.nlvl()[4])].clone() for o, w in zip(outs, wss)]
+    try:
+        want, got = run('layers'), run('persist')
+    finally:
+        ops.set_encoder_mode('layers')
+    for g, w in list(zip(got, want))[:2 if which == 'pair' else 1]:
+        assert float(w.abs().max()) > 0 and float((g - w).abs().max()) < 2e-6
+
+
 def test_segmax(ops):
     rng = np.random.default_rng(5)
     F = torch.from_numpy(rng.normal(size=(777, 128)).astype(np.float32))
