@@ -493,14 +493,18 @@ def main():
 
     # `value`: inputs resident in HBM -> one captured graph per resident scene, replay only
     res_graphs = []
+    stamps = torch.zeros(256, 4, dtype=torch.int64, device=dev)    # live per-launch spans of the conv kernels (scene 0's graph)
     if use_graph:
-        for d in resident:
+        for i, d in enumerate(resident):
             for _ in range(2):
                 model(dict(d))
             torch.cuda.synchronize()
+            if i == 0 and rank == 0:
+                lib.ir_conv_stamps_set(ctypes.c_void_p(stamps.data_ptr()))
             g_ = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_):
                 o_ = model(dict(d))
+            lib.ir_conv_stamps_set(None)
             res_graphs.append((g_, o_))
 
     def step_resident(i):
@@ -594,56 +598,71 @@ def main():
                d2h_bytes_per_step=int(d2h_bytes[0]))
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline pass: event-timed pair-GEMM / reduce launches of the same resident steps
-    roofline, detail = None, None
+    # ---- roofline pass: per-launch spans of the conv kernels measured INSIDE the replayed 4-stream graph (in-kernel GPU
+    # timer: begin = first CTA past its dependency wait, end = last CTA done), L2 flushed before every replay
+    roofline, detail, layers = None, None, None
     if rank == 0:
-        nprof = min(a.steps, 10)
-        model.concurrent = False          # serial launches: the event spans must not overlap other streams
-        lib.ir_profile_enable(8)          # each timed kernel 8x back to back inside its event span (per-launch average)
-        cap = 512
-        gm, rm = (ctypes.c_float * cap)(), (ctypes.c_float * cap)()
+        nprof = min(a.steps, 20)
+        I64MAX = (1 << 63) - 1
+        cap = 256
         meta, nout = (ctypes.c_int32 * (4 * cap))(), ctypes.c_int32(0)
-        acc = {}
-        for i in range(nprof):
-            flush.zero_()
-            model(dict(resident[i % n_scenes]))            # eager launches so the event hooks fire
-            torch.cuda.synchronize()
-            _lib.call('ir_profile_read', gm, rm, meta, cap, ctypes.byref(nout))
-            # pair counts of this step's rulebooks (attribute encoder first, scene encoder second)
+        maps = [0, 5, 1, 1, 6, 2, 2, 7, 3, 3, 8, 4, 4]                  # layer -> kernel map id
+        acc = None
+        if use_graph:
+            _lib.call('ir_conv_stamps_meta', meta, cap, ctypes.byref(nout))
+            n_l = nout.value
+            acc = np.zeros((n_l, 2))
+            for _ in range(nprof):
+                stamps[:, 0] = I64MAX; stamps[:, 2] = I64MAX; stamps[:, 1] = 0; stamps[:, 3] = 0
+                flush.zero_()
+                res_graphs[0][0].replay()
+                torch.cuda.synchronize()
+                st = stamps[:n_l].cpu().numpy()
+                acc[:, 0] += np.where(st[:, 1] > 0, st[:, 1] - st[:, 0], 0) / 1e3        # pair-GEMM us
+                acc[:, 1] += np.where(st[:, 3] > 0, st[:, 3] - st[:, 2], 0) / 1e3        # reduce / stem us
+            acc /= nprof
             kc = [model.attribute.net._last_ws.kcount().cpu().numpy(), model.scene.net._last_ws.kcount().cpu().numpy()]
-            maps = [0, 5, 1, 1, 6, 2, 2, 7, 3, 3, 8, 4, 4]                  # layer -> kernel map id
-            for j in range(nout.value):
+            nl = [model.attribute.net._last_ws.nlvl().cpu().numpy(), model.scene.net._last_ws.nlvl().cpu().numpy()]
+            lvl_of = [0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
+            layers = []
+            for j in range(n_l):
                 enc, layer = divmod(j, 13)
                 cin, cout, K, tc = (meta[4 * j + q] for q in range(4))
                 P = int(kc[enc][maps[layer]][:K].sum())
-                by = P * (4 * cin + 4) + P * 4 * cout + 4 * K * cin * cout     # gather + T write + weights
-                fl = 2 * P * cin * cout
-                key = ('tcgen05' if tc else 'simt', cin, cout, K)
-                e = acc.setdefault(key, [0.0, 0.0, 0, 0, 0.0, 0])
-                e[0] += gm[j]; e[1] += by; e[2] += fl; e[3] += 1; e[4] += rm[j]; e[5] += P
-        lib.ir_profile_enable(0)
-        model.concurrent = True
+                layers.append(dict(encoder=('instance', 'scene')[enc], layer=layer, cin=cin, cout=cout, K=K, tcgen05=bool(tc),
+                                   rows_out=int(nl[enc][lvl_of[layer]]), pairs=P, gemm_us=round(float(acc[j, 0]), 2),
+                                   reduce_us=round(float(acc[j, 1]), 2),
+                                   bytes_gemm=P * (4 * cin + 4) + P * 4 * cout + 4 * K * cin * cout,          # gather + T write + W
+                                   bytes_conv=P * (4 * cin + 4) + P * (4 * cout + 4) + 4 * K * cin * cout))   # G + S + W
         peak, peak_src = load_peak()
-        tc_ms = sum(v[0] for k, v in acc.items() if k[0] == 'tcgen05')
-        tc_by = sum(v[1] for k, v in acc.items() if k[0] == 'tcgen05')
-        tc_n = sum(v[3] for k, v in acc.items() if k[0] == 'tcgen05')
-        all_ms = sum(v[0] + v[4] for v in acc.values())
-        traffic = None
+        traffic = ncu = None
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
-        if tc_ms > 0:
-            ach = tc_by / (tc_ms * 1e-3) / 1e9
-            roofline = dict(bound='hbm', kernel='k_pairgemm_tc (tcgen05 split-fp16 pair-GEMM, 24 launches/step)',
-                            achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic,
-                            peak_source=peak_src, bytes_per_launch=tc_by / tc_n, us_per_launch=tc_ms * 1e3 / tc_n,
-                            share_of_step=tc_ms / nprof / (dev_ms / a.steps),
-                            spconv_share_of_step=all_ms / nprof / (dev_ms / a.steps))
-        detail = {f'{k[0]}_{k[1]}x{k[2]}_k{k[3]}': dict(launches_per_step=v[3] / nprof, gemm_us=v[0] * 1e3 / v[3],
-                                                       reduce_us=v[4] * 1e3 / v[3], pairs=v[5] / v[3],
-                                                       gemm_GBs=v[1] / (max(v[0], 1e-4) * 1e-3) / 1e9,
-                                                       gemm_TFLOPs=v[2] / (max(v[0], 1e-4) * 1e-3) / 1e12)
-                  for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
+            tj = json.load(open(tp))
+            traffic, ncu = tj.get('dram_bytes_per_launch'), tj.get('ncu')
+        if layers:
+            tcl = [l for l in layers if l['tcgen05']]
+            g_us, g_by = sum(l['gemm_us'] for l in tcl), sum(l['bytes_gemm'] for l in tcl)
+            c_us = sum(l['gemm_us'] + l['reduce_us'] for l in layers)
+            c_by = sum(l['bytes_conv'] for l in layers)
+            ach, cach = g_by / (g_us * 1e-6) / 1e9, c_by / (c_us * 1e-6) / 1e9
+            roofline = dict(bound='hbm', kernel=f'k_pairgemm_tc (tcgen05 split-fp16 pair-GEMM, {len(tcl)} launches/step)',
+                            achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
+                            timing='in-kernel GPU-timer span of every launch (first CTA past its dependency wait -> last CTA '
+                                   'done) inside the replayed 4-stream CUDA graph, L2 flushed before each replay, mean of '
+                                   f'{nprof} replays; both encoders run concurrently, so a span includes the time its CTAs '
+                                   'waited for SMs held by the other encoder',
+                            bytes_per_launch=g_by / len(tcl), us_per_launch=g_us / len(tcl),
+                            conv=dict(what='whole sparse conv = pair-GEMM + reduce/epilogue (+ the two fused stems), SURVEY 8(d) '
+                                           'bytes G+S+W over the summed spans of both kernels', achieved=cach, frac=cach / peak,
+                                      us_per_step=c_us, bytes_per_step=c_by),
+                            ncu=ncu)
+            groups = {}
+            for l in layers:
+                e = groups.setdefault(f"{'tcgen05' if l['tcgen05'] else 'direct'}_{l['cin']}x{l['cout']}_k{l['K']}", [0, 0.0, 0.0, 0, 0])
+                e[0] += 1; e[1] += l['gemm_us']; e[2] += l['reduce_us']; e[3] += l['pairs']; e[4] += l['bytes_conv']
+            detail = {k: dict(launches_per_step=v[0], gemm_us=v[1] / v[0], reduce_us=v[2] / v[0], pairs=v[3] / v[0],
+                              conv_GBs=v[4] / ((v[1] + v[2]) * 1e-6) / 1e9) for k, v in groups.items()}
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -669,7 +688,7 @@ def main():
                     impl_detail=dict(parallelism=f'scenes sharded over {world} GPU(s), no data-path collective',
                                      launch='eager' if not use_graph else 'CUDA-graph replay, 4 streams; e2e double-buffered (host of step i+1 overlaps GPU of step i)'),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
-                    cpu_baseline=cb, spconv_detail=detail, train=train)
+                    cpu_baseline=cb, spconv_detail=detail, conv_layers=layers, train=train)
         print(json.dumps(line))
 
 

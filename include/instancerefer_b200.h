@@ -43,6 +43,15 @@ int64_t ir_launch_count(void);
 int ir_profile_enable(int on);
 int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap, int32_t* n_out);
 
+/* Live per-launch spans of the conv kernels (bench.py roofline): while buf != NULL every layer call made through
+ * ir_encoder_features / ir_spconv_layer takes the next 4-u64 slot {pair-GEMM begin, end, reduce-or-stem begin, end} (GPU
+ * timer ns; begin = first CTA past its dependency wait via atomicMin, end = last CTA done via atomicMax — the caller
+ * presets begins to ~0 and ends to 0 before every run).  Slots are assigned at launch (or capture) time in call order, so a
+ * CUDA graph captured while the buffer is set keeps writing its slots on every replay.  buf must hold 4 * 256 u64.
+ * ir_conv_stamps_meta returns (cin, cout, K, used_tcgen05) per slot.  ir_conv_stamps_set(NULL) switches it off. */
+int ir_conv_stamps_set(uint64_t* buf);
+int ir_conv_stamps_meta(int32_t* meta, int32_t cap, int32_t* n_out);
+
 /* Tuning knobs: CTAs per pair-GEMM launch (default 2 per SM = 296) and per reduce / stem launch (default
  * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
 int ir_tune_set(int pairgemm_ctas, int reduce_ctas);

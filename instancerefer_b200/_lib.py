@@ -101,6 +101,8 @@ SIGNATURES = {
     "ir_profile_read": (i32, [p, p, p, i32, p]),
     "ir_debug_set": (i32, [i32]),
     "ir_debug_stamp": (i32, [p, i32, p]),
+    "ir_conv_stamps_set": (i32, [p]),
+    "ir_conv_stamps_meta": (i32, [p, i32, p]),
     "ir_encoder_persist_debug": (i32, [p]),
     "ir_encoder_persist_occupancy": (i32, []),
     "ir_encoder_mode_set": (i32, [i32]),

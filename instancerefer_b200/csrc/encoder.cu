@@ -228,10 +228,39 @@ extern "C" int ir_encoder_build_maps(const int32_t* coords0, int32_t n0, const i
     return irk_kmap_all(ka, rows0, st);
 }
 
-static int conv_layer(const IrConvBatch& b, int cin, int cout, int K, const float* const* wprep, int use_tc,
+// Live per-launch spans (bench.py roofline): while a stamp buffer is set, every conv kernel launched through conv_layer
+// (also under stream capture, so the replayed graph keeps writing them) records {begin, end} GPU-timer ns into slot
+// 2*i / 2*i+1 (pair-GEMM / reduce-or-stem of the i-th layer call); meta = (cin, cout, K, tcgen05) per layer call.
+#define IR_STAMP_MAX 256
+static unsigned long long* g_stamp_buf = nullptr;
+static int g_stamp_n = 0;
+static int g_stamp_meta[IR_STAMP_MAX][4];
+extern "C" int ir_conv_stamps_set(uint64_t* buf) {
+    g_stamp_buf = (unsigned long long*)buf;
+    if (buf) g_stamp_n = 0;               // slots restart with every new buffer; the meta of the last one stays readable
+    return IR_OK;
+}
+extern "C" int ir_conv_stamps_meta(int32_t* meta, int32_t cap, int32_t* n_out) {
+    IR_CHECK_ARG(meta && n_out);
+    const int n = g_stamp_n < cap ? g_stamp_n : cap;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < 4; ++j) meta[4 * i + j] = g_stamp_meta[i][j];
+    *n_out = n;
+    return IR_OK;
+}
+
+static int conv_layer(const IrConvBatch& b_in, int cin, int cout, int K, const float* const* wprep, int use_tc,
                       cudaStream_t st) {
     int r;
+    IrConvBatch b = b_in;
     bool tc = use_tc && cin >= 32;
+    unsigned long long* stamp = nullptr;
+    if (g_stamp_buf && g_stamp_n < IR_STAMP_MAX) {
+        bool tcq = tc;
+        for (int g = 0; g < b.G; ++g) tcq = tcq && wprep[g] != nullptr;
+        g_stamp_meta[g_stamp_n][0] = cin; g_stamp_meta[g_stamp_n][1] = cout; g_stamp_meta[g_stamp_n][2] = K; g_stamp_meta[g_stamp_n][3] = tcq;
+        stamp = g_stamp_buf + 4 * g_stamp_n++;           // {gemm begin, gemm end, reduce begin, reduce end}
+    }
     for (int g = 0; g < b.G; ++g) tc = tc && wprep[g] != nullptr;
     const int pi = (g_prof_on && g_prof_n < IR_PROF_MAX) ? g_prof_n++ : -1;
     if (pi >= 0) {
@@ -241,12 +270,14 @@ static int conv_layer(const IrConvBatch& b, int cin, int cout, int K, const floa
     if (!tc && K == 27 && cout == 32 && cin <= 8 && !g_prof_force_gemm) {
         // stem: direct fused conv (no T round trip); recorded as the "reduce" span of the profile
         if (pi >= 0) cudaEventRecord(prof_event(pi, 1), st);
+        b.stamp = stamp ? stamp + 2 : nullptr;
         r = irk_stem_direct(b, cin, st);
         if (pi >= 0) cudaEventRecord(prof_event(pi, 2), st);
         return r;
     }
     const int rep = (pi >= 0) ? g_prof_rep : 1;      // profiling: idempotent repeats amortise the host launch gap
     for (int it = 0; it < rep; ++it) {
+        b.stamp = stamp;
         if (tc) {
             IrConvBatch bt = b;
             for (int g = 0; g < b.G; ++g) bt.p[g].weight = wprep[g];  // 16-byte aligned copy for the TMA bulk copy
@@ -257,6 +288,7 @@ static int conv_layer(const IrConvBatch& b, int cin, int cout, int K, const floa
         if (r != IR_OK) return r;
     }
     if (pi >= 0) cudaEventRecord(prof_event(pi, 1), st);
+    b.stamp = stamp ? stamp + 2 : nullptr;
     for (int it = 0; it < rep; ++it) {
         r = irk_reduce_epilogue(b, cout, K, st);
         if (r != IR_OK) return r;

@@ -55,7 +55,23 @@ struct IrConvProblem {
 struct IrConvBatch {
     IrConvProblem p[IR_MAX_GROUPS];
     int G;
+    unsigned long long* stamp;   // optional {first CTA past its dependency wait, last CTA done} in GPU-timer ns (atomicMin /
+                                 // atomicMax; the caller presets {~0, 0}), or NULL: live per-launch spans inside a replayed graph
 };
+__device__ __forceinline__ void ir_stamp_begin(unsigned long long* stamp) {
+    if (stamp && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMin(stamp, t);
+    }
+}
+__device__ __forceinline__ void ir_stamp_end(unsigned long long* stamp) {
+    if (stamp && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMax(stamp + 1, t);
+    }
+}
 
 // spconv.cu  (SIMT fp32 pair-GEMM + deterministic reduce/epilogue)
 int irk_pairgemm_simt(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);

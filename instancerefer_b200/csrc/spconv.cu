@@ -132,6 +132,7 @@ k_reduce_epilogue(IrConvBatch b, int K) {
     __syncthreads();
     ir_pdl_trigger();                     // the next layer's pair-GEMM may start staging its weights
     ir_pdl_wait();                        // T comes from the pair-GEMM launched just before
+    ir_stamp_begin(b.stamp);
     const int n = *n_dev;
     float sc[V], sh[V];
 #pragma unroll
@@ -194,6 +195,8 @@ k_reduce_epilogue(IrConvBatch b, int K) {
         amax = warp_max(amax);
         if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned*>(P.out_absmax), __float_as_uint(amax));
     }
+    __syncthreads();
+    ir_stamp_end(b.stamp);
 }
 
 int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) {
@@ -218,37 +221,67 @@ int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) 
 // (slot -> in_idx), folded BN + ReLU in the epilogue.  Replaces stem.0 of models/basic_blocks.py:64-66.
 #define STEM_COUT 32
 #define STEM_MAXCIN 8
-__global__ void __launch_bounds__(256)
+#define STEM_WARPS 8
+// Per output row (one warp): (1) lanes < 27 resolve the neighbour rows through the rulebook (slot -> in_idx), the next
+// row's lookups are issued before this row's arithmetic; (2) the present neighbours are compacted (ascending k) and ALL
+// their feature values (<= 27 x Cin <= 216) are fetched by ONE round of independent loads, 7 per lane, into the warp's
+// shared-memory slab; (3) lane = output channel accumulates over present neighbours only, in ascending k (deterministic),
+// reading the features as shared-memory broadcasts.  Three dependent memory latencies per row instead of one per neighbour.
+__global__ void __launch_bounds__(32 * STEM_WARPS)
 k_stem_direct(IrConvBatch b, int cin) {
     const IrConvProblem& P = b.p[blockIdx.y];
     __shared__ float Ws[27 * STEM_MAXCIN * STEM_COUT];
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < 27 * cin * STEM_COUT; i += 256) Ws[i] = P.weight[i];     // (27, cin, 32), constant
+    __shared__ float Xs[STEM_WARPS][27 * STEM_MAXCIN + 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 27 * cin * STEM_COUT; i += 32 * STEM_WARPS) Ws[i] = P.weight[i];     // (27, cin, 32), constant
     __syncthreads();
     ir_pdl_trigger();
     ir_pdl_wait();
+    ir_stamp_begin(b.stamp);
     const int n = *P.n_out_dev;
     const float sc = P.scale ? P.scale[lane] : 1.f, sh = P.shift ? P.shift[lane] : 0.f;
-    const int wpb = blockDim.x >> 5;
+    const int* __restrict__ slot = P.slot + (long long)lane * P.seg_cap;
+    const int* __restrict__ in_idx = P.in_idx + (long long)lane * P.seg_cap;
+    const float* __restrict__ F = P.fin;
+    float* xs = Xs[warp];
+    const long long stride = (long long)gridDim.x * STEM_WARPS;
     float amax = 0.f;
-    for (long long o = (long long)blockIdx.x * wpb + (tid >> 5); o < n; o += (long long)gridDim.x * wpb) {
-        int my_j = -1;
-        if (lane < 27) {
-            const int pos = P.slot[(long long)lane * P.seg_cap + o];
-            if (pos >= 0) my_j = P.in_idx[(long long)lane * P.seg_cap + pos];
+    long long o = (long long)blockIdx.x * STEM_WARPS + warp;
+    int my_j = -1;
+    if (o < n && lane < 27) {
+        const int pos = slot[o];
+        if (pos >= 0) my_j = in_idx[pos];
+    }
+    for (; o < n; o += stride) {
+        const int cur_j = my_j;
+        // next row's rulebook lookups (two dependent loads) fly while this row is computed
+        int pos_n = -1;
+        if (o + stride < n && lane < 27) pos_n = slot[o + stride];
+        const unsigned present = __ballot_sync(0xffffffffu, cur_j >= 0);
+        const int cnt = __popc(present);
+        // lane L takes over (k, row) of the L-th present neighbour
+        const int src = (lane < cnt) ? (int)__fns(present, 0, lane + 1) : 0;
+        const int cj = __shfl_sync(0xffffffffu, cur_j, src);
+        const int ck = src;
+        // one round of independent loads: element e = (neighbour e / cin, channel e % cin)
+        const int total = cnt * cin;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const int e = lane + 32 * r;
+            const int nb = e / cin, ci = e - nb * cin;
+            const int jr = __shfl_sync(0xffffffffu, cj, nb & 31);
+            if (e < total) xs[e] = __ldg(F + (long long)jr * cin + ci);
         }
-        // (a shuffle-broadcast variant with all 27 rows prefetched was measured slower in the pipeline:
-        //  it is instruction-bound, while this form hides its load latency behind the other warps)
+        my_j = (pos_n >= 0) ? in_idx[pos_n] : -1;
+        __syncwarp();
         float acc = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < 27; ++k) {
-            const int j = __shfl_sync(0xffffffffu, my_j, k);
-            if (j >= 0) {                                                   // warp-uniform
-                const float* f = P.fin + (long long)j * cin;
-                const float* w = Ws + (k * cin) * STEM_COUT + lane;
-                for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(f + ci), w[ci * STEM_COUT], acc);
-            }
+        for (int nb = 0; nb < cnt; ++nb) {
+            const int k = __shfl_sync(0xffffffffu, ck, nb);
+            const float* w = Ws + (k * cin) * STEM_COUT + lane;
+            const float* x = xs + nb * cin;
+            for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], w[ci * STEM_COUT], acc);
         }
+        __syncwarp();
         float y = fmaf(acc, sc, sh);
         if (P.resid) y += P.resid[o * STEM_COUT + lane];
         if (P.relu) y = fmaxf(y, 0.f);
@@ -259,6 +292,8 @@ k_stem_direct(IrConvBatch b, int cin) {
         amax = warp_max(amax);
         if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned*>(P.out_absmax), __float_as_uint(amax));
     }
+    __syncthreads();
+    ir_stamp_end(b.stamp);
 }
 
 int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st) {

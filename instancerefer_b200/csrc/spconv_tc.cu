@@ -335,6 +335,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
             weights_to_tmem(0);
         }
         ir_pdl_wait();                                          // T is still being read by the previous reduce
+        ir_stamp_begin(batch.stamp);
         const float out_s = SCALED ? W_UNSCALE / input_scale() : W_UNSCALE;
         uint32_t acc_it = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {
@@ -368,6 +369,7 @@ k_pairgemm_tc(IrConvBatch batch, int K) {
     }
     tc_fence_before();
     __syncthreads();
+    ir_stamp_end(batch.stamp);
     if (warp == 4) {
         __syncwarp();
         tc_fence_after();
