@@ -52,6 +52,11 @@ int ir_profile_read(float* gemm_ms, float* reduce_ms, int32_t* meta, int32_t cap
 int ir_conv_stamps_set(uint64_t* buf);
 int ir_conv_stamps_meta(int32_t* meta, int32_t cap, int32_t* n_out);
 
+/* Gather of the forward pair-GEMM: 0 = 16-byte global loads issued by the 12 producer warps (k_pairgemm_tc); 1 = TMA
+ * (cp.async.bulk.tensor tile::gather4, one warp issuing 32 gathers of 4 rulebook rows x 128 B per stage) into a raw
+ * fp32 shared-memory stage that the converter warps split into the fp16 hi/lo operand stages (k_pairgemm_tma). */
+int ir_gather_mode_set(int mode);
+
 /* Tuning knobs: CTAs per pair-GEMM launch (default 2 per SM = 296) and per reduce / stem launch (default
  * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
 int ir_tune_set(int pairgemm_ctas, int reduce_ctas);

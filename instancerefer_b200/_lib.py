@@ -106,6 +106,7 @@ SIGNATURES = {
     "ir_encoder_persist_debug": (i32, [p]),
     "ir_encoder_persist_occupancy": (i32, []),
     "ir_encoder_mode_set": (i32, [i32]),
+    "ir_gather_mode_set": (i32, [i32]),
     "ir_tune_set": (i32, [i32, i32]),
     "ir_encoder_layout": (i32, [i64, C.POINTER(EncoderLayout)]),
     "ir_encoder_workspace_bytes": (C.c_size_t, [i64]),

@@ -83,6 +83,9 @@ int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t
 int irk_wgrad_tc(const float* x, int cin, const float* dy, int cout, int K, const int* in_idx, const int* out_idx,
                  const int* count, long long seg_cap, const float* dy_absmax, float* dW, cudaStream_t st);
 
+// spconv_tma.cu  (the same pair-GEMM with the gather done by TMA tile::gather4; fin must be 16-byte aligned, n_max rows)
+int irk_pairgemm_tma(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st);
+
 // encoder_persist.cu  (all conv layers of one or two encoders in one persistent launch; `sync` = 512 zeroed bytes)
 int irk_encoder_persist(int G, const IrConvProblem (*layers)[IR_MAX_GROUPS], const int* cin, const int* cout, const int* K,
                         int n_layers, void* sync, cudaStream_t st);

@@ -626,8 +626,23 @@ int launch_wgrad(const float* x, const float* dy, const int* in_idx, const int* 
 
 }  // namespace tc
 
+// 0: gathered rows by 16-byte global loads of the producer warps (k_pairgemm_tc); 1: by TMA tile::gather4 into a raw
+// shared-memory stage (k_pairgemm_tma, spconv_tma.cu).  Forward shapes only; the dgrad shapes keep the LDG kernel.
+int g_gather_mode = 0;
+extern "C" int ir_gather_mode_set(int mode) {
+    IR_CHECK_ARG(mode == 0 || mode == 1);
+    g_gather_mode = mode;
+    return IR_OK;
+}
+
 int irk_pairgemm_tc(const IrConvBatch& b, int cin, int cout, int K, cudaStream_t st) {
     IR_CHECK_ARG(K <= 27 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
+    if (g_gather_mode == 1 && ((cin == 32 && cout == 64) || (cin == 64 && cout == 64) || (cin == 64 && cout == 128) ||
+                               (cin == 128 && cout == 128))) {
+        bool aligned = true;
+        for (int g = 0; g < b.G; ++g) aligned = aligned && (reinterpret_cast<uintptr_t>(b.p[g].fin) & 15) == 0;
+        if (aligned) return irk_pairgemm_tma(b, cin, cout, K, st);
+    }
     for (int g = 0; g < b.G; ++g) IR_CHECK_ARG(b.p[g].weight != nullptr && (reinterpret_cast<uintptr_t>(b.p[g].weight) & 15) == 0);
     bool scaled = true;
     for (int g = 0; g < b.G; ++g) scaled = scaled && b.p[g].in_absmax != nullptr;

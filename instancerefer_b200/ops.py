@@ -48,6 +48,8 @@ def check_device(device_index=None):
         import os
         if os.environ.get('IR_ENCODER') in ('layers', 'persist'):
             set_encoder_mode(os.environ['IR_ENCODER'])
+        if os.environ.get('IR_GATHER') in ('ldg', 'tma'):
+            set_gather_mode(os.environ['IR_GATHER'])
 
 
 # ----------------------------------------------------------------------------- encoder workspace
@@ -101,6 +103,12 @@ def set_encoder_mode(mode):
     """'layers' (default): one pair-GEMM + one reduce launch per conv layer; 'persist': all 13 layers of an encoder (or of
     both, ``encoder_features_pair``) in one persistent launch.  Environment: IR_ENCODER=layers|persist."""
     call("ir_encoder_mode_set", {'layers': 0, 'persist': 1}[mode])
+
+
+def set_gather_mode(mode):
+    """'ldg' (16-byte loads by the producer warps) or 'tma' (cp.async.bulk.tensor tile::gather4 into a raw stage) for the
+    forward pair-GEMM.  Environment: IR_GATHER=ldg|tma."""
+    call("ir_gather_mode_set", {'ldg': 0, 'tma': 1}[mode])
 
 
 TIMELINE = None          # tools/timeline.py sets this to a Timeline; None = no stamps (zero overhead)

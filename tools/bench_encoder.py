@@ -60,6 +60,18 @@ def stamps(ws):
     t0 = st[31]
     return [(int(st[p]) - int(t0)) / 1e3 for p in range(25)]
 
+if os.environ.get('IR_TMA', '0') == '1':
+    for which in ('inst', 'scene'):
+        outs = {}
+        for gm in ('ldg', 'tma'):
+            ops.set_gather_mode(gm)
+            ts, oa, os_ = run(0, which)
+            outs[gm] = oa if which == 'inst' else os_
+            print(f'{which:5s} layers gather={gm}  warm {ts[0]:7.1f} us  cold {ts[1]:7.1f} us', flush=True)
+        print(f'   max|tma-ldg| = {float((outs["tma"] - outs["ldg"]).abs().max()):.3e}  (max|out| {float(outs["ldg"].abs().max()):.3f})', flush=True)
+    ops.set_gather_mode('ldg')
+    sys.exit(0)
+
 res = {}
 for which in ('inst', 'scene', 'pair'):
     for mode in (0, 1):
