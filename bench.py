@@ -348,6 +348,8 @@ def main_sweep(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     from instancerefer_b200 import synthetic
     model, dev = _forward_setup(local)
+    if os.environ.get('IR_PAIR') == '1':
+        model.pair_encoders = True
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     steps, warmup = max(a.steps, 5), max(a.warmup, 3)
     rows = []

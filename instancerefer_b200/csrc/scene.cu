@@ -30,9 +30,17 @@ k_bev_matvec(const float* __restrict__ F, const int4* __restrict__ coords, const
         f[threadIdx.x] = F[(long long)r * BEV_C + threadIdx.x];
         __syncthreads();
         const float* kz = kern + (long long)(c.z / stride) * BEV_C * BEV_C + threadIdx.x;
+        // 128 taps in 4 batches of 32 independent (coalesced, L2-resident) weight loads: 4 memory latencies per row
+        // instead of 16; the additions keep their order (ci ascending)
         float acc = 0.f;
-#pragma unroll 8
-        for (int ci = 0; ci < BEV_C; ++ci) acc = fmaf(f[ci], kz[(long long)ci * BEV_C], acc);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BEV_C; c0 += 32) {
+            float wv[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) wv[u] = __ldg(kz + (long long)(c0 + u) * BEV_C);
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc = fmaf(f[c0 + u], wv[u], acc);
+        }
         tmp[(long long)r * BEV_C + threadIdx.x] = acc;
         if (threadIdx.x == 0) cell[r] = c.w * (BEV_H * BEV_W) + (c.x / stride) * BEV_W + (c.y / stride);
     }
@@ -120,14 +128,23 @@ k_conv2d_3x3(const float* __restrict__ in, int H, int W, const float* __restrict
     for (int p = 0; p < C2_TPX; ++p) acc[p] = 0.f;
     const int t0 = ks * PER;
     const float* wk = wpack + (long long)t0 * C + co;
-#pragma unroll 8
-    for (int i = 0; i < PER; ++i) {
-        const int t = t0 + i;
-        const int kk = t / C, ci = t - kk * C;
-        const int ky = kk / 3, kx = kk - ky * 3;
-        const float wv = __ldg(wk + (long long)i * C);
+    // 144 taps in 6 batches of 24 independent coalesced weight loads (6 memory latencies per thread instead of 18);
+    // the order of the additions is unchanged
+    constexpr int UB = 24;
+    static_assert(PER % UB == 0, "tap batches");
+#pragma unroll 1
+    for (int i0 = 0; i0 < PER; i0 += UB) {
+        float wv[UB];
 #pragma unroll
-        for (int p = 0; p < C2_TPX; ++p) acc[p] = fmaf(wv, patch[ky][p + kx][ci], acc[p]);
+        for (int u = 0; u < UB; ++u) wv[u] = __ldg(wk + (long long)(i0 + u) * C);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int t = t0 + i0 + u;
+            const int kk = t / C, ci = t - kk * C;
+            const int ky = kk / 3, kx = kk - ky * 3;
+#pragma unroll
+            for (int p = 0; p < C2_TPX; ++p) acc[p] = fmaf(wv[u], patch[ky][p + kx][ci], acc[p]);
+        }
     }
 #pragma unroll
     for (int p = 0; p < C2_TPX; ++p) red[ks][p][co] = acc[p];
@@ -166,11 +183,17 @@ k_scene_attention(const float* __restrict__ feats, const float* __restrict__ q, 
     const float* fb = feats + (long long)b * ncell * C;
     const float* qb = q + (long long)b * C;
     const float inv = 1.0f / sqrtf((float)C);
-    for (int cell = w; cell < ncell; cell += 8) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(fb[(long long)cell * C + c], qb[c], a);
-        a = warp_sum(a);
-        if (lane == 0) s_att[cell] = a * inv;
+    // logits: a warp takes 4 cells at a time (their loads and shuffle reductions are independent: one memory latency per
+    // 4 cells); per-cell arithmetic order is unchanged
+    for (int cell0 = w * 4; cell0 < ncell; cell0 += 32) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (cell0 + u < ncell)
+                for (int c = lane; c < C; c += 32) a[u] = fmaf(fb[(long long)(cell0 + u) * C + c], qb[c], a[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]);
+        if (lane < 4 && cell0 + lane < ncell) s_att[cell0 + lane] = (lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3]) * inv;
     }
     __syncthreads();
     float m = -INFINITY;
@@ -201,7 +224,15 @@ k_scene_attention(const float* __restrict__ feats, const float* __restrict__ q, 
     __syncthreads();
     for (int c = tid; c < C; c += 256) {
         float acc = 0.f;
-        for (int cell = 0; cell < ncell; ++cell) acc = fmaf(fb[(long long)cell * C + c], s_att[cell], acc);
+        int cell = 0;
+        for (; cell + 16 <= ncell; cell += 16) {            // 16 independent loads per batch, additions in cell order
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = fb[(long long)(cell + u) * C + c];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fmaf(v[u], s_att[cell + u], acc);
+        }
+        for (; cell < ncell; ++cell) acc = fmaf(fb[(long long)cell * C + c], s_att[cell], acc);
         scene_feat[(long long)b * C + c] = acc;
     }
 }
