@@ -115,13 +115,26 @@ class SceneModule(nn.Module, PrepCache):
             q = self.embed_language(data_dict)
         atten, scene_feats = ops.scene_attention(x.view(B, h * w, -1), q)
         data_dict['vis_atten'] = atten.view(B, h, w)
-        seg, _ = ops.mlp_head(scene_feats, p['kw1'], p['kb1'], ops.NORM_AFFINE, p['kg'], p['kbeta'],
-                              p['kw2'], p['kb2'], ops.MODE_RAW)
+        # the region classifier and the candidate head both hang off scene_feats and are independent of each other:
+        # the classifier runs on a side stream (fork / join by events, capturable), the candidate head — the one the
+        # step's final softmax waits for — stays on this stream
+        cur = torch.cuda.current_stream(x.device)
+        side = self.__dict__.get('_seg_stream')
+        if side is None or side.device != x.device:
+            side = self.__dict__['_seg_stream'] = torch.cuda.Stream(device=x.device)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            seg, _ = ops.mlp_head(scene_feats, p['kw1'], p['kb1'], ops.NORM_AFFINE, p['kg'], p['kbeta'],
+                                  p['kw2'], p['kb2'], ops.MODE_RAW)
+            join.record(side)
         data_dict['seg_scores'] = seg
         pack = get_pack(data_dict, self.args, x.device)
         _, scores = ops.mlp_head(data_dict['obj_feats'], p['ow1'], p['ob1'], ops.NORM_LAYER, p['og'],
                                  p['obeta'], p['ow2'], p['ob2'], ops.MODE_COS, partner=scene_feats,
                                  seg=pack.cand_scene)
+        cur.wait_event(join)
         data_dict['scene_scores'] = scores
         ops.stamp('scene:matched')
         return data_dict
