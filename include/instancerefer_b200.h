@@ -194,16 +194,28 @@ int ir_segmax(const float* feats, const int32_t* coords, const int32_t* n_dev, i
  * SparseCrop + ToDenseBEVConvolution + BatchNorm2d + ReLU (models/basic_blocks.py:174-243,
  * models/scene_module.py:25-30): keep 0<=xyz<(240,400,80); f' = f @ kernel[z/stride];
  * dense[b, x/stride, y/stride, :] = relu(bn(sum f')), NHWC (B,15,25,128).  tmp: (n_max,128) fp32,
- * cell: int32 (n_max). */
+ * cell: int32 (n_max).  out_absmax (or NULL): device float receiving max|out| (atomicMax on the bit pattern; the caller
+ * zeroes it) — the range scale of the tcgen05 Conv2d behind it. */
 int ir_bev(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
            int32_t stride, const float* kernel, const float* bn_scale, const float* bn_shift,
-           int32_t B, float* tmp, int32_t* cell, float* out, ir_stream_t stream);
+           int32_t B, float* tmp, int32_t* cell, float* out, float* out_absmax, ir_stream_t stream);
 
 /* Conv2d 3x3, no padding, NHWC activations, weight repacked to [ky][kx][Cin][Cout];
  * y = act(scale*(conv + bias) + shift).  (models/scene_module.py:33-38) */
 int ir_conv2d_3x3(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, const float* wpack,
                   const float* bias, const float* scale, const float* shift, int32_t relu,
                   float* out, ir_stream_t stream);
+
+/* The same Conv2d on the tcgen05 rule GEMM: a 3x3 valid convolution over a dense grid is a sparse convolution with a
+ * closed-form rulebook (K = 9; in_idx[k][o] = input pixel of tap k = ky*3+kx of output pixel o, slot[k][o] = o,
+ * count[k] = n_out, all device int32 built once per grid shape by the caller), weight repacked to (9, Cin, Cout) =
+ * [ky][kx][Cin][Cout], 16-byte aligned.  y = act(scale * conv + shift) (the conv bias folded into shift by the caller);
+ * in_absmax / out_absmax as in the sparse layers (range-scaled split-fp16; NULL = unscaled / not recorded).
+ * T: fp32 (9 * n_out, 128) scratch.  C = 128 only.  (models/scene_module.py:33-38) */
+int ir_conv2d_3x3_tc(const float* in, const int32_t* in_idx, const int32_t* slot, const int32_t* count,
+                     const int32_t* n_out_dev, int64_t n_out, const float* wprep, const float* scale,
+                     const float* shift, int32_t relu, const float* in_absmax, float* out_absmax, float* T,
+                     float* out, ir_stream_t stream);
 
 /* Language-guided attention over BEV cells (models/scene_module.py:73-83):
  * atten = softmax_cells(feats . q / sqrt(C)); scene_feat = sum atten * feats. */

@@ -121,7 +121,8 @@ SIGNATURES = {
     "ir_spconv_wprep_floats": (i64, [i32, i32, i32]),
     "ir_spconv_prepare_weights": (i32, [p, i32, i32, i32, p, p]),
     "ir_segmax": (i32, [p, p, p, i64, i32, i32, p, p, p]),
-    "ir_bev": (i32, [p, p, p, i64, i32, p, p, p, i32, p, p, p, p]),
+    "ir_bev": (i32, [p, p, p, i64, i32, p, p, p, i32, p, p, p, p, p]),
+    "ir_conv2d_3x3_tc": (i32, [p, p, p, p, p, i64, p, p, p, i32, p, p, p, p, p]),
     "ir_conv2d_3x3": (i32, [p, i32, i32, i32, i32, p, p, p, p, i32, p, p]),
     "ir_scene_attention": (i32, [p, p, i32, i32, i32, p, p, p]),
     "ir_linear": (i32, [p, i32, i32, p, p, i32, i32, p, p]),

@@ -2,6 +2,8 @@
 // attention over BEV cells.  Reference: models/basic_blocks.py:174-243, models/scene_module.py:25-38,
 // 69-83.  Activations are NHWC; all reductions run in a fixed order (deterministic).
 #include "../../include/instancerefer_b200.h"
+#include <string.h>
+
 #include "common.cuh"
 
 #define BEV_X 240
@@ -49,7 +51,8 @@ k_bev_matvec(const float* __restrict__ F, const int4* __restrict__ coords, const
 // one CTA per dense cell: sum matching rows in ascending row order, BN2d affine, ReLU
 __global__ void __launch_bounds__(BEV_C)
 k_bev_cell(const float* __restrict__ tmp, const int* __restrict__ cell, const int* __restrict__ n_dev,
-           const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+           const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out,
+           float* __restrict__ out_absmax) {
     __shared__ int s_list[16];
     __shared__ int s_wcnt[BEV_C / 32];
     __shared__ int s_total;
@@ -81,20 +84,25 @@ k_bev_cell(const float* __restrict__ tmp, const int* __restrict__ cell, const in
     float acc = 0.f;
     for (int i = 0; i < cnt; ++i) acc += tmp[(long long)s_list[i] * BEV_C + tid];
     // scale == NULL: raw sums (train mode: batch-statistics BN2d + ReLU follow as their own kernel)
-    out[(long long)me * BEV_C + tid] = scale ? fmaxf(fmaf(acc, scale[tid], shift[tid]), 0.f) : acc;
+    const float y = scale ? fmaxf(fmaf(acc, scale[tid], shift[tid]), 0.f) : acc;
+    out[(long long)me * BEV_C + tid] = y;
+    if (out_absmax) {                      // range guard of the tcgen05 Conv2d that consumes the BEV map
+        const float m = warp_max(fabsf(y));
+        if (lane == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned*>(out_absmax), __float_as_uint(m));
+    }
 }
 
 extern "C" int ir_bev(const float* feats, const int32_t* coords, const int32_t* n_dev, int64_t n_max,
                       int32_t stride, const float* kernel, const float* bn_scale,
                       const float* bn_shift, int32_t B, float* tmp, int32_t* cell, float* out,
-                      ir_stream_t stream) {
+                      float* out_absmax, ir_stream_t stream) {
     IR_CHECK_ARG(feats && coords && n_dev && kernel && tmp && cell && out && ((bn_scale == nullptr) == (bn_shift == nullptr)));
     IR_CHECK_ARG(stride == 16 && B > 0 && n_max > 0);
     cudaStream_t st = (cudaStream_t)stream;
     k_bev_matvec<<<ir_min_i(n_max, IR_NUM_SMS * 16), BEV_C, 0, st>>>(feats, (const int4*)coords, n_dev, stride,
                                                                      kernel, B, tmp, cell);
     IR_CHECK_LAUNCH();
-    k_bev_cell<<<B * BEV_H * BEV_W, BEV_C, 0, st>>>(tmp, cell, n_dev, bn_scale, bn_shift, out);
+    k_bev_cell<<<B * BEV_H * BEV_W, BEV_C, 0, st>>>(tmp, cell, n_dev, bn_scale, bn_shift, out, out_absmax);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
@@ -171,6 +179,30 @@ extern "C" int ir_conv2d_3x3(const float* in, int32_t B, int32_t H, int32_t W, i
     k_conv2d_3x3<<<grid, BEV_C * C2_KS, 0, (cudaStream_t)stream>>>(in, H, W, wpack, bias, scale, shift, relu, out);
     IR_CHECK_LAUNCH();
     return IR_OK;
+}
+
+// ------------------------------------------------------------------ conv2d 3x3 on the tcgen05 rule GEMM
+// A 3x3 valid convolution over a dense (B,H,W) grid IS a sparse convolution whose rulebook is known in closed form
+// (tap k = ky*3+kx of output pixel o reads input pixel o + ky*W + kx; every output has all nine pairs), with the
+// conv weight repacked to (9, Cin, Cout).  So the two Conv2d of the scene head run through the same weight-stationary
+// tcgen05 pair-GEMM + ordered reduce as the sparse layers (range-scaled split-fp16, bias / folded BN / ReLU in the
+// reduce epilogue) instead of a SIMT direct convolution: 9 x 299 pairs = 43 tiles for the first conv.
+// Replaces nn.Conv2d x2 of models/scene_module.py:33-38.  The caller builds the rulebook once per grid shape.
+#include "kernels.cuh"
+extern "C" int ir_conv2d_3x3_tc(const float* in, const int32_t* in_idx, const int32_t* slot, const int32_t* count,
+                                const int32_t* n_out_dev, int64_t n_out, const float* wprep, const float* scale,
+                                const float* shift, int32_t relu, const float* in_absmax, float* out_absmax, float* T,
+                                float* out, ir_stream_t stream) {
+    IR_CHECK_ARG(in && in_idx && slot && count && n_out_dev && wprep && T && out && n_out > 0);
+    IR_CHECK_ARG((reinterpret_cast<uintptr_t>(wprep) & 15) == 0);
+    IrConvBatch b;
+    memset(&b, 0, sizeof(b));
+    b.G = 1;
+    b.p[0] = IrConvProblem{in, in_idx, slot, count, n_out_dev, wprep, scale, shift, nullptr, T, out,
+                           (long long)n_out, (long long)n_out, relu, in_absmax, out_absmax};
+    int r = irk_pairgemm_tc(b, BEV_C, BEV_C, 9, (cudaStream_t)stream);
+    if (r != IR_OK) return r;
+    return irk_reduce_epilogue(b, BEV_C, 9, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ attention over BEV cells

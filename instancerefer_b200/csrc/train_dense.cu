@@ -1105,7 +1105,7 @@ __global__ void k_pack_conv_w(const float* __restrict__ w, int cout, int cin, fl
     }
 }
 extern "C" int ir_bev(const float*, const int32_t*, const int32_t*, int64_t, int32_t, const float*, const float*, const float*,
-                      int32_t, float*, int32_t*, float*, ir_stream_t);
+                      int32_t, float*, int32_t*, float*, float*, ir_stream_t);
 
 struct SceneArena {
     float *tmp, *dense, *a0, *st0a, *st0b, *wp1, *col1, *y1, *a1, *st1a, *st1b, *a1d, *wp2, *col2, *bn_scratch;
@@ -1140,7 +1140,7 @@ extern "C" int ir_scene_tail_train_fwd(const ir_scene_tail_t* p, const float* f4
     cudaStream_t st = (cudaStream_t)stream;
     const int B = p->B, C = 128, r0 = B * 375, r1 = B * 299, r2 = B * 231;
     int r;
-    if ((r = ir_bev(f4, coords, n_dev, p->n_rows, 16, p->kernel, nullptr, nullptr, B, a.tmp, a.cell, a.dense, stream)) != IR_OK) return r;
+    if ((r = ir_bev(f4, coords, n_dev, p->n_rows, 16, p->kernel, nullptr, nullptr, B, a.tmp, a.cell, a.dense, nullptr, stream)) != IR_OK) return r;
     if ((r = ir_bn_train_fwd(a.dense, nullptr, r0, C, p->g0, p->be0, nullptr, 1, p->eps, p->mom0, p->rm0, p->rv0, a.bn_scratch,
                              a.st0a, a.st0b, a.a0, stream)) != IR_OK) return r;
     k_pack_conv_w<<<IR_NUM_SMS * 2, 256, 0, st>>>(p->w1, C, C, a.wp1, 0);

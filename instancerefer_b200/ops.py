@@ -217,13 +217,48 @@ def segmax(feats, coords, n_dev, n_max, n_seg):
 
 # ----------------------------------------------------------------------------- scene head
 
-def bev(feats, coords, n_dev, n_max, stride, kernel, scale, shift, B):
+def bev(feats, coords, n_dev, n_max, stride, kernel, scale, shift, B, absmax=None):
+    """absmax: optional zeroed device float receiving max|out| (range scale of the tcgen05 Conv2d behind it)."""
     dev = feats.device
     tmp = torch.empty(n_max, 128, dtype=torch.float32, device=dev)
     cell = torch.empty(n_max, dtype=torch.int32, device=dev)
     out = torch.empty(B, 15, 25, 128, dtype=torch.float32, device=dev)
     call("ir_bev", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), n_max, stride,
-         _p(kernel, torch.float32), _p(scale), _p(shift), B, _p(tmp), _p(cell), _p(out), _stream())
+         _p(kernel, torch.float32), _p(scale), _p(shift), B, _p(tmp), _p(cell), _p(out), _p(absmax), _stream())
+    return out
+
+
+_GRID_RULEBOOKS = {}
+
+
+def grid_rulebook(B, H, W, device):
+    """Closed-form rulebook of a 3x3 valid convolution over a dense (B,H,W) grid in the sparse-conv layout: tap
+    k = ky*3+kx of output pixel o = (b,y,x) reads input pixel (b, y+ky, x+kx); every output has all nine pairs."""
+    key = (B, H, W, str(device))
+    rb = _GRID_RULEBOOKS.get(key)
+    if rb is None:
+        Ho, Wo = H - 2, W - 2
+        b, y, x = torch.meshgrid(torch.arange(B), torch.arange(Ho), torch.arange(Wo), indexing='ij')
+        base = (b * H * W + y * W + x).reshape(-1)
+        n_out = base.numel()
+        in_idx = torch.stack([base + ky * W + kx for ky in range(3) for kx in range(3)]).to(torch.int32)
+        slot = torch.arange(n_out, dtype=torch.int32).repeat(9, 1)
+        rb = dict(in_idx=in_idx.contiguous().to(device), slot=slot.contiguous().to(device),
+                  count=torch.full((9,), n_out, dtype=torch.int32, device=device),
+                  n_out_dev=torch.tensor([n_out], dtype=torch.int32, device=device), n_out=n_out, Ho=Ho, Wo=Wo)
+        _GRID_RULEBOOKS[key] = rb
+    return rb
+
+
+def conv2d_3x3_tc(x, w9, scale, shift, relu, in_absmax=None, out_absmax=None):
+    """x (B,H,W,128) NHWC fp32; w9 (9,128,128) = [ky][kx][Cin][Cout] (16-byte aligned); y = act(scale*conv + shift)."""
+    B, H, W, Cc = x.shape
+    rb = grid_rulebook(B, H, W, x.device)
+    T = torch.empty(9 * rb['n_out'], Cc, dtype=torch.float32, device=x.device)
+    out = torch.empty(B, rb['Ho'], rb['Wo'], Cc, dtype=torch.float32, device=x.device)
+    call("ir_conv2d_3x3_tc", _p(x, torch.float32), _p(rb['in_idx'], torch.int32), _p(rb['slot'], torch.int32),
+         _p(rb['count'], torch.int32), _p(rb['n_out_dev'], torch.int32), rb['n_out'], _p(w9, torch.float32), _p(scale),
+         _p(shift), 1 if relu else 0, _p(in_absmax), _p(out_absmax), _p(T), _p(out), _stream())
     return out
 
 
@@ -540,7 +575,7 @@ def bev_raw(feats, coords, n_dev, n_rows, stride, kernel, B):
     cell = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
     out = torch.empty(B * 375, 128, dtype=torch.float32, device=dev)
     call("ir_bev", _p(feats, torch.float32), _p(coords, torch.int32), _p(n_dev, torch.int32), n_rows, stride,
-         _p(kernel, torch.float32), None, None, B, _p(tmp), _p(cell), _p(out), _stream())
+         _p(kernel, torch.float32), None, None, B, _p(tmp), _p(cell), _p(out), None, _stream())
     return out, cell
 
 

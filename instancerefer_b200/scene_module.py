@@ -2,6 +2,8 @@
 encoder at 5 cm -> crop -> dense BEV 15x25 (z-slice matvec + scatter-sum, BN, ReLU) -> 2x Conv2d
 3x3 -> language-guided attention over 11x21 cells -> 9-way region classifier and cosine(obj, scene).
 Reference lines: models/scene_module.py:10-58 (ctor), :60-108 (forward)."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -49,15 +51,34 @@ class SceneModule(nn.Module, PrepCache):
         c1s, c1b = fold_bn(self.vis_emb_fc[1])
         cs, cb = fold_bn(self.cls[1])
         v1, l = self.vis_emb_fc1, self.lang_emb_fc
+        c1bias, c2bias = f(self.vis_emb_fc[0].bias), f(self.vis_emb_fc[4].bias)
         return dict(bev_kernel=f(self.to_bev[1].kernel), bev_s=bs, bev_b=bb,
-                    c1w=pk(self.vis_emb_fc[0]), c1bias=f(self.vis_emb_fc[0].bias), c1s=c1s, c1b=c1b,
-                    c2w=pk(self.vis_emb_fc[4]), c2bias=f(self.vis_emb_fc[4].bias),
+                    c1w=pk(self.vis_emb_fc[0]), c1bias=c1bias, c1s=c1s, c1b=c1b,
+                    c2w=pk(self.vis_emb_fc[4]), c2bias=c2bias,
+                    # tcgen05 form: weights as (9, Cin, Cout) rule-GEMM operands, conv bias folded into the shift
+                    c1w9=pk(self.vis_emb_fc[0]).view(9, 128, 128), c1shift=(c1s * c1bias + c1b).contiguous(),
+                    c2w9=pk(self.vis_emb_fc[4]).view(9, 128, 128), c2shift=c2bias,
                     ow1=ft(v1[0].weight), ob1=f(v1[0].bias), og=f(v1[1].weight), obeta=f(v1[1].bias),
                     ow2=ft(v1[4].weight), ob2=f(v1[4].bias),
                     lw1=ft(l[0].weight), lb1=f(l[0].bias), lg=f(l[1].weight), lbeta=f(l[1].bias),
                     lw2=ft(l[4].weight), lb2=f(l[4].bias),
                     kw1=ft(self.cls[0].weight), kb1=f(self.cls[0].bias), kg=cs, kbeta=cb,
                     kw2=ft(self.cls[3].weight), kb2=f(self.cls[3].bias))
+
+    conv2d_tc = os.environ.get('IR_CONV2D', 'tc') != 'simt'      # BEV Conv2d on the tcgen05 rule GEMM (default) or the SIMT kernel
+
+    def _bev_tail(self, p, f4, c4, n4, n_max, B):
+        """crop + dense BEV + BN + ReLU (:70), Conv2d-BN-ReLU-Conv2d (:71) -> (B,11,21,128) NHWC."""
+        if not self.conv2d_tc:
+            bev = ops.bev(f4, c4, n4, n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
+            ops.stamp('scene:bev')
+            x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
+            return ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        amax = torch.zeros(2, dtype=torch.float32, device=f4.device)       # max|BEV map|, max|conv1 out|: range scales
+        bev = ops.bev(f4, c4, n4, n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B, absmax=amax[0:1])
+        ops.stamp('scene:bev')
+        x = ops.conv2d_3x3_tc(bev, p['c1w9'], p['c1s'], p['c1shift'], True, in_absmax=amax[0:1], out_absmax=amax[1:2])
+        return ops.conv2d_3x3_tc(x, p['c2w9'], None, p['c2shift'], False, in_absmax=amax[1:2])
 
     def encode_scene(self, data_dict, device):
         """Phase A (no language dependency): whole-scene sparse encoder (:69), crop + dense BEV + BN +
@@ -72,10 +93,7 @@ class SceneModule(nn.Module, PrepCache):
         ops.stamp('scene:start')
         f4, c4, n4 = self.net.encode(ws, F0, C0, data_dict.get('_ir_lidar_rows'))
         ops.stamp('scene:features')
-        bev = ops.bev(f4, c4, n4, ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
-        ops.stamp('scene:bev')
-        x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
-        data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        data_dict['_ir_bev_feats'] = self._bev_tail(p, f4, c4, n4, ws.n_max, B)
         ops.stamp('scene:conv2d')
         return data_dict
 
@@ -93,9 +111,7 @@ class SceneModule(nn.Module, PrepCache):
         """Phase A3: crop + dense BEV + BN + ReLU (:70), Conv2d-BN-ReLU-Conv2d (:71)."""
         p = self.prepared()
         B = data_dict['point_min'].shape[0]
-        bev = ops.bev(f4, ws.coords(4), ws.nlvl()[4:5], ws.n_max, 16, p['bev_kernel'], p['bev_s'], p['bev_b'], B)
-        x = ops.conv2d_3x3(bev, p['c1w'], p['c1bias'], p['c1s'], p['c1b'], True)
-        data_dict['_ir_bev_feats'] = ops.conv2d_3x3(x, p['c2w'], p['c2bias'], None, None, False)
+        data_dict['_ir_bev_feats'] = self._bev_tail(p, f4, ws.coords(4), ws.nlvl()[4:5], ws.n_max, B)
         return data_dict
 
     def embed_language(self, data_dict):
