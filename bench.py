@@ -174,6 +174,15 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
+    # the training step is host-bound (Python issues ~45 library calls and ~20 autograd nodes per step): with N ranks on
+    # one box give every rank its own slice of the host cores so the N interpreters do not migrate onto each other
+    ncpu = os.cpu_count() or 1
+    if world > 1 and hasattr(os, 'sched_setaffinity') and os.environ.get('IR_AFFINITY', '1') == '1':
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except OSError:
+            pass
     _init_dist(world, dev)
     if world > 1:
         import torch.distributed as dist
@@ -182,6 +191,8 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)
     model = model.to(dev).train()
     opt = FlatAdam(model, lr=1e-3, weight_decay=1e-5)          # config/InstanceRefer.yaml:48,53
+    if os.environ.get('IR_OVERLAP') == '0':
+        opt._sync = False                                      # reduce everything at step() (no bucket launches from the hooks)
     cfg = synthetic.SyntheticConfig()                          # dataset-config stand-in (labels -> GT box)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     hosts = []
@@ -263,7 +274,7 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
         e2e=dict(value=world * per_gpu * steps / wall, unit=METRIC, ms_per_step=wall / steps * 1e3,
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
         phases_ms={k: v / steps for k, v in ph.items()}, allreduce_exposed_ms=ph['allreduce+adam'] / steps,
-        gpu_launches=int(launches), clocks=clocks,
+        gpu_launches=int(launches), clocks=clocks, host_cores=ncpu,
         final_loss=losses[-1], first_loss=losses[0], ranks_in_sync=in_sync, cpu_baseline=cb)
 
 
@@ -677,7 +688,7 @@ def main():
         torch.cuda.empty_cache()
         t = train_measure(a.train_steps, 10, rank, world, local, cpu_baseline=False)
         train = {k: t[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'warmup', 'phases_ms', 'allreduce_exposed_ms',
-                                   'ranks_in_sync', 'e2e', 'gpu_launches', 'config', 'first_loss', 'final_loss')}
+                                   'ranks_in_sync', 'e2e', 'gpu_launches', 'host_cores', 'config', 'first_loss', 'final_loss')}
 
     if world > 1:
         dist.barrier()

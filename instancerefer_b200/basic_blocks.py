@@ -106,7 +106,7 @@ class ResidualBlock(nn.Module):
 
 class SparseConvEncoder(nn.Module, PrepCache):
     """stem k3 in->32; 4 x [k2 s2 down, residual k3 k3] to 64,128,128,128
-    (models/basic_blocks.py:59-95).  ``use_tc``: tcgen05 3xTF32 pair-GEMM (default) or the exact
+    (models/basic_blocks.py:59-95).  ``use_tc``: tcgen05 split-fp16 (hi/lo, fp32 accumulate) pair-GEMM (default) or the exact
     SIMT fp32 kernel."""
 
     use_tc = os.environ.get('IR_SPCONV', 'tc') != 'simt'

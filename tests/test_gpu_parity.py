@@ -148,7 +148,7 @@ def test_spconv_layer_simt(ops, cin, cout, ks):
 
 @pytest.mark.parametrize('cin,cout,ks', [(32, 64, 2), (64, 64, 3), (64, 128, 2), (128, 128, 3), (128, 128, 2)])
 def test_spconv_layer_tcgen05(ops, cin, cout, ks):
-    """3xTF32 tensor-core pair-GEMM vs the oracle (fp32-level accuracy required)."""
+    """tcgen05 split-fp16 (hi/lo operands, fp32 accumulation) pair-GEMM vs the oracle (fp32-level accuracy required)."""
     got, want = _layer_case(ops, np.random.default_rng(cin + cout + ks), 5000, cin, cout, ks, True)
     assert float((got - want).abs().max()) < 2e-5
 
