@@ -154,6 +154,20 @@ def cpu_train_leg(steps, warmup, per_gpu=2):
                        f'(torch CPU fp32 autograd, {torch.get_num_threads()} threads, no optimiser step), {dt * 1e3:.0f} ms each'), dt
 
 
+def _pin_rank_to_cores(world, local):
+    """N ranks on one box: give every rank its own slice of the host cores.  The host side of a step (class filter and
+    packing of the instance lists in the forward's e2e path; ~45 library calls and ~20 autograd nodes in the training
+    step) is a sizeable part of it, and N interpreters migrating onto each other's cores cost 6 % at N = 8."""
+    ncpu = os.cpu_count() or 1
+    if world > 1 and hasattr(os, 'sched_setaffinity') and os.environ.get('IR_AFFINITY', '1') == '1':
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except OSError:
+            pass
+    return ncpu
+
+
 def _init_dist(world, dev):
     if world > 1:
         import torch.distributed as dist
@@ -174,15 +188,7 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
-    # the training step is host-bound (Python issues ~45 library calls and ~20 autograd nodes per step): with N ranks on
-    # one box give every rank its own slice of the host cores so the N interpreters do not migrate onto each other
-    ncpu = os.cpu_count() or 1
-    if world > 1 and hasattr(os, 'sched_setaffinity') and os.environ.get('IR_AFFINITY', '1') == '1':
-        per = max(1, ncpu // world)
-        try:
-            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
-        except OSError:
-            pass
+    ncpu = _pin_rank_to_cores(world, local)
     _init_dist(world, dev)
     if world > 1:
         import torch.distributed as dist
@@ -458,6 +464,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.check_device(local)
+    _pin_rank_to_cores(world, local)
     _init_dist(world, dev)
     if world > 1:
         import torch.distributed as dist
