@@ -50,6 +50,9 @@ def check_device(device_index=None):
             set_encoder_mode(os.environ['IR_ENCODER'])
         if os.environ.get('IR_GATHER') in ('ldg', 'tma'):
             set_gather_mode(os.environ['IR_GATHER'])
+        if os.environ.get('IR_TUNE'):                     # "pairgemm_ctas,reduce_ctas" (ir_tune_set)
+            a, b = (int(x) for x in os.environ['IR_TUNE'].split(','))
+            call("ir_tune_set", a, b)
 
 
 # ----------------------------------------------------------------------------- encoder workspace
