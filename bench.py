@@ -473,6 +473,8 @@ def main():
     model = InstanceRefer(7, args)
     model.load_state_dict(synthetic.make_state_dict(123, model=model), strict=True)      # random-init weights (no oracle import on this arm)
     model = model.to(dev).eval()
+    if os.environ.get('IR_PAIR') == '1':
+        model.pair_encoders = True
 
     # ---- this rank's stream of scenes (a few distinct scenes, cycled)
     n_scenes = 4

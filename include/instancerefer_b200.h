@@ -58,7 +58,7 @@ int ir_conv_stamps_meta(int32_t* meta, int32_t cap, int32_t* n_out);
 int ir_gather_mode_set(int mode);
 
 /* Tuning knobs: CTAs per pair-GEMM launch (default 2 per SM = 296) and per reduce / stem launch (default
- * 8 per SM); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
+ * 5 per SM, swept inside the step); values <= 0 leave a knob unchanged.  Smaller grids let the two encoders' chains co-reside. */
 int ir_tune_set(int pairgemm_ctas, int reduce_ctas);
 
 /* Feature-pass mode of ir_encoder_features[_pair]: 0 (default) = one pair-GEMM + one reduce launch per layer, chained

@@ -30,7 +30,7 @@ extern "C" int ir_debug_set(int flags) {
 }
 
 int g_tune_pairgemm_ctas = 2 * IR_NUM_SMS;      // tuning knobs (ir_tune_set): CTAs of a pair-GEMM launch ...
-int g_tune_reduce_ctas = 8 * IR_NUM_SMS;        // ... and of a reduce / stem launch
+int g_tune_reduce_ctas = 5 * IR_NUM_SMS;        // ... and of a reduce / stem launch (swept in the step: 4-5 per SM beats 8)
 extern "C" int ir_tune_set(int pairgemm_ctas, int reduce_ctas) {
     if (pairgemm_ctas > 0) g_tune_pairgemm_ctas = pairgemm_ctas;
     if (reduce_ctas > 0) g_tune_reduce_ctas = reduce_ctas;
