@@ -344,7 +344,7 @@ int ir_region_label(const double* ref_center, const double* point_min, const dou
  * dscore = d loss_scene / d score.  ref_loss = sum(loss_scene) / B.                               */
 int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
                 const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
-                const float* s_scene, float margin, float gamma, float iou_thresh, float* label,
+                const float* s_scene, float margin, float gamma, double iou_thresh, float* label,
                 float* loss_scene, float* dscore, float* iou_max, ir_stream_t stream);
 
 /* get_eval (lib/eval_helper.py:11-114): per scene the candidate with the highest summed score, IoU of

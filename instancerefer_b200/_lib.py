@@ -144,7 +144,7 @@ SIGNATURES = {
     "ir_segmax_bwd": (i32, [p, p, p, i64, i32, i32, p, p, p, p, p]),
     "ir_cross_entropy": (i32, [p, p, i32, i32, p, p, p]),
     "ir_region_label": (i32, [p, p, p, i32, i32, p, p]),
-    "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f32, p, p, p, p, p]),
+    "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f64, p, p, p, p, p]),
     "ir_ref_eval": (i32, [p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p]),
     "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p, p]),
     "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),

@@ -8,39 +8,48 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ cross entropy (mean) + gradient
-// single CTA: warp per row, per-row losses summed in row order (deterministic)
-#define CE_MAXROWS 1024
+// single CTA: warp per row; the per-row losses are summed in row order, tile by tile of CE_TILE rows, by one thread
+// (deterministic for any B: the reference's CrossEntropyLoss has no batch limit either)
+#define CE_TILE 1024
 __global__ void __launch_bounds__(256)
 k_cross_entropy(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int N,
                 float* __restrict__ loss, float* __restrict__ dlogits) {
-    __shared__ float s_loss[CE_MAXROWS];
+    __shared__ float s_loss[CE_TILE];
+    __shared__ float s_total;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float invB = 1.f / B;
-    for (int r = w; r < B; r += 8) {
-        const float* z = logits + (long long)r * N;
-        float m = -INFINITY;
-        for (int j = lane; j < N; j += 32) m = fmaxf(m, z[j]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int j = lane; j < N; j += 32) s += expf(z[j] - m);
-        s = warp_sum(s);
-        const float lse = m + logf(s);
-        const int y = (int)labels[r];
-        for (int j = lane; j < N; j += 32)
-            dlogits[(long long)r * N + j] = (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * invB;
-        if (lane == 0) s_loss[r] = lse - z[y];
+    if (threadIdx.x == 0) s_total = 0.f;
+    for (int r0 = 0; r0 < B; r0 += CE_TILE) {
+        const int nr = min(CE_TILE, B - r0);
+        for (int rr = w; rr < nr; rr += 8) {
+            const int r = r0 + rr;
+            const float* z = logits + (long long)r * N;
+            float m = -INFINITY;
+            for (int j = lane; j < N; j += 32) m = fmaxf(m, z[j]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int j = lane; j < N; j += 32) s += expf(z[j] - m);
+            s = warp_sum(s);
+            const float lse = m + logf(s);
+            const int y = (int)labels[r];
+            for (int j = lane; j < N; j += 32)
+                dlogits[(long long)r * N + j] = (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * invB;
+            if (lane == 0) s_loss[rr] = lse - z[y];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = s_total;
+            for (int rr = 0; rr < nr; ++rr) t += s_loss[rr];
+            s_total = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int r = 0; r < B; ++r) t += s_loss[r];
-        loss[0] = t * invB;
-    }
+    if (threadIdx.x == 0) loss[0] = s_total * invB;
 }
 
 extern "C" int ir_cross_entropy(const float* logits, const int64_t* labels, int32_t B, int32_t N,
                                 float* loss, float* dlogits, ir_stream_t stream) {
-    IR_CHECK_ARG(logits && labels && loss && dlogits && B > 0 && B <= CE_MAXROWS && N > 0);
+    IR_CHECK_ARG(logits && labels && loss && dlogits && B > 0 && N > 0);
     k_cross_entropy<<<1, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)labels, B, N, loss, dlogits);
     IR_CHECK_LAUNCH();
     return IR_OK;
@@ -106,7 +115,7 @@ __device__ void box_min_max(const double* o, double mn[3], double mx[3]) {
 __global__ void __launch_bounds__(32)
 k_ref_loss(const double* __restrict__ pred_obb, const int* __restrict__ obb_ofs, const double* __restrict__ gt_obb,
            const int* __restrict__ score_ofs, const float* __restrict__ sa, const float* __restrict__ sr,
-           const float* __restrict__ ss, float margin, float gamma, float iou_thresh,
+           const float* __restrict__ ss, float margin, float gamma, double iou_thresh,
            float* __restrict__ label, float* __restrict__ loss_scene, float* __restrict__ dscore,
            float* __restrict__ iou_max_out) {
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -136,7 +145,7 @@ k_ref_loss(const double* __restrict__ pred_obb, const int* __restrict__ obb_ofs,
     if (lane == 0) iou_max_out[b] = (float)best;
     const int s0 = score_ofs[b];
     if (s0 < 0 || n < 2) return;
-    if (best < (double)iou_thresh) {
+    if (best < iou_thresh) {                 // fp64 threshold like the reference's `max_iou < 0.2` (lib/loss_helper.py:246)
         for (int j = lane; j < n; j += 32) dscore[s0 + j] = 0.f;
         return;
     }
@@ -170,7 +179,7 @@ k_ref_loss(const double* __restrict__ pred_obb, const int* __restrict__ obb_ofs,
 
 extern "C" int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const double* gt_obb,
                            const int32_t* score_ofs, int32_t B, const float* s_attr, const float* s_rel,
-                           const float* s_scene, float margin, float gamma, float iou_thresh, float* label,
+                           const float* s_scene, float margin, float gamma, double iou_thresh, float* label,
                            float* loss_scene, float* dscore, float* iou_max, ir_stream_t stream) {
     IR_CHECK_ARG(pred_obb && obb_ofs && gt_obb && score_ofs && s_attr && s_rel && s_scene && label &&
                  loss_scene && dscore && iou_max && B > 0);

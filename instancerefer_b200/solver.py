@@ -10,7 +10,7 @@ per-iteration order (forward -> get_loss -> backward + step -> get_eval), the sa
 
 One process per GPU: under ``torchrun`` every rank runs the loop on its own shard of the loader (give the
 loader a ``DistributedSampler``), ``FlatAdam.step`` does the one gradient all-reduce, validation metrics are
-averaged over ranks with one small all-reduce, and only rank 0 writes files.  TensorBoard export and the
+combined over ranks with one small all-reduce of their sums and counts, and only rank 0 writes files.  TensorBoard export and the
 report templates of the reference are host-side cosmetics and are not reproduced."""
 import os
 import time
@@ -116,14 +116,18 @@ class Solver:
                               ', '.join('{} {:.4f}'.format(k, np.mean([r[k] for r in last])) for k in METRICS) +
                               ', {:.1f} ms/iter'.format((time.time() - t0) / len(recs) * 1e3))
         ious = np.asarray([v for r in recs for v in r['ref_iou']])
-        out = {k: float(np.mean([r[k] for r in recs])) for k in METRICS}
-        out['iou_rate_0.25'] = float((ious >= 0.25).mean()) if ious.size else 0.0
-        out['iou_rate_0.5'] = float((ious >= 0.5).mean()) if ious.size else 0.0
-        if self.world > 1:                                                       # average the summary over ranks
-            keys = sorted(out)
-            t = torch.tensor([out[k] for k in keys], dtype=torch.float64, device='cuda')
+        # sums and counts first, ratios last: under torchrun the ranks may hold different numbers of iterations / samples
+        # (last partial batch), so numerators and denominators are all-reduced and divided once
+        sums = [float(np.sum([r[k] for r in recs])) for k in METRICS] + \
+               [float((ious >= 0.25).sum()), float((ious >= 0.5).sum()), float(len(recs)), float(ious.size)]
+        if self.world > 1:
+            t = torch.tensor(sums, dtype=torch.float64, device='cuda')
             torch.distributed.all_reduce(t)
-            out = {k: float(v) / self.world for k, v in zip(keys, t.tolist())}
+            sums = t.tolist()
+        n_it, n_iou = max(sums[-2], 1.0), max(sums[-1], 1.0)
+        out = {k: sums[i] / n_it for i, k in enumerate(METRICS)}
+        out['iou_rate_0.25'] = sums[len(METRICS)] / n_iou
+        out['iou_rate_0.5'] = sums[len(METRICS) + 1] / n_iou
         self.history[phase].append(out)
         return out
 

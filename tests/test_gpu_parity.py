@@ -254,6 +254,35 @@ def test_segmax(ops):
 
 # ----------------------------------------------------------------------------- scene head
 
+def test_conv2d_on_the_rule_gemm_matches_simt_and_torch(ops):
+    """ir_conv2d_3x3_tc: the BEV Conv2d as a sparse conv with a closed-form dense-grid rulebook on the tcgen05 pair-GEMM
+    (range-scaled) against the SIMT direct kernel and torch's conv2d, with BN-fold + ReLU and with plain bias."""
+    g = torch.Generator().manual_seed(4)
+    B, H, W, Cc = 2, 15, 25, 128
+    x = torch.randn(B, H, W, Cc, generator=g).cuda() * 3.0
+    w = (torch.randn(Cc, Cc, 3, 3, generator=g) / (9 * Cc) ** 0.5).cuda()
+    bias, sc, sh = torch.randn(Cc, generator=g).cuda(), (torch.rand(Cc, generator=g) + 0.5).cuda(), torch.randn(Cc, generator=g).cuda()
+    wp = w.permute(2, 3, 1, 0).contiguous()                        # [ky][kx][Cin][Cout]
+    for relu, s_, b_ in ((True, sc, sh), (False, None, None)):
+        want = torch.nn.functional.conv2d(x.cpu().permute(0, 3, 1, 2), w.cpu(), bias.cpu()).permute(0, 2, 3, 1)   # fp32 on the CPU
+        if s_ is not None:
+            want = want * s_.cpu() + b_.cpu()
+        if relu:
+            want = want.relu()
+        want = want.cuda()
+        simt = ops.conv2d_3x3(x, wp, bias, s_, b_, relu)
+        amax = x.abs().max().reshape(1).float()
+        shift = (s_ * bias + b_) if s_ is not None else bias
+        out_amax = torch.zeros(1, device='cuda')
+        tc = ops.conv2d_3x3_tc(x, wp.view(9, Cc, Cc), s_, shift.contiguous(), relu, in_absmax=amax, out_absmax=out_amax)
+        assert float((simt - want).abs().max()) < 1e-4
+        assert float((tc - want).abs().max()) < 1e-4 and tc.shape == want.shape
+        assert abs(float(out_amax) - float(tc.abs().max())) < 1e-6
+    big = ops.conv2d_3x3_tc(x * 1e5, wp.view(9, Cc, Cc), None, bias, False, in_absmax=(x * 1e5).abs().max().reshape(1))
+    want = torch.nn.functional.conv2d((x * 1e5).cpu().permute(0, 3, 1, 2), w.cpu(), bias.cpu()).permute(0, 2, 3, 1).cuda()
+    assert torch.isfinite(big).all() and float((big - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
 def test_bev_conv_attention(ops, state_dict):
     rng = np.random.default_rng(6)
     sd = {k: v.float() for k, v in state_dict.items()}
