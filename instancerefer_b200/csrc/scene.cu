@@ -254,18 +254,40 @@ k_scene_attention(const float* __restrict__ feats, const float* __restrict__ q, 
         atten[(long long)b * ncell + i] = a;
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float acc = 0.f;
-        int cell = 0;
-        for (; cell + 16 <= ncell; cell += 16) {            // 16 independent loads per batch, additions in cell order
-            float v[16];
+    // weighted sum: warp w takes cells w, w+8, ... for all channels (lane = 4 consecutive channels, one 512-byte row per
+    // load instruction, 8 rows in flight), the 8 per-warp partials are added in warp order (deterministic)
+    __shared__ float s_part[8][BEV_C];
+    if (C == BEV_C) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = w; c0 < ncell; c0 += 64) {
+            float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = fb[(long long)(cell + u) * C + c];
+            for (int u = 0; u < 8; ++u) {
+                const int cell = c0 + 8 * u;
+                v[u] = (cell < ncell) ? *reinterpret_cast<const float4*>(fb + (long long)cell * C + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) acc = fmaf(v[u], s_att[cell + u], acc);
+            for (int u = 0; u < 8; ++u) {
+                const int cell = c0 + 8 * u;
+                const float a = (cell < ncell) ? s_att[cell] : 0.f;
+                acc.x = fmaf(v[u].x, a, acc.x); acc.y = fmaf(v[u].y, a, acc.y);
+                acc.z = fmaf(v[u].z, a, acc.z); acc.w = fmaf(v[u].w, a, acc.w);
+            }
         }
-        for (; cell < ncell; ++cell) acc = fmaf(fb[(long long)cell * C + c], s_att[cell], acc);
-        scene_feat[(long long)b * C + c] = acc;
+        *reinterpret_cast<float4*>(&s_part[w][lane * 4]) = acc;
+        __syncthreads();
+        if (tid < BEV_C) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += s_part[q][tid];
+            scene_feat[(long long)b * C + tid] = t;
+        }
+    } else {
+        for (int c = tid; c < C; c += 256) {
+            float acc = 0.f;
+            for (int cell = 0; cell < ncell; ++cell) acc = fmaf(fb[(long long)cell * C + c], s_att[cell], acc);
+            scene_feat[(long long)b * C + c] = acc;
+        }
     }
 }
 

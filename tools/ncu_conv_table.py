@@ -16,7 +16,10 @@ def main(csv_path, layers_path, out_path=None):
     layers = meta['layers']
     conv = [(n, t) for n, t in rows if any(k in n for k in ('k_pairgemm_tc', 'k_pairgemm_tma', 'k_reduce_epilogue', 'k_stem_direct'))]
     per_fwd = 2 * (1 + 12 * 2)                       # two encoders: stem + 12 x (pair-GEMM, reduce)
-    last = conv[-per_fwd:]                           # the last forward of the run
+    tail = 4                                         # the two BEV Conv2d run on the same kernels (pair-GEMM + reduce each) after the encoders
+    if len(conv) % (per_fwd + tail) != 0:
+        tail = 0                                     # IR_CONV2D=simt
+    last = conv[-(per_fwd + tail):len(conv) - tail]  # the encoder layers of the last forward of the run
     peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
     out, i = [], 0
     print(f'{"encoder":9s} {"L":>2s} {"Cin>Cout":>9s} {"K":>2s} {"rows":>6s} {"pairs":>7s} | {"gemm us":>8s} {"gather GB/s":>11s} | {"reduce us":>9s} {"scatter GB/s":>12s} | {"conv GB/s":>9s} {"of HBM":>6s}')
