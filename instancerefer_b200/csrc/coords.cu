@@ -7,11 +7,15 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-// ------------------------------------------------------------------ chained ordered compaction
-// Single-pass ordered stream compaction: tiles are handed out by an atomic ticket; each tile waits
-// for its predecessor's inclusive prefix (one 64-bit word: ready bit | prefix).
+// ------------------------------------------------------------------ single-pass ordered compaction
+// Ordered stream compaction with decoupled look-back: tiles are handed out by an atomic ticket; a tile publishes its
+// own count at once (status 1 = aggregate), then one warp looks back over up to 32 predecessors per step, adding
+// aggregates until it meets a tile whose inclusive prefix is known (status 2), and publishes its own inclusive prefix.
+// One 64-bit word per tile (status << 32 | value): all tiles count concurrently and the look-back costs one or two L2
+// round trips instead of one per tile (a chain of 16 tiles used to cost ~20 us for 32 k points).  Integer arithmetic:
+// the result does not depend on the order in which tiles finish.
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 8
+#define SCAN_ITEMS 2
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 template <class FlagFn, class EmitFn>
@@ -52,14 +56,31 @@ __device__ __forceinline__ void compact_ordered(int n, unsigned long long* state
             }
             const int tile_sum = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
             if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - ws;      // exclusive warp offsets
-            if (lane == 0) {
-                unsigned long long p = 0;
-                if (tile > 0) {
-                    volatile unsigned long long* prev = state + 1 + (tile - 1);
-                    do { p = *prev; } while (p == 0ull);
+            volatile unsigned long long* st = state + 1;
+            unsigned prefix = 0;
+            if (tile > 0) {
+                if (lane == 0) st[tile] = (1ull << 32) | (unsigned long long)(unsigned)tile_sum;      // aggregate available
+                int look = tile - 1;
+                while (true) {
+                    const int idx = look - lane;                     // lane 0 = nearest predecessor
+                    unsigned long long v = 2ull << 32;               // before tile 0: inclusive prefix 0
+                    if (idx >= 0) {
+                        unsigned spins = 0;
+                        do { v = st[idx]; if (++spins > (1u << 27)) __trap(); } while ((v >> 32) == 0ull);      // bounded: a protocol bug traps
+                    }
+                    const unsigned status = (unsigned)(v >> 32), val = (unsigned)(v & 0xFFFFFFFFull);
+                    const unsigned inc_mask = __ballot_sync(0xffffffffu, status == 2u);
+                    const int first_inc = __ffs(inc_mask) - 1;       // nearest tile with a known inclusive prefix
+                    unsigned c = (first_inc < 0 || lane <= first_inc) ? val : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    prefix += c;
+                    if (first_inc >= 0) break;
+                    look -= 32;
                 }
-                const unsigned prefix = (unsigned)(p & 0xFFFFFFFFull);
-                atomicExch(state + 1 + tile, (1ull << 32) | (unsigned long long)(prefix + (unsigned)tile_sum));
+            }
+            if (lane == 0) {
+                st[tile] = (2ull << 32) | (unsigned long long)(prefix + (unsigned)tile_sum);          // inclusive prefix available
                 s_prefix = (int)prefix;
                 if (tile == ntiles - 1) *n_out = (int)prefix + tile_sum;
             }

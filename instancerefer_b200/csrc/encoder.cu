@@ -111,7 +111,7 @@ extern "C" int ir_encoder_layout(int64_t n_max, ir_encoder_layout_t* L) {
     auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 1024); return o; };
     L->off_nlvl = take(8 * 4);
     L->off_kcount = take(9 * 32 * 4);
-    L->scan_stride = 1 + (n_max + 2047) / 2048 + 1;
+    L->scan_stride = 1 + (n_max + 511) / 512 + 1;          // ticket + one word per 512-row scan tile (coords.cu SCAN_TILE)
     L->off_scan = take(5 * L->scan_stride * 8);
     L->off_sync = take(512);               // ticket / phase counters of the persistent encoder kernel
     L->zero_bytes = off - L->off_nlvl;
