@@ -206,7 +206,7 @@ int irk_reduce_epilogue(const IrConvBatch& b, int cout, int K, cudaStream_t st) 
     IR_CHECK_ARG(K <= 32 && b.G >= 1 && b.G <= IR_MAX_GROUPS);
     long long rows = 1;
     for (int g = 0; g < b.G; ++g) rows = rows > b.p[g].n_max ? rows : b.p[g].n_max;
-    const dim3 grid(ir_min_i(ir_div_up(rows, 8), g_tune_reduce_ctas), b.G);
+    const dim3 grid(ir_min_i(ir_div_up(rows, 8), rows <= 8192 ? (g_tune_reduce_ctas + 1) / 2 : g_tune_reduce_ctas), b.G);
     switch (cout) {
         case 32: IR_CHECK_CUDA(ir_launch_pdl(k_reduce_epilogue<32>, grid, dim3(256), 0, st, b, K)); break;
         case 64: IR_CHECK_CUDA(ir_launch_pdl(k_reduce_epilogue<64>, grid, dim3(256), 0, st, b, K)); break;
@@ -303,7 +303,7 @@ int irk_stem_direct(const IrConvBatch& b, int cin, cudaStream_t st) {
     IR_CHECK_ARG(cin >= 1 && cin <= STEM_MAXCIN && b.G >= 1 && b.G <= IR_MAX_GROUPS);
     long long rows = 1;
     for (int g = 0; g < b.G; ++g) rows = rows > b.p[g].n_max ? rows : b.p[g].n_max;
-    const dim3 grid(ir_min_i(ir_div_up(rows, 8), g_tune_reduce_ctas), b.G);
+    const dim3 grid(ir_min_i(ir_div_up(rows, 8), rows <= 8192 ? (g_tune_reduce_ctas + 1) / 2 : g_tune_reduce_ctas), b.G);
     IR_CHECK_CUDA(ir_launch_pdl(k_stem_direct, grid, dim3(256), 0, st, b, cin));
     IR_CHECK_LAUNCH();
     return IR_OK;

@@ -385,9 +385,15 @@ int launch(const IrConvBatch& b, int K, cudaStream_t st) {
         IR_CHECK_CUDA(cudaFuncSetAttribute(k_pairgemm_tc<CIN, COUT, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_done = true;
     }
-    long long tiles_max = 0;
-    for (int g = 0; g < b.G; ++g) tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
-    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, g_tune_pairgemm_ctas);   // default: two CTAs per SM
+    long long tiles_max = 0, rows_cap = 0;
+    for (int g = 0; g < b.G; ++g) {
+        tiles_max += (long long)K * b.p[g].n_max / TILE_M + K;
+        rows_cap += b.p[g].n_max;
+    }
+    // default: two CTAs per SM; one per SM when the whole problem is capped at 8 k rows (small scenes: measured in the
+    // 10 k-point x 8-instance sweep point, the narrower launches of the two encoders overlap instead of queueing)
+    const int width = rows_cap <= 8192 ? (g_tune_pairgemm_ctas + 1) / 2 : g_tune_pairgemm_ctas;
+    const int grid = ir_min_i(tiles_max > 0 ? tiles_max : 1, width);
     IR_CHECK_CUDA(ir_launch_pdl(k_pairgemm_tc<CIN, COUT, SCALED>, dim3(grid), dim3(N_THREADS), (size_t)C::SMEM_BYTES, st, b, K));
     IR_CHECK_LAUNCH();
     return IR_OK;
