@@ -237,15 +237,45 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # --- eager leg (short): the four phases of the step by CUDA events, and the eager step time for the record
     for i in range(warmup):
         step(i, False)
     barrier()
+    n_eager = min(steps, 8)
+    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0 = lib.ir_launch_count()
+    te0.record()
+    losses = [step(i, True) for i in range(n_eager)]
+    te1.record()
+    barrier()
+    eager_ms = te0.elapsed_time(te1) / n_eager
+    launches_eager = (lib.ir_launch_count() - c0) // n_eager
+    phases = {k: v / n_eager for k, v in ph.items()}
+    # --- the measured step: the whole iteration replayed from one CUDA graph per batch signature (train_graph.py);
+    #     IR_TRAIN_STEP=eager times the eager iteration instead
+    mode = os.environ.get('IR_TRAIN_STEP', 'graph')
+    stepper = None
+    if mode == 'graph':
+        from instancerefer_b200.train_graph import GraphedTrainStep
+        stepper = GraphedTrainStep(model, opt, cfg)
+        for i in range(2 * len(hosts) + warmup):             # per signature: eager, capture + replay; then replays
+            float(stepper(hosts[i % len(hosts)])['loss'])
+        stepper.profile = []
+        assert stepper.replays >= warmup and len(stepper.cache) >= 1
+
+        def run(i):
+            return float(stepper(hosts[i % len(hosts)])['loss'])          # D2H of the step's result, every step
+    else:
+        def run(i):
+            return step(i, False)
+    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     c0 = lib.ir_launch_count()
+    r0 = stepper.launches_replayed if stepper else 0
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    losses = [step(i, True) for i in range(steps)]
+    losses = [run(i) for i in range(steps)]
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -254,7 +284,13 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
         t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall = float(t[0]), float(t[1])
-    launches = lib.ir_launch_count() - c0
+    launches = lib.ir_launch_count() - c0 + ((stepper.launches_replayed - r0) if stepper else 0)
+    replay = None
+    if stepper and stepper.profile:
+        pr = stepper.profile[-steps:]
+        replay = dict(graph_ms=sum(a.elapsed_time(b) for _, a, b in pr) / len(pr), host_stage_ms=sum(t for t, _, _ in pr) / len(pr) * 1e3,
+                      note='graph_ms: CUDA events around the replay of the captured iteration; host_stage_ms: class filter + '
+                           'packing + queueing the H2D copies, on the host before each replay')
     clocks = sampler.stop() if sampler else None
     # data-parallel sanity: every rank applied the same averaged gradients, so the parameter buffers must be
     # bitwise identical across ranks (BatchNorm running statistics are per rank and live outside the flat buffer)
@@ -279,7 +315,11 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
                                 f'stream as each branch\'s backward finishes, Adam replicated'),
         e2e=dict(value=world * per_gpu * steps / wall, unit=METRIC, ms_per_step=wall / steps * 1e3,
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
-        phases_ms={k: v / steps for k, v in ph.items()}, allreduce_exposed_ms=ph['allreduce+adam'] / steps,
+        step_mode=('one CUDA graph per batch signature: forward + get_loss + backward + bucketed all-reduce + Adam '
+                   f'({len(stepper.cache)} graphs, {stepper.replays} replays)') if stepper else 'eager',
+        eager=dict(ms_per_step=eager_ms, phases_ms=phases, allreduce_exposed_ms=phases['allreduce+adam'],
+                   launches_per_step=int(launches_eager), steps=n_eager),
+        phases_ms=phases, allreduce_exposed_ms=phases['allreduce+adam'], replay=replay,
         gpu_launches=int(launches), clocks=clocks, host_cores=ncpu,
         final_loss=losses[-1], first_loss=losses[0], ranks_in_sync=in_sync, cpu_baseline=cb)
 
@@ -697,7 +737,8 @@ def main():
         torch.cuda.empty_cache()
         t = train_measure(a.train_steps, 10, rank, world, local, cpu_baseline=False)
         train = {k: t[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'warmup', 'phases_ms', 'allreduce_exposed_ms',
-                                   'ranks_in_sync', 'e2e', 'gpu_launches', 'host_cores', 'config', 'first_loss', 'final_loss')}
+                                   'ranks_in_sync', 'e2e', 'gpu_launches', 'host_cores', 'config', 'first_loss', 'final_loss', 'step_mode',
+                                   'eager', 'replay')}
 
     if world > 1:
         dist.barrier()

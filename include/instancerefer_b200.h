@@ -363,6 +363,14 @@ int ir_ref_eval(const double* pred_obb, const int32_t* obb_ofs, const double* gt
 int ir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                  float grad_scale, const uint8_t* block_skip, ir_stream_t stream);
+/* The same update for a launch replayed from a CUDA graph (instancerefer_b200/train_graph.py): the three scalars
+ * that change per step — lr (lib/solver.py:119-125 steps a scheduler on it), 1-beta1^step, sqrt(1-beta2^step) — are
+ * computed on the host by ir_adam_hyper exactly as ir_adam_step does, copied to hyper_dev (float[3]) by the caller
+ * before the replay, and read on the device.                                                                  */
+int ir_adam_hyper(float lr, float beta1, float beta2, int32_t step, float* hyper3);
+int ir_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const float* hyper_dev, float beta1, float beta2, float eps, float weight_decay,
+                     float grad_scale, const uint8_t* block_skip, ir_stream_t stream);
 
 /* ------------------------------------------------------------------ one-call encoder training passes
  * All 13 [conv -> train-mode BN (-> + skip) -> ReLU] layers forward, and their backward, as one chain
@@ -428,6 +436,10 @@ int ir_relu_bwd(const float* dy, const float* y, int64_t n, float* dx, ir_stream
 int ir_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, float* y, uint8_t* mask,
                    ir_stream_t stream);
 int ir_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, ir_stream_t stream);
+/* Process-wide: every later dropout launch (ir_dropout_fwd and the fused heads / language / scene-tail passes) also
+ * folds *step_dev (device uint64, or NULL to switch off) into its seed on the device — a step replayed from a CUDA
+ * graph then draws a fresh mask although its host seed was fixed at capture.                                  */
+int ir_dropout_seed_step(const uint64_t* step_dev);
 /* nn.LayerNorm(N) (+ReLU) over the rows of (M,N) and its backward (dgamma/dbeta overwritten). */
 int ir_layernorm_fwd(const float* x, int32_t M, int32_t N, const float* gamma, const float* beta, float eps,
                      int32_t relu, float* y, float* mean, float* rstd, ir_stream_t stream);

@@ -147,6 +147,8 @@ SIGNATURES = {
     "ir_ref_loss": (i32, [p, p, p, p, i32, p, p, p, f32, f32, f64, p, p, p, p, p]),
     "ir_ref_eval": (i32, [p, p, p, p, i32, p, p, p, p, p, p, p, p, p, p]),
     "ir_adam_step": (i32, [p, p, p, p, i64, f32, f32, f32, f32, f32, i32, f32, p, p]),
+    "ir_adam_hyper": (i32, [f32, f32, f32, i32, p]),
+    "ir_adam_step_dev": (i32, [p, p, p, p, i64, p, f32, f32, f32, f32, f32, p, p]),
     "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),
     "ir_encoder_train_forward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p]),
     "ir_encoder_train_backward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p, C.POINTER(EncoderTrainGrads), p]),
@@ -154,6 +156,7 @@ SIGNATURES = {
     "ir_colsum": (i32, [p, i32, i32, p, p]),
     "ir_relu_bwd": (i32, [p, p, i64, p, p]),
     "ir_dropout_fwd": (i32, [p, i64, f32, C.c_uint64, p, p, p]),
+    "ir_dropout_seed_step": (i32, [p]),
     "ir_dropout_bwd": (i32, [p, p, i64, f32, p, p]),
     "ir_layernorm_fwd": (i32, [p, i32, i32, p, p, f32, i32, p, p, p, p]),
     "ir_layernorm_bwd": (i32, [p, p, p, i32, i32, p, p, p, i32, p, p, p, p]),

@@ -158,9 +158,13 @@ __device__ __forceinline__ float u01(unsigned long long seed, unsigned long long
     k ^= k >> 33;
     return (float)(k >> 40) * (1.0f / 16777216.0f);
 }
+// seed_step (optional, device): a per-step counter folded into the seed on the device, so that a launch replayed
+// from a CUDA graph (host seed baked in at capture) still draws a fresh mask every step
 __global__ void k_dropout(const float* __restrict__ x, long long n, float p, unsigned long long seed,
-                          float* __restrict__ y, unsigned char* __restrict__ mask) {
+                          const unsigned long long* __restrict__ seed_step, float* __restrict__ y,
+                          unsigned char* __restrict__ mask) {
     const float scale = 1.f / (1.f - p);
+    if (seed_step) seed += *seed_step * 0xD1B54A32D192ED03ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const bool keep = u01(seed, (unsigned long long)i) >= p;
         mask[i] = keep;
@@ -172,10 +176,16 @@ __global__ void k_dropout_bwd(const float* __restrict__ dy, const unsigned char*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dx[i] = mask[i] ? dy[i] * scale : 0.f;
 }
+static const unsigned long long* g_dropout_seed_step = nullptr;
+extern "C" int ir_dropout_seed_step(const uint64_t* step_dev) {
+    g_dropout_seed_step = (const unsigned long long*)step_dev;
+    return IR_OK;
+}
 extern "C" int ir_dropout_fwd(const float* x, int64_t n, float p, uint64_t seed, float* y, uint8_t* mask,
                               ir_stream_t stream) {
     IR_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f);
-    k_dropout<<<ir_min_i(ir_div_up(n, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, y, mask);
+    k_dropout<<<ir_min_i(ir_div_up(n, 256), IR_NUM_SMS * 8), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, g_dropout_seed_step,
+                                                                                           y, mask);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

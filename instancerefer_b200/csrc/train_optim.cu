@@ -195,7 +195,8 @@ extern "C" int ir_ref_loss(const double* pred_obb, const int32_t* obb_ofs, const
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
-       const unsigned char* __restrict__ block_skip) {
+       const unsigned char* __restrict__ block_skip, const float* __restrict__ hyper) {
+    if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }     // per-step scalars of a graph-replayed step
     const float step = lr / bc1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (block_skip && block_skip[i >> 6]) continue;      // parameter without a gradient this step: torch.optim.Adam skips it
@@ -217,7 +218,28 @@ extern "C" int ir_adam_step(float* params, const float* grads, float* exp_avg, f
     const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
     k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                   weight_decay, bc1, sqrtf(bc2), grad_scale, block_skip);
+                                                   weight_decay, bc1, sqrtf(bc2), grad_scale, block_skip, nullptr);
+    IR_CHECK_LAUNCH();
+    return IR_OK;
+}
+
+// The three scalars that change from step to step (lr: a scheduler may move it; the two bias corrections) as they
+// are needed by a launch replayed from a CUDA graph: ir_adam_hyper computes them on the host exactly like
+// ir_adam_step, the caller copies them to the device before the replay, ir_adam_step_dev reads them there.
+extern "C" int ir_adam_hyper(float lr, float beta1, float beta2, int32_t step, float* hyper3) {
+    IR_CHECK_ARG(hyper3 && step >= 1);
+    hyper3[0] = lr;
+    hyper3[1] = (float)(1.0 - pow((double)beta1, (double)step));
+    hyper3[2] = sqrtf((float)(1.0 - pow((double)beta2, (double)step)));
+    return IR_OK;
+}
+extern "C" int ir_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const float* hyper_dev, float beta1, float beta2, float eps, float weight_decay,
+                                float grad_scale, const uint8_t* block_skip, ir_stream_t stream) {
+    IR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && hyper_dev);
+    const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
+    k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2, eps,
+                                                   weight_decay, 1.f, 1.f, grad_scale, block_skip, hyper_dev);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -48,7 +48,9 @@ class InstanceRefer(nn.Module):
         history; same chain and dict keys as the reference (models/instancerefer.py:56-70)."""
         from . import training as T
         a = self.args
-        data_dict.pop(_PACK_KEY, None)
+        pack = data_dict.pop(_PACK_KEY, None)
+        if not getattr(pack, 'resident', False):               # a pre-staged pack (graph replay) is reused
+            pack = None
         full = bool(a.attribute_module and a.relation_module and a.scene_module and a.use_gt_lang)
         prep_a = prep_s = None
         if full:
@@ -56,10 +58,11 @@ class InstanceRefer(nn.Module):
             # their level sizes, before any feature kernel is queued: the rest of the step is issued without
             # a host synchronisation
             dev = data_dict['lang_feat'].device
-            pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+            if pack is None:
+                pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
             prep_a, prep_s = T.prepare_encoder_maps(self, data_dict, pack)
         data_dict = T.lang_forward_train(self.lang, data_dict)
-        if not full:
+        if not full and pack is None:
             dev = data_dict['lang_feat'].device
             pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
         data_dict[_PACK_KEY] = pack

@@ -73,11 +73,9 @@ def _gt_obb(data_dict, config):
 BOXES = '_ir_boxes'       # packed candidate / ground-truth boxes on the device, shared by get_loss and get_eval
 
 
-def pack_boxes(data_dict, config, dev):
-    """pred_obb_batch (host list of (c_b,7) float64) + the GT boxes -> one H2D copy.
-    -> dict(pred (Nc,7) f64, gt (B,7) f64, obb_ofs (B+1) i32, score_ofs (B) i32 [-1: scene not scored], counts)."""
-    pred = data_dict['pred_obb_batch']
-    B = len(pred)
+def boxes_host(pred, gt):
+    """pred: host list of (c_b,7) float64 candidate boxes per scene, gt (B,7) -> (f64 [all pred | gt] flat,
+    i32 [obb_ofs (B+1) | score_ofs (B)], counts, obb_ofs): what goes to the device, as two host arrays."""
     counts = [int(np.asarray(p).reshape(-1, 7).shape[0]) if len(p) else 0 for p in pred]
     obb_ofs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     score_ofs, s = [], 0
@@ -85,10 +83,26 @@ def pack_boxes(data_dict, config, dev):
         score_ofs.append(s if c >= 2 else -1)
         s += c if c >= 2 else 0
     allobb = np.concatenate([np.asarray(p, np.float64).reshape(-1, 7) for p in pred if len(p)] or [np.zeros((1, 7))], 0)
-    devbuf = torch.from_numpy(np.concatenate([allobb.reshape(-1), _gt_obb(data_dict, config).reshape(-1)])).to(dev)
-    ints = torch.from_numpy(np.concatenate([obb_ofs, np.asarray(score_ofs, np.int32)])).to(dev)
-    return dict(pred=devbuf[:allobb.size].view(-1, 7), gt=devbuf[allobb.size:].view(B, 7), obb_ofs=ints[:B + 1],
-                score_ofs=ints[B + 1:], counts=counts, host_ofs=obb_ofs)
+    f64 = np.concatenate([allobb.reshape(-1), np.asarray(gt, np.float64).reshape(-1)])
+    i32 = np.concatenate([obb_ofs, np.asarray(score_ofs, np.int32)])
+    return f64, i32, counts, obb_ofs
+
+
+def boxes_views(devbuf, ints, counts, obb_ofs):
+    B, n = len(counts), devbuf.numel() - 7 * len(counts)
+    return dict(pred=devbuf[:n].view(-1, 7), gt=devbuf[n:].view(B, 7), obb_ofs=ints[:B + 1], score_ofs=ints[B + 1:],
+                counts=counts, host_ofs=obb_ofs)
+
+
+def pack_boxes(data_dict, config, dev):
+    """pred_obb_batch (host list of (c_b,7) float64) + the GT boxes -> one H2D copy.
+    -> dict(pred (Nc,7) f64, gt (B,7) f64, obb_ofs (B+1) i32, score_ofs (B) i32 [-1: scene not scored], counts).
+    A dict already staged by the caller (``static``: train_graph.GraphedTrainStep) is used as it is."""
+    bx = data_dict.get(BOXES)
+    if bx is not None and bx.get('static'):
+        return bx
+    f64, i32, counts, obb_ofs = boxes_host(data_dict['pred_obb_batch'], _gt_obb(data_dict, config))
+    return boxes_views(torch.from_numpy(f64).to(dev), torch.from_numpy(i32).to(dev), counts, obb_ofs)
 
 
 def get_loss(data_dict, config):

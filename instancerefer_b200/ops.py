@@ -469,6 +469,24 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
          float(weight_decay), int(step), float(grad_scale), _p(block_skip, torch.uint8), _stream())
 
 
+def adam_hyper(lr, beta1, beta2, step, out):
+    """out: pinned/host float32[3] <- (lr, 1-beta1^step, sqrt(1-beta2^step)), the host arithmetic of ir_adam_step."""
+    call("ir_adam_hyper", float(lr), float(beta1), float(beta2), int(step), C.c_void_p(out.data_ptr()))
+
+
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, hyper_dev, beta1, beta2, eps, weight_decay, grad_scale=1.0,
+                  block_skip=None):
+    """adam_step with lr and the bias corrections read from hyper_dev (device float32[3]): graph-replayable."""
+    call("ir_adam_step_dev", _p(params, torch.float32), _p(grads, torch.float32), _p(exp_avg, torch.float32),
+         _p(exp_avg_sq, torch.float32), params.numel(), _p(hyper_dev, torch.float32), float(beta1), float(beta2),
+         float(eps), float(weight_decay), float(grad_scale), _p(block_skip, torch.uint8), _stream())
+
+
+def dropout_seed_step(step_dev):
+    """Device uint64 (as an int64 tensor) folded into every later dropout seed on the device, or None: off."""
+    call("ir_dropout_seed_step", _p(step_dev, torch.int64) if step_dev is not None else None)
+
+
 # ----------------------------------------------------------------------------- dense training-step operators
 
 def gemm(A, B, ta=False, tb=False, bias=None, relu=False, out=None, accumulate=False):

@@ -84,6 +84,8 @@ class FlatAdam(torch.optim.Optimizer):
         self._packed = [False] * self.n_buckets
         self.overlap = self.world > 1               # launch bucket all-reduces from the backward hooks
         self._sync = True
+        self._hyper_dev = self._hyper_host = None   # per-step scalars on the device (graph-replayed steps)
+        self._staged = False
         if self.overlap:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
@@ -192,6 +194,32 @@ class FlatAdam(torch.optim.Optimizer):
             self._skip_key, self._skip_mask = key, m.to(self.flat.device)
         return self._skip_mask
 
+    # --- steps replayed from a CUDA graph (train_graph.GraphedTrainStep) ----------------------------------------------
+    def stage_step(self):
+        """Host half of a step whose device half is (or is being) captured: advance the step count and put the scalars
+        that change per step — lr as the scheduler left it, the two bias corrections — on the device (async, current
+        stream).  The next ``step()`` call, or the replay of a captured one, reads them there."""
+        if self._hyper_dev is None:
+            self._hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.flat.device)
+            self._hyper_host = torch.zeros(16, 4, dtype=torch.float32).pin_memory()     # ring: copies in flight keep theirs
+        self.step_count += 1
+        g = self.param_groups[0]
+        h = self._hyper_host[self.step_count % 16]
+        ops.adam_hyper(g['lr'], g['betas'][0], g['betas'][1], self.step_count, h)
+        self._hyper_dev.copy_(h, non_blocking=True)
+        self._staged = True
+
+    def after_replay(self):
+        """Host bookkeeping of a replayed step (what ``step()`` does beside launching kernels)."""
+        self._staged = False
+        from .basic_blocks import bump_weights_epoch
+        bump_weights_epoch()
+
+    def graph_key(self):
+        """Everything a captured step bakes in as launch arguments."""
+        g = self.param_groups[0]
+        return (tuple(g['betas']), g['eps'], g['weight_decay'], self.world, self._sync)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -200,14 +228,19 @@ class FlatAdam(torch.optim.Optimizer):
                 loss = closure()
         missing = self.gather_grads()
         self.allreduce()
-        self.step_count += 1
         if not all(self.has_state):
             gone = set(missing)
             self.has_state = [h or (i not in gone) for i, h in enumerate(self.has_state)]
         g = self.param_groups[0]
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g['lr'], g['betas'][0],
-                      g['betas'][1], g['eps'], g['weight_decay'], self.step_count, 1.0 / self.world,
-                      self._block_skip(missing))
+        if self._staged:                               # scalars already on the device (stage_step)
+            self._staged = False
+            ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._hyper_dev, g['betas'][0],
+                              g['betas'][1], g['eps'], g['weight_decay'], 1.0 / self.world, self._block_skip(missing))
+        else:
+            self.step_count += 1
+            ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g['lr'], g['betas'][0],
+                          g['betas'][1], g['eps'], g['weight_decay'], self.step_count, 1.0 / self.world,
+                          self._block_skip(missing))
         from .basic_blocks import bump_weights_epoch
         bump_weights_epoch()           # the kernel wrote the parameters through raw pointers: tensor versions did not move
         return loss

@@ -242,6 +242,9 @@ class EncoderTrainGraphed(Function):
             else:
                 _lib.call("ir_encoder_train_backward", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena),
                           ops._p(st.dout), C.byref(st.Gr), ops._stream())
+        if torch.cuda.is_current_stream_capturing():          # whole-step capture (train_graph.GraphedTrainStep)
+            launch()
+            return
         runs = st.fwd_runs if which == 'fwd' else st.bwd_runs
         graph = st.fwd_graph if which == 'fwd' else st.bwd_graph
         if graph is not None:
@@ -772,7 +775,8 @@ class LangTrain(Function):
         _lib.call("ir_lang_train_view", C.byref(P), C.byref(of), C.byref(oa))
         feats = arena[of.value:of.value + B * L * 256 * 4].view(torch.float32).view(B, L, 256)
         atten = arena[oa.value:oa.value + 4 * B * L * 4].view(torch.float32).view(4, B, L)
-        ctx.state = (P, keep, arena, x, lengths, pooled, [tuple(t.shape) for t in params])
+        ctx.state = (P, keep, arena, x, lengths, [tuple(t.shape) for t in params])
+        ctx.save_for_backward(pooled)        # an OUTPUT: kept as a plain attribute it would tie node and tensor into a cycle
         ctx.mark_non_differentiable(feats, atten)
         return pooled, scores, feats, atten
 
@@ -780,7 +784,8 @@ class LangTrain(Function):
     def backward(ctx, dpooled, dscores, _df, _da):
         import ctypes as C
         from . import _lib
-        P, keep, arena, x, lengths, pooled, shapes = ctx.state
+        P, keep, arena, x, lengths, shapes = ctx.state
+        (pooled,) = ctx.saved_tensors
         dev = x.device
         H3 = 3 * 128
         # flat gradient buffer; the per-direction bias gradients of a layer and the four fc_* gradients are
@@ -846,7 +851,9 @@ def lang_forward_train(m, data_dict):
     x, length = data_dict['lang_feat'], data_dict['lang_len']
     dev = x.device
     host = data_dict.get('_ir_host_labels', {}).get('lang_len')
-    L = int((host if host is not None else length.detach().to('cpu')).max())
+    L = data_dict.get('_ir_lang_len_max')
+    if L is None:
+        L = int((host if host is not None else length.detach().to('cpu')).max())
     B = x.shape[0]
     len_dev = length.to(dev, torch.int64).contiguous()
     wp = m.word_projection
@@ -887,7 +894,9 @@ def lang_forward_train(m, data_dict):
 def prepare_encoder_maps(model, data_dict, pack):
     """Coordinate phase of BOTH sparse encoders (voxelise the candidates @2 cm, hash the loader's 5 cm
     voxels, levels + kernel maps), then ONE D2H copy of the ten level row counts — the only host
-    synchronisation of the train-mode forward after the token-length read."""
+    synchronisation of the train-mode forward after the token-length read.  ``_ir_capacity`` in the dict (set by
+    train_graph.GraphedTrainStep): no read-back at all — every buffer downstream is laid out for the workspace
+    capacity and the row counts are read on the device, which is what makes the step capturable."""
     dev = pack.points.device
     am, sm = model.attribute, model.scene
     ws_a = am.net.workspace(pack.M * pack.points.shape[1], dev)
@@ -898,8 +907,11 @@ def prepare_encoder_maps(model, data_dict, pack):
     F0 = lidar.F.to(dev, torch.float32).contiguous()
     C0 = lidar.C.to(dev, torch.int32).contiguous()
     ws_s = sm.net.workspace(F0.shape[0], dev)
-    ops.encoder_build_maps(ws_s, C0)
-    n = torch.cat([ws_a.nlvl(), ws_s.nlvl()]).tolist()
+    ops.encoder_build_maps(ws_s, C0, data_dict.get('_ir_lidar_rows'))
+    if data_dict.get('_ir_capacity'):
+        n = [ws_a.n_max] * 5 + [ws_s.n_max] * 5
+    else:
+        n = torch.cat([ws_a.nlvl(), ws_s.nlvl()]).tolist()
     return (ws_a, EncoderGraph(ws_a, n[:5])), (ws_s, EncoderGraph(ws_s, n[5:]), F0, C0)
 
 

@@ -834,3 +834,104 @@ def test_gradient_accumulation_over_two_backwards(lib_built, state_dict, args):
     for k, g in acc.items():
         want = single[0][k] + single[1][k]
         assert float((g - want).abs().max()) < 2e-3 * max(float(want.abs().max()), 1e-3 * scale), k
+
+
+def test_graphed_train_step_matches_eager_step(lib_built, state_dict, args):
+    """train_graph.GraphedTrainStep (forward + get_loss + backward + Adam replayed from one CUDA graph, capacity-mode
+    encoders, device-side Adam scalars) against the eager iteration of lib/solver.py:195-205 from IDENTICAL state:
+    the optimiser / BatchNorm state of the eager model is copied into the graphed one before every compared step, so
+    the comparison sees one step's arithmetic (Adam amplifies rounding noise of near-zero gradients to ±lr, which
+    would otherwise accumulate).  Steps 1-2 run eagerly inside the wrapper (first sight of each signature), 3-4 are
+    the capture + first replay, 5-8 pure replays with a learning-rate change in between (the scheduler's effect)."""
+    from instancerefer_b200 import SparseTensor
+    from instancerefer_b200.loss_helper import get_loss, stash_host_labels
+    from instancerefer_b200.optim import FlatAdam
+    from instancerefer_b200.train_graph import GraphedTrainStep
+    cfg = train_ref.SyntheticConfig()
+    hosts = []
+    for s_, nc in ((5, [4, 3]), (6, [2, 5])):
+        b = synthetic.make_batch(s_, batch_size=2, num_points=6000, n_inst=8, n_cand=nc, n_tokens=[6, 9])
+        hosts.append({k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if isinstance(v, np.ndarray) else v)
+                      for k, v in b.items()})
+    ma, mb = make_train_model(state_dict, args), make_train_model(state_dict, args)
+    oa, ob = FlatAdam(ma, lr=1e-3, weight_decay=1e-5), FlatAdam(mb, lr=1e-3, weight_decay=1e-5)
+    stepper = GraphedTrainStep(mb, ob, cfg, min_hits=1)
+    bufs = lambda m: [v for k, v in sorted(m.state_dict().items()) if 'running' in k or 'tracked' in k]
+
+    def eager(h):
+        d = stash_host_labels(dict(h))
+        d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}
+        d['lidar'] = SparseTensor(d.pop('lidar_feats'), d.pop('lidar_coords'))
+        oa.zero_grad()
+        d = get_loss(ma(d), cfg)
+        d['loss'].backward()
+        oa.step()
+        return d
+
+    for it in range(8):
+        h = hosts[it % 2]
+        if it == 6:
+            oa.param_groups[0]['lr'] = ob.param_groups[0]['lr'] = 2.5e-4
+        ob.flat.copy_(oa.flat); ob.exp_avg.copy_(oa.exp_avg); ob.exp_avg_sq.copy_(oa.exp_avg_sq)
+        ob.step_count, ob.has_state = oa.step_count, list(oa.has_state)
+        for x, y in zip(bufs(mb), bufs(ma)):
+            x.copy_(y)
+        before = oa.flat.clone()
+        da, db = eager(h), stepper(h)
+        torch.cuda.synchronize()
+        print(it, {k: (float(da[k].detach().reshape(-1)[0]), float(db[k].detach().reshape(-1)[0])) for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss')},
+              {k: float((da[k] - db[k]).abs().max()) for k in ('attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'lang_scores', 'obj_feats')})
+        for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss'):
+            # typically 1e-6; BatchNorm1d over the two language rows of this batch can amplify a rounding difference
+            va, vb = float(da[k].detach().reshape(-1)[0]), float(db[k].detach().reshape(-1)[0])
+            assert abs(va - vb) < 1e-3 * max(1.0, abs(va)), (it, k, va, vb)
+        for k in ('attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'lang_scores'):
+            assert float((da[k] - db[k]).abs().max()) < 2e-3, (it, k)
+        assert all(torch.equal(x, y) for x, y in zip(da['cluster_label'], db['cluster_label']))
+        ga = {k: oa.grad_views[i].detach().cpu() for i, (k, _) in enumerate(ma.named_parameters())}
+        gb = {k: ob.grad_views[i].detach().cpu() for i, (k, _) in enumerate(mb.named_parameters())}
+        scale = max(float(g.abs().max()) for g in ga.values())
+        try:
+            # capacity mode partitions the BatchNorm sums differently: more activations within rounding of 0 land
+            # on the other side than between two runs of the same path, hence the wider "tight" band
+            assert_grads_agree({k: (gb[k], ga[k]) for k in ga}, scale, tight=1e-2)
+        except AssertionError as e:
+            raise AssertionError(f'step {it}: {str(e)[:600]}')
+        assert oa.step_count == ob.step_count == it + 1
+        # one Adam step from the same state: the bulk of the update must coincide (entries whose gradient is rounding
+        # noise move by ~lr in either direction on both sides)
+        ua, ub = oa.flat - before, ob.flat - before
+        lr = oa.param_groups[0]['lr']
+        assert float(ua.abs().max()) <= 4 * lr and float(ub.abs().max()) <= 4 * lr
+        assert float((ua - ub).abs().mean()) < 0.02 * lr, (it, float((ua - ub).abs().mean()))
+        for x, y in zip(bufs(mb), bufs(ma)):
+            assert torch.allclose(x.float(), y.float(), atol=1e-5, rtol=1e-4), it
+    assert stepper.eager_steps == 2 and stepper.replays == 6 and len(stepper.cache) == 2
+
+
+def test_graphed_train_step_draws_fresh_dropout_masks(lib_built, state_dict, args):
+    """A replayed step must not repeat the dropout mask baked in at capture: with lr = 0 (weights and moments
+    frozen... Adam still moves nothing) the same batch replayed twice gives different losses when Dropout is on,
+    identical ones when it is off."""
+    from instancerefer_b200.instancerefer import InstanceRefer
+    from instancerefer_b200.optim import FlatAdam
+    from instancerefer_b200.train_graph import GraphedTrainStep
+    b = synthetic.make_batch(5, batch_size=2, num_points=6000, n_inst=8, n_cand=[4, 3], n_tokens=[6, 9])
+    h = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+    for drop_on in (True, False):
+        m = InstanceRefer(7, args)
+        m.load_state_dict(state_dict, strict=True)
+        m = m.cuda().train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.momentum = 0.0
+            if isinstance(mod, torch.nn.Dropout) and not drop_on:
+                mod.p = 0.0
+        opt = FlatAdam(m, lr=0.0)
+        stepper = GraphedTrainStep(m, opt, train_ref.SyntheticConfig())
+        losses = [float(stepper(h)['loss']) for _ in range(5)][1:]             # first sight of a signature runs eagerly
+        assert stepper.replays == 4 and stepper.eager_steps == 1
+        if drop_on:
+            assert len(set(losses)) == 4, losses
+        else:
+            assert max(losses) - min(losses) < 1e-4 * abs(losses[0]), losses
