@@ -5,6 +5,7 @@ Module names given in the YAML are resolved inside this package first (``lang_mo
 ``instancerefer_b200.lang_module``), then as plain import names, so the reference's
 config/InstanceRefer.yaml works unchanged."""
 import importlib
+import os
 
 import torch
 import torch.nn as nn
@@ -60,6 +61,8 @@ class InstanceRefer(nn.Module):
             dev = data_dict['lang_feat'].device
             if pack is None:
                 pack = CandidatePack(data_dict, target_classes(data_dict, a), dev)
+            if self.concurrent and data_dict.get('_ir_capacity') and os.environ.get('IR_TRAIN_STREAMS', '1') != '0':
+                return self._forward_train_streams(data_dict, pack, dev)
             prep_a, prep_s = T.prepare_encoder_maps(self, data_dict, pack)
         data_dict = T.lang_forward_train(self.lang, data_dict)
         if not full and pack is None:
@@ -72,6 +75,48 @@ class InstanceRefer(nn.Module):
             data_dict = T.relation_forward_train(self.relation, data_dict, pack)
         if a.scene_module:
             data_dict = T.scene_forward_train(self.scene, data_dict, pack, prep_s)
+        return data_dict
+
+    def _forward_train_streams(self, data_dict, pack, dev):
+        """The train-mode chain on four streams, for the captured iteration (train_graph.GraphedTrainStep; capacity
+        mode, so nothing below touches the host): instance encoder, scene encoder and relation graph start at once on
+        three side streams while the language branch runs on the caller's; each branch's matching head joins the
+        language event, the scene head also the pooled instance features.  Autograd replays every node on the stream
+        its forward ran on, so the backward of the three branches forms parallel chains of the same CUDA graph —
+        their latency-bound launches (a few thousand rows each) overlap instead of queueing behind each other.
+        Cross-stream tensors (language features, obj_feats, scores) stay referenced by ``data_dict`` until the step
+        returns, so no block is recycled while another stream still reads it; gradients crossing streams are
+        synchronised and recorded by the autograd engine itself."""
+        from . import training as T
+        main = torch.cuda.current_stream(dev)
+        sa, ss, sr = self._streams(dev)
+        data_dict[_PACK_KEY] = pack
+        for s_ in (sa, ss, sr):
+            s_.wait_stream(main)
+        ev_obj, ev_lang = torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.stream(sa):
+            ws_a = T.prepare_attribute_maps(self, pack)
+            T.attribute_encode_train(self.attribute, data_dict, pack, (ws_a, T.EncoderGraph(ws_a, [ws_a.n_max] * 5)))
+            ev_obj.record(sa)
+        with torch.cuda.stream(ss):
+            ws_s, F0, C0 = T.prepare_scene_maps(self, data_dict, dev)
+            T.scene_encode_train(self.scene, data_dict, pack, (ws_s, T.EncoderGraph(ws_s, [ws_s.n_max] * 5), F0, C0))
+        with torch.cuda.stream(sr):
+            T.relation_encode_train(self.relation, data_dict, pack)
+        data_dict = T.lang_forward_train(self.lang, data_dict)
+        ev_lang.record(main)
+        with torch.cuda.stream(sa):
+            sa.wait_event(ev_lang)
+            T.attribute_match_train(self.attribute, data_dict, pack)
+        with torch.cuda.stream(sr):
+            sr.wait_event(ev_lang)
+            T.relation_match_train(self.relation, data_dict, pack)
+        with torch.cuda.stream(ss):
+            ss.wait_event(ev_lang)
+            ss.wait_event(ev_obj)
+            T.scene_match_train(self.scene, data_dict, pack)
+        for s_ in (sa, ss, sr):
+            main.wait_stream(s_)
         return data_dict
 
     def forward(self, data_dict):

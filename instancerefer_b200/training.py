@@ -891,23 +891,33 @@ def lang_forward_train(m, data_dict):
     return data_dict
 
 
-def prepare_encoder_maps(model, data_dict, pack):
-    """Coordinate phase of BOTH sparse encoders (voxelise the candidates @2 cm, hash the loader's 5 cm
-    voxels, levels + kernel maps), then ONE D2H copy of the ten level row counts — the only host
-    synchronisation of the train-mode forward after the token-length read.  ``_ir_capacity`` in the dict (set by
-    train_graph.GraphedTrainStep): no read-back at all — every buffer downstream is laid out for the workspace
-    capacity and the row counts are read on the device, which is what makes the step capturable."""
-    dev = pack.points.device
-    am, sm = model.attribute, model.scene
-    ws_a = am.net.workspace(pack.M * pack.points.shape[1], dev)
+def prepare_attribute_maps(model, pack):
+    """Coordinate phase of the instance encoder: voxelise the candidates @2 cm, levels + kernel maps -> workspace."""
+    am = model.attribute
+    ws_a = am.net.workspace(pack.M * pack.points.shape[1], pack.points.device)
     ops.encoder_reset(ws_a)
     ops.voxelize(pack.points, pack.cand_rows, float(am.voxel_size[0]), ws_a)
     ops.encoder_build_maps(ws_a)
+    return ws_a
+
+
+def prepare_scene_maps(model, data_dict, dev):
+    """Coordinate phase of the scene encoder: hash the loader's 5 cm voxels, levels + kernel maps."""
     lidar = data_dict['lidar']
     F0 = lidar.F.to(dev, torch.float32).contiguous()
     C0 = lidar.C.to(dev, torch.int32).contiguous()
-    ws_s = sm.net.workspace(F0.shape[0], dev)
+    ws_s = model.scene.net.workspace(F0.shape[0], dev)
     ops.encoder_build_maps(ws_s, C0, data_dict.get('_ir_lidar_rows'))
+    return ws_s, F0, C0
+
+
+def prepare_encoder_maps(model, data_dict, pack):
+    """Coordinate phase of BOTH sparse encoders, then ONE D2H copy of the ten level row counts — the only host
+    synchronisation of the train-mode forward after the token-length read.  ``_ir_capacity`` in the dict (set by
+    train_graph.GraphedTrainStep): no read-back at all — every buffer downstream is laid out for the workspace
+    capacity and the row counts are read on the device, which is what makes the step capturable."""
+    ws_a = prepare_attribute_maps(model, pack)
+    ws_s, F0, C0 = prepare_scene_maps(model, data_dict, pack.points.device)
     if data_dict.get('_ir_capacity'):
         n = [ws_a.n_max] * 5 + [ws_s.n_max] * 5
     else:
@@ -915,10 +925,9 @@ def prepare_encoder_maps(model, data_dict, pack):
     return (ws_a, EncoderGraph(ws_a, n[:5])), (ws_s, EncoderGraph(ws_s, n[5:]), F0, C0)
 
 
-def attribute_forward_train(m, data_dict, pack, prepared=None):
-    """models/attribute_module.py:83-131 in train mode."""
+def attribute_encode_train(m, data_dict, pack, prepared=None):
+    """models/attribute_module.py:83-111 in train mode: the language-independent half (encoder, pooling, visual head)."""
     dev = pack.points.device
-    lang = L2Norm.apply(mlp_head(m.lang_emb_fc, data_dict['lang_attr_feats'], 1, 3))
     data_dict['num_filtered_objs'] = pack.num_filtered
     data_dict['pred_obb_batch'] = pack.pred_obb_batch
     if prepared is None:
@@ -931,16 +940,26 @@ def attribute_forward_train(m, data_dict, pack, prepared=None):
         f4, G = encoder_forward_train(m.net, ws, G=G)
     obj = SegMax.apply(f4, ws.coords(4), G.nlvl_dev[4:5], G.n[4], pack.M)
     data_dict['obj_feats'] = obj
-    vis = mlp_head(m.vis_emb_fc, obj, 1, 3)
-    data_dict['attribute_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 0)
+    data_dict['_ir_attr_vis'] = mlp_head(m.vis_emb_fc, obj, 1, 3)
     return data_dict
 
 
-def relation_forward_train(m, data_dict, pack):
-    """models/relation_module.py:80-107 in train mode: kNN graph, edge MLPs as edge-batched GEMMs,
-    max aggregation, cosine match."""
+def attribute_match_train(m, data_dict, pack):
+    """models/attribute_module.py:113-131: language embedding + normalised dot product."""
+    lang = L2Norm.apply(mlp_head(m.lang_emb_fc, data_dict['lang_attr_feats'], 1, 3))
+    data_dict['attribute_scores'] = Match.apply(data_dict.pop('_ir_attr_vis'), lang, pack.cand_scene, pack.scene_ofs(), 0)
+    return data_dict
+
+
+def attribute_forward_train(m, data_dict, pack, prepared=None):
+    """models/attribute_module.py:83-131 in train mode."""
+    return attribute_match_train(m, attribute_encode_train(m, data_dict, pack, prepared), pack)
+
+
+def relation_encode_train(m, data_dict, pack):
+    """models/relation_module.py:80-100 in train mode: kNN graph, edge MLPs as edge-batched GEMMs, max aggregation,
+    visual head (the language-independent half)."""
     dev = pack.points.device
-    lang = mlp_head(m.lang_emb_fc, data_dict['lang_rel_feats'], 1, 4, 3)
     mean = ops.instance_mean(pack.points)
     ncls = m.args.num_classes
     onehot = (pack.centres_cls[:, 3:4] == torch.arange(ncls, device=dev, dtype=torch.float32)[None, :]).float()
@@ -948,28 +967,36 @@ def relation_forward_train(m, data_dict, pack):
     feats = torch.cat([xyz, mean[:, 3:], onehot], 1).contiguous()
     gcn = m.gcn
     nbr = ops.knn(xyz, pack.inst_ofs, pack.cand_rows, pack.cand_seg, gcn.k)                  # (M,k), -1 padded
-    import os
     if os.environ.get('IR_TRAIN_EDGECONV', 'fused') != 'ops':
         g = EdgeConvTrain.apply(feats, xyz, pack.cand_rows, nbr, ncls, gcn.weight[0].weight, gcn.weight[0].bias,
                                 gcn.weight[2].weight, gcn.weight[2].bias, gcn.mlp[0].weight, gcn.mlp[0].bias,
                                 gcn.mlp[2].weight, gcn.mlp[2].bias)
-        vis = mlp_head(m.vis_emb_fc, g, 1, 4, 3)
-        data_dict['relation_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 1)
-        return data_dict
-    w_in = ops.edge_inputs(feats, xyz, pack.cand_rows, nbr, ncls)
-    w = Linear.apply(Linear.apply(w_in, gcn.weight[0].weight, gcn.weight[0].bias, True),
-                     gcn.weight[2].weight, gcn.weight[2].bias, False)
-    e_in = EdgeConcat.apply(w, feats, xyz, pack.cand_rows, nbr, ncls)
-    msg = Linear.apply(Linear.apply(e_in, gcn.mlp[0].weight, gcn.mlp[0].bias, True),
-                       gcn.mlp[2].weight, gcn.mlp[2].bias, False)
-    g = EdgeMax.apply(msg, nbr)
-    vis = mlp_head(m.vis_emb_fc, g, 1, 4, 3)
-    data_dict['relation_scores'] = Match.apply(vis, lang, pack.cand_scene, pack.scene_ofs(), 1)
+    else:
+        w_in = ops.edge_inputs(feats, xyz, pack.cand_rows, nbr, ncls)
+        w = Linear.apply(Linear.apply(w_in, gcn.weight[0].weight, gcn.weight[0].bias, True),
+                         gcn.weight[2].weight, gcn.weight[2].bias, False)
+        e_in = EdgeConcat.apply(w, feats, xyz, pack.cand_rows, nbr, ncls)
+        msg = Linear.apply(Linear.apply(e_in, gcn.mlp[0].weight, gcn.mlp[0].bias, True),
+                           gcn.mlp[2].weight, gcn.mlp[2].bias, False)
+        g = EdgeMax.apply(msg, nbr)
+    data_dict['_ir_rel_vis'] = mlp_head(m.vis_emb_fc, g, 1, 4, 3)
     return data_dict
 
 
-def scene_forward_train(m, data_dict, pack, prepared=None):
-    """models/scene_module.py:60-108 in train mode."""
+def relation_match_train(m, data_dict, pack):
+    """models/relation_module.py:101-107: language embedding + cosine match."""
+    lang = mlp_head(m.lang_emb_fc, data_dict['lang_rel_feats'], 1, 4, 3)
+    data_dict['relation_scores'] = Match.apply(data_dict.pop('_ir_rel_vis'), lang, pack.cand_scene, pack.scene_ofs(), 1)
+    return data_dict
+
+
+def relation_forward_train(m, data_dict, pack):
+    """models/relation_module.py:80-107 in train mode."""
+    return relation_match_train(m, relation_encode_train(m, data_dict, pack), pack)
+
+
+def scene_encode_train(m, data_dict, pack, prepared=None):
+    """models/scene_module.py:60-71 in train mode: scene encoder + BEV + the two Conv2d blocks (language-independent)."""
     dev = pack.points.device
     B = data_dict['point_min'].shape[0]
     if prepared is None:
@@ -994,7 +1021,15 @@ def scene_forward_train(m, data_dict, pack, prepared=None):
         x = BatchNormAct.apply(x.reshape(-1, x.shape[-1]), ve[1].weight, ve[1].bias, ve[1], True).view(x.shape)
         x = dropout(x, ve[3])
         x = Conv3x3.apply(x, ve[4].weight, ve[4].bias)                                           # (B,11,21,128)
-    h, w = x.shape[1], x.shape[2]
+    data_dict['_ir_scene_map'] = x
+    return data_dict
+
+
+def scene_match_train(m, data_dict, pack):
+    """models/scene_module.py:73-108: language query, attention over the BEV cells, region classifier, cosine match
+    of the candidates' pooled features against the attended scene feature."""
+    x = data_dict.pop('_ir_scene_map')
+    B, h, w = x.shape[0], x.shape[1], x.shape[2]
     q = mlp_head(m.lang_emb_fc, data_dict['lang_scene_feats'], 1, 4, 3)
     scene_feats, atten = SceneAttention.apply(x.view(B, h * w, -1), q)
     data_dict['vis_atten'] = atten.view(B, h, w)
@@ -1002,3 +1037,8 @@ def scene_forward_train(m, data_dict, pack, prepared=None):
     obj = mlp_head(m.vis_emb_fc1, data_dict['obj_feats'], 1, 4, 3)
     data_dict['scene_scores'] = Match.apply(obj, scene_feats, pack.cand_scene, pack.scene_ofs(), 1)
     return data_dict
+
+
+def scene_forward_train(m, data_dict, pack, prepared=None):
+    """models/scene_module.py:60-108 in train mode."""
+    return scene_match_train(m, scene_encode_train(m, data_dict, pack, prepared), pack)
