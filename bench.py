@@ -258,13 +258,18 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     if mode == 'graph':
         from instancerefer_b200.train_graph import GraphedTrainStep
         stepper = GraphedTrainStep(model, opt, cfg)
-        for i in range(2 * len(hosts) + warmup):             # per signature: eager, capture + replay; then replays
-            float(stepper(hosts[i % len(hosts)])['loss'])
+        for i in range(3 * len(hosts) + warmup):             # per signature: eager, two slots captured; then replays
+            stepper(hosts[i % len(hosts)])['result'].loss()
         stepper.profile = []
         assert stepper.replays >= warmup and len(stepper.cache) >= 1
 
+        pending = []
+
         def run(i):
-            return float(stepper(hosts[i % len(hosts)])['loss'])          # D2H of the step's result, every step
+            # every step's scalars come back through their own async D2H copy (train_graph.StepResult); the host reads
+            # step i-1 after it has queued step i, like a training loop that logs one iteration behind
+            pending.append(stepper(hosts[i % len(hosts)])['result'])
+            return pending.pop(0).loss() if len(pending) > 1 else None
     else:
         def run(i):
             return step(i, False)
@@ -276,6 +281,8 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     losses = [run(i) for i in range(steps)]
+    if stepper:
+        losses = [v for v in losses if v is not None] + [r.loss() for r in pending]      # the last step's read-back
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -314,9 +321,10 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
                     parallelism=f'dp{world}: scenes sharded, gradient all-reduce in {opt.n_buckets} buckets launched on a side '
                                 f'stream as each branch\'s backward finishes, Adam replicated'),
         e2e=dict(value=world * per_gpu * steps / wall, unit=METRIC, ms_per_step=wall / steps * 1e3,
-                 h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
+                 h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=20 if stepper else 4),
         step_mode=('one CUDA graph per batch signature: forward + get_loss + backward + bucketed all-reduce + Adam '
-                   f'({len(stepper.cache)} graphs, {stepper.replays} replays)') if stepper else 'eager',
+                   f'({len(stepper.cache)} signatures x {stepper.depth} slots, {stepper.replays} replays; per-step scalars read '
+                   'back one step behind)') if stepper else 'eager',
         eager=dict(ms_per_step=eager_ms, phases_ms=phases, allreduce_exposed_ms=phases['allreduce+adam'],
                    launches_per_step=int(launches_eager), steps=n_eager),
         phases_ms=phases, allreduce_exposed_ms=phases['allreduce+adam'], replay=replay,

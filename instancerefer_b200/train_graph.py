@@ -37,14 +37,34 @@ class _Slot:
     pass
 
 
+class StepResult:
+    """The five scalars of an iteration (loss, ref_loss, lang_loss, seg_loss, seg_acc) on their way to the host: one
+    async D2H copy into a pinned ring entry queued right behind the step.  ``get()`` waits for THAT copy only, so a
+    training loop can log iteration i after it has queued iteration i+1 and the host never idles the GPU."""
+
+    def __init__(self, host, event):
+        self._host, self._event, self._vals = host, event, None
+
+    def get(self):
+        if self._vals is None:
+            self._event.synchronize()
+            self._vals = dict(zip(RESULT_KEYS, self._host.tolist()))
+        return self._vals
+
+    def loss(self):
+        return self.get()['loss']
+
+
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, config, min_hits=1, max_graphs=8):
+    def __init__(self, model, optimizer, config, min_hits=1, max_graphs=8, depth=2):
         a = model.args
         if not (a.use_gt_lang and a.attribute_module and a.relation_module and a.scene_module):
             raise NotImplementedError("graph replay of the training step needs the full model with use_gt_lang: True "
                                       "(the class filter runs on the host before the language branch)")
         self.model, self.opt, self.config = model, optimizer, config
         self.min_hits, self.max_graphs = max(1, min_hits), max_graphs    # first sight is always eager: it warms lazy state
+        self.depth = max(1, depth)       # slots (static inputs + graph) per signature, used alternately: the H2D copies of
+                                         # iteration i+1 run on a copy stream beside the replay of iteration i
         self.cache, self.hits = {}, {}
         self.replays = self.eager_steps = self.launches_replayed = 0
         self.profile = None              # set to a list: (host seconds of staging, event before, event after the replay)
@@ -54,6 +74,10 @@ class GraphedTrainStep:
         # parameter's AccumulateGrad node to the stream of the iteration that created it, and a node living on the
         # legacy default stream (which cannot capture) would invalidate the capture of the backward.
         self.stream = torch.cuda.Stream(device=optimizer.flat.device)
+        self.copy_stream = torch.cuda.Stream(device=optimizer.flat.device)
+        self._ring = torch.zeros(8, len(RESULT_KEYS), dtype=torch.float32).pin_memory()
+        self._ring_ev = [None] * 8
+        self._n_results = 0
 
     # ------------------------------------------------------------------ host side of every step
     @staticmethod
@@ -84,6 +108,7 @@ class GraphedTrainStep:
         d['loss'].backward()
         self.opt.step()
         self.eager_steps += 1
+        d['result'] = self._result(d)
         return d
 
     def _new_slot(self, batch, target, tag):
@@ -106,30 +131,37 @@ class GraphedTrainStep:
         s.box_dev = torch.zeros(f64.size, dtype=torch.float64, device=dev)
         s.box_ints = torch.from_numpy(i32).to(dev)                     # offsets: constant per slot as well
         s.boxes = dict(boxes_views(s.box_dev, s.box_ints, counts, obb_ofs), static=True)
-        s.staged = torch.cuda.Event()
+        s.staged, s.graph_done = torch.cuda.Event(), torch.cuda.Event()
         s.staged.record()
+        s.graph_done.record()
         s.graph = None
         return s
 
     def _stage(self, s, batch, target):
-        """Host filter + pack + every H2D copy of the step, into the slot's static buffers (current stream)."""
+        """Host filter + pack + every H2D copy of the step into the slot's static buffers, on the copy stream: they
+        wait for the slot's previous replay (which read these buffers) and run beside whatever the step stream does."""
         dev = self.opt.flat.device
         s.staged.synchronize()                       # earlier copies out of this slot's pinned buffers are done
         d = stash_host_labels(dict(batch))
-        pack = CandidatePack(d, target, dev, static=s.pack_static, tag=s.tag)
-        pack._scene_ofs = s.scene_ofs
-        pack.resident = True
-        for k in DEVICE_KEYS:
-            s.dev[k].copy_(batch[k], non_blocking=True)
-        F, C = self._lidar(batch)
-        n0 = F.shape[0]
-        s.lidar_F[:n0].copy_(F, non_blocking=True)
-        s.lidar_C[:n0].copy_(C, non_blocking=True)
-        s.n0_host[0] = n0
-        s.n0_dev.copy_(s.n0_host, non_blocking=True)
-        f64, _, _, _ = boxes_host(pack.pred_obb_batch, _gt_obb(d, self.config))
-        s.box_host.numpy()[:] = f64
-        s.box_dev.copy_(s.box_host, non_blocking=True)
+        cs = self.copy_stream
+        with torch.cuda.stream(cs):
+            cs.wait_event(s.graph_done)
+            pack = CandidatePack(d, target, dev, static=s.pack_static, tag=s.tag)
+            pack._scene_ofs = s.scene_ofs
+            pack.resident = True
+            for k in DEVICE_KEYS:
+                s.dev[k].copy_(batch[k], non_blocking=True)
+            F, C = self._lidar(batch)
+            n0 = F.shape[0]
+            s.lidar_F[:n0].copy_(F, non_blocking=True)
+            s.lidar_C[:n0].copy_(C, non_blocking=True)
+            s.n0_host[0] = n0
+            s.n0_dev.copy_(s.n0_host, non_blocking=True)
+            f64, _, _, _ = boxes_host(pack.pred_obb_batch, _gt_obb(d, self.config))
+            s.box_host.numpy()[:] = f64
+            s.box_dev.copy_(s.box_host, non_blocking=True)
+            s.staged.record(cs)
+        # per-step scalars read by the replay itself: on the step stream, behind the previous replay
         if self._seed_dev is None:
             self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             self._seed_host = torch.zeros(16, dtype=torch.int64).pin_memory()
@@ -138,10 +170,25 @@ class GraphedTrainStep:
         h = self._seed_host[self._seed_n % 16:self._seed_n % 16 + 1]
         h[0] = self._seed_n
         self._seed_dev.copy_(h, non_blocking=True)
-        s.staged.record()
         self.h2d_bytes = (pack.h2d_bytes + sum(t.numel() * t.element_size() for t in s.dev.values()) +
                           n0 * (F.shape[1] + 4) * 4 + 4 + f64.size * 8 + 8 + 16)
         return pack, d
+
+    def _result(self, d):
+        """Queue the D2H copy of the step's scalars (current stream) -> StepResult."""
+        res = d.get('_ir_result')
+        if res is None:
+            res = torch.stack([d[k].detach().reshape(-1)[0].float() for k in RESULT_KEYS])
+        i = self._n_results % 8
+        self._n_results += 1
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()           # the entry's previous copy landed (8 iterations ago)
+        host = self._ring[i]
+        host.copy_(res, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+        return StepResult(host, ev)
 
     def _device_step(self, s, pack, lmax):
         d = dict(s.dev)
@@ -154,6 +201,7 @@ class GraphedTrainStep:
         d = get_loss(self.model(d), self.config)
         d['loss'].backward()
         self.opt.step()
+        d['_ir_result'] = torch.stack([d[k].detach().reshape(-1)[0].float() for k in RESULT_KEYS])
         return d
 
     # ------------------------------------------------------------------ public API
@@ -175,8 +223,8 @@ class GraphedTrainStep:
         tgt = batch['object_cat']
         target = (tgt.detach().to('cpu') if tgt.is_cuda else tgt).tolist()
         key = self._signature(batch, target)
-        s = self.cache.get(key)
-        if s is None:
+        e = self.cache.get(key)
+        if e is None:
             n = self.hits.get(key, 0)
             if n < self.min_hits:
                 if len(self.hits) > 4096:
@@ -185,8 +233,10 @@ class GraphedTrainStep:
                 return self._eager(batch)
             if len(self.cache) >= self.max_graphs:
                 self.cache.pop(next(iter(self.cache)))
-            s = self._new_slot(batch, target, f't{len(self.cache)}')
-            self.cache[key] = s
+            e = dict(slots=[self._new_slot(batch, target, f't{len(self.cache)}s{j}') for j in range(self.depth)], i=0)
+            self.cache[key] = e
+        s = e['slots'][e['i'] % self.depth]
+        e['i'] += 1
         import time
         t0 = time.perf_counter()
         pack, host = self._stage(s, batch, target)
@@ -214,6 +264,7 @@ class GraphedTrainStep:
             s.keep = [dict(n.__dict__.get('_train_graphs', {})) for n in (self.model.attribute.net, self.model.scene.net)]
             s.graph = g
             self.opt._staged = True                  # the capture consumed the flag, the replay reads the same scalars
+        self.stream.wait_event(s.staged)
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -222,10 +273,12 @@ class GraphedTrainStep:
             self.profile.append((t_stage, e0, e1))
         else:
             s.graph.replay()
+        s.graph_done.record()
         self.opt.after_replay()
         self.replays += 1
         self.launches_replayed += s.launches
         out = dict(s.out)
+        out['result'] = self._result(out)
         out['num_filtered_objs'] = pack.num_filtered
         out['pred_obb_batch'] = pack.pred_obb_batch
         out['_ir_host_labels'] = host.get('_ir_host_labels', {})

@@ -888,6 +888,8 @@ def test_graphed_train_step_matches_eager_step(lib_built, state_dict, args):
         for k in ('attribute_scores', 'relation_scores', 'scene_scores', 'seg_scores', 'lang_scores'):
             assert float((da[k] - db[k]).abs().max()) < 2e-3, (it, k)
         assert all(torch.equal(x, y) for x, y in zip(da['cluster_label'], db['cluster_label']))
+        r = db['result'].get()                                # the async read-back of the same scalars
+        assert abs(r['loss'] - float(db['loss'].detach().reshape(-1)[0])) < 1e-6 * max(1.0, abs(r['loss'])) and 0 <= r['seg_acc'] <= 1
         ga = {k: oa.grad_views[i].detach().cpu() for i, (k, _) in enumerate(ma.named_parameters())}
         gb = {k: ob.grad_views[i].detach().cpu() for i, (k, _) in enumerate(mb.named_parameters())}
         scale = max(float(g.abs().max()) for g in ga.values())
