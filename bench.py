@@ -238,7 +238,7 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
             torch.cuda.synchronize()
 
     # --- eager leg (short): the four phases of the step by CUDA events, and the eager step time for the record
-    for i in range(warmup):
+    for i in range(max(warmup, 2 * len(hosts) + 2)):        # every batch shape seen twice: lazy state and the encoder graphs exist
         step(i, False)
     barrier()
     n_eager = min(steps, 8)

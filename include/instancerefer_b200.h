@@ -413,7 +413,8 @@ int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl, int32_t cin, ir
 /* feats0 == NULL: level-0 features voxelised into `ws`.  The encoder output is arena + off_out[12]. */
 int ir_encoder_train_forward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
                              const int32_t* n_lvl, void* arena, ir_stream_t stream);
-/* dout (n_lvl[4],128) = gradient w.r.t. the encoder output; same arena as the forward call.          */
+/* dout (n_lvl[4],128) = gradient w.r.t. the encoder output; same arena as the forward call, which also left the
+ * transposed rulebooks and W^T of this step in it (built on a helper stream beside the 13 layers).   */
 int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
                               const int32_t* n_lvl, void* arena, const float* dout,
                               const ir_encoder_train_grads* g, ir_stream_t stream);

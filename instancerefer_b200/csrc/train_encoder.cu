@@ -6,8 +6,42 @@
 // ~200 per-operator calls.  Activations live in a caller-owned arena (ir_encoder_train_layout).
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/instancerefer_b200.h"
 #include "common.cuh"
+
+// A helper stream per calling stream, owned by the library: work that does not sit on the layer-to-layer dependency chain
+// (transposed rulebooks and W^T during the forward, each layer's wgrad during the backward) is forked onto it and joined
+// back with events, so it runs beside the chain — also inside a CUDA-graph capture, where fork/join become graph edges.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+static SideStream* side_stream_for(cudaStream_t main) {
+    static std::unordered_map<cudaStream_t, SideStream> pool;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = pool.find(main);
+    if (it != pool.end()) return &it->second;
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;        // creation may happen while `main` is capturing
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    SideStream ss;
+    bool ok = cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    if (!ok) return nullptr;
+    return &(pool[main] = ss);
+}
+static int side_fork(SideStream* ss, cudaStream_t main) {
+    IR_CHECK_CUDA(cudaEventRecord(ss->fork, main));
+    IR_CHECK_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    return IR_OK;
+}
+static int side_join(SideStream* ss, cudaStream_t main) {
+    IR_CHECK_CUDA(cudaEventRecord(ss->join, ss->s));
+    IR_CHECK_CUDA(cudaStreamWaitEvent(main, ss->join, 0));
+    return IR_OK;
+}
 
 static const int kCh[5] = {32, 64, 128, 128, 128};
 // layer -> (input level, output level, K, map id in kcount: 0-4 = k3 at level l, 5-8 = k2 l->l+1)
@@ -115,6 +149,25 @@ extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const 
     int r;
     if ((r = tr_open(p, ws, n_max, n_lvl, arena, &t)) != IR_OK) return r;
     const float* f0 = feats0 ? feats0 : (const float*)(t.ws + t.W.off_feat0);
+    cudaStream_t st = (cudaStream_t)stream;
+    SideStream* ss = side_stream_for(st);
+    IR_CHECK_ARG(ss);
+    // What the backward needs beside the activations — the transposed rulebooks of all nine maps (out_idx for wgrad,
+    // slot_in for the dgrad reduce) and W^T of every layer with an input gradient — depends only on the maps and on
+    // the weights of this step: built here, on the helper stream beside the 13 layers, instead of in front of the
+    // backward chain.
+    if ((r = side_fork(ss, st)) != IR_OK) return r;
+    for (int m = 0; m < 9; ++m) {
+        const int K = m < 5 ? 27 : 8, lout = m < 5 ? m : m - 5 + 1;
+        if ((r = ir_rulebook_transpose(t.in_idx(m), t.slot(m), K, n_max, t.nlvl_dev() + lout, t.n[lout], t.tr_out(m),
+                                       t.tr_slot(m), (ir_stream_t)ss->s)) != IR_OK) return r;
+    }
+    for (int i = 1; i < IR_ENC_LAYERS; ++i) {
+        const LayerInfo li = layer_info(i, p->cin);
+        const long long tot = (long long)li.K * li.cin * li.cout;
+        k_transpose_w<<<ir_min_i(ir_div_up(tot, 256), IR_NUM_SMS * 4), 256, 0, ss->s>>>(p->weight[i], li.K, li.cin, li.cout, t.wt(i, p->cin));
+        IR_CHECK_LAUNCH();
+    }
     for (int i = 0; i < IR_ENC_LAYERS; ++i) {
         const LayerInfo li = layer_info(i, p->cin);
         const float* fin = (i == 0) ? f0 : t.out(i - 1);
@@ -127,7 +180,7 @@ extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const 
                                  p->running_mean[i], p->running_var[i], t.bn_scratch(), t.mean(i), t.rstd(i), t.out(i),
                                  stream)) != IR_OK) return r;
     }
-    return IR_OK;
+    return side_join(ss, st);
 }
 
 extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
@@ -139,20 +192,9 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
     IR_CHECK_ARG(dout && g);
     cudaStream_t st = (cudaStream_t)stream;
     const float* f0 = feats0 ? feats0 : (const float*)(t.ws + t.W.off_feat0);
-    // transposed rulebooks of all nine maps (out_idx for wgrad, slot_in for the dgrad reduce)
-    for (int m = 0; m < 9; ++m) {
-        const int K = m < 5 ? 27 : 8, lout = m < 5 ? m : m - 5 + 1;
-        if ((r = ir_rulebook_transpose(t.in_idx(m), t.slot(m), K, n_max, t.nlvl_dev() + lout, t.n[lout], t.tr_out(m),
-                                       t.tr_slot(m), stream)) != IR_OK) return r;
-    }
-    // W^T of every layer with an input gradient, up front: the tcgen05 dgrad stages its weights by TMA in its
-    // PDL prologue (before it waits on its stream predecessor), so they must be final long before it launches
-    for (int i = 1; i < IR_ENC_LAYERS; ++i) {
-        const LayerInfo li = layer_info(i, p->cin);
-        const long long tot = (long long)li.K * li.cin * li.cout;
-        k_transpose_w<<<ir_min_i(ir_div_up(tot, 256), IR_NUM_SMS * 4), 256, 0, st>>>(p->weight[i], li.K, li.cin, li.cout, t.wt(i, p->cin));
-        IR_CHECK_LAUNCH();
-    }
+    // (transposed rulebooks and W^T were built by ir_encoder_train_forward on the same arena)
+    SideStream* ss = side_stream_for(st);
+    IR_CHECK_ARG(ss);
     const float* up = dout;                        // gradient w.r.t. the output of the layer being processed
     float *S0 = t.grad(0), *S1 = t.grad(1), *S2 = t.grad(2), *S3 = t.grad(3);
     // one layer: BN backward (-> DY in S1, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`
@@ -162,8 +204,11 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         int rr;
         if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), t.ndev(li.lout), t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
                                   t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], t.absmax(), stream)) != IR_OK) return rr;
+        // wgrad and dgrad both read DY and nothing of each other: wgrad goes to the helper stream and joins before the
+        // next layer's BN backward overwrites S1
+        if ((rr = side_fork(ss, st)) != IR_OK) return rr;
         if ((rr = ir_spconv_wgrad_scaled(xin, li.cin, S1, t.absmax(), li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map),
-                                         t.kcount(li.map), n_max, (p->use_tc >> 2) & 1, g->dweight[i], stream)) != IR_OK) return rr;
+                                         t.kcount(li.map), n_max, (p->use_tc >> 2) & 1, g->dweight[i], (ir_stream_t)ss->s)) != IR_OK) return rr;
         if (dx) {
             // dgrad = forward pipeline on the transposed rulebook with W^T; `add` (the skip gradient) rides in the
             // reduce epilogue's residual slot.  use_tc bit 1: tcgen05 pair-GEMM with the gathered gradient rows
@@ -172,7 +217,7 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
                                              t.kcount(li.map), t.nlvl_dev() + li.lin, t.n[li.lin], t.wt(i, p->cin), (p->use_tc >> 1) & 1,
                                              add, t.T(), dx, stream)) != IR_OK) return rr;
         }
-        return IR_OK;
+        return side_join(ss, st);
     };
     for (int s = 4; s >= 1; --s) {
         const int a = 1 + 3 * (s - 1), b = a + 1, c = a + 2;
