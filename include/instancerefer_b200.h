@@ -404,7 +404,9 @@ typedef struct {
     int64_t off_mean[IR_ENC_LAYERS], off_rstd[IR_ENC_LAYERS];
     int64_t off_bn_scratch;
     int64_t off_tr_out[9], off_tr_slot[9];                     /* transposed rulebooks, int32 [K][n_max]  */
-    int64_t off_grad[4];                                       /* fp32 (max rows, 128) gradient buffers   */
+    int64_t off_grad[6];                                       /* fp32 (max rows, 128) gradient buffers: 0, 2, 3 carry the
+                                                                * layer-to-layer gradients, 1, 4, 5 are a ring of dY buffers
+                                                                * (the wgrad of a layer may lag the chain by two layers)  */
     int64_t off_wt;                                            /* fp32 transposed weights (K,Cout,Cin), layers 1..12 */
     int64_t off_absmax;                                        /* fp32 scalar: max |dY| of the current layer */
 } ir_encoder_train_layout_t;

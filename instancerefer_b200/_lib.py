@@ -47,7 +47,7 @@ class EncoderTrainGrads(C.Structure):
 class EncoderTrainLayout(C.Structure):
     _fields_ = [("total_bytes", i64), ("off_y", i64 * ENC_LAYERS), ("off_out", i64 * ENC_LAYERS),
                 ("off_mean", i64 * ENC_LAYERS), ("off_rstd", i64 * ENC_LAYERS), ("off_bn_scratch", i64),
-                ("off_tr_out", i64 * 9), ("off_tr_slot", i64 * 9), ("off_grad", i64 * 4), ("off_wt", i64),
+                ("off_tr_out", i64 * 9), ("off_tr_slot", i64 * 9), ("off_grad", i64 * 6), ("off_wt", i64),
                 ("off_absmax", i64)]
 
 

@@ -476,17 +476,20 @@ k_bev_bwd_feats(const float* __restrict__ ddense, const int4* __restrict__ coord
         }
     }
 }
-// grid (BV_C/8, n_z): CTA owns dkern[z][ci0..ci0+7][:], thread = output channel, rows scanned in order
-__global__ void __launch_bounds__(BV_C)
+// grid (BV_C/8, n_z): CTA owns dkern[z][ci0..ci0+7][:]; 8 row groups x 128 output channels: group g scans rows g, g+8, ...
+// in order, the eight partial tiles are added in group order (fixed summation order, no atomics)
+#define BVK_GROUPS 8
+__global__ void __launch_bounds__(BV_C * BVK_GROUPS)
 k_bev_bwd_kernel(const float* __restrict__ ddense, const float* __restrict__ F, const int4* __restrict__ coords,
                  const int* __restrict__ cell, const int* __restrict__ n_dev, int stride, float* __restrict__ dkern) {
-    const int n = *n_dev, z = blockIdx.y, ci0 = blockIdx.x * 8, co = threadIdx.x;
+    __shared__ float sh[BVK_GROUPS][8][BV_C];
+    const int n = *n_dev, z = blockIdx.y, ci0 = blockIdx.x * 8, co = threadIdx.x % BV_C, grp = threadIdx.x / BV_C;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int r = 0; r < n; ++r) {
+    for (int r = grp; r < n; r += BVK_GROUPS) {
         const int cl = cell[r];
-        if (cl < 0 || coords[r].z / stride != z) continue;         // CTA-uniform
+        if (cl < 0 || coords[r].z / stride != z) continue;         // uniform over the group's four warps
         const float gv = ddense[(long long)cl * BV_C + co];
         const float4 f0 = *reinterpret_cast<const float4*>(F + (long long)r * BV_C + ci0);
         const float4 f1 = *reinterpret_cast<const float4*>(F + (long long)r * BV_C + ci0 + 4);
@@ -496,7 +499,12 @@ k_bev_bwd_kernel(const float* __restrict__ ddense, const float* __restrict__ F, 
         acc[6] = fmaf(f1.z, gv, acc[6]); acc[7] = fmaf(f1.w, gv, acc[7]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dkern[((long long)z * BV_C + ci0 + i) * BV_C + co] = acc[i];
+    for (int i = 0; i < 8; ++i) sh[grp][i][co] = acc[i];
+    __syncthreads();
+    float s = 0.f;                                                  // thread (grp, co) finishes output row i = grp
+#pragma unroll
+    for (int q = 0; q < BVK_GROUPS; ++q) s += sh[q][grp][co];
+    dkern[((long long)z * BV_C + ci0 + grp) * BV_C + co] = s;
 }
 extern "C" int ir_bev_bwd(const float* ddense, const float* feats, const int32_t* coords, const int32_t* cell,
                           const int32_t* n_dev, int64_t n_max, int32_t stride, const float* kernel, int32_t n_z,
@@ -505,7 +513,7 @@ extern "C" int ir_bev_bwd(const float* ddense, const float* feats, const int32_t
     cudaStream_t st = (cudaStream_t)stream;
     k_bev_bwd_feats<<<ir_min_i(n_max, IR_NUM_SMS * 16), BV_C, 0, st>>>(ddense, (const int4*)coords, cell, n_dev, stride, kernel, dfeats);
     IR_CHECK_LAUNCH();
-    k_bev_bwd_kernel<<<dim3(BV_C / 8, n_z), BV_C, 0, st>>>(ddense, feats, (const int4*)coords, cell, n_dev, stride, dkernel);
+    k_bev_bwd_kernel<<<dim3(BV_C / 8, n_z), BV_C * BVK_GROUPS, 0, st>>>(ddense, feats, (const int4*)coords, cell, n_dev, stride, dkernel);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

@@ -15,7 +15,7 @@
 // A helper stream per calling stream, owned by the library: work that does not sit on the layer-to-layer dependency chain
 // (transposed rulebooks and W^T during the forward, each layer's wgrad during the backward) is forked onto it and joined
 // back with events, so it runs beside the chain — also inside a CUDA-graph capture, where fork/join become graph edges.
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join, ring[3]; };
 static SideStream* side_stream_for(cudaStream_t main) {
     static std::unordered_map<cudaStream_t, SideStream> pool;
     static std::mutex mu;
@@ -28,6 +28,7 @@ static SideStream* side_stream_for(cudaStream_t main) {
     bool ok = cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3; ++i) ok = ok && cudaEventCreateWithFlags(&ss.ring[i], cudaEventDisableTiming) == cudaSuccess;
     cudaThreadExchangeStreamCaptureMode(&mode);
     if (!ok) return nullptr;
     return &(pool[main] = ss);
@@ -80,7 +81,7 @@ extern "C" int ir_encoder_train_layout(int64_t n_max, const int32_t* n_lvl_in, i
         L->off_tr_out[m] = take((int64_t)K * n_max * 4);
         L->off_tr_slot[m] = take((int64_t)K * n_max * 4);
     }
-    for (int i = 0; i < 4; ++i) L->off_grad[i] = take(rows_max * 128 * 4);
+    for (int i = 0; i < 6; ++i) L->off_grad[i] = take(rows_max * 128 * 4);
     {   // transposed weights (K,Cout,Cin) of layers 1..12, back to back (256-byte aligned each)
         int64_t tot = 0;
         for (int i = 1; i < IR_ENC_LAYERS; ++i) { const LayerInfo li = layer_info(i, cin); tot += al((int64_t)li.K * li.cin * li.cout * 4); }
@@ -196,28 +197,38 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
     SideStream* ss = side_stream_for(st);
     IR_CHECK_ARG(ss);
     const float* up = dout;                        // gradient w.r.t. the output of the layer being processed
-    float *S0 = t.grad(0), *S1 = t.grad(1), *S2 = t.grad(2), *S3 = t.grad(3);
-    // one layer: BN backward (-> DY in S1, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`
+    float *S0 = t.grad(0), *S2 = t.grad(2), *S3 = t.grad(3);
+    float* dyb[3] = {t.grad(1), t.grad(4), t.grad(5)};         // ring of dY buffers (+ one range scalar each)
+    bool ring_used[3] = {false, false, false};
+    // one layer: BN backward (-> DY, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`.
+    // wgrad and dgrad both read DY and nothing of each other, and at the large levels the wgrad is the longer of the two:
+    // it goes to the helper stream and is NOT joined per layer — DY lives in a ring of three buffers, so the chain
+    // (BN backward -> dgrad -> next layer) runs up to two layers ahead of the weight gradients, and only a layer that
+    // wants a ring slot back waits for the wgrad that still reads it.
     auto layer_bwd = [&](int i, const float* gin, float* dres, float* dx, const float* add) -> int {
         const LayerInfo li = layer_info(i, p->cin);
         const float* xin = (i == 0) ? f0 : t.out(i - 1);
+        const int slot = i % 3;
+        float* DY = dyb[slot];
+        float* amax = t.absmax() + slot;
         int rr;
+        if (ring_used[slot]) IR_CHECK_CUDA(cudaStreamWaitEvent(st, ss->ring[slot], 0));
         if ((rr = ir_bn_train_bwd(gin, t.out(i), t.y(i), t.ndev(li.lout), t.n[li.lout], li.cout, t.mean(i), t.rstd(i), p->gamma[i], 1,
-                                  t.bn_scratch(), S1, dres, g->dgamma[i], g->dbeta[i], t.absmax(), stream)) != IR_OK) return rr;
-        // wgrad and dgrad both read DY and nothing of each other: wgrad goes to the helper stream and joins before the
-        // next layer's BN backward overwrites S1
+                                  t.bn_scratch(), DY, dres, g->dgamma[i], g->dbeta[i], amax, stream)) != IR_OK) return rr;
         if ((rr = side_fork(ss, st)) != IR_OK) return rr;
-        if ((rr = ir_spconv_wgrad_scaled(xin, li.cin, S1, t.absmax(), li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map),
+        if ((rr = ir_spconv_wgrad_scaled(xin, li.cin, DY, amax, li.cout, li.K, t.in_idx(li.map), t.tr_out(li.map),
                                          t.kcount(li.map), n_max, (p->use_tc >> 2) & 1, g->dweight[i], (ir_stream_t)ss->s)) != IR_OK) return rr;
+        IR_CHECK_CUDA(cudaEventRecord(ss->ring[slot], ss->s));
+        ring_used[slot] = true;
         if (dx) {
             // dgrad = forward pipeline on the transposed rulebook with W^T; `add` (the skip gradient) rides in the
             // reduce epilogue's residual slot.  use_tc bit 1: tcgen05 pair-GEMM with the gathered gradient rows
             // range-scaled by max|dY| (written by the BN backward above); otherwise the exact fp32 SIMT pair-GEMM.
-            if ((rr = ir_spconv_layer_scaled(S1, t.absmax(), li.cout, li.cin, li.K, t.tr_out(li.map), n_max, t.tr_slot(li.map),
+            if ((rr = ir_spconv_layer_scaled(DY, amax, li.cout, li.cin, li.K, t.tr_out(li.map), n_max, t.tr_slot(li.map),
                                              t.kcount(li.map), t.nlvl_dev() + li.lin, t.n[li.lin], t.wt(i, p->cin), (p->use_tc >> 1) & 1,
                                              add, t.T(), dx, stream)) != IR_OK) return rr;
         }
-        return side_join(ss, st);
+        return IR_OK;
     };
     for (int s = 4; s >= 1; --s) {
         const int a = 1 + 3 * (s - 1), b = a + 1, c = a + 2;
@@ -226,5 +237,6 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         if ((r = layer_bwd(a, S3, nullptr, S0, nullptr)) != IR_OK) return r; // d out[prev] -> S0
         up = S0;
     }
-    return layer_bwd(0, up, nullptr, nullptr, nullptr);                       // stem: no input gradient
+    if ((r = layer_bwd(0, up, nullptr, nullptr, nullptr)) != IR_OK) return r;  // stem: no input gradient
+    return side_join(ss, st);                                                 // all weight gradients are final
 }

@@ -198,15 +198,39 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
        const unsigned char* __restrict__ block_skip, const float* __restrict__ hyper) {
     if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }     // per-step scalars of a graph-replayed step
     const float step = lr / bc1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if (block_skip && block_skip[i >> 6]) continue;      // parameter without a gradient this step: torch.optim.Adam skips it
-        const float pv = p[i];
-        const float gv = fmaf(wd, pv, grad_scale * g[i]);
-        const float mv = b1 * m[i] + (1.f - b1) * gv;
-        const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
-        m[i] = mv;
-        v[i] = vv;
-        p[i] = pv - step * mv / (sqrtf(vv) / bc2_sqrt + eps);
+    // 16-byte accesses (a skip byte covers 16 of them), scalar tail for n % 4 elements
+    const long long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        if (block_skip && block_skip[i >> 4]) continue;      // parameter without a gradient this step: torch.optim.Adam skips it
+        const float4 P = p4[i], G = g4[i], M = m4[i], V = v4[i];
+        float pv[4] = {P.x, P.y, P.z, P.w}, mv[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+        const float gg[4] = {G.x, G.y, G.z, G.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float gv = fmaf(wd, pv[u], grad_scale * gg[u]);
+            mv[u] = b1 * mv[u] + (1.f - b1) * gv;
+            vv[u] = b2 * vv[u] + (1.f - b2) * gv * gv;
+            pv[u] = pv[u] - step * mv[u] / (sqrtf(vv[u]) / bc2_sqrt + eps);
+        }
+        m4[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        p4[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            if (block_skip && block_skip[i >> 6]) continue;
+            const float pv = p[i];
+            const float gv = fmaf(wd, pv, grad_scale * g[i]);
+            const float mv = b1 * m[i] + (1.f - b1) * gv;
+            const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+            m[i] = mv;
+            v[i] = vv;
+            p[i] = pv - step * mv / (sqrtf(vv) / bc2_sqrt + eps);
+        }
     }
 }
 
@@ -214,6 +238,8 @@ extern "C" int ir_adam_step(float* params, const float* grads, float* exp_avg, f
                             float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                             float grad_scale, const uint8_t* block_skip, ir_stream_t stream) {
     IR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1);
+    IR_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                   reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0);
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
@@ -237,6 +263,8 @@ extern "C" int ir_adam_step_dev(float* params, const float* grads, float* exp_av
                                 const float* hyper_dev, float beta1, float beta2, float eps, float weight_decay,
                                 float grad_scale, const uint8_t* block_skip, ir_stream_t stream) {
     IR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && hyper_dev);
+    IR_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                   reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0);
     const int grid = ir_min_i(ir_div_up(n, 256 * 4), IR_NUM_SMS * 8);
     k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2, eps,
                                                    weight_decay, 1.f, 1.f, grad_scale, block_skip, hyper_dev);

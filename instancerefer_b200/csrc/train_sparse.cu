@@ -242,96 +242,119 @@ extern "C" int ir_spconv_wgrad_scaled(const float* x, int32_t cin, const float* 
 // ------------------------------------------------------------------ BatchNorm, train mode, (rows, C)
 // Used for spnn.BatchNorm over voxels, nn.BatchNorm1d over samples and nn.BatchNorm2d over NHWC cells
 // (rows = B*H*W).  Two-level deterministic reductions: every CTA writes fp32 partial sums of its row
-// stripe to scratch[part][2*C]; a finalize kernel adds the <= BN_MAX_PARTS partials in fp64.
+// stripe to scratch[part][2*C]; the consuming kernel adds the <= BN_MAX_PARTS partials in fp64 in its prologue.
 // scratch: float[BN_MAX_PARTS * 2 * C] (ir_bn_scratch_floats).
-#define BN_MAX_PARTS (IR_NUM_SMS * 2)
+#define BN_MAX_PARTS 128
 #define BN_ROWS_PER_CTA 32
-static inline int bn_parts(long long n) { return ir_min_i(ir_div_up(n > 0 ? n : 1, BN_ROWS_PER_CTA), BN_MAX_PARTS); }
+// few, fat partial CTAs: every CTA of the consuming kernel re-adds all partials of all channels in its prologue
+static inline int bn_parts(long long n, int C) { return ir_min_i(ir_div_up(n > 0 ? n : 1, BN_ROWS_PER_CTA), C >= 128 ? 64 : BN_MAX_PARTS); }
 extern "C" int64_t ir_bn_scratch_floats(int32_t C) { return (int64_t)BN_MAX_PARTS * 2 * C; }
 
-// mode 0: (sum x, sum x^2);  mode 1 (backward): g = dy*[y>0]; (sum g, sum g*xhat)
+// mode 0: (sum x, sum x^2);  mode 1 (backward): g = dy*[y>0]; (sum g, sum g*xhat).  A thread owns four adjacent
+// channels (16-byte loads); C/4 threads cover a row, the 256/(C/4) thread groups of a CTA stride over its rows.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_bn_partials(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
               const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
-              const float* __restrict__ rstd, int relu, float* __restrict__ scratch) {
+              const float* __restrict__ rstd, int relu, float* __restrict__ scratch, float* __restrict__ absmax_out) {
+    if (absmax_out && blockIdx.x == 0 && threadIdx.x == 0) *absmax_out = 0.f;    // k_bn_bwd_apply (next launch) maxes into it
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    const int tid = threadIdx.x;
-    const int c = tid % C, g = tid / C, G = blockDim.x / C;
-    float mu = 0.f, rs = 1.f;
-    if (MODE == 1) { mu = mean[c]; rs = rstd[c]; }
-    float s0 = 0.f, s1 = 0.f;
+    const int tid = threadIdx.x, C4 = C >> 2;
+    const int c4 = tid % C4, g = tid / C4, G = blockDim.x / C4;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f};
+    if (MODE == 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { mu[u] = mean[c4 * 4 + u]; rs[u] = rstd[c4 * 4 + u]; }
+    }
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     const long long step = (long long)gridDim.x * G;
 #pragma unroll 4
     for (long long r = (long long)blockIdx.x * G + g; r < n; r += step) {
-        const float xv = x[r * C + c];
-        if (MODE == 0) { s0 += xv; s1 = fmaf(xv, xv, s1); }
-        else {
-            float gv = dy[r * C + c];
-            if (relu && !(y[r * C + c] > 0.f)) gv = 0.f;
-            s0 += gv;
-            s1 = fmaf(gv, (xv - mu) * rs, s1);
+        const float4 q = reinterpret_cast<const float4*>(x)[r * C4 + c4];
+        const float xv[4] = {q.x, q.y, q.z, q.w};
+        if (MODE == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s0[u] += xv[u]; s1[u] = fmaf(xv[u], xv[u], s1[u]); }
+        } else {
+            const float4 d = reinterpret_cast<const float4*>(dy)[r * C4 + c4];
+            float gv[4] = {d.x, d.y, d.z, d.w};
+            if (relu) {
+                const float4 yy = reinterpret_cast<const float4*>(y)[r * C4 + c4];
+                if (!(yy.x > 0.f)) gv[0] = 0.f;
+                if (!(yy.y > 0.f)) gv[1] = 0.f;
+                if (!(yy.z > 0.f)) gv[2] = 0.f;
+                if (!(yy.w > 0.f)) gv[3] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s0[u] += gv[u]; s1[u] = fmaf(gv[u], (xv[u] - mu[u]) * rs[u], s1[u]); }
         }
     }
-    __shared__ float sh[2][256];
-    sh[0][tid] = s0; sh[1][tid] = s1;
+    __shared__ float sh[2][4][256];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sh[0][u][tid] = s0[u]; sh[1][u][tid] = s1[u]; }
     __syncthreads();
     if (g == 0) {
-        for (int q = 1; q < G; ++q) { s0 += sh[0][q * C + c]; s1 += sh[1][q * C + c]; }
-        scratch[(long long)blockIdx.x * 2 * C + c] = s0;
-        scratch[(long long)blockIdx.x * 2 * C + C + c] = s1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float a = s0[u], b = s1[u];
+            for (int q = 1; q < G; ++q) { a += sh[0][u][q * C4 + c4]; b += sh[1][u][q * C4 + c4]; }
+            scratch[(long long)blockIdx.x * 2 * C + c4 * 4 + u] = a;
+            scratch[(long long)blockIdx.x * 2 * C + C + c4 * 4 + u] = b;
+        }
     }
 }
 
-// grid = C/32 CTAs of 1024 threads: lane = channel, the 32 warps split the <= 296 partials (<= 10 independent
-// loads each), fp64 accumulation in a fixed order
-#define BN_FIN_THREADS 1024
-static_assert(BN_MAX_PARTS <= 32 * 10, "bn_sum_parts covers 10 partials per warp");
-__device__ __forceinline__ void bn_sum_parts(const float* __restrict__ scratch, int parts, int C, int c, double& s, double& ss) {
-    __shared__ double sh[2][32][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float fa[10], fb[10];
-#pragma unroll
-    for (int q = 0; q < 10; ++q) {
-        const int p = w + 32 * q;
-        const bool ok = c < C && p < parts;
-        fa[q] = ok ? scratch[(long long)p * 2 * C + c] : 0.f;
-        fb[q] = ok ? scratch[(long long)p * 2 * C + C + c] : 0.f;
+// Second level of the reduction, done by EVERY CTA of the consuming (apply) kernel in its prologue instead of by a
+// launch of its own: the <= 64 partials of each channel are added in fp64 in one fixed order (thread group h takes
+// partials h, h+H, ...; the groups are combined in order), so all CTAs hold bit-identical sums.  256 threads, C | 256.
+__device__ __forceinline__ void bn_sum_parts(const float* __restrict__ scratch, int parts, int C, double& s, double& ss) {
+    __shared__ double sh[2][4][256];
+    const int tid = threadIdx.x, C4 = C >> 2, c4 = tid % C4, h = tid / C4, H = 256 / C4;      // 16-byte loads, H >= 4 groups
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int p = h; p < parts; p += H) {
+        const float4 qa = reinterpret_cast<const float4*>(scratch + (long long)p * 2 * C)[c4];
+        const float4 qb = reinterpret_cast<const float4*>(scratch + (long long)p * 2 * C + C)[c4];
+        a[0] += (double)qa.x; a[1] += (double)qa.y; a[2] += (double)qa.z; a[3] += (double)qa.w;
+        b[0] += (double)qb.x; b[1] += (double)qb.y; b[2] += (double)qb.z; b[3] += (double)qb.w;
     }
-    double a = 0.0, b = 0.0;
 #pragma unroll
-    for (int q = 0; q < 10; ++q) { a += fa[q]; b += fb[q]; }
-    sh[0][w][lane] = a; sh[1][w][lane] = b;
+    for (int u = 0; u < 4; ++u) { sh[0][u][tid] = a[u]; sh[1][u][tid] = b[u]; }
     __syncthreads();
     s = 0.0; ss = 0.0;
-    for (int q = 0; q < 32; ++q) { s += sh[0][q][lane]; ss += sh[1][q][lane]; }
+    if (tid < C) {
+        const int u = tid & 3, cc = tid >> 2;                                               // channel tid = 4*cc + u
+        for (int q = 0; q < H; ++q) { s += sh[0][u][q * C4 + cc]; ss += sh[1][u][q * C4 + cc]; }
+    }
 }
 
-__global__ void __launch_bounds__(BN_FIN_THREADS)
-k_bn_finalize(const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
-              int C, float eps, float momentum, float* __restrict__ running_mean,
-              float* __restrict__ running_var, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    double s, ss;
-    bn_sum_parts(scratch, parts, C, c, s, ss);
-    if (c >= C || threadIdx.x >= 32) return;
-    const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    const double inv = n > 0 ? 1.0 / n : 0.0;
-    const double m = s * inv;
-    double var = ss * inv - m * m;
-    if (var < 0) var = 0;
-    mean_out[c] = (float)m;
-    rstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
-    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(n > 1 ? var * n / (n - 1) : var);
-}
-
+// y = relu?((x - mean) * rstd * gamma + beta + resid); prologue: batch statistics from the partials (CTA 0 also
+// publishes mean / rstd for the backward and updates the running statistics)
 __global__ void __launch_bounds__(256)
-k_bn_apply(const float* __restrict__ x, const int* __restrict__ n_dev, int n_host, int C,
-           const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+k_bn_apply(const float* __restrict__ x, const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host,
+           int C, float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+           float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ gamma,
            const float* __restrict__ beta, const float* __restrict__ resid, int relu, float* __restrict__ y) {
+    __shared__ float s_mean[256], s_rstd[256];
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
+    double s, ss;
+    bn_sum_parts(scratch, parts, C, s, ss);
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        const double inv = n > 0 ? 1.0 / n : 0.0;
+        const double m = s * inv;
+        double var = ss * inv - m * m;
+        if (var < 0) var = 0;
+        const float mf = (float)m, rf = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[c] = mf; s_rstd[c] = rf;
+        if (blockIdx.x == 0) {
+            mean_out[c] = mf;
+            rstd_out[c] = rf;
+            if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+            if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(n > 1 ? var * n / (n - 1) : var);
+        }
+    }
+    __syncthreads();
     const long long total4 = (long long)n * C / 4;                 // C is a multiple of 4
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* r4 = reinterpret_cast<const float4*>(resid);
@@ -344,12 +367,14 @@ k_bn_apply(const float* __restrict__ x, const int* __restrict__ n_dev, int n_hos
         if (resid) { const float4 q = r4[i]; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float o = (v[u] - mean[c + u]) * rstd[c + u] * gamma[c + u] + beta[c + u] + r[u];
+            float o = (v[u] - s_mean[c + u]) * s_rstd[c + u] * gamma[c + u] + beta[c + u] + r[u];
             v[u] = relu ? fmaxf(o, 0.f) : o;
         }
         y4[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
+
+static inline int bn_apply_grid(long long n, int C) { return ir_min_i(ir_div_up(n * C, 1024), IR_NUM_SMS * 2); }
 
 extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, int32_t C, const float* gamma,
                                const float* beta, const float* resid, int32_t relu, float eps, float momentum,
@@ -357,36 +382,32 @@ extern "C" int ir_bn_train_fwd(const float* x, const int32_t* n_dev, int32_t n, 
                                float* rstd, float* y, ir_stream_t stream) {
     IR_CHECK_ARG(x && gamma && beta && scratch && mean && rstd && y && n > 0 && C >= 4 && C <= 256 && 256 % C == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    const int parts = bn_parts(n);
-    k_bn_partials<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, n_dev, n, C, nullptr, nullptr, 0, scratch);
+    const int parts = bn_parts(n, C);
+    k_bn_partials<0><<<parts, 256, 0, st>>>(x, nullptr, nullptr, n_dev, n, C, nullptr, nullptr, 0, scratch, nullptr);
     IR_CHECK_LAUNCH();
-    k_bn_finalize<<<ir_div_up(C, 32), BN_FIN_THREADS, 0, st>>>(scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd);
-    IR_CHECK_LAUNCH();
-    k_bn_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(x, n_dev, n, C, mean, rstd, gamma, beta, resid, relu, y);
+    k_bn_apply<<<bn_apply_grid(n, C), 256, 0, st>>>(x, scratch, parts, n_dev, n, C, eps, momentum, running_mean, running_var, mean, rstd,
+                                                    gamma, beta, resid, relu, y);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }
 
 // backward: g = dy * [y > 0] (if relu); dbeta = sum g; dgamma = sum g*xhat;
 //           dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n); dresid = g
-__global__ void __launch_bounds__(BN_FIN_THREADS)
-k_bn_bwd_finalize(const float* __restrict__ scratch, int parts, int C, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, float* __restrict__ absmax_out) {
-    if (absmax_out && blockIdx.x == 0 && threadIdx.x == 0) *absmax_out = 0.f;    // k_bn_bwd_apply (next launch) maxes into it
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    double s, sx;
-    bn_sum_parts(scratch, parts, C, c, s, sx);
-    if (c >= C || threadIdx.x >= 32) return;
-    dbeta[c] = (float)s;
-    dgamma[c] = (float)sx;
-}
-
+// prologue: dgamma / dbeta from the partials (published by CTA 0)
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
-               const int* __restrict__ n_dev, int n_host, int C, const float* __restrict__ mean,
-               const float* __restrict__ rstd, const float* __restrict__ gamma, int relu,
-               const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx,
+               const float* __restrict__ scratch, int parts, const int* __restrict__ n_dev, int n_host, int C,
+               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma, int relu,
+               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
                float* __restrict__ dresid, float* __restrict__ absmax_out) {
+    __shared__ float s_dg[256], s_db[256];
+    double s, sx;
+    bn_sum_parts(scratch, parts, C, s, sx);
+    if (threadIdx.x < C) {
+        s_db[threadIdx.x] = (float)s; s_dg[threadIdx.x] = (float)sx;
+        if (blockIdx.x == 0) { dbeta[threadIdx.x] = (float)s; dgamma[threadIdx.x] = (float)sx; }
+    }
+    __syncthreads();
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const float inv = n > 0 ? 1.f / n : 0.f;
     const long long total4 = (long long)n * C / 4;
@@ -408,7 +429,7 @@ k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float xh = (xv[u] - mean[c + u]) * rstd[c + u];
-            o[u] = gamma[c + u] * rstd[c + u] * (g[u] - dbeta[c + u] * inv - xh * dgamma[c + u] * inv);
+            o[u] = gamma[c + u] * rstd[c + u] * (g[u] - s_db[c + u] * inv - xh * s_dg[c + u] * inv);
             amax = fmaxf(amax, fabsf(o[u]));
         }
         reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -427,13 +448,11 @@ extern "C" int ir_bn_train_bwd(const float* dy, const float* y, const float* x, 
     IR_CHECK_ARG(dy && x && mean && rstd && gamma && scratch && dx && dgamma && dbeta && n > 0 && C >= 4 && C <= 256 && 256 % C == 0);
     IR_CHECK_ARG(!relu || y);
     cudaStream_t st = (cudaStream_t)stream;
-    const int parts = bn_parts(n);
-    k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch);
+    const int parts = bn_parts(n, C);
+    k_bn_partials<1><<<parts, 256, 0, st>>>(x, dy, y, n_dev, n, C, mean, rstd, relu, scratch, absmax_out);
     IR_CHECK_LAUNCH();
-    k_bn_bwd_finalize<<<ir_div_up(C, 32), BN_FIN_THREADS, 0, st>>>(scratch, parts, C, dgamma, dbeta, absmax_out);
-    IR_CHECK_LAUNCH();
-    k_bn_bwd_apply<<<ir_min_i(ir_div_up((long long)n * C, 1024), IR_NUM_SMS * 8), 256, 0, st>>>(
-        dy, y, x, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta, dx, dresid, absmax_out);
+    k_bn_bwd_apply<<<bn_apply_grid(n, C), 256, 0, st>>>(dy, y, x, scratch, parts, n_dev, n, C, mean, rstd, gamma, relu, dgamma, dbeta,
+                                                        dx, dresid, absmax_out);
     IR_CHECK_LAUNCH();
     return IR_OK;
 }

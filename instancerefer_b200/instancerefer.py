@@ -94,29 +94,40 @@ class InstanceRefer(nn.Module):
         for s_ in (sa, ss, sr):
             s_.wait_stream(main)
         ev_obj, ev_lang = torch.cuda.Event(), torch.cuda.Event()
+        ops.stamp('fwd:start')
         with torch.cuda.stream(sa):
             ws_a = T.prepare_attribute_maps(self, pack)
+            ops.stamp('fwd:attr:maps')
             T.attribute_encode_train(self.attribute, data_dict, pack, (ws_a, T.EncoderGraph(ws_a, [ws_a.n_max] * 5)))
             ev_obj.record(sa)
+            ops.stamp('fwd:attr:encoded')
         with torch.cuda.stream(ss):
             ws_s, F0, C0 = T.prepare_scene_maps(self, data_dict, dev)
+            ops.stamp('fwd:scene:maps')
             T.scene_encode_train(self.scene, data_dict, pack, (ws_s, T.EncoderGraph(ws_s, [ws_s.n_max] * 5), F0, C0))
+            ops.stamp('fwd:scene:encoded')
         with torch.cuda.stream(sr):
             T.relation_encode_train(self.relation, data_dict, pack)
+            ops.stamp('fwd:rel:encoded')
         data_dict = T.lang_forward_train(self.lang, data_dict)
         ev_lang.record(main)
+        ops.stamp('fwd:lang:done')
         with torch.cuda.stream(sa):
             sa.wait_event(ev_lang)
             T.attribute_match_train(self.attribute, data_dict, pack)
+            ops.stamp('fwd:attr:matched')
         with torch.cuda.stream(sr):
             sr.wait_event(ev_lang)
             T.relation_match_train(self.relation, data_dict, pack)
+            ops.stamp('fwd:rel:matched')
         with torch.cuda.stream(ss):
             ss.wait_event(ev_lang)
             ss.wait_event(ev_obj)
             T.scene_match_train(self.scene, data_dict, pack)
+            ops.stamp('fwd:scene:matched')
         for s_ in (sa, ss, sr):
             main.wait_stream(s_)
+        ops.stamp('fwd:joined')
         return data_dict
 
     def forward(self, data_dict):

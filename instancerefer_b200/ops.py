@@ -389,7 +389,7 @@ def spconv_wgrad(x, dy, in_idx, out_idx, count, dy_absmax=None, use_tc=False):
     return dW
 
 
-BN_PARTS = 148 * 2          # ir_bn_scratch_floats(C) = BN_PARTS * 2 * C
+BN_PARTS = 128              # ir_bn_scratch_floats(C) = BN_PARTS * 2 * C
 
 
 def bn_train_fwd(x, gamma, beta, resid, relu, eps, momentum, running_mean, running_var):

@@ -199,8 +199,11 @@ class GraphedTrainStep:
         d[KEY] = pack
         d[BOXES] = s.boxes
         d = get_loss(self.model(d), self.config)
+        ops.stamp('loss')
         d['loss'].backward()
+        ops.stamp('bwd:joined')
         self.opt.step()
+        ops.stamp('adam')
         d['_ir_result'] = torch.stack([d[k].detach().reshape(-1)[0].float() for k in RESULT_KEYS])
         return d
 

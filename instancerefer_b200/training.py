@@ -279,8 +279,10 @@ class EncoderTrainGraphed(Function):
     @staticmethod
     def backward(ctx, dout):
         st = ctx.st
+        ops.stamp(f'bwd:enc{st.P.cin}:start')
         st.dout[:ctx.n4].copy_(dout)
         EncoderTrainGraphed._run(st, 'bwd', ctx.ws)
+        ops.stamp(f'bwd:enc{st.P.cin}:end')
         # one copy of the static gradient buffer per backward (a single D2D kernel), returned as views: autograd
         # adopts them as .grad without per-parameter kernels, and nothing the caller holds aliases the buffer the
         # next replay overwrites (gradient accumulation over several backwards stays correct)
@@ -664,7 +666,9 @@ class EdgeConvTrain(Function):
         flat = torch.empty(o, dtype=torch.float32, device=arena.device)
         G = _lib.EdgeConvGrads()
         G.dww1, G.dbw1, G.dww2, G.dbw2, G.dwm1, G.dbm1, G.dwm2, G.dbm2 = (flat.data_ptr() + 4 * a for a in offs)
+        ops.stamp('bwd:edgeconv:start')
         _lib.call("ir_edgeconv_train_bwd", C.byref(P), ops._p(arena), ops._p(dout.contiguous(), torch.float32), C.byref(G), ops._stream())
+        ops.stamp('bwd:edgeconv:end')
         return (None, None, None, None, None, *(flat[a:a + n].view(sh) for a, n, sh in zip(offs, numel, shapes)))
 
 
@@ -704,6 +708,7 @@ class SceneTailTrain(Function):
         import ctypes as C
         from . import _lib
         P, keep, arena, f4, coords, n_dev, shapes = ctx.state
+        ops.stamp('bwd:scene_tail:start')
         numel = [int(torch.Size(sh).numel()) for sh in shapes]
         offs, o = [], 0
         for n in numel:
@@ -715,6 +720,7 @@ class SceneTailTrain(Function):
         df4 = torch.empty_like(f4)
         _lib.call("ir_scene_tail_train_bwd", C.byref(P), ops._p(f4), ops._p(coords), ops._p(n_dev), ops._p(arena),
                   ops._p(dout.contiguous(), torch.float32), ops._p(df4), C.byref(G), ops._stream())
+        ops.stamp('bwd:scene_tail:end')
         return (df4, None, None, None, None, None, None, None, *(flat[a:a + n].view(sh) for a, n, sh in zip(offs, numel, shapes)))
 
 
@@ -785,6 +791,7 @@ class LangTrain(Function):
         import ctypes as C
         from . import _lib
         P, keep, arena, x, lengths, shapes = ctx.state
+        ops.stamp('bwd:lang:start')
         (pooled,) = ctx.saved_tensors
         dev = x.device
         H3 = 3 * 128
@@ -827,6 +834,7 @@ class LangTrain(Function):
         _lib.call("ir_lang_train_bwd", C.byref(P), ops._p(x), ops._p(lengths, torch.int64), ops._p(arena), ops._p(pooled),
                   ops._p(dpooled.contiguous(), torch.float32), ops._p(ds), C.byref(G), ops._stream())
         grads = [flat[offs[i]:offs[i] + numel[i]].view(shapes[i]) for i in order]
+        ops.stamp('bwd:lang:end')
         return (None, None, None, None, None, *grads)
 
 

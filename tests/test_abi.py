@@ -69,7 +69,7 @@ def test_struct_sizes_match_the_library(lib_built):
     assert _lib.call('ir_lang_train_view', ctypes.byref(P), ctypes.byref(of), ctypes.byref(oa)) == 0
     assert 0 < of.value < oa.value < a
     assert _lib.load().ir_mlp_head_arena_bytes(64, 256) > 64 * 256 * 4 * 5
-    assert _lib.load().ir_bn_scratch_floats(128) == 148 * 2 * 2 * 128
+    assert _lib.load().ir_bn_scratch_floats(128) == 128 * 2 * 128
     assert _lib.load().ir_scene_tail_arena_bytes(200, 4) > 4 * 299 * 1152 * 4 * 2
     assert ctypes.sizeof(_lib.SceneTail) == 8 + 8 + 16 + 8 + 13 * 8 and ctypes.sizeof(_lib.SceneTailGrads) == 72
 
