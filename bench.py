@@ -202,7 +202,7 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
     cfg = synthetic.SyntheticConfig()                          # dataset-config stand-in (labels -> GT box)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     hosts = []
-    for b in train_batches(rank):
+    for b in train_batches(int(os.environ.get('IR_BATCH_RANK', rank))):     # IR_BATCH_RANK: another rank's batches on one GPU
         h = {k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
         hosts.append(h)
     h2d = sum(v.numel() * v.element_size() for v in hosts[0].values() if torch.is_tensor(v))

@@ -420,6 +420,14 @@ int ir_encoder_train_forward(const ir_encoder_train_params* p, const float* feat
 int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
                               const int32_t* n_lvl, void* arena, const float* dout,
                               const ir_encoder_train_grads* g, ir_stream_t stream);
+/* Stages stage_hi..stage_lo of the same pass (4..1 = residual stages from the output down, 0 = stem; (4,0) is the whole
+ * backward): the deep stages hold 2/3 of an encoder's parameters and finish long before the large shallow levels, so a
+ * data-parallel caller runs (4,3), starts the all-reduce of those gradients (lib/solver.py:200-205 under DDP), then (2,0).
+ * dout is read only when stage_hi = 4; the gradient between two calls stays in the arena.                          */
+int ir_encoder_train_backward_range(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                                    const int32_t* n_lvl, void* arena, const float* dout,
+                                    const ir_encoder_train_grads* g, int32_t stage_hi, int32_t stage_lo,
+                                    ir_stream_t stream);
 
 /* ------------------------------------------------------------------ dense training-step operators
  * (nn.Linear / LayerNorm / Dropout / F.normalize / cosine heads, Conv2d as im2col + GEMM, and the

@@ -152,6 +152,7 @@ SIGNATURES = {
     "ir_encoder_train_layout": (i32, [i64, p, i32, C.POINTER(EncoderTrainLayout)]),
     "ir_encoder_train_forward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p]),
     "ir_encoder_train_backward": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p, C.POINTER(EncoderTrainGrads), p]),
+    "ir_encoder_train_backward_range": (i32, [C.POINTER(EncoderTrainParams), p, p, i64, p, p, p, C.POINTER(EncoderTrainGrads), i32, i32, p]),
     "ir_gemm": (i32, [i32, i32, i32, p, i32, i32, p, i32, i32, p, i32, p, i32, i32, p]),
     "ir_colsum": (i32, [p, i32, i32, p, p]),
     "ir_relu_bwd": (i32, [p, p, i64, p, p]),

@@ -187,17 +187,28 @@ extern "C" int ir_encoder_train_forward(const ir_encoder_train_params* p, const 
 extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
                                          const int32_t* n_lvl, void* arena, const float* dout,
                                          const ir_encoder_train_grads* g, ir_stream_t stream) {
+    return ir_encoder_train_backward_range(p, feats0, ws, n_max, n_lvl, arena, dout, g, 4, 0, stream);
+}
+
+// Stages stage_hi .. stage_lo of the backward (4 .. 1 = the residual stages from the output down, 0 = the stem).  A
+// caller that wants the gradients of the deep stages early — they hold 2/3 of an encoder's parameters and are final long
+// before the large shallow levels are done — splits the pass in two calls on the same arena (the gradient between them
+// stays in the arena) and starts their all-reduce in between.
+extern "C" int ir_encoder_train_backward_range(const ir_encoder_train_params* p, const float* feats0, void* ws, int64_t n_max,
+                                               const int32_t* n_lvl, void* arena, const float* dout,
+                                               const ir_encoder_train_grads* g, int32_t stage_hi, int32_t stage_lo,
+                                               ir_stream_t stream) {
     Tr t;
     int r;
     if ((r = tr_open(p, ws, n_max, n_lvl, arena, &t)) != IR_OK) return r;
-    IR_CHECK_ARG(dout && g);
+    IR_CHECK_ARG(g && stage_hi <= 4 && stage_lo >= 0 && stage_lo <= stage_hi && (dout || stage_hi < 4));
     cudaStream_t st = (cudaStream_t)stream;
     const float* f0 = feats0 ? feats0 : (const float*)(t.ws + t.W.off_feat0);
     // (transposed rulebooks and W^T were built by ir_encoder_train_forward on the same arena)
     SideStream* ss = side_stream_for(st);
     IR_CHECK_ARG(ss);
-    const float* up = dout;                        // gradient w.r.t. the output of the layer being processed
     float *S0 = t.grad(0), *S2 = t.grad(2), *S3 = t.grad(3);
+    const float* up = stage_hi == 4 ? dout : S0;   // gradient w.r.t. the output of the layer being processed
     float* dyb[3] = {t.grad(1), t.grad(4), t.grad(5)};         // ring of dY buffers (+ one range scalar each)
     bool ring_used[3] = {false, false, false};
     // one layer: BN backward (-> DY, skip gradient in `dres`), wgrad, optional dgrad (+ `add`) into `dx`.
@@ -230,13 +241,13 @@ extern "C" int ir_encoder_train_backward(const ir_encoder_train_params* p, const
         }
         return IR_OK;
     };
-    for (int s = 4; s >= 1; --s) {
+    for (int s = stage_hi; s >= 1 && s >= stage_lo; --s) {
         const int a = 1 + 3 * (s - 1), b = a + 1, c = a + 2;
         if ((r = layer_bwd(c, up, S2, S3, nullptr)) != IR_OK) return r;      // skip gradient -> S2, d out[b] -> S3
         if ((r = layer_bwd(b, S3, nullptr, S3, S2)) != IR_OK) return r;      // d out[a] = dgrad + skip -> S3 (S3 was consumed by BN bwd)
         if ((r = layer_bwd(a, S3, nullptr, S0, nullptr)) != IR_OK) return r; // d out[prev] -> S0
         up = S0;
     }
-    if ((r = layer_bwd(0, up, nullptr, nullptr, nullptr)) != IR_OK) return r;  // stem: no input gradient
+    if (stage_lo == 0 && (r = layer_bwd(0, up, nullptr, nullptr, nullptr)) != IR_OK) return r;  // stem: no input gradient
     return side_join(ss, st);                                                 // all weight gradients are final
 }

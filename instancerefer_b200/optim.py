@@ -19,7 +19,18 @@ import torch
 from . import ops
 
 ALIGN = 64          # floats (256 B): keeps every parameter 16-byte aligned for TMA bulk copies
-BUCKET_FLOATS = 1 << 21   # >= 8 MB of gradients per all-reduce bucket (8.02 M floats -> 4 buckets)
+BUCKET_FLOATS = 1 << 21   # >= 8 MB of gradients per all-reduce bucket when only sizes are known (8.02 M floats -> 4 buckets)
+
+
+def _availability_key(name):
+    """Parameters whose gradients become final together during the backward share a key: a sub-module of the model, with
+    each sparse encoder (``<module>.net``) cut into its deep stages (stage3/4: 2/3 of its parameters, finished first)
+    and its shallow ones.  Buckets cut along these keys are complete — and their all-reduce in flight — as early as the
+    backward allows, instead of waiting for the last gradient of a size-based range that straddles two branches."""
+    parts = name.split('.')
+    if len(parts) > 2 and parts[1] == 'net':
+        return parts[0], 'net.hi' if parts[2] in ('stage3', 'stage4') else 'net.lo'
+    return parts[0], ''
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -33,7 +44,9 @@ class FlatAdam(torch.optim.Optimizer):
     moment decay) and own no optimizer state."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        names = None
         if isinstance(params, torch.nn.Module):
+            names = [n for n, p in params.named_parameters() if p.requires_grad]
             params = params.parameters()
         params = list(params)
         if params and isinstance(params[0], dict):
@@ -71,24 +84,40 @@ class FlatAdam(torch.optim.Optimizer):
             self.world = torch.distributed.get_world_size(process_group)
         # --- gradient buckets (contiguous parameter ranges of >= BUCKET_FLOATS) for the overlapped all-reduce
         self.buckets, lo = [], 0
-        for i in range(len(self.params)):
-            end = ofs[i + 1] if i + 1 < len(ofs) else total
-            if end - ofs[lo] >= BUCKET_FLOATS or i + 1 == len(self.params):
-                self.buckets.append((lo, i + 1, ofs[lo], end))          # params [lo, i+1), floats [ofs[lo], end)
-                lo = i + 1
+        end_of = lambda i: ofs[i + 1] if i + 1 < len(ofs) else total
+        if names is not None and len(names) == len(self.params):
+            # cut where the availability key changes; runs of small groups (< 1/8 bucket) are merged
+            small = BUCKET_FLOATS // 8
+            for i in range(len(self.params)):
+                if i + 1 == len(self.params) or _availability_key(names[i + 1]) != _availability_key(names[i]):
+                    new = (lo, i + 1, ofs[lo], end_of(i))
+                    if self.buckets and new[3] - new[2] < small and self.buckets[-1][3] - self.buckets[-1][2] < small:
+                        new = (self.buckets[-1][0], i + 1, self.buckets[-1][2], end_of(i))
+                        self.buckets.pop()
+                    self.buckets.append(new)                                # params [lo, i+1), floats [ofs[lo], end)
+                    lo = i + 1
+        else:
+            for i in range(len(self.params)):
+                if end_of(i) - ofs[lo] >= BUCKET_FLOATS or i + 1 == len(self.params):
+                    self.buckets.append((lo, i + 1, ofs[lo], end_of(i)))
+                    lo = i + 1
         self.n_buckets = len(self.buckets)
         self._bucket_of = [b for b, (l, h, _, _) in enumerate(self.buckets) for _ in range(h - l)]
         self._fired = [0] * self.n_buckets          # gradients seen in this backward, per bucket
         self._expect = [0] * self.n_buckets         # ... in the previous step (0 = unknown: no early launch)
         self._work = [None] * self.n_buckets        # in-flight all-reduce of the bucket (launched from the hook)
         self._packed = [False] * self.n_buckets
+        self._early = set()                         # parameters whose gradient was handed over by early_grads()
+        self._index = {id(p): i for i, p in enumerate(self.params)}
         self.overlap = self.world > 1               # launch bucket all-reduces from the backward hooks
         self._sync = True
         self._hyper_dev = self._hyper_host = None   # per-step scalars on the device (graph-replayed steps)
         self._staged = False
         if self.overlap:
             for i, p in enumerate(self.params):
-                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+            from . import training
+            training.EARLY_GRAD_HOOK = self.early_grads
 
     # hyper-parameters live in the param group (what a scheduler mutates); attribute access for convenience
     lr = property(lambda self: self.param_groups[0]['lr'], lambda self, v: self.param_groups[0].__setitem__('lr', v))
@@ -103,14 +132,41 @@ class FlatAdam(torch.optim.Optimizer):
             p.grad = None
         self._fired = [0] * self.n_buckets
         self._packed = [False] * self.n_buckets
+        self._early = set()
 
     # --- overlapped bucket all-reduce -------------------------------------------------------------------
-    def _make_hook(self, b):
+    def _make_hook(self, i):
+        b = self._bucket_of[i]
+
         def hook(_p):
+            if i in self._early:                      # already counted (and copied) by early_grads
+                return
             self._fired[b] += 1
             if self._sync and self._fired[b] == self._expect[b] and self._work[b] is None and not self._packed[b]:
                 self._launch(b)
         return hook
+
+    def early_grads(self, params, grads):
+        """Gradients that are final before the autograd node computing them returns (the deep stages of an encoder,
+        training.EncoderTrainGraphed): copied into the flat buffer now, counted towards their buckets, and a bucket
+        they complete starts its all-reduce at once.  The node still returns the same gradients to autograd later;
+        the hook and the packing then skip these parameters.  -> False when nothing is reduced early (no_sync,
+        single process): the caller has nothing else to do either way."""
+        if not (self.overlap and self._sync):
+            return False
+        idx = [self._index[id(p)] for p in params]
+        torch._foreach_copy_([self.grad_views[i] for i in idx], list(grads))
+        touched = []
+        for i in idx:
+            self._early.add(i)
+            b = self._bucket_of[i]
+            self._fired[b] += 1
+            if b not in touched:
+                touched.append(b)
+        for b in touched:
+            if self._fired[b] == self._expect[b] and self._work[b] is None and not self._packed[b]:
+                self._launch(b)
+        return True
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -129,6 +185,8 @@ class FlatAdam(torch.optim.Optimizer):
         src, dst, zero, missing = [], [], [], []
         for i in range(lo, hi):
             v, p = self.grad_views[i], self.params[i]
+            if i in self._early:                      # already in the flat buffer; autograd still owes p.grad (the same
+                continue                              # values): pointing it at the view now would make that an in-place add
             if p.grad is None:
                 zero.append(v)
                 missing.append(i)
@@ -160,7 +218,9 @@ class FlatAdam(torch.optim.Optimizer):
                 missing += self._pack(b)
             else:
                 lo, hi, _, _ = self.buckets[b]
-                missing += [i for i in range(lo, hi) if self.params[i].grad is None]
+                missing += [i for i in range(lo, hi) if self.params[i].grad is None and i not in self._early]
+        for i in self._early:
+            self.params[i].grad = self.grad_views[i]
         return missing
 
     def allreduce(self):

@@ -164,6 +164,11 @@ class EncoderTrain(Function):
         return (None, None, None, *grads)
 
 
+# Set by optim.FlatAdam when it overlaps the data-parallel all-reduce with the backward: callable(params, grads) -> bool,
+# handed gradients that are final although the autograd node producing them has not returned yet.
+EARLY_GRAD_HOOK = None
+
+
 class _EncoderGraphState:
     """Static buffers + captured CUDA graphs of one encoder at one workspace capacity (n_max bucket)."""
 
@@ -239,9 +244,12 @@ class EncoderTrainGraphed(Function):
             f0 = ops._p(st.f0)
             if which == 'fwd':
                 _lib.call("ir_encoder_train_forward", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena), ops._stream())
-            else:
+            elif which == 'bwd':
                 _lib.call("ir_encoder_train_backward", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena),
                           ops._p(st.dout), C.byref(st.Gr), ops._stream())
+            else:                                            # ('range', stage_hi, stage_lo): whole-step capture only
+                _lib.call("ir_encoder_train_backward_range", C.byref(st.P), f0, ws.ptr, ws.n_max, None, ops._p(st.arena),
+                          ops._p(st.dout), C.byref(st.Gr), which[1], which[2], ops._stream())
         if torch.cuda.is_current_stream_capturing():          # whole-step capture (train_graph.GraphedTrainStep)
             launch()
             return
@@ -273,7 +281,7 @@ class EncoderTrainGraphed(Function):
             st.f0[:feats0.shape[0]].copy_(feats0)
         EncoderTrainGraphed._run(st, 'fwd', ws)
         torch._foreach_add_([bn.num_batches_tracked for _, bn in net._layers()], 1)
-        ctx.st, ctx.ws, ctx.n4 = st, ws, G.n[4]
+        ctx.st, ctx.ws, ctx.n4, ctx.params = st, ws, G.n[4], params
         return st.f4[:G.n[4]]
 
     @staticmethod
@@ -281,7 +289,15 @@ class EncoderTrainGraphed(Function):
         st = ctx.st
         ops.stamp(f'bwd:enc{st.P.cin}:start')
         st.dout[:ctx.n4].copy_(dout)
-        EncoderTrainGraphed._run(st, 'bwd', ctx.ws)
+        if EARLY_GRAD_HOOK is not None and torch.cuda.is_current_stream_capturing():
+            # data parallel, captured step: stages 4..3 first (layers 7..12, 2/3 of the parameters, small levels), hand
+            # their gradients to the optimiser so that their all-reduce runs beside the large shallow levels
+            EncoderTrainGraphed._run(st, ('range', 4, 3), ctx.ws)
+            lo = 3 * 7
+            EARLY_GRAD_HOOK(ctx.params[lo:], [st.gflat[o:o + n].view(sh) for o, n, sh in st.gslices[lo:]])
+            EncoderTrainGraphed._run(st, ('range', 2, 0), ctx.ws)
+        else:
+            EncoderTrainGraphed._run(st, 'bwd', ctx.ws)
         ops.stamp(f'bwd:enc{st.P.cin}:end')
         # one copy of the static gradient buffer per backward (a single D2D kernel), returned as views: autograd
         # adopts them as .grad without per-parameter kernels, and nothing the caller holds aliases the buffer the

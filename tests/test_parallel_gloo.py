@@ -127,10 +127,24 @@ def _grad_worker(rank, world, port, q):
     want = [sum(local2[r][i] for r in range(world)) for i in range(len(local2[0]))]
     ok &= early == opt.n_buckets and miss == [] and all(w is None for w in opt._work)
     ok &= all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6) for p, w in zip(model.parameters(), want))
+    # third backward: the last layer's gradients are handed over EARLY (as the encoder's backward node does for its deep
+    # stages): their bucket is in flight before backward() is even called, the later hooks skip them, the sums agree
+    opt.zero_grad()
+    out = model(x2).square().sum()
+    last = [model[2].weight, model[2].bias]
+    ok &= opt.early_grads(last, list(torch.autograd.grad(out, last, retain_graph=True)))
+    ok &= opt._work[opt._bucket_of[opt._index[id(last[0])]]] is not None and sum(w is not None for w in opt._work) == 1
+    out.backward()
+    ok &= sum(w is not None for w in opt._work) == opt.n_buckets
+    miss = opt.gather_grads()
+    opt.allreduce()
+    ok &= miss == [] and all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6) for p, w in zip(model.parameters(), want))
+    ok &= all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(opt.params, opt.grad_views))
     with opt.no_sync():                                            # accumulation: nothing is reduced before step
         opt.zero_grad()
         model(x2).square().sum().backward()
         ok &= all(w is None for w in opt._work)
+        ok &= opt.early_grads(last, [torch.zeros_like(t) for t in last]) is False
     try:
         opt.step()
         refused = False

@@ -231,3 +231,27 @@ def test_eval_after_flat_adam_steps_uses_the_updated_weights(lib_built, state_di
     for k in ('attribute_scores', 'relation_scores', 'scene_scores'):
         assert float((g1[k] - want[k].cpu()).abs().max()) < 1e-5, k
         assert float((g1[k] - g0[k]).abs().max()) > 1e-4, k
+
+
+def test_flat_adam_buckets_follow_gradient_availability(args):
+    """All-reduce buckets of the data-parallel step are cut where gradients become final together: per sub-module,
+    each sparse encoder split into deep (stage3/4, finished first, handed over early) and shallow stages; a
+    plain parameter list falls back to size-based ranges.  Buckets tile the flat buffer without gaps."""
+    from instancerefer_b200.instancerefer import InstanceRefer
+    from instancerefer_b200.optim import FlatAdam
+    model = InstanceRefer(7, args)
+    names = [n for n, _ in model.named_parameters()]
+    opt = FlatAdam(model, lr=1e-3)
+    spans = [(names[lo], names[hi - 1]) for lo, hi, _, _ in opt.buckets]
+    assert opt.buckets[0][2] == 0 and opt.buckets[-1][3] == opt.numel
+    assert all(a[3] == b[2] and a[1] == b[0] for a, b in zip(opt.buckets, opt.buckets[1:]))
+    firsts = [s[0] for s in spans]
+    assert firsts[0].startswith('lang.') and any(f.startswith('attribute.net.stem') for f in firsts)
+    for mod in ('attribute', 'scene'):
+        b = [i for i, (lo, hi, _, _) in enumerate(opt.buckets) if names[lo].startswith(f'{mod}.net.stage3.0')]
+        assert len(b) == 1, spans
+        lo, hi, _, _ = opt.buckets[b[0]]
+        assert all(n.startswith((f'{mod}.net.stage3', f'{mod}.net.stage4')) for n in names[lo:hi]) and hi - lo == 18
+    assert 5 <= opt.n_buckets <= 8, spans
+    by_size = FlatAdam(list(InstanceRefer(7, args).parameters()), lr=1e-3)
+    assert by_size.n_buckets == 4 and by_size.buckets[-1][3] == by_size.numel
