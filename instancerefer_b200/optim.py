@@ -178,11 +178,11 @@ class FlatAdam(torch.optim.Optimizer):
         finally:
             self._sync = old
 
-    def _pack(self, b):
-        """Copy bucket b's gradients of this backward into the flat buffer (missing ones as zeros), point .grad at
-        the views.  -> indices of its parameters without a gradient."""
+    def _collect(self, b, src, dst, zero):
+        """Bucket b's share of a pack: appends (gradient -> flat view) copy pairs and the views of parameters without a
+        gradient (packed as zeros), points .grad at the views.  -> indices of its parameters without a gradient."""
         lo, hi, _, _ = self.buckets[b]
-        src, dst, zero, missing = [], [], [], []
+        missing = []
         for i in range(lo, hi):
             v, p = self.grad_views[i], self.params[i]
             if i in self._early:                      # already in the flat buffer; autograd still owes p.grad (the same
@@ -194,11 +194,22 @@ class FlatAdam(torch.optim.Optimizer):
                 dst.append(v)
                 src.append(p.grad)
             p.grad = v
+        self._packed[b] = True
+        return missing
+
+    @staticmethod
+    def _flush(src, dst, zero):
         if zero:
             torch._foreach_zero_(zero)
         if src:
             torch._foreach_copy_(dst, src)
-        self._packed[b] = True
+
+    def _pack(self, b):
+        """Copy bucket b's gradients of this backward into the flat buffer (missing ones as zeros), point .grad at
+        the views.  -> indices of its parameters without a gradient."""
+        src, dst, zero = [], [], []
+        missing = self._collect(b, src, dst, zero)
+        self._flush(src, dst, zero)
         return missing
 
     def _launch(self, b):
@@ -212,13 +223,14 @@ class FlatAdam(torch.optim.Optimizer):
         """Pack the per-parameter gradients of this backward into the flat buffer (one multi-tensor
         copy; parameters that received no gradient contribute zeros and are masked out of the update)
         and point .grad at the views.  -> indices of the parameters without a gradient."""
-        missing = []
+        missing, src, dst, zero = [], [], [], []
         for b in range(self.n_buckets):
             if self._work[b] is None:                 # buckets already in flight were packed by their hook
-                missing += self._pack(b)
+                missing += self._collect(b, src, dst, zero)
             else:
                 lo, hi, _, _ = self.buckets[b]
                 missing += [i for i in range(lo, hi) if self.params[i].grad is None and i not in self._early]
+        self._flush(src, dst, zero)                   # one multi-tensor copy for everything still unpacked
         for i in self._early:
             self.params[i].grad = self.grad_views[i]
         return missing
