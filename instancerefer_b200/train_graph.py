@@ -108,6 +108,9 @@ class GraphedTrainStep:
         d['loss'].backward()
         self.opt.step()
         self.eager_steps += 1
+        # like a replayed step: results without autograd history (a caller holding the dict would otherwise keep this
+        # iteration's AccumulateGrad nodes — pinned to this stream — alive into the capture of the next one)
+        d = {k: (v.detach() if torch.is_tensor(v) else [t.detach() for t in v] if k == 'cluster_label' else v) for k, v in d.items()}
         d['result'] = self._result(d)
         return d
 
