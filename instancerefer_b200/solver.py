@@ -29,7 +29,7 @@ METRICS = ('loss', 'ref_loss', 'lang_loss', 'seg_loss', 'lang_acc', 'ref_acc', '
 
 class Solver:
     def __init__(self, model, config, dataloader, optimizer, stamp, val_step=10, lr_decay_step=None,
-                 lr_decay_rate=None, bn_decay_step=None, bn_decay_rate=None, output_root='outputs'):
+                 lr_decay_rate=None, bn_decay_step=None, bn_decay_rate=None, output_root='outputs', graph_train=False):
         self.model, self.config, self.dataloader, self.optimizer = model, config, dataloader, optimizer
         self.stamp, self.val_step = stamp, val_step
         self.lr_decay_step, self.lr_decay_rate = lr_decay_step, lr_decay_rate
@@ -43,6 +43,12 @@ class Solver:
         if self.rank == 0:
             os.makedirs(self.root, exist_ok=True)
         self.history = {'train': [], 'val': []}
+        # graph_train: training iterations whose batch shape repeats are replayed from one CUDA graph
+        # (train_graph.GraphedTrainStep; FlatAdam only); others run the ordinary eager iteration below
+        self._graph_step = None
+        if graph_train:
+            from .train_graph import GraphedTrainStep
+            self._graph_step = GraphedTrainStep(model, optimizer, config)
         self._global_iter_id = 0
         self.start_epoch = 0
 
@@ -88,6 +94,15 @@ class Solver:
 
     def _step(self, data_dict, phase):
         train = phase == 'train'
+        if train and self._graph_step is not None:
+            # _forward, _compute_loss, _backward (lib/solver.py:195-205) as one replayed graph over the HOST batch
+            data_dict = self._graph_step(data_dict)
+            with torch.no_grad():
+                data_dict = get_eval(data_dict, self.config)
+            rec = {k: float(data_dict[k].detach()) for k in ('loss', 'ref_loss', 'lang_loss', 'seg_loss', 'lang_acc', 'seg_acc')}
+            rec['ref_acc'] = float(np.mean(data_dict['ref_acc']))
+            rec['ref_iou'] = list(data_dict['ref_iou'])
+            return rec
         data_dict = self._to_device(data_dict)
         with torch.set_grad_enabled(train):
             if train:

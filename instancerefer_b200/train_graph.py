@@ -70,6 +70,7 @@ class GraphedTrainStep:
         self.profile = None              # set to a list: (host seconds of staging, event before, event after the replay)
         self.h2d_bytes = 0
         self._seed_dev = None
+        self._bns = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
         # Everything — eager first sights, staging, capture, replay — runs on ONE private stream: autograd pins each
         # parameter's AccumulateGrad node to the stream of the iteration that created it, and a node living on the
         # legacy default stream (which cannot capture) would invalidate the capture of the backward.
@@ -93,6 +94,7 @@ class GraphedTrainStep:
         pts0 = batch['instance_points'][0][0]
         return (tuple(batch['lang_feat'].shape), int(batch['lang_len'].max()), tuple(len(cl) for cl in cls), n_c,
                 tuple(pts0.shape), ops.round_rows(F.shape[0]), F.shape[1], self.opt.graph_key(),
+                tuple(m.momentum for m in self._bns),          # launch arguments: a BN-momentum schedule re-captures
                 tuple(tuple(batch[k].shape) + (str(batch[k].dtype),) for k in DEVICE_KEYS))
 
     def _eager(self, batch):

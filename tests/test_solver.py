@@ -71,7 +71,10 @@ def test_saved_model_loads_into_reference(tmp_path, state_dict, args):
 
 
 @pytest.mark.gpu
-def test_solver_trains_and_resumes(tmp_path, lib_built, state_dict, args):
+@pytest.mark.parametrize('graph_train', [False, True])
+def test_solver_trains_and_resumes(tmp_path, lib_built, state_dict, args, graph_train):
+    """graph_train: the same epochs with every training iteration going through train_graph.GraphedTrainStep (first sight
+    of a signature eager, then captured / replayed; the BN-momentum schedule changes the signature every epoch)."""
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     import train_ref
@@ -99,8 +102,10 @@ def test_solver_trains_and_resumes(tmp_path, lib_built, state_dict, args):
     opt = FlatAdam(model, lr=1e-3, weight_decay=1e-5)
     dl = {'train': Loader(loader([5, 6, 7])), 'val': Loader(loader([8]))}
     s = Solver(model, train_ref.SyntheticConfig(), dl, opt, 'run', lr_decay_step=[1], lr_decay_rate=0.1, bn_decay_step=1,
-               bn_decay_rate=0.5, output_root=str(tmp_path))
+               bn_decay_rate=0.5, output_root=str(tmp_path), graph_train=graph_train)
     best = s(3, verbose=2)
+    if graph_train:
+        assert s._graph_step.replays == 6 and s._graph_step.eager_steps == 3
     root = tmp_path / 'run'
     assert all((root / f).is_file() for f in ('model.pth', 'model_last.pth', 'checkpoint.tar', 'log.txt'))
     tr = [h['loss'] for h in s.history['train']]
