@@ -93,10 +93,82 @@ k_gemm(int M, int N, int K, const float* __restrict__ A, int lda, int ta, const 
     }
 }
 
+// Skinny GEMMs of the heads (M <= 16 rows: one row per scene or per candidate, A not transposed): the 64x64-tile kernel
+// above spends its time on one CTA's serial K loop (or on a memset + split-K atomics); here every output column gets its
+// own warp (B given as (N,K): lanes stride over K, coalesced) or the K range is cut over the eight warps of a CTA (B given
+// as (K,N): lanes over columns, coalesced), all loads of a thread in flight at once, sums in a fixed order.
+#define GS_MAXM 16
+__global__ void __launch_bounds__(256)
+k_gemm_skinny_nk(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                 float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu, int accumulate) {
+    const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float acc[GS_MAXM];
+#pragma unroll
+    for (int m = 0; m < GS_MAXM; ++m) acc[m] = 0.f;
+    const float* brow = B + (long long)n * ldb;
+#pragma unroll 4
+    for (int k = lane; k < K; k += 32) {
+        const float b = brow[k];
+#pragma unroll
+        for (int m = 0; m < GS_MAXM; ++m)
+            if (m < M) acc[m] = fmaf(A[(long long)m * lda + k], b, acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < GS_MAXM; ++m) {
+        if (m >= M) break;
+        float v = warp_sum(acc[m]);
+        if (lane == 0) {
+            if (bias) v += bias[n];
+            if (accumulate) v += C[(long long)m * ldc + n];
+            if (relu) v = fmaxf(v, 0.f);
+            C[(long long)m * ldc + n] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+k_gemm_skinny_kn(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                 float* __restrict__ C, int ldc, const float* __restrict__ bias, int relu, int accumulate) {
+    __shared__ float sh[8][GS_MAXM][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, n = blockIdx.x * 32 + lane;
+    float acc[GS_MAXM];
+#pragma unroll
+    for (int m = 0; m < GS_MAXM; ++m) acc[m] = 0.f;
+    if (n < N) {
+#pragma unroll 4
+        for (int k = g; k < K; k += 8) {
+            const float b = B[(long long)k * ldb + n];
+#pragma unroll
+            for (int m = 0; m < GS_MAXM; ++m)
+                if (m < M) acc[m] = fmaf(A[(long long)m * lda + k], b, acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < GS_MAXM; ++m) sh[g][m][lane] = acc[m];
+    __syncthreads();
+    // thread (g, lane) finishes rows g and g + 8 of column n
+    for (int m = g; m < M; m += 8) {
+        if (n >= N) break;
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += sh[q][m][lane];
+        if (bias) v += bias[n];
+        if (accumulate) v += C[(long long)m * ldc + n];
+        if (relu) v = fmaxf(v, 0.f);
+        C[(long long)m * ldc + n] = v;
+    }
+}
+
 extern "C" int ir_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
                        const float* B, int32_t ldb, int32_t trans_b, float* C, int32_t ldc, const float* bias,
                        int32_t relu, int32_t accumulate, ir_stream_t stream) {
     IR_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
+    if (!trans_a && M <= GS_MAXM && K >= 32) {
+        if (trans_b) k_gemm_skinny_nk<<<ir_div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, accumulate);
+        else k_gemm_skinny_kn<<<ir_div_up(N, 32), 256, 0, (cudaStream_t)stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, accumulate);
+        IR_CHECK_LAUNCH();
+        return IR_OK;
+    }
     dim3 grid(ir_div_up(N, GM_BN), ir_div_up(M, GM_BM));
     // few output tiles and a long K (im2col conv GEMMs, weight gradients): split K over gridDim.z so the
     // launch fills the GPU; partial tiles are added with atomics into a zeroed (or accumulated-into) C

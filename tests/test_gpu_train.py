@@ -322,7 +322,10 @@ def test_fused_mlp_head(ops, norm, M, K, N1, N2):
         return Fn.linear(torch.relu(h), w2, b2)
     _check(lambda x, w1, b1, g, be, w2, b2: MLPHead.apply(x, w1, b1, g, be, w2, b2, nm_g, 0.0), ref,
            [R(M, K), R(N1, K, scale=K ** -0.5), R(N1, scale=0.1), R(N1) * 0.2 + 1, R(N1, seed=3) * 0.1,
-            R(N2, N1, scale=N1 ** -0.5), R(N2, scale=0.1)], tol=2e-4, nondiff=(2,) if norm == 'bn' else ())
+            R(N2, N1, scale=N1 ** -0.5), R(N2, scale=0.1)],
+           # BatchNorm over TWO rows: x_hat = +-1 and d x_hat / dx ~ 2 / |x1 - x2|, so the summation order of the GEMM in
+           # front of it (torch on the CPU vs the skinny kernel) is amplified in the input gradient
+           tol=1e-3 if (norm == 'bn' and M <= 2) else 2e-4, nondiff=(2,) if norm == 'bn' else ())
     if norm == 'bn':
         assert float((nm_g.running_var.cpu() - rv).abs().max()) < 1e-5 and int(nm_g.num_batches_tracked) == 1
     # dropout inside the fused head: the kept fraction and the mask reuse in backward
