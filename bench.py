@@ -318,7 +318,7 @@ def train_measure(steps, warmup, rank, world, local, cpu_baseline=True):
         dtype='f32 (rule GEMM, dgrad and wgrad on tcgen05 as split-fp16 hi/lo with fp32 accumulation)', data='synthetic',
         config=dict(workload=TRAIN_WORKLOAD_NAME, scenes_per_gpu=per_gpu, global_batch=world * per_gpu,
                     l2='inputs (2.6 MB) and activations change every step; working set > L2 over a step',
-                    parallelism=f'dp{world}: scenes sharded, gradient all-reduce in {opt.n_buckets} buckets launched on a side '
+                    parallelism=f'dp{world}: scenes sharded, gradient all-reduce in {opt.n_buckets} availability buckets launched on a side '
                                 f'stream as each branch\'s backward finishes, Adam replicated'),
         e2e=dict(value=world * per_gpu * steps / wall, unit=METRIC, ms_per_step=wall / steps * 1e3,
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=20 if stepper else 4),

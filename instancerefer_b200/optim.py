@@ -1,15 +1,19 @@
 """Optimiser side of the training step (scripts/train.py:93, lib/solver.py:200-205) for one process
 per GPU: all parameters live in ONE flat fp32 buffer (each tensor a 256-byte-aligned view), so
 
-  * ``zero_grad``      is one memset,
-  * the data-parallel gradient reduction is ONE NCCL all-reduce over 8.02 M floats,
-  * ``step``           is one fused Adam kernel (``ir_adam_step``) with the 1/world_size average
-                       folded into its gradient read.
+  * ``zero_grad``      drops the per-parameter gradients (the next backward hands new ones over without an add),
+  * the data-parallel gradient reduction is a handful of NCCL all-reduces over contiguous slices of ONE buffer of
+                       8.02 M floats,
+  * ``step``           is one fused Adam kernel (``ir_adam_step`` / ``ir_adam_step_dev``) with the 1/world_size
+                       average folded into its gradient read.
 
-Data parallel (world > 1): the flat gradient buffer is cut into a few contiguous buckets; a post-accumulate hook on
-every parameter counts the gradients of its bucket and, when the bucket is complete, packs it and launches its
-all-reduce asynchronously (NCCL's own stream) while the rest of the backward is still running — only the bucket that
-finishes last is exposed (lib/solver.py:200-205 is the step this serves).
+Data parallel (world > 1): the flat gradient buffer is cut into contiguous buckets along gradient availability (per
+sub-module; each sparse encoder's deep and shallow stages apart); a post-accumulate hook on every parameter counts the
+gradients of its bucket and, when the bucket is complete, packs it and launches its all-reduce asynchronously (NCCL's own
+stream) while the rest of the backward is still running — only the bucket that finishes last is exposed (SURVEY §5 /
+§8(e); lib/solver.py:200-205 is the step this serves).  ``early_grads`` lets a backward node hand over gradients that
+are final before it returns; ``stage_step`` / ``after_replay`` are the host halves of a step replayed from a CUDA graph
+(train_graph.GraphedTrainStep).
 
 ``torch.distributed`` is plumbing only (process group + all-reduce call)."""
 import contextlib
@@ -19,7 +23,7 @@ import torch
 from . import ops
 
 ALIGN = 64          # floats (256 B): keeps every parameter 16-byte aligned for TMA bulk copies
-BUCKET_FLOATS = 1 << 21   # >= 8 MB of gradients per all-reduce bucket when only sizes are known (8.02 M floats -> 4 buckets)
+BUCKET_FLOATS = 1 << 21   # >= 8 MB of gradients per all-reduce bucket when only sizes are known (a plain parameter list)
 
 
 def _availability_key(name):
